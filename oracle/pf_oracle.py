@@ -1,0 +1,141 @@
+"""ctypes wrapper of oracle/pf_oracle.c (the CPU restatement; TEST INFRASTRUCTURE ONLY).
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
+import this module.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+from dataclasses import dataclass
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SRC = os.path.join(_HERE, "pf_oracle.c")
+_LIB = os.path.join(_HERE, "libpf_oracle.so")
+
+
+class PfoParams(C.Structure):
+    _fields_ = [("k_min", C.c_int32), ("k_max", C.c_int32), ("table_size", C.c_uint64),
+                ("min_gc", C.c_double), ("max_gc", C.c_double), ("min_tm", C.c_double), ("max_tm", C.c_double),
+                ("max_repeat", C.c_int32), ("thal_mode", C.c_int32), ("temp_tolerance", C.c_double),
+                ("mv", C.c_double), ("dv", C.c_double), ("dntp", C.c_double), ("dna", C.c_double),
+                ("dmso", C.c_double), ("dmso_fact", C.c_double), ("formamide", C.c_double),
+                ("n_threads", C.c_int32), ("_pad", C.c_int32)]
+
+
+class PfoResult(C.Structure):
+    _fields_ = [("n_shared", C.c_uint64), ("n_genomes", C.c_int32),
+                ("k", C.POINTER(C.c_uint8)), ("word", C.POINTER(C.c_uint64)), ("flags", C.POINTER(C.c_uint8)),
+                ("gc_count", C.POINTER(C.c_int32)), ("tm", C.POINTER(C.c_double)),
+                ("contig", C.POINTER(C.c_int32)), ("start", C.POINTER(C.c_int64)), ("strand", C.POINTER(C.c_uint8)),
+                ("n_allowed", C.POINTER(C.c_uint64)), ("err", C.c_char * 256)]
+
+
+def build(force: bool = False) -> str:
+    """gcc -O2 -fopenmp -shared; rebuilt when the source is newer"""
+    if force or not os.path.exists(_LIB) or (os.path.exists(_SRC) and os.path.getmtime(_SRC) > os.path.getmtime(_LIB)):
+        subprocess.check_call(["gcc", "-O2", "-fopenmp", "-fno-fast-math", "-ffp-contract=off", "-shared", "-fPIC",
+                               "-o", _LIB, _SRC, "-lm"])
+    return _LIB
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        path = build()
+        _lib = C.CDLL(path)
+        _lib.pfo_run.restype = C.POINTER(PfoResult)
+        _lib.pfo_run.argtypes = [C.c_int32, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_int32),
+                                 C.POINTER(PfoParams)]
+        _lib.pfo_free.argtypes = [C.POINTER(PfoResult)]
+        _lib.pfo_free.restype = None
+        _lib.pfo_calc_tm.restype = C.c_double
+        _lib.pfo_calc_tm.argtypes = [C.c_char_p, C.POINTER(PfoParams)]
+        _lib.pfo_max_threads.restype = C.c_int
+    return _lib
+
+
+def default_params(k_min=16, k_max=20, min_gc=40.0, max_gc=60.0, min_tm=55.0, max_tm=68.0, max_repeat=4,
+                   thal_mode=0, temp_tolerance=5.0, table_size=9999991, n_threads=0) -> PfoParams:
+    return PfoParams(k_min=k_min, k_max=k_max, table_size=table_size, min_gc=min_gc, max_gc=max_gc, min_tm=min_tm,
+                     max_tm=max_tm, max_repeat=max_repeat, thal_mode=thal_mode, temp_tolerance=temp_tolerance,
+                     mv=50.0, dv=1.5, dntp=0.6, dna=50.0, dmso=0.0, dmso_fact=0.6, formamide=0.8,
+                     n_threads=n_threads)
+
+
+@dataclass
+class OracleResult:
+    n_shared: int
+    k: np.ndarray          # [N] uint8
+    word: np.ndarray       # [N] uint64 forward 2-bit word of the key string
+    flags: np.ndarray      # [N] uint8: 1 gc ok, 2 tm ok, 4 no repeat, 8 picked
+    gc_count: np.ndarray   # [N] int32
+    tm: np.ndarray         # [N] float64
+    contig: np.ndarray     # [G, N] int32
+    start: np.ndarray      # [G, N] int64 leftmost (+) coordinate
+    strand: np.ndarray     # [G, N] uint8 (0 '+', 1 '-')
+    n_allowed: np.ndarray  # [G, nk]
+
+    def kmer_strings(self) -> list:
+        return [word_to_str(int(w), int(k)) for w, k in zip(self.word, self.k)]
+
+
+_LET = "ATCG"
+
+
+def word_to_str(w: int, k: int) -> str:
+    return "".join(_LET[(w >> (2 * (k - 1 - i))) & 3] for i in range(k))
+
+
+def calc_tm(seq: str, params: PfoParams | None = None) -> float:
+    p = params or default_params()
+    return float(lib().pfo_calc_tm(seq.encode("ascii"), C.byref(p)))
+
+
+def max_threads() -> int:
+    return int(lib().pfo_max_threads())
+
+
+def run(genomes, params: PfoParams) -> OracleResult:
+    """genomes: list of objects with ``.contigs`` (list of uint8 ASCII arrays); genome 0 is the first genome"""
+    L = lib()
+    G = len(genomes)
+    bases_keep, offs_keep = [], []
+    for gen in genomes:
+        contigs = [np.ascontiguousarray(c, dtype=np.uint8) for c in gen.contigs]
+        cat = np.concatenate(contigs) if contigs else np.zeros(0, np.uint8)
+        off = np.zeros(len(contigs) + 1, dtype=np.int64)
+        off[1:] = np.cumsum([c.size for c in contigs])
+        bases_keep.append(np.ascontiguousarray(cat))
+        offs_keep.append(off)
+    bptr = (C.c_void_p * G)(*[b.ctypes.data for b in bases_keep])
+    optr = (C.c_void_p * G)(*[o.ctypes.data for o in offs_keep])
+    nct = (C.c_int32 * G)(*[len(g.contigs) for g in genomes])
+    rp = L.pfo_run(G, bptr, optr, nct, C.byref(params))
+    try:
+        r = rp.contents
+        err = r.err.decode()
+        if err:
+            raise RuntimeError(f"oracle: {err}")
+        N = int(r.n_shared)
+        nk = params.k_max - params.k_min + 1
+
+        def arr(ptr, n, dt):
+            if n == 0:
+                return np.zeros(0, dtype=dt)
+            return np.ctypeslib.as_array(ptr, shape=(n,)).astype(dt, copy=True)
+
+        out = OracleResult(
+            n_shared=N, k=arr(r.k, N, np.uint8), word=arr(r.word, N, np.uint64), flags=arr(r.flags, N, np.uint8),
+            gc_count=arr(r.gc_count, N, np.int32), tm=arr(r.tm, N, np.float64),
+            contig=arr(r.contig, N * G, np.int32).reshape(G, N), start=arr(r.start, N * G, np.int64).reshape(G, N),
+            strand=arr(r.strand, N * G, np.uint8).reshape(G, N), n_allowed=arr(r.n_allowed, G * nk, np.uint64).reshape(G, nk))
+    finally:
+        L.pfo_free(rp)
+    return out
