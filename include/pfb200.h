@@ -1,0 +1,142 @@
+/*
+ * pfb200.h -- C ABI of libpfb200.so, the B200 (sm_100a) implementation of primerForge's
+ * candidate-k-mer stage.
+ *
+ * The reference has no FFI: the stage is the Python function
+ *   _getAllCandidateKmers(params, sharedExists)        /root/reference/bin/getCandidateKmers.py:517
+ * called from bin/main.py:86.  These entry points are what a ctypes binding behind that function
+ * binds (see INTEGRATION.md and primerforge_b200/_lib.py); each one cites the reference code it
+ * replaces.  Plain pointers and sizes only; the library owns all device memory, the caller owns
+ * all host buffers.  Every function returns 0 on success or a negative PFB_E* code and never
+ * throws; pfb_last_error() gives the message.  A context is not thread-safe; use one per
+ * process / per GPU.
+ */
+#ifndef PFB200_H
+#define PFB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PFB_OK            0
+#define PFB_EINVAL       -1   /* bad argument / parameter out of range */
+#define PFB_ECUDA        -2   /* CUDA runtime error (no device, out of memory, launch failure) */
+#define PFB_ESTATE       -3   /* call sequence error */
+#define PFB_ENOSHARED    -4   /* no k-mer is shared by all ingroup genomes (getCandidateKmers.py:566-568) */
+#define PFB_ETOOLARGE    -5   /* a genome exceeds 2^26 padded bases */
+
+typedef struct pfb_ctx pfb_ctx;
+
+/* Stage parameters: the fields of bin/Parameters.py the stage reads plus the
+ * constants of the third-party code it calls. */
+typedef struct pfb_params {
+    int32_t  k_min, k_max;        /* params.minLen / maxLen (getCandidateKmers.py:103); 1 <= k_min <= k_max <= 32 */
+    uint32_t table_size;          /* khmer Countgraph(k, 1e7, 1) table prime = 9999991 (:46-47) */
+    int32_t  max_repeat;          /* params.maxRepeatLen: homopolymer length that is rejected (:406-409) */
+    double   min_gc, max_gc;      /* params.minGc / maxGc, inclusive (:303) */
+    double   min_tm, max_tm;      /* params.minTm / maxTm, inclusive (:307) */
+    /* primer3.calc_tm defaults (bin/Primer.py:104 passes none): mM, mM, mM, nM, %, -, mol/l */
+    double   mv_conc, dv_conc, dntp_conc, dna_conc, dmso_conc, dmso_fact, formamide_conc;
+    int32_t  prefilter;           /* 1: apply GC / repeat / Tm to genome 1's k-mers BEFORE the cross-genome join
+                                     (records are only the k-mers that pass; same candidate set, fewer records);
+                                     0: report every shared k-mer with its filter flags (== the reference's
+                                     sharedKmers dict, getCandidateKmers.py:190-219) */
+    int32_t  reserved;
+} pfb_params;
+
+/* One shared k-mer, in the reference's dict insertion order (genome-1 contig, end ascending,
+ * longest first; getCandidateKmers.py:171-187 + pyahocorasick's emission order). */
+typedef struct pfb_record {
+    uint64_t word;      /* the k-mer as it reads on genome 1's (+) strand: 2 bits per base, A0 T1 C2 G3,
+                           first base most significant */
+    double   tm;        /* primer3.calc_tm equivalent (Primer.py:102-104) */
+    uint32_t slot;      /* internal id (stable across the run) */
+    uint16_t gc_count;  /* gcPer = gc_count / k * 100 (Primer.py:89-100) */
+    uint8_t  k;
+    uint8_t  flags;     /* PFB_F_* */
+} pfb_record;
+
+#define PFB_F_GC_OK     1u   /* minGc <= gcPer <= maxGc  (getCandidateKmers.py:301-303) */
+#define PFB_F_TM_OK     2u   /* minTm <= Tm <= maxTm     (:305-307) */
+#define PFB_F_REP_OK    4u   /* no homopolymer >= maxRepeatLen (:309-320) */
+#define PFB_F_PICK      8u   /* first k-mer passing the three filters at its (contig, start) in at least one
+                                genome (:376-388 with hairpin / homodimer left to the caller) */
+#define PFB_F_PALIN    16u   /* reverse-complement palindrome */
+
+/* Position of one record in one genome (getCandidateKmers.py:173-187): contig index in the order
+ * the contigs were added, leftmost (+)-strand coordinate, strand (0 '+', 1 '-'). */
+typedef struct pfb_pos {
+    uint32_t contig;
+    uint32_t start;
+    uint32_t strand;
+} pfb_pos;
+
+/* CUDA-event timings of the last pfb_run (milliseconds) and the counts the roofline uses */
+typedef struct pfb_timing {
+    float    ms_upload;        /* host -> device copies of the ASCII bases */
+    float    ms_encode;        /* 2-bit packing */
+    float    ms_first;         /* genome-1 sketch count + select + key table build */
+    float    ms_scan;          /* all other genomes against the key table */
+    float    ms_finalize;      /* per-genome uniqueness rules, ordered emit, grouping, positions */
+    float    ms_total;         /* encode .. finalize (device resident -> device resident) */
+    uint64_t n_bases;          /* sum of ingroup bases on this context */
+    uint64_t n_windows;        /* k-mer windows hashed (all genomes, all k) */
+    uint64_t n_slots;          /* genome-1 k-mers entered into the key table */
+    uint64_t n_records;        /* shared k-mers reported */
+    uint64_t n_picked;
+    uint64_t n_launches;       /* kernels launched by the last run */
+} pfb_timing;
+
+/* lifecycle ------------------------------------------------------------------------------ */
+int  pfb_create(pfb_ctx **out, int device, const pfb_params *params);
+void pfb_destroy(pfb_ctx *ctx);
+const char *pfb_last_error(const pfb_ctx *ctx);   /* ctx may be NULL: error of the last failed pfb_create */
+int  pfb_default_params(pfb_params *p);           /* bin/Parameters.py:30-52 + primer3 defaults */
+
+/* input: one call per ingroup genome, in params.ingroupFns order; the first one added is "the first
+ * genome" of getCandidateKmers.py:85,108.  `bases` = the contigs concatenated without separators
+ * (ASCII; only upper-case A C G T are nucleotides), `contig_off` = n_contigs+1 offsets into it.
+ * Replaces the SeqIO.parse + '~'-join at getCandidateKmers.py:89-100.  The buffers are borrowed
+ * until pfb_run / pfb_upload returns (pinned memory makes the copy asynchronous). */
+int  pfb_add_genome(pfb_ctx *ctx, const uint8_t *bases, uint64_t n_bases,
+                    const uint64_t *contig_off, uint32_t n_contigs);
+int  pfb_clear_genomes(pfb_ctx *ctx);
+
+/* run: pfb_run == pfb_upload + pfb_compute.  pfb_compute can be repeated on resident inputs.
+ * Replaces __getSharedKmers (:190-219) and the GC / Tm / repeat part of __evaluateKmersAtOnePosition
+ * (:276-320, 376-388) + grouping (:222-247). */
+int  pfb_upload(pfb_ctx *ctx);
+int  pfb_compute(pfb_ctx *ctx);
+int  pfb_run(pfb_ctx *ctx);
+
+/* multi-GPU (one context per rank; genome 0 is added on every rank, the other genomes are
+ * sharded): pfb_compute == stage 0,1,2.  Between stage 0 and 1 the caller min-reduces the
+ * PFB_BUF_ALIVE buffer over ranks, between stage 1 and 2 it max-reduces PFB_BUF_PICK. */
+int  pfb_compute_stage(pfb_ctx *ctx, int stage);
+#define PFB_BUF_ALIVE 0   /* uint8 [n_slots]: 1 while the slot's k-mer is unique in every genome seen */
+#define PFB_BUF_PICK  1   /* uint8 [n_records] */
+int  pfb_device_buffer(pfb_ctx *ctx, int which, void **dev_ptr, uint64_t *n_bytes);
+int  pfb_sync(pfb_ctx *ctx);
+
+/* output ---------------------------------------------------------------------------------- */
+int  pfb_result_counts(pfb_ctx *ctx, uint64_t *n_records, uint64_t *n_picked);
+int  pfb_result_records(pfb_ctx *ctx, pfb_record *out, uint64_t cap);
+/* positions of every record (picked_only = 0) or of the picked records only, in record order, in
+ * the genome that was added as number `genome_idx` on this context */
+int  pfb_result_positions(pfb_ctx *ctx, uint32_t genome_idx, int picked_only, pfb_pos *out, uint64_t cap);
+int  pfb_timings(pfb_ctx *ctx, pfb_timing *out);
+/* per-(genome-1, k) number of k-mers that passed the sketch (debug / tests): out[nk]; counted only
+ * when pfb_set_debug_counts(ctx, 1) was called before the run */
+int  pfb_set_debug_counts(pfb_ctx *ctx, int on);
+int  pfb_first_genome_allowed(pfb_ctx *ctx, uint64_t *out, uint32_t cap);
+
+/* single-oligo helper running the device Tm / GC code on one sequence (known-answer tests,
+ * README.md:375-377); returns PFB_EINVAL for non-ACGT input */
+int  pfb_oligo_tm(pfb_ctx *ctx, const char *seq, double *tm, double *gc_percent);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PFB200_H */

@@ -1,0 +1,108 @@
+"""ctypes binding of libpfb200.so (include/pfb200.h).
+
+The CUDA library is the product: there is no CPU path.  Importing this module never touches the
+GPU; ``load()`` raises ``RuntimeError`` when the shared library has not been built and every
+call that needs a device raises when CUDA is unavailable.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libpfb200.so")
+SRC_PATH = os.path.join(_HERE, "csrc", "pfb200.cu")
+INCLUDE_DIR = os.path.join(os.path.dirname(_HERE), "include")
+
+PFB_OK, PFB_EINVAL, PFB_ECUDA, PFB_ESTATE, PFB_ENOSHARED, PFB_ETOOLARGE = 0, -1, -2, -3, -4, -5
+PFB_BUF_ALIVE, PFB_BUF_PICK = 0, 1
+F_GC_OK, F_TM_OK, F_REP_OK, F_PICK, F_PALIN = 1, 2, 4, 8, 16
+
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+              "-Xcompiler", "-fPIC", "-shared"]
+
+# every symbol include/pfb200.h declares
+EXPORTS = ["pfb_create", "pfb_destroy", "pfb_last_error", "pfb_default_params", "pfb_add_genome",
+           "pfb_clear_genomes", "pfb_upload", "pfb_compute", "pfb_run", "pfb_compute_stage",
+           "pfb_device_buffer", "pfb_sync", "pfb_result_counts", "pfb_result_records",
+           "pfb_result_positions", "pfb_timings", "pfb_set_debug_counts", "pfb_first_genome_allowed",
+           "pfb_oligo_tm"]
+
+
+class PfbParams(C.Structure):
+    _fields_ = [("k_min", C.c_int32), ("k_max", C.c_int32), ("table_size", C.c_uint32), ("max_repeat", C.c_int32),
+                ("min_gc", C.c_double), ("max_gc", C.c_double), ("min_tm", C.c_double), ("max_tm", C.c_double),
+                ("mv_conc", C.c_double), ("dv_conc", C.c_double), ("dntp_conc", C.c_double), ("dna_conc", C.c_double),
+                ("dmso_conc", C.c_double), ("dmso_fact", C.c_double), ("formamide_conc", C.c_double),
+                ("prefilter", C.c_int32), ("reserved", C.c_int32)]
+
+
+class PfbTiming(C.Structure):
+    _fields_ = [("ms_upload", C.c_float), ("ms_encode", C.c_float), ("ms_first", C.c_float), ("ms_scan", C.c_float),
+                ("ms_finalize", C.c_float), ("ms_total", C.c_float), ("n_bases", C.c_uint64), ("n_windows", C.c_uint64),
+                ("n_slots", C.c_uint64), ("n_records", C.c_uint64), ("n_picked", C.c_uint64), ("n_launches", C.c_uint64)]
+
+
+RECORD_DTYPE = np.dtype([("word", "<u8"), ("tm", "<f8"), ("slot", "<u4"), ("gc_count", "<u2"), ("k", "u1"), ("flags", "u1")])
+POS_DTYPE = np.dtype([("contig", "<u4"), ("start", "<u4"), ("strand", "<u4")])
+assert RECORD_DTYPE.itemsize == 24 and POS_DTYPE.itemsize == 12
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    """nvcc -gencode arch=compute_100a,code=sm_100a ... -> primerforge_b200/libpfb200.so (in tree)"""
+    stale = (not os.path.exists(LIB_PATH)) or os.path.getmtime(SRC_PATH) > os.path.getmtime(LIB_PATH) or \
+        os.path.getmtime(os.path.join(INCLUDE_DIR, "pfb200.h")) > os.path.getmtime(LIB_PATH)
+    if force or stale:
+        cmd = ["nvcc"] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH, SRC_PATH]
+        subprocess.check_call(cmd)
+    return LIB_PATH
+
+
+_lib = None
+
+
+def load():
+    """dlopen libpfb200.so; fails loudly when it has not been built (no fallback exists)"""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                           "(nvcc, sm_100a); primerforge_b200 has no CPU fallback")
+    lib = C.CDLL(LIB_PATH)
+    vp, u64, u32, i32 = C.c_void_p, C.c_uint64, C.c_uint32, C.c_int
+    lib.pfb_create.argtypes = [C.POINTER(vp), i32, C.POINTER(PfbParams)]
+    lib.pfb_destroy.argtypes = [vp]
+    lib.pfb_destroy.restype = None
+    lib.pfb_last_error.argtypes = [vp]
+    lib.pfb_last_error.restype = C.c_char_p
+    lib.pfb_default_params.argtypes = [C.POINTER(PfbParams)]
+    lib.pfb_add_genome.argtypes = [vp, vp, u64, vp, u32]
+    lib.pfb_clear_genomes.argtypes = [vp]
+    for fn in ("pfb_upload", "pfb_compute", "pfb_run", "pfb_sync"):
+        getattr(lib, fn).argtypes = [vp]
+    lib.pfb_compute_stage.argtypes = [vp, i32]
+    lib.pfb_device_buffer.argtypes = [vp, i32, C.POINTER(vp), C.POINTER(u64)]
+    lib.pfb_result_counts.argtypes = [vp, C.POINTER(u64), C.POINTER(u64)]
+    lib.pfb_result_records.argtypes = [vp, vp, u64]
+    lib.pfb_result_positions.argtypes = [vp, u32, i32, vp, u64]
+    lib.pfb_timings.argtypes = [vp, C.POINTER(PfbTiming)]
+    lib.pfb_set_debug_counts.argtypes = [vp, i32]
+    lib.pfb_first_genome_allowed.argtypes = [vp, vp, u32]
+    lib.pfb_oligo_tm.argtypes = [vp, C.c_char_p, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    for name in EXPORTS:
+        if name not in ("pfb_destroy", "pfb_last_error"):
+            getattr(lib, name).restype = C.c_int
+    _lib = lib
+    return lib
+
+
+def default_params() -> PfbParams:
+    p = PfbParams()
+    rc = load().pfb_default_params(C.byref(p))
+    if rc != PFB_OK:
+        raise RuntimeError("pfb_default_params failed")
+    return p

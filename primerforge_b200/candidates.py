@@ -1,0 +1,193 @@
+"""Drop-in for primerForge's candidate-k-mer stage.
+
+    from primerforge_b200.candidates import _getAllCandidateKmers
+    import bin.main; bin.main._getAllCandidateKmers = _getAllCandidateKmers
+
+Same entry point, arguments, return value, error strings and side effects as
+/root/reference/bin/getCandidateKmers.py:517-624.  The arithmetic (sketch counting, strand algebra,
+cross-genome intersection, relocation, GC / Tm / repeat filters, per-position grouping) runs in
+libpfb200.so on the GPU; hairpin / homodimer screening stays primer3 on the host, evaluated lazily
+group by group exactly like :376-388.
+"""
+from __future__ import annotations
+
+import os
+import time
+
+import numpy as np
+
+from . import _lib, seqio
+from .engine import ERR_NO_CANDIDATES, ERR_NO_SHARED, Engine, PfbError, words_to_strings
+from .primer import make_primer, primer_class
+
+_GAP = " " * 4
+_SHARED, _CAND = 1, 2        # bin/Parameters.py: pickles[_SHARED], pickles[_CAND]
+
+
+def _thal_provider(params, thal):
+    """returns f(seq_str, rc_str) -> (hairpinTm, rcHairpin, homodimerTm, rcHomodimer) or None (no screening)"""
+    if thal == "off":
+        return None
+    if callable(thal):
+        return thal
+    try:
+        import primer3  # type: ignore
+    except ImportError as exc:
+        raise ImportError("primer3-py is required for hairpin / homodimer screening "
+                          "(getCandidateKmers.py:322-370); pass thal='off' to skip it") from exc
+    kw = dict(mv_conc=params.p3_mvConc, dv_conc=params.p3_dvConc, dntp_conc=params.p3_dntpConc,
+              dna_conc=params.p3_dnaConc, temp_c=params.p3_tempC, max_loop=params.p3_maxLoop)
+
+    def run(seq, rc):
+        return (primer3.calc_hairpin_tm(seq, **kw), primer3.calc_hairpin_tm(rc, **kw),
+                primer3.calc_homodimer_tm(seq, **kw), primer3.calc_homodimer_tm(rc, **kw))
+    return run
+
+
+_RC = str.maketrans("ACGT", "TGCA")
+
+
+def screen_groups(records, positions, kmers, thal_fn, limit: float):
+    """host part of __evaluateKmersAtOnePosition (:322-388) for records that already passed GC, Tm
+    and the repeat filter on the GPU: per genome, per (contig, start) group, in dict order, the first
+    k-mer whose four secondary-structure Tms are all < limit is picked.  Returns (picked mask, thal
+    values per picked record)."""
+    n = records.size
+    cache = {}
+    picked = np.zeros(n, dtype=bool)
+
+    def passes(r):
+        v = cache.get(r)
+        if v is None:
+            s = kmers[r]
+            v = thal_fn(s, s[::-1].translate(_RC))
+            cache[r] = v
+        # hairpins first, homodimers only if the hairpins pass (:386-387); values are pure functions
+        return v[0] < limit and v[1] < limit and v[2] < limit and v[3] < limit
+
+    ok_filter = (records["flags"] & 7) == 7
+    idx_all = np.flatnonzero(ok_filter)
+    for pos in positions:
+        key = (pos["contig"][idx_all].astype(np.int64) << 32) | pos["start"][idx_all].astype(np.int64)
+        order = np.argsort(key, kind="stable")          # members of a group stay in dict (rank) order
+        ks = key[order]
+        starts = np.flatnonzero(np.r_[True, ks[1:] != ks[:-1]])
+        ends = np.r_[starts[1:], ks.size]
+        members = idx_all[order]
+        for a, b in zip(starts, ends):
+            for r in members[a:b]:
+                r = int(r)
+                if picked[r] or passes(r):
+                    picked[r] = True
+                    break
+    return picked, cache
+
+
+def build_output(names, contig_ids, records, positions, kmers, thal_values=None):
+    """__buildOutput (:442-489) + the per-contig sort (:598-602): genome -> contig -> list[Primer]"""
+    cls = primer_class()
+    k = records["k"].astype(np.int64)
+    gc_per = records["gc_count"] / records["k"] * 100
+    tm = records["tm"]
+    out = {}
+    for g, name in enumerate(names):
+        pos = positions[g]
+        order = np.lexsort((pos["strand"], k, pos["start"], pos["contig"]))
+        per_contig = {}
+        ids = contig_ids[g]
+        for r in order:
+            r = int(r)
+            cname = ids[int(pos["contig"][r])]
+            th = thal_values.get(r) if thal_values is not None else None
+            per_contig.setdefault(cname, []).append(
+                make_primer(cls, kmers[r], cname, int(pos["start"][r]), int(k[r]), bool(pos["strand"][r]),
+                            float(tm[r]), float(gc_per[r]), th))
+        out[name] = per_contig
+    return out
+
+
+def run_stage(genomes, *, k_min=16, k_max=20, min_gc=40.0, max_gc=60.0, min_tm=55.0, max_tm=68.0, max_repeat=4,
+              table_size=9999991, prefilter=True, device=0, debug_counts=False):
+    """genomes: list of (contig id list, list of uint8 ASCII arrays).  Returns (StageResult, engine timing)."""
+    with Engine(device=device, k_min=k_min, k_max=k_max, min_gc=min_gc, max_gc=max_gc, min_tm=min_tm, max_tm=max_tm,
+                max_repeat=max_repeat, table_size=table_size, prefilter=int(bool(prefilter))) as eng:
+        if debug_counts:
+            eng.set_debug_counts(True)
+        for _ids, contigs in genomes:
+            eng.add_genome(contigs)
+        eng.run()
+        n, _ = eng.counts()
+        if n == 0:
+            raise RuntimeError(ERR_NO_SHARED)
+        res = eng.result()
+        if debug_counts:
+            res.timing["first_genome_allowed"] = eng.first_genome_allowed()
+        return res
+
+
+def _getAllCandidateKmers(params, sharedExists: bool, thal="auto", device: int | None = None):
+    """gets all the candidate kmer sequences for a given ingroup (GPU implementation).
+
+    Args / Raises / Returns: as /root/reference/bin/getCandidateKmers.py:517-530.  `sharedExists` is
+    accepted for signature compatibility; the shared k-mers are recomputed (milliseconds on the GPU)
+    instead of being unpickled.
+    """
+    log = params.log
+    log.rename(_getAllCandidateKmers.__name__)
+    msg1 = f"{_GAP}getting shared ingroup kmers that appear once in each genome"
+    log.info(msg1)
+    print(msg1, end=" ... ", flush=True)
+    t0 = time.time()
+    device = int(os.environ.get("PFB200_DEVICE", "0")) if device is None else device
+    thal_fn = _thal_provider(params, os.environ.get("PFB200_THAL", thal) if thal == "auto" else thal)
+
+    names, contig_ids, genomes = [], [], []
+    for fn in params.ingroupFns:
+        ids, contigs = seqio.read_genome(fn, params.format)
+        names.append(os.path.basename(fn))
+        contig_ids.append(ids)
+        genomes.append((ids, contigs))
+    try:
+        res = run_stage(genomes, k_min=params.minLen, k_max=params.maxLen, min_gc=params.minGc, max_gc=params.maxGc,
+                        min_tm=params.minTm, max_tm=params.maxTm, max_repeat=params.maxRepeatLen, device=device)
+    except RuntimeError as exc:
+        if str(exc) == ERR_NO_SHARED:
+            log.error(ERR_NO_SHARED)
+        raise
+    print(f"done {time.time() - t0:.2f}s")
+    log.info(f"{_GAP}done {time.time() - t0:.2f}s")
+
+    msg2 = f"{_GAP}evaluating {res.records.size} kmers"
+    log.info(msg2)
+    print(msg2, end=" ... ", flush=True)
+    t1 = time.time()
+    if thal_fn is None:
+        picked = res.picked
+        thal_values = None
+    else:
+        all_kmers = res.kmer_strings()
+        picked, thal_values = screen_groups(res.records, res.positions, all_kmers, thal_fn, params.minTm - params.tempTolerance)
+    sel = np.flatnonzero(picked)
+    if sel.size == 0:
+        log.error(ERR_NO_CANDIDATES)
+        raise RuntimeError(ERR_NO_CANDIDATES)
+    rec = res.records[sel]
+    kmers = words_to_strings(rec["word"], rec["k"])
+    pos = [p[sel] for p in res.positions]
+    if thal_values is not None:
+        thal_values = {i: thal_values[int(r)] for i, r in enumerate(sel)}
+    out = build_output(names, contig_ids, rec, pos, kmers, thal_values)
+    print(f"done {time.time() - t1:.2f}s")
+    num = sum(len(v) for v in out[names[0]].values())
+    print(f"{_GAP}identified {num} candidate kmers")
+    log.info(f"{_GAP}done {time.time() - t1:.2f}s")
+    log.info(f"{_GAP}identified {num} candidate kmers")
+    params.dumpObj(out, params.pickles[_CAND], "candidate kmers", prefix=_GAP)
+    return out
+
+
+def install():
+    """splice into an importable primerForge: bin.main resolves the name at call time (main.py:12,86)"""
+    import bin.main as ref_main  # type: ignore
+    ref_main._getAllCandidateKmers = _getAllCandidateKmers
+    return ref_main

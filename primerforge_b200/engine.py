@@ -1,0 +1,185 @@
+"""Host-side driver of the CUDA candidate-k-mer engine (thin layer over the C ABI)."""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import _lib
+
+ERR_NO_SHARED = "failed to identify a set of kmers shared between the ingroup genomes"     # getCandidateKmers.py:538
+ERR_NO_CANDIDATES = "none of the ingroup kmers are suitable for use as a primer"            # getCandidateKmers.py:539
+
+_LETTERS = np.frombuffer(b"ATCG", dtype=np.uint8)
+
+
+class PfbError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"libpfb200 error {code}: {msg}")
+        self.code = code
+
+
+@dataclass
+class StageResult:
+    records: np.ndarray      # RECORD_DTYPE [N] in the reference's dict order
+    positions: list          # per local genome: POS_DTYPE [N]
+    timing: dict
+
+    @property
+    def picked(self) -> np.ndarray:
+        return (self.records["flags"] & _lib.F_PICK) != 0
+
+    def kmer_strings(self, idx=None) -> list:
+        rec = self.records if idx is None else self.records[idx]
+        return words_to_strings(rec["word"], rec["k"])
+
+
+def words_to_strings(words: np.ndarray, ks: np.ndarray) -> list:
+    """2-bit words (A0 T1 C2 G3, first base most significant) -> str"""
+    words = np.asarray(words, dtype=np.uint64)
+    ks = np.asarray(ks, dtype=np.int64)
+    n = words.size
+    if n == 0:
+        return []
+    kmax = int(ks.max())
+    shifts = (2 * (ks[:, None] - 1 - np.arange(kmax)[None, :])).clip(min=0).astype(np.uint64)
+    codes = ((words[:, None] >> shifts) & np.uint64(3)).astype(np.intp)
+    chars = _LETTERS[codes]
+    raw = chars.tobytes()
+    return [raw[i * kmax:i * kmax + int(ks[i])].decode("ascii") for i in range(n)]
+
+
+class Engine:
+    """one CUDA context (= one GPU).  Usage: add_genome()* -> run() -> result()"""
+
+    def __init__(self, device: int = 0, **params):
+        self._lib = _lib.load()
+        p = _lib.default_params()
+        for key, val in params.items():
+            if not hasattr(p, key):
+                raise TypeError(f"unknown parameter {key!r}")
+            setattr(p, key, val)
+        self.params = p
+        self._ctx = C.c_void_p()
+        rc = self._lib.pfb_create(C.byref(self._ctx), int(device), C.byref(p))
+        if rc != _lib.PFB_OK:
+            raise PfbError(rc, self._lib.pfb_last_error(None).decode())
+        self._keep = []
+        self.n_genomes = 0
+
+    # -- plumbing
+    def _check(self, rc: int):
+        if rc != _lib.PFB_OK:
+            raise PfbError(rc, self._lib.pfb_last_error(self._ctx).decode())
+
+    def close(self):
+        if getattr(self, "_ctx", None) and self._ctx.value:
+            self._lib.pfb_destroy(self._ctx)
+            self._ctx = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    # -- input
+    def add_genome(self, contigs=None, bases: np.ndarray | None = None, offsets: np.ndarray | None = None):
+        """contigs: list of uint8 ASCII arrays; or a pre-concatenated (bases, offsets) pair (zero copy)"""
+        if bases is None:
+            contigs = [np.ascontiguousarray(c, dtype=np.uint8) for c in contigs]
+            bases = np.concatenate(contigs) if len(contigs) > 1 else (contigs[0] if contigs else np.zeros(0, np.uint8))
+            offsets = np.zeros(len(contigs) + 1, dtype=np.uint64)
+            offsets[1:] = np.cumsum([c.size for c in contigs])
+        bases = np.ascontiguousarray(bases, dtype=np.uint8)
+        offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+        self._keep.append((bases, offsets))
+        self._check(self._lib.pfb_add_genome(self._ctx, bases.ctypes.data, bases.size, offsets.ctypes.data, offsets.size - 1))
+        self.n_genomes += 1
+
+    def add_genome_ptr(self, ptr: int, n_bases: int, offsets: np.ndarray):
+        """bases already in (pinned) host memory at address `ptr`"""
+        offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+        self._keep.append((None, offsets))
+        self._check(self._lib.pfb_add_genome(self._ctx, ptr, n_bases, offsets.ctypes.data, offsets.size - 1))
+        self.n_genomes += 1
+
+    def clear(self):
+        self._check(self._lib.pfb_clear_genomes(self._ctx))
+        self._keep = []
+        self.n_genomes = 0
+
+    # -- run
+    def upload(self):
+        self._check(self._lib.pfb_upload(self._ctx))
+
+    def compute(self):
+        self._check(self._lib.pfb_compute(self._ctx))
+
+    def compute_stage(self, stage: int):
+        self._check(self._lib.pfb_compute_stage(self._ctx, stage))
+
+    def run(self):
+        self._check(self._lib.pfb_run(self._ctx))
+
+    def sync(self):
+        self._check(self._lib.pfb_sync(self._ctx))
+
+    def set_debug_counts(self, on: bool = True):
+        self._check(self._lib.pfb_set_debug_counts(self._ctx, int(on)))
+
+    def device_buffer(self, which: int):
+        ptr, n = C.c_void_p(), C.c_uint64()
+        self._check(self._lib.pfb_device_buffer(self._ctx, which, C.byref(ptr), C.byref(n)))
+        return ptr.value or 0, int(n.value)
+
+    # -- output
+    def counts(self):
+        n, m = C.c_uint64(), C.c_uint64()
+        rc = self._lib.pfb_result_counts(self._ctx, C.byref(n), C.byref(m))
+        if rc not in (_lib.PFB_OK, _lib.PFB_ENOSHARED):
+            self._check(rc)
+        return int(n.value), int(m.value)
+
+    def timing(self) -> dict:
+        t = _lib.PfbTiming()
+        self._check(self._lib.pfb_timings(self._ctx, C.byref(t)))
+        return {name: getattr(t, name) for name, _ in t._fields_}
+
+    def first_genome_allowed(self) -> np.ndarray:
+        nk = self.params.k_max - self.params.k_min + 1
+        out = np.zeros(nk, dtype=np.uint64)
+        self._check(self._lib.pfb_first_genome_allowed(self._ctx, out.ctypes.data, nk))
+        return out
+
+    def records(self) -> np.ndarray:
+        n, _ = self.counts()
+        out = np.empty(n, dtype=_lib.RECORD_DTYPE)
+        self._check(self._lib.pfb_result_records(self._ctx, out.ctypes.data, n))
+        return out
+
+    def positions(self, genome_idx: int, picked_only: bool = False) -> np.ndarray:
+        n, m = self.counts()
+        cnt = m if picked_only else n
+        out = np.empty(cnt, dtype=_lib.POS_DTYPE)
+        self._check(self._lib.pfb_result_positions(self._ctx, genome_idx, int(picked_only), out.ctypes.data, cnt))
+        return out
+
+    def result(self, picked_only: bool = False) -> StageResult:
+        rec = self.records()
+        if picked_only:
+            rec = rec[(rec["flags"] & _lib.F_PICK) != 0]
+        pos = [self.positions(g, picked_only) for g in range(self.n_genomes)]
+        return StageResult(records=rec, positions=pos, timing=self.timing())
+
+    def oligo_tm(self, seq: str):
+        tm, gc = C.c_double(), C.c_double()
+        self._check(self._lib.pfb_oligo_tm(self._ctx, seq.encode("ascii"), C.byref(tm), C.byref(gc)))
+        return tm.value, gc.value

@@ -1,0 +1,71 @@
+"""Ingroup file readers: FASTA / GenBank -> contig ids + ASCII base arrays.
+
+Takes the place of Bio.SeqIO.parse at /root/reference/bin/getCandidateKmers.py:93,212 (biopython
+is not a dependency of this package).  Record id rules follow biopython: FASTA id = header up to
+the first whitespace (sequence case preserved); GenBank id = VERSION accession if present, else the
+LOCUS name (sequence upper-cased).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+_NL, _CR, _SP, _GT = 10, 13, 32, 62
+
+
+def read_fasta(path: str):
+    data = np.fromfile(path, dtype=np.uint8)
+    if data.size == 0:
+        return [], []
+    gt = np.flatnonzero(data == _GT)
+    if gt.size:
+        at_line_start = np.ones(gt.size, dtype=bool)
+        nz = gt > 0
+        at_line_start[nz] = data[gt[nz] - 1] == _NL
+        gt = gt[at_line_start]
+    nl = np.flatnonzero(data == _NL)
+    ids, contigs = [], []
+    for i, st in enumerate(gt):
+        end = int(gt[i + 1]) if i + 1 < gt.size else data.size
+        j = np.searchsorted(nl, st)
+        hdr_end = int(nl[j]) if j < nl.size and nl[j] < end else end
+        header = data[st + 1:hdr_end].tobytes().decode("latin-1").strip("\r")
+        parts = header.split(None, 1)
+        ids.append(parts[0] if parts else "")
+        body = data[min(hdr_end + 1, end):end]
+        keep = (body != _NL) & (body != _CR) & (body != _SP)
+        contigs.append(np.ascontiguousarray(body[keep]))
+    return ids, contigs
+
+
+def read_genbank(path: str):
+    ids, contigs = [], []
+    locus = version = None
+    chunks = None
+    with open(path, "r") as fh:
+        for line in fh:
+            if line.startswith("LOCUS"):
+                f = line.split()
+                locus, version, chunks = (f[1] if len(f) > 1 else "<unknown id>"), None, None
+            elif line.startswith("VERSION"):
+                f = line.split()
+                version = f[1] if len(f) > 1 else None
+            elif line.startswith("ORIGIN"):
+                chunks = []
+            elif line.startswith("//"):
+                if locus is not None:
+                    seq = "".join(chunks or []).upper()
+                    ids.append(version or locus)
+                    contigs.append(np.frombuffer(seq.encode("latin-1"), dtype=np.uint8).copy())
+                locus = version = chunks = None
+            elif chunks is not None:
+                chunks.append("".join(ch for ch in line if ch.isalpha()))
+    return ids, contigs
+
+
+def read_genome(path: str, fmt: str):
+    fmt = fmt.lower()
+    if fmt == "fasta":
+        return read_fasta(path)
+    if fmt in ("genbank", "gb"):
+        return read_genbank(path)
+    raise ValueError(f"unsupported ingroup format {fmt!r}")

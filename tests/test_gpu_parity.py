@@ -1,0 +1,175 @@
+"""GPU parity tests: libpfb200.so (through the C ABI) against the committed reference outputs and
+against the CPU oracle on seeded inputs.  Integer / index / strand results are compared bit for
+bit; Tm and GC % must agree within 0.01 (BASELINE.json north_star) -- they are in fact identical."""
+import zlib
+
+import numpy as np
+import pytest
+
+from tests.util import candidate_set_from_arrays, golden_candidate_set, golden_cases, load_golden
+
+pytestmark = pytest.mark.gpu
+
+TOL = 0.01
+
+
+def _engine(gold_or_kw, prefilter):
+    from primerforge_b200.engine import Engine
+    kw = gold_or_kw if isinstance(gold_or_kw, dict) else dict(
+        k_min=gold_or_kw.k_min, k_max=gold_or_kw.k_max, min_gc=gold_or_kw.min_gc, max_gc=gold_or_kw.max_gc,
+        min_tm=gold_or_kw.min_tm, max_tm=gold_or_kw.max_tm, max_repeat=gold_or_kw.max_repeat,
+        table_size=gold_or_kw.table_size)
+    return Engine(device=0, prefilter=int(prefilter), **kw)
+
+
+def _pseudo_thal(seq, rc):
+    def one(s, salt):
+        return ((zlib.crc32(s.encode("ascii")) ^ ((salt * 0x9E3779B1) & 0xFFFFFFFF)) % 6400) / 100.0
+    return one(seq, 1), one(rc, 1), one(seq, 2), one(rc, 2)
+
+
+def _run(genomes, kw, prefilter):
+    eng = _engine(kw, prefilter)
+    eng.set_debug_counts(True)
+    for g in genomes:
+        eng.add_genome(g.contigs)
+    eng.run()
+    res = eng.result()
+    allowed = eng.first_genome_allowed()
+    eng.close()
+    return res, allowed
+
+
+def _picked(res, thal, limit):
+    from primerforge_b200.candidates import screen_groups
+    if thal == "pseudo":
+        picked, _ = screen_groups(res.records, res.positions, res.kmer_strings(), _pseudo_thal, limit)
+        return picked
+    return res.picked
+
+
+@pytest.mark.parametrize("name", golden_cases())
+def test_full_mode_equals_reference_shared_dict(name):
+    gold = load_golden(name)
+    res, _ = _run(gold.genomes, gold, prefilter=False)
+    kmers = res.kmer_strings()
+    assert kmers == gold.shared                      # set AND dict insertion order
+    for gi in range(len(gold.genomes)):
+        pos = res.positions[gi]
+        assert np.array_equal(pos["contig"], gold.z[f"g{gi}_sh_contig"])
+        assert np.array_equal(pos["start"].astype(np.int64), gold.z[f"g{gi}_sh_start"])
+        assert np.array_equal(pos["strand"].astype(np.uint8), gold.z[f"g{gi}_sh_strand"])
+    picked = _picked(res, gold.thal, gold.min_tm - gold.temp_tolerance)
+    for gi in range(len(gold.genomes)):
+        pos = res.positions[gi]
+        mine = candidate_set_from_arrays(kmers, res.records["k"], picked, pos["contig"], pos["start"], pos["strand"])
+        assert mine == golden_candidate_set(gold, gi)
+    # Tm / GC of the reference's candidates
+    z = gold.z
+    idx = z["g0_cand_kmer"]
+    assert np.max(np.abs(res.records["tm"][idx] - z["g0_cand_tm"]), initial=0.0) <= TOL
+    gc = res.records["gc_count"][idx] / res.records["k"][idx] * 100
+    assert np.max(np.abs(gc - z["g0_cand_gc"]), initial=0.0) <= TOL
+
+
+@pytest.mark.parametrize("name", golden_cases())
+def test_prefilter_mode_equals_reference_candidates(name):
+    gold = load_golden(name)
+    res, _ = _run(gold.genomes, gold, prefilter=True)
+    assert np.all((res.records["flags"] & 7) == 7)
+    kmers = res.kmer_strings()
+    picked = _picked(res, gold.thal, gold.min_tm - gold.temp_tolerance)
+    for gi in range(len(gold.genomes)):
+        pos = res.positions[gi]
+        mine = candidate_set_from_arrays(kmers, res.records["k"], picked, pos["contig"], pos["start"], pos["strand"])
+        assert mine == golden_candidate_set(gold, gi)
+
+
+CASES = [
+    dict(n=3, length=200_000, seed=201, n_contigs=1, kw=dict()),
+    dict(n=5, length=60_000, seed=202, n_contigs=7, kw=dict(table_size=1000003)),
+    dict(n=4, length=50_000, seed=203, n_contigs=3, n_frac=0.0005, kw=dict(table_size=65521, k_min=12, k_max=30, max_repeat=3)),
+    dict(n=2, length=30_000, seed=204, n_contigs=40, kw=dict(table_size=20011, k_min=10, k_max=32)),
+    dict(n=1, length=50_000, seed=205, n_contigs=2, kw=dict()),
+    dict(n=6, length=40_000, seed=206, n_contigs=1, kw=dict(k_min=20, k_max=20, min_gc=30.0, max_gc=70.0, min_tm=50.0, max_tm=75.0)),
+]
+
+
+@pytest.mark.parametrize("case", CASES, ids=lambda c: f"seed{c['seed']}")
+@pytest.mark.parametrize("prefilter", [False, True])
+def test_against_oracle(case, prefilter):
+    from oracle import pf_oracle as po
+    from primerforge_b200 import synth
+    gens = synth.make_genomes(case["n"], case["length"], seed=case["seed"], snp_rate=0.003, n_inversions=3,
+                              n_contigs=case["n_contigs"], n_frac=case.get("n_frac", 0.0))
+    kw = dict(k_min=16, k_max=20, min_gc=40.0, max_gc=60.0, min_tm=55.0, max_tm=68.0, max_repeat=4, table_size=9999991)
+    kw.update(case["kw"])
+    o = po.run(gens, po.default_params(**kw))
+    res, allowed = _run(gens, kw, prefilter)
+    rec = res.records
+    if not prefilter:
+        assert np.array_equal(allowed, o.n_allowed[0])          # per-k size of genome 1's F - R
+        assert rec.size == o.n_shared
+        assert np.array_equal(rec["word"], o.word) and np.array_equal(rec["k"], o.k)
+        assert np.array_equal(rec["flags"] & 15, o.flags)
+        assert np.array_equal(rec["gc_count"].astype(np.int32), o.gc_count)
+        assert np.max(np.abs(rec["tm"] - o.tm), initial=0.0) <= TOL
+        assert np.array_equal(rec["tm"], o.tm)                   # same IEEE operations -> identical doubles
+        for gi in range(len(gens)):
+            pos = res.positions[gi]
+            assert np.array_equal(pos["contig"].astype(np.int32), o.contig[gi])
+            assert np.array_equal(pos["start"].astype(np.int64), o.start[gi])
+            assert np.array_equal(pos["strand"].astype(np.uint8), o.strand[gi])
+    else:
+        keep = (o.flags & 7) == 7
+        assert rec.size == int(keep.sum())
+        assert np.array_equal(rec["word"], o.word[keep]) and np.array_equal(rec["k"], o.k[keep])
+        assert np.array_equal((rec["flags"] & 8) != 0, (o.flags[keep] & 8) != 0)
+        for gi in range(len(gens)):
+            pos = res.positions[gi]
+            assert np.array_equal(pos["contig"].astype(np.int32), o.contig[gi][keep])
+            assert np.array_equal(pos["start"].astype(np.int64), o.start[gi][keep])
+            assert np.array_equal(pos["strand"].astype(np.uint8), o.strand[gi][keep])
+
+
+def test_readme_tm_rows_on_device():
+    from primerforge_b200.engine import Engine
+    from tests.test_oracle_tm import README_ROWS
+    from oracle import pf_oracle as po
+    with Engine(device=0) as eng:
+        for seq, tm, gc in README_ROWS + [("GAATTCGAATTC", None, None), ("AGAGTTTGATCCTGGCTCAG", None, None)]:
+            dtm, dgc = eng.oligo_tm(seq)
+            assert dtm == po.calc_tm(seq)
+            if tm is not None:
+                assert round(dtm, 1) == tm and round(dgc, 1) == gc
+
+
+def test_no_shared_kmers_raises():
+    from primerforge_b200 import synth
+    from primerforge_b200.candidates import run_stage
+    from primerforge_b200.engine import ERR_NO_SHARED
+    a = synth.make_genomes(1, 5000, seed=301)[0]
+    b = synth.make_genomes(1, 5000, seed=302)[0]
+    with pytest.raises(RuntimeError, match=ERR_NO_SHARED):
+        run_stage([(a.contig_ids, a.contigs), (b.contig_ids, b.contigs)])
+
+
+def test_empty_and_ragged_inputs():
+    from primerforge_b200 import synth
+    from primerforge_b200.engine import Engine, PfbError
+    from oracle import pf_oracle as po
+    gens = synth.make_genomes(3, 20_000, seed=303, snp_rate=0.002, n_inversions=1)
+    # ragged: an empty contig, a 1-base contig and a contig shorter than k in the middle of genome 2
+    a = gens[1].contigs[0]
+    gens[1].contigs = [a[:5000], a[5000:5000], a[5000:5001], a[5001:5012], a[5012:]]
+    gens[1].contig_ids = [f"c{i}" for i in range(5)]
+    kw = dict(k_min=16, k_max=20, min_gc=40.0, max_gc=60.0, min_tm=55.0, max_tm=68.0, max_repeat=4, table_size=9999991)
+    o = po.run(gens, po.default_params(**kw))
+    res, _ = _run(gens, kw, prefilter=False)
+    assert np.array_equal(res.records["word"], o.word)
+    for gi in range(3):
+        assert np.array_equal(res.positions[gi]["contig"].astype(np.int32), o.contig[gi])
+        assert np.array_equal(res.positions[gi]["start"].astype(np.int64), o.start[gi])
+    with Engine(device=0) as eng:
+        with pytest.raises(PfbError):
+            eng.run()                                   # no genome added
