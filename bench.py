@@ -1,0 +1,323 @@
+#!/usr/bin/env python
+"""bench.py -- candidate-k-mer stage throughput (ingroup Mbp/s) on N B200s, one JSON line.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--config 2] [--impl reference]
+
+A step = one full pass of the stage (2-bit encode, genome-1 sketch, key table, scan of every other
+genome, uniqueness rules, ordered emit, filters, grouping) over one batch of synthetic genomes of
+BASELINE.json's config (default: configs[1] = 10 x 5 Mbp, primer_len 16-20, default GC/Tm).
+
+  value : device-resident ASCII bases -> device-resident records, CUDA events on the library's
+          stream, L2 flushed between steps, max over ranks.
+  e2e   : the same stage through the C ABI with HOST (pinned) buffers: H2D of the bases, compute,
+          D2H of the records and of the picked candidates' coordinates in every genome.
+  N > 1 : launched by torchrun, one rank per GPU; every rank holds genome 0 (it defines the key
+          table) plus its own shard of the other genomes; the only exchanges are a MIN all-reduce of
+          the per-key alive bytes and a MAX all-reduce of the pick bytes (NCCL).  Weak scaling:
+          1 + 9 genomes per rank, throughput counts DISTINCT ingroup bases.
+  --impl reference : the CPU restatement of the reference (oracle/pf_oracle.c, OpenMP, all host
+          threads) on a bounded sample of the same workload; the reference itself is pure Python +
+          khmer/primer3/pyahocorasick which are not installable in this image.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "candidate-k-mer stage ingroup Mbp/s"
+UNIT = "Mbp/s"
+SURVEY_BYTES_PER_BASE = {1: 139.0, 2: 99.0, 3: 99.0, 4: 99.0, 5: 248.0}   # SURVEY.md 8(d) worked estimates
+L2_PROBE_PEAK_G = 290.0   # measured random 32 B-sector loads, profiles/r01_ubench_l2_smem.txt
+
+
+def measured_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "measured"
+    except Exception:
+        return 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)"""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self) -> dict:
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], None, set()
+        for row in self.rows:
+            f = [x.strip() for x in row.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                smax = float(f[2])
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        busy = [x for x in sm if smax and x > 0.5 * smax] or sm
+        return {"sm_mhz": float(np.median(busy)) if busy else None, "sm_max_mhz": smax, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def cpu_sample_run(cfg_index: int, threads: int = 0):
+    """the CPU restatement on a bounded sample: 3 genomes x 1 Mbp of the same generator / parameters"""
+    from oracle import pf_oracle as po
+    from primerforge_b200 import synth
+    cfg = synth.CONFIGS[cfg_index]
+    n_g, length = 3, 1_000_000
+    gens = synth.make_genomes(n_g, length, seed=synth.BASE_SEED + cfg_index, n_contigs=cfg["n_contigs"])
+    par = po.default_params(k_min=cfg["k_min"], k_max=cfg["k_max"], max_repeat=cfg["max_repeats"], n_threads=threads)
+    t0 = time.perf_counter()
+    o = po.run(gens, par)
+    dt = time.perf_counter() - t0
+    cores = threads or po.max_threads()
+    return dict(value=n_g * length / 1e6 / dt, unit=UNIT, cores=cores, kind="port",
+                sample=f"{n_g} x {length} bp genomes of the config-{cfg_index} generator, k {cfg['k_min']}-{cfg['k_max']}, "
+                       f"oracle/pf_oracle.c (OpenMP), {dt:.2f} s, {o.n_shared} shared k-mers"), dt
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    vals, last = [], None
+    for i in range(args.warmup + args.steps):
+        cb, dt = cpu_sample_run(args.config)
+        if i >= args.warmup:
+            vals.append((cb["value"], dt))
+        last = cb
+    value = float(np.mean([v for v, _ in vals]))
+    ms = float(np.mean([d for _, d in vals]) * 1e3)
+    last["value"] = value
+    cfg = workload_config(args.config, 1)
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64",
+            "data": "synthetic", "impl": "reference", "config": cfg, "cpu_baseline": last,
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+def workload_config(index: int, n_gpus: int) -> dict:
+    from primerforge_b200 import synth
+    cfg = synth.CONFIGS[index]
+    per_rank = cfg["n_genomes"]
+    total = per_rank if n_gpus == 1 else 1 + (per_rank - 1) * n_gpus
+    return {"workload": f"BASELINE config {index}: {per_rank} synthetic {cfg['length'] / 1e6:g} Mbp ingroup genomes per GPU "
+                        f"({total} distinct genomes in the job), primer_len {cfg['k_min']},{cfg['k_max']}, default GC/Tm, "
+                        f"max_repeats {cfg['max_repeats']}, {cfg['n_contigs']} contig(s) per genome",
+            "genomes_per_gpu": per_rank, "distinct_genomes": total, "genome_bp": cfg["length"], "k_min": cfg["k_min"],
+            "k_max": cfg["k_max"], "table_size": 9999991, "prefilter": 1, "l2": "flushed between steps (256 MiB write)",
+            "parallelism": f"genome-sharded x{n_gpus}, key table replicated" if n_gpus > 1 else "single GPU"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--config", type=int, default=2)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--genomes", type=int, default=None, help="override genomes per GPU (debug)")
+    ap.add_argument("--length", type=int, default=None, help="override genome length (debug)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 0)
+
+    if args.impl == "reference":
+        run_reference_arm(args)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from primerforge_b200 import _lib, synth
+    from primerforge_b200.dist import allreduce_stage_buffers
+    from primerforge_b200.engine import Engine
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU path)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    cfg = dict(synth.CONFIGS[args.config])
+    if args.genomes:
+        cfg["n_genomes"] = args.genomes
+    if args.length:
+        cfg["length"] = args.length
+    per_rank = cfg["n_genomes"]
+    n_distinct = per_rank if world == 1 else 1 + (per_rank - 1) * world
+    # the generator is sequential in the genome index: every rank generates the prefix it needs
+    last_needed = per_rank if world == 1 else 1 + (per_rank - 1) * (rank + 1)
+    gens = synth.make_genomes(last_needed, cfg["length"], seed=synth.BASE_SEED + args.config, n_contigs=cfg["n_contigs"])
+    mine = gens[:per_rank] if world == 1 else [gens[0]] + gens[1 + (per_rank - 1) * rank: 1 + (per_rank - 1) * (rank + 1)]
+    del gens
+    distinct_bases = n_distinct * cfg["length"]
+
+    # pinned host buffers (the e2e leg copies from these every step)
+    pinned = []
+    for g in mine:
+        cat = np.concatenate(g.contigs) if len(g.contigs) > 1 else g.contigs[0]
+        t = torch.empty(cat.size, dtype=torch.uint8).pin_memory()
+        t.numpy()[:] = cat
+        off = np.zeros(len(g.contigs) + 1, dtype=np.uint64)
+        off[1:] = np.cumsum([c.size for c in g.contigs])
+        pinned.append((t, off))
+    del mine
+
+    eng = Engine(device=local, k_min=cfg["k_min"], k_max=cfg["k_max"], max_repeat=cfg["max_repeats"], prefilter=1)
+    for t, off in pinned:
+        eng.add_genome_ptr(t.data_ptr(), t.numel(), off)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def compute_once():
+        if world == 1:
+            eng.compute()
+        else:
+            eng.compute_stage(0)
+            allreduce_stage_buffers(eng, _lib.PFB_BUF_ALIVE, "min")
+            eng.compute_stage(1)
+            allreduce_stage_buffers(eng, _lib.PFB_BUF_PICK, "max")
+            eng.compute_stage(2)
+
+    def fetch_results():
+        rec = eng.records()
+        pos = [eng.positions(g, picked_only=True) for g in range(eng.n_genomes)]
+        return rec, pos
+
+    # ---- device-resident leg
+    eng.upload()
+    for _ in range(args.warmup):
+        flush.zero_()
+        barrier()
+        compute_once()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    dev_ms, launches, scan_ms = [], 0, []
+    barrier()
+    wall0 = time.perf_counter()
+    for _ in range(args.steps):
+        flush.zero_()
+        barrier()
+        compute_once()
+        tm = eng.timing()
+        dev_ms.append(tm["ms_total"])
+        scan_ms.append(tm["ms_scan"])
+        launches += tm["n_launches"]
+    barrier()
+    wall = time.perf_counter() - wall0
+    tm = eng.timing()
+
+    # ---- end-to-end leg (host buffers -> host results through the C ABI)
+    e2e_s = []
+    h2d = sum(t.numel() for t, _ in pinned)
+    d2h = 0
+    for i in range(max(1, args.warmup // 2) + args.steps):
+        flush.zero_()
+        barrier()
+        t0 = time.perf_counter()
+        eng.upload()
+        compute_once()
+        rec, pos = fetch_results()
+        eng.sync()
+        dt = time.perf_counter() - t0
+        if i >= max(1, args.warmup // 2):
+            e2e_s.append(dt)
+            d2h = rec.nbytes + sum(p.nbytes for p in pos)
+    clocks = sampler.stop() if rank == 0 else None
+
+    step_ms = float(np.mean(dev_ms))
+    e2e_ms = float(np.mean(e2e_s) * 1e3)
+    if world > 1:
+        red = torch.tensor([step_ms, e2e_ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(red, op=dist.ReduceOp.MAX)
+        step_ms, e2e_ms = red.tolist()
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    value = distinct_bases / 1e6 / (step_ms / 1e3)
+    e2e_val = distinct_bases / 1e6 / (e2e_ms / 1e3)
+    peak, peak_kind = measured_peaks()
+    # roofline of the dominant kernel (k_scan<SCAN>: every genome but the first)
+    scan_bases = tm["n_bases"] - cfg["length"]
+    bpb = SURVEY_BYTES_PER_BASE[args.config]
+    ms_scan = float(np.mean(scan_ms))
+    alg_bytes = bpb * scan_bases
+    achieved = alg_bytes / (ms_scan / 1e3) / 1e9 if ms_scan > 0 else 0.0
+    nk = cfg["k_max"] - cfg["k_min"] + 1
+    probes = scan_bases * nk
+    roofline = {"bound": "hbm", "kernel": "k_scan<SCAN>", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": None, "peak_kind": peak_kind,
+                "algorithmic_bytes_per_launch": alg_bytes, "bytes_per_base": bpb, "ms_per_launch": ms_scan,
+                "share_of_step": ms_scan / step_ms if step_ms else None,
+                "actual_limiter": {"kind": "L2 random 32B-sector probes (one per window and k)",
+                                   "achieved_gprobes_s": probes / (ms_scan / 1e3) / 1e9 if ms_scan > 0 else 0.0,
+                                   "peak_gprobes_s": L2_PROBE_PEAK_G,
+                                   "frac": (probes / (ms_scan / 1e3) / 1e9) / L2_PROBE_PEAK_G if ms_scan > 0 else 0.0}}
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64",
+            "data": "synthetic", "config": workload_config(args.config, world) | ({"genomes_per_gpu": per_rank, "genome_bp": cfg["length"]}),
+            "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_ms},
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
+            "phases_ms": {k: tm[k] for k in ("ms_encode", "ms_first", "ms_scan", "ms_finalize", "ms_total", "ms_upload")},
+            "counts": {k: int(tm[k]) for k in ("n_bases", "n_windows", "n_slots", "n_records", "n_picked")},
+            "wall_s_timed_loop": wall}
+    if world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"], _ = cpu_sample_run(args.config)
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

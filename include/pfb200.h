@@ -77,8 +77,8 @@ typedef struct pfb_pos {
 typedef struct pfb_timing {
     float    ms_upload;        /* host -> device copies of the ASCII bases */
     float    ms_encode;        /* 2-bit packing */
-    float    ms_first;         /* genome-1 sketch count + select + key table build */
-    float    ms_scan;          /* all other genomes against the key table */
+    float    ms_first;         /* genome-1 candidate table + key table build */
+    float    ms_scan;          /* every genome against the key table (the hot kernel) */
     float    ms_finalize;      /* per-genome uniqueness rules, ordered emit, grouping, positions */
     float    ms_total;         /* encode .. finalize (device resident -> device resident) */
     uint64_t n_bases;          /* sum of ingroup bases on this context */
@@ -87,6 +87,7 @@ typedef struct pfb_timing {
     uint64_t n_records;        /* shared k-mers reported */
     uint64_t n_picked;
     uint64_t n_launches;       /* kernels launched by the last run */
+    uint64_t used_filter;      /* 1: the scan probed through the shared-memory filter (k_scan_filtered) */
 } pfb_timing;
 
 /* lifecycle ------------------------------------------------------------------------------ */
@@ -127,10 +128,9 @@ int  pfb_result_records(pfb_ctx *ctx, pfb_record *out, uint64_t cap);
  * the genome that was added as number `genome_idx` on this context */
 int  pfb_result_positions(pfb_ctx *ctx, uint32_t genome_idx, int picked_only, pfb_pos *out, uint64_t cap);
 int  pfb_timings(pfb_ctx *ctx, pfb_timing *out);
-/* per-(genome-1, k) number of k-mers that passed the sketch (debug / tests): out[nk]; counted only
- * when pfb_set_debug_counts(ctx, 1) was called before the run */
-int  pfb_set_debug_counts(pfb_ctx *ctx, int on);
-int  pfb_first_genome_allowed(pfb_ctx *ctx, uint64_t *out, uint32_t cap);
+/* how the scan probes the key bitmap: 0 auto (default), 1 plain L2 probe (k_scan<SCAN>), 2 through the
+ * 192 KB shared-memory filter (k_scan_filtered).  Results are identical; tests run both. */
+int  pfb_set_scan_mode(pfb_ctx *ctx, int mode);
 
 /* single-oligo helper running the device Tm / GC code on one sequence (known-answer tests,
  * README.md:375-377); returns PFB_EINVAL for non-ACGT input */

@@ -28,8 +28,7 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", 
 EXPORTS = ["pfb_create", "pfb_destroy", "pfb_last_error", "pfb_default_params", "pfb_add_genome",
            "pfb_clear_genomes", "pfb_upload", "pfb_compute", "pfb_run", "pfb_compute_stage",
            "pfb_device_buffer", "pfb_sync", "pfb_result_counts", "pfb_result_records",
-           "pfb_result_positions", "pfb_timings", "pfb_set_debug_counts", "pfb_first_genome_allowed",
-           "pfb_oligo_tm"]
+           "pfb_result_positions", "pfb_timings", "pfb_set_scan_mode", "pfb_oligo_tm"]
 
 
 class PfbParams(C.Structure):
@@ -43,7 +42,8 @@ class PfbParams(C.Structure):
 class PfbTiming(C.Structure):
     _fields_ = [("ms_upload", C.c_float), ("ms_encode", C.c_float), ("ms_first", C.c_float), ("ms_scan", C.c_float),
                 ("ms_finalize", C.c_float), ("ms_total", C.c_float), ("n_bases", C.c_uint64), ("n_windows", C.c_uint64),
-                ("n_slots", C.c_uint64), ("n_records", C.c_uint64), ("n_picked", C.c_uint64), ("n_launches", C.c_uint64)]
+                ("n_slots", C.c_uint64), ("n_records", C.c_uint64), ("n_picked", C.c_uint64), ("n_launches", C.c_uint64),
+                ("used_filter", C.c_uint64)]
 
 
 RECORD_DTYPE = np.dtype([("word", "<u8"), ("tm", "<f8"), ("slot", "<u4"), ("gc_count", "<u2"), ("k", "u1"), ("flags", "u1")])
@@ -90,8 +90,7 @@ def load():
     lib.pfb_result_records.argtypes = [vp, vp, u64]
     lib.pfb_result_positions.argtypes = [vp, u32, i32, vp, u64]
     lib.pfb_timings.argtypes = [vp, C.POINTER(PfbTiming)]
-    lib.pfb_set_debug_counts.argtypes = [vp, i32]
-    lib.pfb_first_genome_allowed.argtypes = [vp, vp, u32]
+    lib.pfb_set_scan_mode.argtypes = [vp, i32]
     lib.pfb_oligo_tm.argtypes = [vp, C.c_char_p, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     for name in EXPORTS:
         if name not in ("pfb_destroy", "pfb_last_error"):

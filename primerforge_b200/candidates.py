@@ -107,22 +107,18 @@ def build_output(names, contig_ids, records, positions, kmers, thal_values=None)
 
 
 def run_stage(genomes, *, k_min=16, k_max=20, min_gc=40.0, max_gc=60.0, min_tm=55.0, max_tm=68.0, max_repeat=4,
-              table_size=9999991, prefilter=True, device=0, debug_counts=False):
+              table_size=9999991, prefilter=True, device=0, scan_mode=0):
     """genomes: list of (contig id list, list of uint8 ASCII arrays).  Returns (StageResult, engine timing)."""
     with Engine(device=device, k_min=k_min, k_max=k_max, min_gc=min_gc, max_gc=max_gc, min_tm=min_tm, max_tm=max_tm,
                 max_repeat=max_repeat, table_size=table_size, prefilter=int(bool(prefilter))) as eng:
-        if debug_counts:
-            eng.set_debug_counts(True)
+        eng.set_scan_mode(scan_mode)
         for _ids, contigs in genomes:
             eng.add_genome(contigs)
         eng.run()
         n, _ = eng.counts()
         if n == 0:
             raise RuntimeError(ERR_NO_SHARED)
-        res = eng.result()
-        if debug_counts:
-            res.timing["first_genome_allowed"] = eng.first_genome_allowed()
-        return res
+        return eng.result()
 
 
 def _getAllCandidateKmers(params, sharedExists: bool, thal="auto", device: int | None = None):

@@ -9,23 +9,25 @@
 //
 //   * every contig is packed to 2 bits per base (A0 T1 C2 G3, khmer's code) + 1 invalid bit, each
 //     contig word-aligned in one arena (k_encode);
-//   * genome 1 alone needs the full sketch: 2 bits per bin (seen once / seen again) updated with
-//     L2-resident atomicOr (k_scan<COUNT1>), strand-specific polluters (windows touching a '~'
-//     junction or a non-ACGT byte) go to two side bitmaps (k_junction, COUNT1);
-//   * a genome-1 k-mer that survives the sketch owns its bin, so (k, bin) is a perfect hash of the
-//     key set: a bitmap over bins + popcount ranks gives a dense slot id (k_scan<SELECT1>, k_rank,
-//     k_scan<FILL1>) -- this replaces both the string sets and the Aho-Corasick automaton;
-//   * every other genome is ONE pass (k_scan<SCAN>): window -> bin -> bitmap probe (L2); on a hit the
-//     64-bit canonical word is compared with the slot's key: equal = an occurrence (position and
-//     orientation OR-ed into the genome's row, a second one raises DUP), different = a sketch
-//     collision in that genome (POLL).  A slot is shared iff every genome has exactly one
-//     occurrence and no collision on the strand table the reference would have read;
+//   * genome 1's CANDIDATE windows (one end G/C, ACGT only, and -- with prefilter -- GC / repeat / Tm
+//     in range) are entered into a 2-bit-per-bin table (seen once / seen again) with L2-resident
+//     atomicOr (k_scan<CAND1>).  A candidate that is alone in its bin owns the bin, so (k, bin) is a
+//     perfect hash of the key set: a bitmap over bins + popcount ranks gives a dense slot id
+//     (k_candbits, k_scan_p*, k_scan<FILL1>) -- this replaces the string sets and the Aho-Corasick
+//     automaton;
+//   * every genome, the first included, is then ONE pass (k_scan<SCAN> / k_scan_filtered):
+//     window -> bin -> bitmap probe; on a hit the 64-bit canonical word is compared with the slot's
+//     key: equal = an occurrence (position and orientation OR-ed into the genome's row, a second one
+//     raises DUP), different = a sketch collision in that genome (POLL); windows touching a '~'
+//     junction or a non-ACGT byte pollute only one strand's table (JF / JR; k_junction).  A slot is
+//     shared iff every genome has exactly one occurrence and a clean bin in the strand table the
+//     reference would have read.  The probe goes through a per-k Bloom-style filter held in shared
+//     memory (192 KB per CTA) so that only ~1 in 6 windows reaches L2;
 //   * survivors are emitted in the reference's dict order by an ordered compaction over genome 1
 //     (k_scan<EMIT_*>), filters are evaluated in fp64 with the reference's operation order, the
 //     per-position "first k-mer that passes" pick is an atomicMin over a direct-mapped array.
 //
-// No tensor cores: nothing here is a contraction.  The hot kernel (SCAN) is bound by L2 sector
-// reads (one 32 B sector per window and k), see DESIGN.md / profiles/.
+// No tensor cores: nothing here is a contraction.
 
 #include "../../include/pfb200.h"
 
@@ -51,15 +53,23 @@ constexpr uint32_t ROW_JF = 1u << 30;           // forward-string-only polluter 
 constexpr uint32_t ROW_JR = 1u << 31;           // reverse-string-only polluter
 constexpr uint32_t MAX_GENOME_WORDS = 1u << 21; // 2^26 padded bases
 
-enum Mode { COUNT1 = 0, SELECT1 = 1, SCAN = 2, FILL1 = 3, EMIT_COUNT = 4, EMIT_WRITE = 5 };
+constexpr uint32_t FILTER_BYTES = 192u * 1024u; // shared-memory filter of k_scan_filtered
+constexpr uint32_t FILTER_BITS = FILTER_BYTES * 8u;
+constexpr uint32_t FILTER_WORDS = FILTER_BYTES / 4u;
+constexpr int SCAN_TILE = 2048;                 // elements per block of the device-wide scans
+
+enum Mode { CAND1 = 0, FILL1 = 1, SCAN = 2, EMIT_COUNT = 3, EMIT_WRITE = 4 };
 
 struct K {  // kernel arguments (by value)
     int kmin, kmax, nk;
-    uint32_t P, PW, SW;       // table prime, words per 1-bit bitmap, words per 2-bit sketch
+    uint32_t P, PW;           // table prime, words per 1-bit bitmap (the 2-bit table has 2 * PW words)
     uint64_t barrett;         // floor(2^64 / P)
-    int max_repeat, prefilter, dbg_counts;
-    double min_gc, max_gc, min_tm, max_tm;
-    double ln_salt, ln_dna4, ln_dna1, dmso_term, formamide;
+    uint32_t fscale;          // floor(FILTER_BITS * 2^32 / P): bin -> filter bit
+    int max_repeat, prefilter;
+    double min_tm, max_tm;
+    double ln_salt, ln_dna4, ln_dna1, dmso_term;
+    uint64_t gc_ok[33];       // per k: bit c set <=> gc count c is inside [minGc, maxGc]
+    const double *fterm;      // [33][33] formamide term per (k, gc count)
     // arena
     const uint8_t *raw;
     uint64_t *seq2;
@@ -69,10 +79,8 @@ struct K {  // kernel arguments (by value)
     const uint64_t *cRawStart;
     const uint32_t *gWordStart, *gFirstContig, *gNumContigs, *gVirtLen;
     uint32_t nContigs, nGenomes, totalWords;
-    // genome-1 sketch + key table
-    uint32_t *sk, *jf, *jr, *bits, *rank, *slotBase;
-    uint32_t *g1flags;        // [0] != 0: genome 1 has strand-specific polluters
-    unsigned long long *allowedCnt;
+    // genome-1 candidate table + key table
+    uint32_t *sk, *bits, *rank, *filter;
     uint32_t *passmask1;
     uint64_t *canon1;
     uint8_t *slotK;
@@ -82,7 +90,6 @@ struct K {  // kernel arguments (by value)
     // output
     uint32_t *emitCnt;        // per genome-1 word
     pfb_record *rec;
-    uint32_t *recCount;
     pfb_pos *pos;             // [nGenomes][nrec]
     uint32_t *minRank;        // [totalWords*32]
     uint8_t *pick;
@@ -113,32 +120,30 @@ __device__ __forceinline__ uint32_t mod_p(uint64_t x, const K &p) {
     return r >= p.P ? r - p.P : r;
 }
 
-// GC / repeat / Tm of one k-mer given as forward word (first base most significant).
-// Operation order mirrors primer3's oligotm() as restated in oracle/pf_oracle.c so that the doubles
-// agree bit for bit (no FMA contraction: explicit _rn intrinsics).
 __device__ __forceinline__ int gc_count(uint64_t h) { return __popcll(h & 0xAAAAAAAAAAAAAAAAull); }
 
-__device__ double oligo_tm(uint64_t h, int k, const K &p) {
-    int dh = 0, ds = 0;
+// Tm of one k-mer given as forward word (first base most significant).  Operation order mirrors
+// primer3's oligotm() as restated in oracle/pf_oracle.c so that the doubles agree bit for bit
+// (explicit _rn intrinsics: no FMA contraction).  nn = 16-entry table in shared memory (bank =
+// index, so a warp's divergent lookups never conflict).
+__device__ __forceinline__ double oligo_tm(uint64_t h, int k, int gc, const K &p, const uint32_t *nn) {
     uint64_t rc = rc64(h) >> (64 - 2 * k);
     bool sym = ((k & 1) == 0) && rc == h;
+    uint32_t acc = 0;
+#pragma unroll 4
+    for (int i = 0; i < k - 1; i++) acc += nn[(h >> (2 * i)) & 15];
+    int dh = (int)(acc & 0xFFFF), ds = (int)(acc >> 16);
     if (sym) ds += 14;
     int first = (int)((h >> (2 * k - 2)) & 3), last = (int)(h & 3);
     if (first < 2) { ds += -41; dh += -23; } else { ds += 28; dh += -1; }
     if (last < 2)  { ds += -41; dh += -23; } else { ds += 28; dh += -1; }
-    for (int i = 0; i < k - 1; i++) {
-        uint32_t v = c_nn[(h >> (2 * i)) & 15];
-        dh += (int)(v & 0xFFFF);
-        ds += (int)(v >> 16);
-    }
-    int gc = gc_count(h);
     double delta_h = __dmul_rn((double)dh, -100.0);
     double delta_s = __dmul_rn((double)ds, -0.1);
     delta_s = __dadd_rn(delta_s, __dmul_rn(__dmul_rn(0.368, (double)(k - 1)), p.ln_salt));
     double ln_dna = sym ? p.ln_dna1 : p.ln_dna4;
     double tm = __dsub_rn(__ddiv_rn(delta_h, __dadd_rn(delta_s, __dmul_rn(1.987, ln_dna))), 273.15);
     tm = __dsub_rn(tm, p.dmso_term);
-    tm = __dadd_rn(tm, __dmul_rn(__dsub_rn(__dmul_rn(0.453, __ddiv_rn((double)gc, (double)k)), 2.88), p.formamide));
+    tm = __dadd_rn(tm, p.fterm[k * 33 + gc]);
     return tm;
 }
 
@@ -152,26 +157,35 @@ __device__ __forceinline__ bool has_long_repeat(uint64_t h, int k, int R) {
     return y != 0;
 }
 
-__device__ __forceinline__ uint32_t filter_flags(uint64_t h, int k, const K &p, double *tm_out) {
+// the three sequence filters of __evaluateKmersAtOnePosition (:301-320), cheapest first
+__device__ __forceinline__ bool passes_filters(uint64_t h, int k, const K &p, const uint32_t *nn) {
+    int gc = gc_count(h);
+    if (!((p.gc_ok[k] >> gc) & 1ull)) return false;
+    if (has_long_repeat(h, k, p.max_repeat)) return false;
+    double tm = oligo_tm(h, k, gc, p, nn);
+    return tm >= p.min_tm && tm <= p.max_tm;
+}
+
+__device__ __forceinline__ uint32_t filter_flags(uint64_t h, int k, const K &p, const uint32_t *nn, double *tm_out) {
     uint32_t f = 0;
-    double gcper = __dmul_rn(__ddiv_rn((double)gc_count(h), (double)k), 100.0);   // Primer.py:100
-    if (gcper >= p.min_gc && gcper <= p.max_gc) f |= PFB_F_GC_OK;
+    int gc = gc_count(h);
+    if ((p.gc_ok[k] >> gc) & 1ull) f |= PFB_F_GC_OK;
     if (!has_long_repeat(h, k, p.max_repeat)) f |= PFB_F_REP_OK;
-    double tm = oligo_tm(h, k, p);
+    double tm = oligo_tm(h, k, gc, p, nn);
     if (tm >= p.min_tm && tm <= p.max_tm) f |= PFB_F_TM_OK;
-    if (tm_out) *tm_out = tm;
+    *tm_out = tm;
     return f;
 }
 
-// slot id of a set bit
+// slot id of a set bit (rank is the exclusive popcount prefix over the concatenated per-k bitmaps)
 __device__ __forceinline__ uint32_t slot_of(const K &p, int ki, uint32_t bin, uint32_t word) {
-    return p.slotBase[ki] + p.rank[(size_t)ki * p.PW + (bin >> 5)] + __popc(word & ((1u << (bin & 31)) - 1u));
+    return p.rank[(size_t)ki * p.PW + (bin >> 5)] + __popc(word & ((1u << (bin & 31)) - 1u));
 }
 
 // ------------------------------------------------------------------------------------------
 // k_encode: ASCII -> 2 bits / base (+ invalid mask); one thread per 32-base word.
 // Replaces str(rec.seq) / reverse_complement / '~'.join (getCandidateKmers.py:93-100).
-__global__ void __launch_bounds__(256) k_encode(K p, uint32_t w0, uint32_t w1) {
+__global__ void __launch_bounds__(256) k_encode(const __grid_constant__ K p, uint32_t w0, uint32_t w1) {
     uint32_t w = w0 + blockIdx.x * blockDim.x + threadIdx.x;
     if (w >= w1) return;
     // owning contig: last contig whose first word is <= w
@@ -207,46 +221,64 @@ __global__ void __launch_bounds__(256) k_encode(K p, uint32_t w0, uint32_t w1) {
         inval |= (nb & 0xFu) << (28 - 4 * t);
     }
     if (nvalid < 32) {   // tail of the contig: pad = invalid
-        uint32_t padmask = 0xFFFFFFFFu >> nvalid;
-        inval |= padmask;
+        inval |= 0xFFFFFFFFu >> nvalid;
         packed |= ~0ull >> (2 * nvalid);
     }
     p.seq2[w] = packed;
     p.nmask[w] = inval;
     p.wordContig[w] = c;
-    if (p.cGenome[c] == 0) {
-        uint32_t real = nvalid < 32 ? inval & ~(0xFFFFFFFFu >> nvalid) : inval;
-        if (real) atomicOr(&p.g1flags[0], 1u);
-    }
 }
 
 // ------------------------------------------------------------------------------------------
-// polluter bookkeeping shared by the scan kernels and k_junction
-template <bool FIRST>
+// bookkeeping of one probe hit; shared by the scan kernels and k_junction
+__device__ __forceinline__ void on_hit(const K &p, int ki, uint32_t g, uint32_t bin, uint32_t word, uint64_t canon,
+                                       bool h_is_canon, uint32_t start) {
+    uint32_t idx = slot_of(p, ki, bin, word);
+    uint32_t *row = &p.rows[(size_t)g * p.nslots + idx];
+    if (p.canon1[idx] == canon) {
+        uint32_t old = atomicOr(row, ROW_HAS | (h_is_canon ? ROW_ORI : 0u) | start);
+        if (old & ROW_HAS) atomicOr(row, ROW_DUP);
+    } else {
+        atomicOr(row, ROW_POLL);
+    }
+}
+
 __device__ __forceinline__ void pollute(const K &p, int ki, uint32_t g, uint64_t canon, bool rev_table) {
     uint32_t bin = mod_p(canon, p);
-    if (FIRST) {
-        uint32_t *bm = rev_table ? p.jr : p.jf;
-        atomicOr(&bm[(size_t)ki * p.PW + (bin >> 5)], 1u << (bin & 31));
-    } else {
-        uint32_t word = p.bits[(size_t)ki * p.PW + (bin >> 5)];
-        if ((word >> (bin & 31)) & 1u) {
-            uint32_t idx = slot_of(p, ki, bin, word);
-            atomicOr(&p.rows[(size_t)g * p.nslots + idx], rev_table ? ROW_JR : ROW_JF);
-        }
+    uint32_t word = p.bits[(size_t)ki * p.PW + (bin >> 5)];
+    if ((word >> (bin & 31)) & 1u) {
+        uint32_t idx = slot_of(p, ki, bin, word);
+        atomicOr(&p.rows[(size_t)g * p.nslots + idx], rev_table ? ROW_JR : ROW_JF);
     }
+}
+
+// window with >= 1 non-ACGT byte: a strand-specific polluter.  The forward string hashes the byte as
+// (3, comp 2); the reverse-complement string keeps the byte, so there it is again (3, comp 2).
+__device__ __noinline__ void pollute_invalid_window(const K &p, int ki, int k, uint32_t g, uint64_t h, uint64_t r, uint32_t wn) {
+    uint64_t canon_f = h < r ? h : r;
+    uint64_t h2 = r, r2 = h;
+    for (int t = 0; t < k; t++)
+        if ((wn >> t) & 1u) { h2 |= 1ull << (2 * (k - 1 - t)); r2 &= ~(1ull << (2 * t)); }
+    uint64_t canon_r = h2 < r2 ? h2 : r2;
+    pollute(p, ki, g, canon_f, false);
+    pollute(p, ki, g, canon_r, true);
 }
 
 // ------------------------------------------------------------------------------------------
 // k_scan: one thread per 32-base word = 32 window end positions x nk lengths.
-//   COUNT1   genome 1: sketch update (fkh.consume / rkh.consume, getCandidateKmers.py:46-51)
-//   SELECT1  genome 1: the set comprehension + F - R (:54-59) (+ GC / repeat / Tm when prefilter)
-//   FILL1    genome 1: write key / position of every slot
-//   SCAN     other genomes: F ^ R membership (:54-55, 62-63), the per-k intersection (:127-142) and
-//            the relocation (:160-187) in one probe
+//   CAND1    genome 1: candidate windows -> 2-bit table (the part of fkh.consume + the set
+//            comprehension of getCandidateKmers.py:46-55 that can matter for the result)
+//   FILL1    genome 1: key of every slot
+//   SCAN     all genomes: sketch membership (:54-55), strand algebra (:58-63), the per-k intersection
+//            (:127-142) and the relocation (:160-187) in one probe (plain L2 version)
 //   EMIT_*   ordered compaction of the surviving slots in the reference's dict order
 template <int MODE>
-__global__ void __launch_bounds__(256) k_scan(K p, uint32_t w0, uint32_t w1) {
+__global__ void __launch_bounds__(256) k_scan(const __grid_constant__ K p, uint32_t w0, uint32_t w1) {
+    __shared__ uint32_t s_nn[16];
+    if (MODE == CAND1 || MODE == EMIT_WRITE) {
+        if (threadIdx.x < 16) s_nn[threadIdx.x] = c_nn[threadIdx.x];
+        __syncthreads();
+    }
     uint32_t w = w0 + blockIdx.x * blockDim.x + threadIdx.x;
     if (w >= w1) return;
     uint32_t c = p.wordContig[w];
@@ -258,9 +290,7 @@ __global__ void __launch_bounds__(256) k_scan(K p, uint32_t w0, uint32_t w1) {
     uint32_t qbase = 32u * i;
     int nj = (int)min(32u, clen - qbase);
     uint32_t gpos0 = 32u * (w - p.gWordStart[g]);   // genome-local padded coordinate of base j = 0
-    const bool g1poll = (MODE == SELECT1) ? (p.g1flags[0] != 0) : false;
-    uint32_t emitted = 0;
-    uint32_t emit_at = 0;
+    uint32_t emitted = 0, emit_at = 0;
     if (MODE == EMIT_WRITE) emit_at = p.emitCnt[w - w0];
 
     for (int j = 0; j < nj; j++) {
@@ -273,10 +303,6 @@ __global__ void __launch_bounds__(256) k_scan(K p, uint32_t w0, uint32_t w1) {
         if (MODE == FILL1 || MODE == EMIT_COUNT || MODE == EMIT_WRITE) {
             pm = p.passmask1[gpos0 + j];
             if (!pm) continue;
-        }
-        const uint64_t nmw = nm >> (31 - j);
-
-        if (MODE == EMIT_COUNT || MODE == EMIT_WRITE || MODE == FILL1) {
             // longest first at one end position (pyahocorasick emission order)
             for (int k = khi; k >= p.kmin; k--) {
                 int ki = k - p.kmin;
@@ -285,17 +311,17 @@ __global__ void __launch_bounds__(256) k_scan(K p, uint32_t w0, uint32_t w1) {
                 uint64_t canon = h < r ? h : r;
                 uint32_t bin = mod_p(canon, p);
                 uint32_t word = p.bits[(size_t)ki * p.PW + (bin >> 5)];
+                if (!((word >> (bin & 31)) & 1u)) continue;     // candidate was not alone in its bin
                 uint32_t idx = slot_of(p, ki, bin, word);
                 if (MODE == FILL1) {
                     p.canon1[idx] = canon;
                     p.slotK[idx] = (uint8_t)k;
-                    p.rows[idx] = ROW_HAS | (h <= r ? ROW_ORI : 0u) | (gpos0 + j - k + 1);
                 } else {
                     if (!p.alive[idx]) continue;
                     if (MODE == EMIT_WRITE) {
                         pfb_record rec;
                         double tm;
-                        uint32_t f = filter_flags(h, k, p, &tm);
+                        uint32_t f = filter_flags(h, k, p, s_nn, &tm);
                         if (h == r) f |= PFB_F_PALIN;
                         rec.word = h; rec.tm = tm; rec.slot = idx; rec.gc_count = (uint16_t)gc_count(h);
                         rec.k = (uint8_t)k; rec.flags = (uint8_t)f;
@@ -307,75 +333,112 @@ __global__ void __launch_bounds__(256) k_scan(K p, uint32_t w0, uint32_t w1) {
             continue;
         }
 
+        const uint64_t nmw = nm >> (31 - j);
         for (int k = p.kmin; k <= khi; k++) {
             int ki = k - p.kmin;
             uint64_t h = hf & kmask2(k), r = hr >> (64 - 2 * k);
             uint32_t wn = (uint32_t)(nmw & kmask1(k));      // invalid bases inside the window (bit t = age t)
-            if (wn) {
-                if (MODE == SELECT1) continue;
-                // strand-specific polluter: the forward string hashes the byte as (3, comp 2); the
-                // reverse-complement string keeps the byte, so there it is again (3, comp 2)
-                uint64_t canon_f = h < r ? h : r;
-                uint64_t h2 = r, r2 = h;
-                for (int t = 0; t < k; t++)
-                    if ((wn >> t) & 1u) { h2 |= 1ull << (2 * (k - 1 - t)); r2 &= ~(1ull << (2 * t)); }
-                uint64_t canon_r = h2 < r2 ? h2 : r2;
-                pollute<MODE == COUNT1>(p, ki, g, canon_f, false);
-                pollute<MODE == COUNT1>(p, ki, g, canon_r, true);
-                continue;
-            }
-            uint64_t canon = h < r ? h : r;
-            if (MODE == SELECT1) {
-                // isOneEndGc (:29-33) before touching memory
-                if (((h >> (2 * k - 2)) & 3) < 2 && (h & 3) < 2) continue;
-            }
-            uint32_t bin = mod_p(canon, p);
-            if (MODE == COUNT1) {
-                uint32_t *cell = &p.sk[(size_t)ki * p.SW + (bin >> 4)];
+            if (MODE == CAND1) {
+                if (wn) continue;                                                  // not a k-mer (:40-43 / non-ACGT)
+                if (((h >> (2 * k - 2)) & 3) < 2 && (h & 3) < 2) continue;          // isOneEndGc (:29-33)
+                if (p.prefilter && !passes_filters(h, k, p, s_nn)) continue;
+                uint64_t canon = h < r ? h : r;
+                uint32_t bin = mod_p(canon, p);
+                uint32_t *cell = &p.sk[(size_t)ki * 2 * p.PW + (bin >> 4)];
                 uint32_t b = bin & 15u;
                 uint32_t old = atomicOr(cell, 1u << b);
                 if ((old >> b) & 1u) atomicOr(cell, 1u << (16 + b));
-            } else if (MODE == SELECT1) {
-                uint32_t st = p.sk[(size_t)ki * p.SW + (bin >> 4)];
-                uint32_t b = bin & 15u;
-                if (!((st >> b) & 1u) || ((st >> (16 + b)) & 1u)) continue;   // get(x) == 1 (:35-38)
-                bool inF = true, inR = true;
-                if (g1poll) {
-                    inF = !((p.jf[(size_t)ki * p.PW + (bin >> 5)] >> (bin & 31)) & 1u);
-                    inR = !((p.jr[(size_t)ki * p.PW + (bin >> 5)] >> (bin & 31)) & 1u);
-                }
-                bool keep = (h == r) ? (inF && !inR) : inF;   // first genome: F - R (:58-59)
-                if (!keep) continue;
-                if (p.dbg_counts) atomicAdd(&p.allowedCnt[ki], 1ull);
-                if (p.prefilter && (filter_flags(h, k, p, nullptr) & 7u) != 7u) continue;
-                atomicOr(&p.bits[(size_t)ki * p.PW + (bin >> 5)], 1u << (bin & 31));
                 pm |= 1u << ki;
-            } else if (MODE == SCAN) {
+            } else {  // SCAN
+                if (wn) { pollute_invalid_window(p, ki, k, g, h, r, wn); continue; }
+                uint64_t canon = h < r ? h : r;
+                uint32_t bin = mod_p(canon, p);
                 uint32_t word = __ldg(&p.bits[(size_t)ki * p.PW + (bin >> 5)]);
-                if ((word >> (bin & 31)) & 1u) {
-                    uint32_t idx = slot_of(p, ki, bin, word);
-                    uint32_t *row = &p.rows[(size_t)g * p.nslots + idx];
-                    if (p.canon1[idx] == canon) {
-                        uint32_t val = ROW_HAS | (h <= r ? ROW_ORI : 0u) | (gpos0 + j - k + 1);
-                        uint32_t old = atomicOr(row, val);
-                        if (old & ROW_HAS) atomicOr(row, ROW_DUP);
-                    } else {
-                        atomicOr(row, ROW_POLL);
-                    }
-                }
+                if ((word >> (bin & 31)) & 1u) on_hit(p, ki, g, bin, word, canon, h <= r, gpos0 + j - k + 1);
             }
         }
-        if (MODE == SELECT1) p.passmask1[gpos0 + j] = pm;
+        if (MODE == CAND1) p.passmask1[gpos0 + j] = pm;
     }
     if (MODE == EMIT_COUNT) p.emitCnt[w - w0] = emitted;
+}
+
+// ------------------------------------------------------------------------------------------
+// k_scan_filtered: the SCAN pass with the probe staged through shared memory.  One persistent CTA
+// per SM; for each k a CTA copies that k's 192 KB filter (1 bit per ~6.4 bins, set when any bin of
+// the range holds a key) into shared memory and walks its share of the arena: only windows whose
+// filter bit is set go on to the exact bitmap in L2.
+__global__ void __launch_bounds__(1024, 1) k_scan_filtered(const __grid_constant__ K p, uint32_t w0, uint32_t w1) {
+    extern __shared__ uint32_t s_filter[];
+    const uint32_t stride = gridDim.x * blockDim.x;
+    for (int ki = 0; ki < p.nk; ki++) {
+        const int k = p.kmin + ki;
+        __syncthreads();
+        {
+            const uint4 *src = (const uint4 *)(p.filter + (size_t)ki * FILTER_WORDS);
+            uint4 *dst = (uint4 *)s_filter;
+            for (uint32_t t = threadIdx.x; t < FILTER_WORDS / 4; t += blockDim.x) dst[t] = __ldg(src + t);
+        }
+        __syncthreads();
+        const uint64_t km2 = kmask2(k);
+        const uint64_t km1 = kmask1(k);
+        const int rsh = 64 - 2 * k;
+        for (uint32_t w = w0 + blockIdx.x * blockDim.x + threadIdx.x; w < w1; w += stride) {
+            uint32_t c = p.wordContig[w];
+            uint32_t cws = p.cWordStart[c], clen = p.cLen[c];
+            uint32_t i = w - cws;
+            uint32_t qbase = 32u * i;
+            int nj = (int)min(32u, clen - qbase);
+            int jlo = (int)qbase + 1 >= k ? 0 : k - 1 - (int)qbase;   // first end position with a full window
+            if (jlo >= nj) continue;
+            uint32_t g = p.cGenome[c];
+            uint64_t cur = p.seq2[w], prev = i ? p.seq2[w - 1] : 0ull;
+            uint64_t nm = ((uint64_t)(i ? p.nmask[w - 1] : 0u) << 32) | p.nmask[w];
+            uint32_t gpos0 = 32u * (w - p.gWordStart[g]);
+            // state after base jlo - 1
+            uint64_t hf = jlo ? ((prev << (2 * jlo)) | (cur >> (64 - 2 * jlo))) : prev;
+            uint64_t hr = rc64(hf);
+#pragma unroll 4
+            for (int j = jlo; j < nj; j++) {
+                uint32_t code = (uint32_t)(cur >> (62 - 2 * j)) & 3u;
+                hf = (hf << 2) | code;
+                hr = (hr >> 2) | ((uint64_t)(code ^ 1u) << 62);
+                uint64_t h = hf & km2, r = hr >> rsh;
+                if (nm) {
+                    uint32_t wn = (uint32_t)((nm >> (31 - j)) & km1);
+                    if (wn) { pollute_invalid_window(p, ki, k, g, h, r, wn); continue; }
+                }
+                uint64_t canon = h < r ? h : r;
+                uint32_t bin = mod_p(canon, p);
+                uint32_t fb = __umulhi(bin, p.fscale);
+                if (!((s_filter[fb >> 5] >> (fb & 31)) & 1u)) continue;
+                uint32_t word = __ldg(&p.bits[(size_t)ki * p.PW + (bin >> 5)]);
+                if ((word >> (bin & 31)) & 1u) on_hit(p, ki, g, bin, word, canon, h <= r, gpos0 + j - k + 1);
+            }
+        }
+    }
+}
+
+// filter bit of every key bin
+__global__ void __launch_bounds__(256) k_build_filter(const __grid_constant__ K p) {
+    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (uint32_t)p.nk * p.PW) return;
+    uint32_t word = p.bits[t];
+    if (!word) return;
+    uint32_t ki = t / p.PW, wi = t - ki * p.PW;
+    uint32_t *f = p.filter + (size_t)ki * FILTER_WORDS;
+    while (word) {
+        int b = __ffs(word) - 1;
+        word &= word - 1;
+        uint32_t fb = __umulhi(wi * 32u + b, p.fscale);
+        atomicOr(&f[fb >> 5], 1u << (fb & 31));
+    }
 }
 
 // ------------------------------------------------------------------------------------------
 // k_junction: windows of the '~'-joined strings that touch a junction (getCandidateKmers.py:99-100):
 // they never become k-mers (:40-43) but khmer counts them ('~' hashes like G).  One thread per
 // (contig boundary, k, strand string, window offset) in the virtual joined coordinates.
-template <bool FIRST>
-__global__ void __launch_bounds__(128) k_junction(K p, uint32_t c0, uint32_t c1) {
+__global__ void __launch_bounds__(128) k_junction(const __grid_constant__ K p, uint32_t c0, uint32_t c1) {
     const int T = 2 * p.kmax - 1;
     unsigned long long tid = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
     int t = (int)(tid % T); tid /= T;
@@ -410,22 +473,40 @@ __global__ void __launch_bounds__(128) k_junction(K p, uint32_t c0, uint32_t c1)
         h = (h << 2) | cf;
         r = (r >> 2) | ((uint64_t)cc << (2 * (k - 1)));
     }
-    uint64_t canon = h < r ? h : r;
-    if (FIRST) atomicOr(&p.g1flags[0], 1u);
-    pollute<FIRST>(p, ki, g, canon, rev != 0);
+    pollute(p, ki, g, h < r ? h : r, rev != 0);
 }
 
 // ------------------------------------------------------------------------------------------
-// k_rank: exclusive popcount prefix of each k's bitmap (one block per k) -> dense slot ids
-__global__ void __launch_bounds__(1024) k_rank(K p, uint32_t *ktotal) {
-    __shared__ uint32_t sm[1024];
-    int ki = blockIdx.x;
-    const uint32_t *bm = p.bits + (size_t)ki * p.PW;
-    uint32_t *rk = p.rank + (size_t)ki * p.PW;
-    uint32_t per = (p.PW + blockDim.x - 1) / blockDim.x;
-    uint32_t a = min(p.PW, threadIdx.x * per), b = min(p.PW, a + per);
+// bits = seen once and not seen again
+__global__ void __launch_bounds__(256) k_candbits(const __grid_constant__ K p) {
+    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (uint32_t)p.nk * p.PW) return;
+    uint32_t lo = p.sk[2 * (size_t)t], hi = p.sk[2 * (size_t)t + 1];
+    p.bits[t] = ((lo & ~(lo >> 16)) & 0xFFFFu) | ((hi & ~(hi >> 16)) << 16);
+}
+
+// device-wide exclusive scan in three launches; POPC: the value of an element is its popcount
+template <bool POPC>
+__global__ void __launch_bounds__(256) k_scan_p1(const uint32_t *in, uint32_t n, uint32_t *blockSums) {
+    __shared__ uint32_t sm[8];
+    uint32_t base = blockIdx.x * SCAN_TILE;
     uint32_t s = 0;
-    for (uint32_t x = a; x < b; x++) s += __popc(bm[x]);
+    for (int t = 0; t < SCAN_TILE / 256; t++) {
+        uint32_t x = base + t * 256 + threadIdx.x;
+        if (x < n) s += POPC ? __popc(in[x]) : in[x];
+    }
+    for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xFFFFFFFFu, s, o);
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) { uint32_t tot = 0; for (int i = 0; i < 8; i++) tot += sm[i]; blockSums[blockIdx.x] = tot; }
+}
+
+__global__ void __launch_bounds__(1024) k_scan_p2(uint32_t *blockSums, uint32_t nb, uint32_t *total) {
+    __shared__ uint32_t sm[1024];
+    uint32_t per = (nb + 1023) / 1024;
+    uint32_t lo = min(nb, threadIdx.x * per), hi = min(nb, lo + per);
+    uint32_t s = 0;
+    for (uint32_t x = lo; x < hi; x++) s += blockSums[x];
     sm[threadIdx.x] = s;
     __syncthreads();
     for (int off = 1; off < 1024; off <<= 1) {
@@ -435,65 +516,70 @@ __global__ void __launch_bounds__(1024) k_rank(K p, uint32_t *ktotal) {
         __syncthreads();
     }
     uint32_t run = sm[threadIdx.x] - s;
-    for (uint32_t x = a; x < b; x++) { rk[x] = run; run += __popc(bm[x]); }
-    if (threadIdx.x == 1023) ktotal[ki] = sm[1023];
-}
-
-__global__ void k_slotbase(K p, const uint32_t *ktotal) {
-    if (threadIdx.x == 0 && blockIdx.x == 0) {
-        uint32_t s = 0;
-        for (int ki = 0; ki < p.nk; ki++) { p.slotBase[ki] = s; s += ktotal[ki]; }
-        p.slotBase[p.nk] = s;
-    }
-}
-
-// exclusive scan of a uint32 array, single block (n up to a few million; used on per-word counts)
-__global__ void __launch_bounds__(1024) k_exscan(uint32_t *a, uint32_t n, uint32_t *total) {
-    __shared__ uint32_t sm[1024];
-    uint32_t per = (n + blockDim.x - 1) / blockDim.x;
-    uint32_t lo = min(n, threadIdx.x * per), hi = min(n, lo + per);
-    uint32_t s = 0;
-    for (uint32_t x = lo; x < hi; x++) s += a[x];
-    sm[threadIdx.x] = s;
-    __syncthreads();
-    for (int off = 1; off < 1024; off <<= 1) {
-        uint32_t v = threadIdx.x >= off ? sm[threadIdx.x - off] : 0;
-        __syncthreads();
-        sm[threadIdx.x] += v;
-        __syncthreads();
-    }
-    uint32_t run = sm[threadIdx.x] - s;
-    for (uint32_t x = lo; x < hi; x++) { uint32_t v = a[x]; a[x] = run; run += v; }
+    for (uint32_t x = lo; x < hi; x++) { uint32_t v = blockSums[x]; blockSums[x] = run; run += v; }
     if (threadIdx.x == 1023) *total = sm[1023];
 }
 
-// ------------------------------------------------------------------------------------------
-// k_alive: per slot, the reference's rules for every other genome on this context.
-//   occurrence on the forward string ('+'): needs count == 1 in fkh  -> no JF polluter
-//   occurrence on the rc string ('-')     : needs count == 1 in rkh  -> no JR polluter
-//   palindrome: in F ^ R  <=>  exactly one of the two tables reads 1 (:62-63)
-__device__ __forceinline__ bool row_ok(uint32_t v, bool ori1, bool pal) {
-    if (!(v & ROW_HAS) || (v & (ROW_DUP | ROW_POLL))) return false;
-    if (pal) return ((v & ROW_JF) != 0) != ((v & ROW_JR) != 0);
-    bool minus = ((v & ROW_ORI) != 0) != ori1;
-    return minus ? !(v & ROW_JR) : !(v & ROW_JF);
+template <bool POPC>
+__global__ void __launch_bounds__(256) k_scan_p3(const uint32_t *in, uint32_t *out, uint32_t n, const uint32_t *blockSums) {
+    __shared__ uint32_t sm[8];
+    uint32_t base = blockIdx.x * SCAN_TILE + threadIdx.x * (SCAN_TILE / 256);
+    uint32_t v[SCAN_TILE / 256];
+    uint32_t s = 0;
+#pragma unroll
+    for (int t = 0; t < SCAN_TILE / 256; t++) {
+        uint32_t x = base + t;
+        v[t] = x < n ? (POPC ? __popc(in[x]) : in[x]) : 0;
+        s += v[t];
+    }
+    uint32_t incl = s;
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t y = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+        if ((threadIdx.x & 31) >= o) incl += y;
+    }
+    if ((threadIdx.x & 31) == 31) sm[threadIdx.x >> 5] = incl;
+    __syncthreads();
+    uint32_t woff = 0;
+    for (int i = 0; i < (int)(threadIdx.x >> 5); i++) woff += sm[i];
+    uint32_t run = blockSums[blockIdx.x] + woff + incl - s;
+#pragma unroll
+    for (int t = 0; t < SCAN_TILE / 256; t++) {
+        uint32_t x = base + t;
+        if (x < n) out[x] = run;
+        run += v[t];
+    }
 }
 
-__global__ void __launch_bounds__(256) k_alive(K p) {
+// ------------------------------------------------------------------------------------------
+// k_alive: per slot, the reference's rules for every genome on this context.
+//   occurrence on the forward string ('+'): needs count == 1 in fkh  -> no JF polluter
+//   occurrence on the rc string ('-')     : needs count == 1 in rkh  -> no JR polluter
+//   palindrome, other genomes: in F ^ R  <=>  exactly one of the two tables reads 1 (:62-63)
+//   palindrome, first genome : in F - R  <=>  fkh reads 1 and rkh does not      (:58-59)
+__device__ __forceinline__ bool row_ok(uint32_t v, bool ori1, bool pal, bool first) {
+    if (!(v & ROW_HAS) || (v & (ROW_DUP | ROW_POLL))) return false;
+    bool jf = (v & ROW_JF) != 0, jr = (v & ROW_JR) != 0;
+    if (pal) return first ? (!jf && jr) : (jf != jr);
+    bool minus = ((v & ROW_ORI) != 0) != ori1;
+    return minus ? !jr : !jf;
+}
+
+__global__ void __launch_bounds__(256) k_alive(const __grid_constant__ K p) {
     uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= p.nslots) return;
     uint64_t canon = p.canon1[idx];
     int k = p.slotK[idx];
     bool pal = (rc64(canon) >> (64 - 2 * k)) == canon;
-    bool ori1 = (p.rows[idx] & ROW_ORI) != 0;
-    bool ok = true;
-    for (uint32_t g = 1; g < p.nGenomes; g++) ok = ok && row_ok(p.rows[(size_t)g * p.nslots + idx], ori1, pal);
+    uint32_t v0 = p.rows[idx];
+    bool ori1 = (v0 & ROW_ORI) != 0;
+    bool ok = row_ok(v0, ori1, pal, true);
+    for (uint32_t g = 1; g < p.nGenomes && ok; g++) ok = row_ok(p.rows[(size_t)g * p.nslots + idx], ori1, pal, false);
     p.alive[idx] = ok ? 1 : 0;
 }
 
 // k_positions: (contig, leftmost start, strand) of every record in every genome
 // (getCandidateKmers.py:173-187); also seeds the grouping array with the smallest passing rank
-__global__ void __launch_bounds__(256) k_positions(K p) {
+__global__ void __launch_bounds__(256) k_positions(const __grid_constant__ K p) {
     uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     uint32_t g = blockIdx.y;
     if (r >= p.nrec) return;
@@ -514,7 +600,7 @@ __global__ void __launch_bounds__(256) k_positions(K p) {
 
 // k_pick: a record is picked when it is the first passing k-mer of its (contig, start) group in
 // some genome (getCandidateKmers.py:222-247, 376-388)
-__global__ void __launch_bounds__(256) k_pick(K p) {
+__global__ void __launch_bounds__(256) k_pick(const __grid_constant__ K p) {
     uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     uint32_t g = blockIdx.y;
     if (r >= p.nrec) return;
@@ -525,15 +611,20 @@ __global__ void __launch_bounds__(256) k_pick(K p) {
     if (p.minRank[(size_t)p.gWordStart[g] * 32u + lp] == (uint32_t)r) p.pick[r] = 1;
 }
 
-__global__ void k_apply_pick(K p, unsigned long long *npick) {
+__global__ void k_apply_pick(const __grid_constant__ K p, unsigned long long *npick) {
     uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= p.nrec) return;
-    if (p.pick[r]) { p.rec[r].flags |= PFB_F_PICK; atomicAdd(npick, 1ull); }
+    bool pk = r < p.nrec && p.pick[r];
+    if (pk) p.rec[r].flags |= PFB_F_PICK;
+    unsigned m = __ballot_sync(0xFFFFFFFFu, pk);
+    if ((threadIdx.x & 31) == 0 && m) atomicAdd(npick, (unsigned long long)__popc(m));
 }
 
-__global__ void k_oligo(K p, uint64_t h, int k, double *out) {
-    out[0] = oligo_tm(h, k, p);
-    out[1] = __dmul_rn(__ddiv_rn((double)gc_count(h), (double)k), 100.0);
+__global__ void k_oligo(const __grid_constant__ K p, uint64_t h, int k, double *out) {
+    __shared__ uint32_t s_nn[16];
+    for (int i = 0; i < 16; i++) s_nn[i] = c_nn[i];
+    int gc = gc_count(h);
+    out[0] = oligo_tm(h, k, gc, p, s_nn);
+    out[1] = __dmul_rn(__ddiv_rn((double)gc, (double)k), 100.0);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -552,7 +643,8 @@ struct HostGenome {
 
 struct pfb_ctx {
     int device = 0;
-    int dbg_counts = 0;
+    int num_sms = 148;
+    int scan_mode = 0;   // 0 auto, 1 plain L2 probe, 2 shared-memory filter
     pfb_params prm{};
     std::string err;
     cudaStream_t stream = nullptr;
@@ -566,13 +658,13 @@ struct pfb_ctx {
     bool uploaded = false, computed = false;
     int stage_done = -1;
     // device
-    DevBuf raw, seq2, nmask, wordContig, tabs32, tabs64, sk, jf, jr, bits, rank, misc, passmask1, canon1, slotK,
-        rows, alive, emitCnt, rec, pos, minRank, pick;
+    DevBuf raw, seq2, nmask, wordContig, tabs32, tabs64, sk, bits, rank, filter, fterm, scanTmp, misc, passmask1, canon1,
+        slotK, rows, alive, emitCnt, rec, pos, minRank, pick;
     K k{};
     uint64_t nslots = 0, nrec = 0, npick = 0;
     uint64_t launches = 0;
+    bool used_filter = false;
     pfb_timing tm{};
-    std::vector<uint64_t> allowed;
 };
 
 static std::string g_create_err;
@@ -611,9 +703,34 @@ inline unsigned nblk(uint64_t n, unsigned bs) { return (unsigned)((n + bs - 1) /
 int validate(const pfb_params *p, std::string &why) {
     if (!p) { why = "params is NULL"; return PFB_EINVAL; }
     if (p->k_min < 1 || p->k_max > 32 || p->k_min > p->k_max) { why = "need 1 <= k_min <= k_max <= 32"; return PFB_EINVAL; }
-    if (p->table_size < 64) { why = "table_size too small"; return PFB_EINVAL; }
+    if (p->table_size < 64 || p->table_size >= (1u << 31)) { why = "table_size out of range"; return PFB_EINVAL; }
     if (p->max_repeat < 1) { why = "max_repeat must be >= 1"; return PFB_EINVAL; }
     return PFB_OK;
+}
+
+// constants of oligotm() and the GC window, computed with the host libm / IEEE doubles exactly like
+// the reference's C and Python code does
+void fill_filter_constants(const pfb_params &P, K &k, std::vector<double> &fterm) {
+    double dv = P.dv_conc, dntp = P.dntp_conc;
+    if (dv == 0) dntp = 0;
+    if (dv < dntp) dv = dntp;
+    double k_mm = P.mv_conc + 120.0 * std::sqrt(dv - dntp);
+    k.ln_salt = std::log(k_mm / 1000.0);
+    k.ln_dna4 = std::log(P.dna_conc / 4000000000.0);
+    k.ln_dna1 = std::log(P.dna_conc / 1000000000.0);
+    k.dmso_term = P.dmso_conc * P.dmso_fact;
+    k.min_tm = P.min_tm; k.max_tm = P.max_tm;
+    fterm.assign(33 * 33, 0.0);
+    for (int kk = 1; kk <= 32; kk++) {
+        uint64_t ok = 0;
+        for (int gc = 0; gc <= kk; gc++) {
+            double per = (double)gc / kk * 100;                                   // Primer.py:100
+            if (per >= P.min_gc && per <= P.max_gc) ok |= 1ull << gc;              // getCandidateKmers.py:303
+            fterm[kk * 33 + gc] = (0.453 * ((double)gc / kk) - 2.88) * P.formamide_conc;
+        }
+        k.gc_ok[kk] = ok;
+    }
+    k.gc_ok[0] = 0;
 }
 
 // layout of the arena from the host-side genome list
@@ -653,6 +770,21 @@ int build_layout(pfb_ctx *ctx) {
     return PFB_OK;
 }
 
+// device-wide exclusive scan helper (out may alias in)
+template <bool POPC>
+int device_exscan(pfb_ctx *ctx, const uint32_t *in, uint32_t *out, uint32_t n, uint32_t *total_dev) {
+    cudaStream_t st = ctx->stream;
+    uint32_t nb = (n + SCAN_TILE - 1) / SCAN_TILE;
+    int rc = ensure(ctx, ctx->scanTmp, (size_t)(nb + 1) * 4);
+    if (rc != PFB_OK) return rc;
+    uint32_t *bs = (uint32_t *)ctx->scanTmp.p;
+    k_scan_p1<POPC><<<nb, 256, 0, st>>>(in, n, bs);
+    k_scan_p2<<<1, 1024, 0, st>>>(bs, nb, total_dev);
+    k_scan_p3<POPC><<<nb, 256, 0, st>>>(in, out, n, bs);
+    ctx->launches += 3;
+    return PFB_OK;
+}
+
 }  // namespace
 
 // ==========================================================================================
@@ -687,7 +819,10 @@ int pfb_create(pfb_ctx **out, int device, const pfb_params *params) {
     ctx = new pfb_ctx();
     ctx->device = device;
     ctx->prm = *params;
+    cudaDeviceGetAttribute(&ctx->num_sms, cudaDevAttrMultiProcessorCount, device);
     e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(k_scan_filtered, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FILTER_BYTES);
     if (e != cudaSuccess) { std::string m = cudaGetErrorString(e); delete ctx; return fail(nullptr, PFB_ECUDA, m); }
     for (auto &ev : ctx->ev) cudaEventCreate(&ev);
     *out = ctx;
@@ -698,9 +833,9 @@ void pfb_destroy(pfb_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    DevBuf *all[] = {&ctx->raw, &ctx->seq2, &ctx->nmask, &ctx->wordContig, &ctx->tabs32, &ctx->tabs64, &ctx->sk, &ctx->jf,
-                     &ctx->jr, &ctx->bits, &ctx->rank, &ctx->misc, &ctx->passmask1, &ctx->canon1, &ctx->slotK, &ctx->rows,
-                     &ctx->alive, &ctx->emitCnt, &ctx->rec, &ctx->pos, &ctx->minRank, &ctx->pick};
+    DevBuf *all[] = {&ctx->raw, &ctx->seq2, &ctx->nmask, &ctx->wordContig, &ctx->tabs32, &ctx->tabs64, &ctx->sk, &ctx->bits,
+                     &ctx->rank, &ctx->filter, &ctx->fterm, &ctx->scanTmp, &ctx->misc, &ctx->passmask1, &ctx->canon1,
+                     &ctx->slotK, &ctx->rows, &ctx->alive, &ctx->emitCnt, &ctx->rec, &ctx->pos, &ctx->minRank, &ctx->pick};
     for (auto *b : all) release(*b);
     for (auto &ev : ctx->ev) if (ev) cudaEventDestroy(ev);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -732,6 +867,13 @@ int pfb_sync(pfb_ctx *ctx) {
     if (!ctx) return PFB_EINVAL;
     CK(cudaSetDevice(ctx->device));
     CK(cudaStreamSynchronize(ctx->stream));
+    return PFB_OK;
+}
+
+int pfb_set_scan_mode(pfb_ctx *ctx, int mode) {
+    if (!ctx) return PFB_EINVAL;
+    if (mode < 0 || mode > 2) return fail(ctx, PFB_EINVAL, "scan mode must be 0 (auto), 1 (L2 probe) or 2 (shared-memory filter)");
+    ctx->scan_mode = mode;
     return PFB_OK;
 }
 
@@ -782,75 +924,50 @@ static int stage0(pfb_ctx *ctx) {
     int rc;
     const int nk = P.k_max - P.k_min + 1;
     k.kmin = P.k_min; k.kmax = P.k_max; k.nk = nk;
-    k.P = P.table_size; k.PW = (P.table_size + 31) / 32; k.SW = (P.table_size + 15) / 16;
+    k.P = P.table_size; k.PW = (P.table_size + 31) / 32;
     k.barrett = (uint64_t)((((unsigned __int128)1) << 64) / P.table_size);
-    k.max_repeat = P.max_repeat; k.prefilter = P.prefilter; k.dbg_counts = ctx->dbg_counts;
-    k.min_gc = P.min_gc; k.max_gc = P.max_gc; k.min_tm = P.min_tm; k.max_tm = P.max_tm;
-    {   // constants of oligotm(), computed with the host libm exactly like the reference's C code does
-        double dv = P.dv_conc, dntp = P.dntp_conc;
-        if (dv == 0) dntp = 0;
-        if (dv < dntp) dv = dntp;
-        double k_mm = P.mv_conc + 120.0 * std::sqrt(dv - dntp);
-        k.ln_salt = std::log(k_mm / 1000.0);
-        k.ln_dna4 = std::log(P.dna_conc / 4000000000.0);
-        k.ln_dna1 = std::log(P.dna_conc / 1000000000.0);
-        k.dmso_term = P.dmso_conc * P.dmso_fact;
-        k.formamide = P.formamide_conc;
-    }
+    k.fscale = (uint64_t)FILTER_BITS >= P.table_size
+                   ? 0xFFFFFFFFu
+                   : (uint32_t)((((unsigned __int128)FILTER_BITS) << 32) / P.table_size);
+    k.max_repeat = P.max_repeat; k.prefilter = P.prefilter;
+    std::vector<double> fterm;
+    fill_filter_constants(P, k, fterm);
     const uint32_t W = ctx->totalWords;
     const uint32_t W1 = ctx->genomes.size() > 1 ? ctx->gWordStart[1] : W;   // genome 1 = words [0, W1)
+    const uint32_t NB = (uint32_t)nk * k.PW;                                // words of the concatenated bitmaps
     ctx->launches = 0;
     // buffers
     if ((rc = ensure(ctx, ctx->seq2, (size_t)(W + 1) * 8)) != PFB_OK) return rc;
     if ((rc = ensure(ctx, ctx->nmask, (size_t)(W + 1) * 4)) != PFB_OK) return rc;
     if ((rc = ensure(ctx, ctx->wordContig, (size_t)(W + 1) * 4)) != PFB_OK) return rc;
-    if ((rc = ensure(ctx, ctx->sk, (size_t)nk * k.SW * 4)) != PFB_OK) return rc;
-    if ((rc = ensure(ctx, ctx->jf, (size_t)nk * k.PW * 4)) != PFB_OK) return rc;
-    if ((rc = ensure(ctx, ctx->jr, (size_t)nk * k.PW * 4)) != PFB_OK) return rc;
-    if ((rc = ensure(ctx, ctx->bits, (size_t)nk * k.PW * 4)) != PFB_OK) return rc;
-    if ((rc = ensure(ctx, ctx->rank, (size_t)nk * k.PW * 4)) != PFB_OK) return rc;
+    if ((rc = ensure(ctx, ctx->sk, (size_t)NB * 2 * 4)) != PFB_OK) return rc;
+    if ((rc = ensure(ctx, ctx->bits, (size_t)NB * 4)) != PFB_OK) return rc;
+    if ((rc = ensure(ctx, ctx->rank, (size_t)NB * 4)) != PFB_OK) return rc;
+    if ((rc = ensure(ctx, ctx->filter, (size_t)nk * FILTER_BYTES)) != PFB_OK) return rc;
+    if ((rc = ensure(ctx, ctx->fterm, 33 * 33 * 8)) != PFB_OK) return rc;
     if ((rc = ensure(ctx, ctx->misc, 4096)) != PFB_OK) return rc;
     if ((rc = ensure(ctx, ctx->passmask1, (size_t)W1 * 32 * 4 + 4)) != PFB_OK) return rc;
     if ((rc = ensure(ctx, ctx->emitCnt, (size_t)(W1 + 1) * 4)) != PFB_OK) return rc;
     k.seq2 = (uint64_t *)ctx->seq2.p; k.nmask = (uint32_t *)ctx->nmask.p; k.wordContig = (uint32_t *)ctx->wordContig.p;
-    k.sk = (uint32_t *)ctx->sk.p; k.jf = (uint32_t *)ctx->jf.p; k.jr = (uint32_t *)ctx->jr.p;
-    k.bits = (uint32_t *)ctx->bits.p; k.rank = (uint32_t *)ctx->rank.p;
-    // misc: [0..63] slotBase, [64] g1flags, [65] recCount, [66..67] npick, [128..191] ktotal, [256..] allowedCnt (u64)
-    uint32_t *misc = (uint32_t *)ctx->misc.p;
-    k.slotBase = misc; k.g1flags = misc + 64; k.recCount = misc + 65;
-    uint32_t *ktotal = misc + 128;
-    k.allowedCnt = (unsigned long long *)(misc + 256);
+    k.sk = (uint32_t *)ctx->sk.p; k.bits = (uint32_t *)ctx->bits.p; k.rank = (uint32_t *)ctx->rank.p;
+    k.filter = (uint32_t *)ctx->filter.p; k.fterm = (const double *)ctx->fterm.p;
+    uint32_t *misc = (uint32_t *)ctx->misc.p;   // [0] nslots, [1] nrec, [2..3] npick (u64)
     k.passmask1 = (uint32_t *)ctx->passmask1.p; k.emitCnt = (uint32_t *)ctx->emitCnt.p;
 
     CK(cudaEventRecord(ctx->ev[2], st));
+    CK(cudaMemcpyAsync(ctx->fterm.p, fterm.data(), 33 * 33 * 8, cudaMemcpyHostToDevice, st));
     CK(cudaMemsetAsync(ctx->misc.p, 0, 4096, st));
-    CK(cudaMemsetAsync(ctx->sk.p, 0, (size_t)nk * k.SW * 4, st));
-    CK(cudaMemsetAsync(ctx->jf.p, 0, (size_t)nk * k.PW * 4, st));
-    CK(cudaMemsetAsync(ctx->jr.p, 0, (size_t)nk * k.PW * 4, st));
-    CK(cudaMemsetAsync(ctx->bits.p, 0, (size_t)nk * k.PW * 4, st));
-    if (ctx->gNumContigs[0] > 1) {
-        uint32_t one = 1;
-        CK(cudaMemcpyAsync(k.g1flags, &one, 4, cudaMemcpyHostToDevice, st));
-    }
-    // encode everything
+    CK(cudaMemsetAsync(ctx->sk.p, 0, (size_t)NB * 2 * 4, st));
     if (W) { k_encode<<<nblk(W, 256), 256, 0, st>>>(k, 0, W); ctx->launches++; }
     CK(cudaEventRecord(ctx->ev[3], st));
-    // genome 1
-    if (W1) { k_scan<COUNT1><<<nblk(W1, 256), 256, 0, st>>>(k, 0, W1); ctx->launches++; }
-    if (ctx->gNumContigs[0] > 1) {
-        uint64_t nthr = (uint64_t)ctx->gNumContigs[0] * nk * 2 * (2 * P.k_max - 1);
-        k_junction<true><<<nblk(nthr, 128), 128, 0, st>>>(k, 0, ctx->gNumContigs[0]);
-        ctx->launches++;
-    }
-    if (W1) { k_scan<SELECT1><<<nblk(W1, 256), 256, 0, st>>>(k, 0, W1); ctx->launches++; }
-    k_rank<<<nk, 1024, 0, st>>>(k, ktotal); ctx->launches++;
-    k_slotbase<<<1, 32, 0, st>>>(k, ktotal); ctx->launches++;
-    uint32_t hmisc[64 + 1];
-    CK(cudaMemcpyAsync(hmisc, misc, sizeof(hmisc), cudaMemcpyDeviceToHost, st));
-    ctx->allowed.assign(nk, 0);
-    CK(cudaMemcpyAsync(ctx->allowed.data(), k.allowedCnt, (size_t)nk * 8, cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
-    ctx->nslots = hmisc[nk];
+    // genome 1: candidates -> key table
+    if (W1) { k_scan<CAND1><<<nblk(W1, 256), 256, 0, st>>>(k, 0, W1); ctx->launches++; }
+    k_candbits<<<nblk(NB, 256), 256, 0, st>>>(k); ctx->launches++;
+    if ((rc = device_exscan<true>(ctx, k.bits, k.rank, NB, misc)) != PFB_OK) return rc;
+    uint32_t ns = 0;
+    CK(cudaMemcpyAsync(&ns, misc, 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));   // fterm (host vector) is also consumed by now
+    ctx->nslots = ns;
     k.nslots = ctx->nslots;
     const size_t NS = ctx->nslots ? ctx->nslots : 1;
     const size_t nG = ctx->genomes.size();
@@ -861,15 +978,24 @@ static int stage0(pfb_ctx *ctx) {
     k.canon1 = (uint64_t *)ctx->canon1.p; k.slotK = (uint8_t *)ctx->slotK.p;
     k.rows = (uint32_t *)ctx->rows.p; k.alive = (uint8_t *)ctx->alive.p;
     CK(cudaMemsetAsync(ctx->rows.p, 0, NS * nG * 4, st));
+    // the filter pays off while it stays sparse: expected fill 1 - exp(-keys_per_k / FILTER_BITS)
+    bool use_filter = ctx->scan_mode == 2 ||
+                      (ctx->scan_mode == 0 && (double)ctx->nslots / nk < 0.35 * FILTER_BITS && W >= 4096);
+    ctx->used_filter = use_filter;
     if (W1 && ctx->nslots) { k_scan<FILL1><<<nblk(W1, 256), 256, 0, st>>>(k, 0, W1); ctx->launches++; }
+    if (use_filter && ctx->nslots) {
+        CK(cudaMemsetAsync(ctx->filter.p, 0, (size_t)nk * FILTER_BYTES, st));
+        k_build_filter<<<nblk(NB, 256), 256, 0, st>>>(k); ctx->launches++;
+    }
     CK(cudaEventRecord(ctx->ev[4], st));
-    // every other genome: one pass against the key table
-    if (W > W1 && ctx->nslots) {
-        k_scan<SCAN><<<nblk(W - W1, 256), 256, 0, st>>>(k, W1, W); ctx->launches++;
-        uint32_t c0 = ctx->gFirstContig[1], c1 = (uint32_t)ctx->cLen.size();
-        if (c1 - c0 > nG - 1) {   // some genome has more than one contig
-            uint64_t nthr = (uint64_t)(c1 - c0) * nk * 2 * (2 * P.k_max - 1);
-            k_junction<false><<<nblk(nthr, 128), 128, 0, st>>>(k, c0, c1);
+    // every genome (the first included): one pass against the key table
+    if (W && ctx->nslots) {
+        if (use_filter) k_scan_filtered<<<ctx->num_sms, 1024, FILTER_BYTES, st>>>(k, 0, W);
+        else k_scan<SCAN><<<nblk(W, 256), 256, 0, st>>>(k, 0, W);
+        ctx->launches++;
+        if (ctx->cLen.size() > nG) {   // some genome has more than one contig
+            uint64_t nthr = (uint64_t)ctx->cLen.size() * nk * 2 * (2 * P.k_max - 1);
+            k_junction<<<nblk(nthr, 128), 128, 0, st>>>(k, 0, (uint32_t)ctx->cLen.size());
             ctx->launches++;
         }
     }
@@ -886,12 +1012,13 @@ static int stage1(pfb_ctx *ctx) {
     const uint32_t W = ctx->totalWords;
     const uint32_t W1 = ctx->genomes.size() > 1 ? ctx->gWordStart[1] : W;
     const size_t nG = ctx->genomes.size();
+    uint32_t *misc = (uint32_t *)ctx->misc.p;
     ctx->nrec = 0; ctx->npick = 0;
     if (ctx->nslots && W1) {
         k_scan<EMIT_COUNT><<<nblk(W1, 256), 256, 0, st>>>(k, 0, W1); ctx->launches++;
-        k_exscan<<<1, 1024, 0, st>>>(k.emitCnt, W1, k.recCount); ctx->launches++;
+        if ((rc = device_exscan<false>(ctx, k.emitCnt, k.emitCnt, W1, misc + 1)) != PFB_OK) return rc;
         uint32_t n = 0;
-        CK(cudaMemcpyAsync(&n, k.recCount, 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(&n, misc + 1, 4, cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
         ctx->nrec = n;
     }
@@ -918,7 +1045,7 @@ static int stage1(pfb_ctx *ctx) {
 static int stage2(pfb_ctx *ctx) {
     cudaStream_t st = ctx->stream;
     K &k = ctx->k;
-    unsigned long long *npick = (unsigned long long *)(k.recCount + 1);
+    unsigned long long *npick = (unsigned long long *)((uint32_t *)ctx->misc.p + 2);
     if (ctx->nrec) {
         k_apply_pick<<<nblk(ctx->nrec, 256), 256, 0, st>>>(k, npick); ctx->launches++;
     }
@@ -935,7 +1062,6 @@ static int stage2(pfb_ctx *ctx) {
     cudaEventElapsedTime(&t.ms_finalize, ctx->ev[5], ctx->ev[6]);
     cudaEventElapsedTime(&t.ms_total, ctx->ev[2], ctx->ev[6]);
     uint64_t nb = 0, nw = 0;
-    const int nk = ctx->prm.k_max - ctx->prm.k_min + 1;
     for (auto &g : ctx->genomes) {
         nb += g.n_bases;
         for (size_t c = 0; c + 1 < g.off.size(); c++) {
@@ -943,9 +1069,9 @@ static int stage2(pfb_ctx *ctx) {
             for (int kk = ctx->prm.k_min; kk <= ctx->prm.k_max; kk++) if (len >= (uint64_t)kk) nw += len - kk + 1;
         }
     }
-    (void)nk;
     t.n_bases = nb; t.n_windows = nw; t.n_slots = ctx->nslots; t.n_records = ctx->nrec; t.n_picked = ctx->npick;
     t.n_launches = ctx->launches;
+    t.used_filter = ctx->used_filter ? 1 : 0;
     ctx->computed = true;
     return PFB_OK;
 }
@@ -1039,20 +1165,6 @@ int pfb_timings(pfb_ctx *ctx, pfb_timing *out) {
     return PFB_OK;
 }
 
-int pfb_set_debug_counts(pfb_ctx *ctx, int on) {
-    if (!ctx) return PFB_EINVAL;
-    ctx->dbg_counts = on ? 1 : 0;
-    return PFB_OK;
-}
-
-int pfb_first_genome_allowed(pfb_ctx *ctx, uint64_t *out, uint32_t cap) {
-    if (!ctx || !out) return PFB_EINVAL;
-    if (ctx->stage_done < 0) return fail(ctx, PFB_ESTATE, "stage 0 has not run");
-    if (cap < ctx->allowed.size()) return fail(ctx, PFB_EINVAL, "buffer too small");
-    for (size_t i = 0; i < ctx->allowed.size(); i++) out[i] = ctx->allowed[i];
-    return PFB_OK;
-}
-
 int pfb_oligo_tm(pfb_ctx *ctx, const char *seq, double *tm, double *gc_percent) {
     if (!ctx || !seq) return PFB_EINVAL;
     size_t n = strlen(seq);
@@ -1065,18 +1177,14 @@ int pfb_oligo_tm(pfb_ctx *ctx, const char *seq, double *tm, double *gc_percent) 
         h = (h << 2) | c;
     }
     CK(cudaSetDevice(ctx->device));
-    // oligotm constants (same derivation as stage0)
     K k = ctx->k;
-    const pfb_params &P = ctx->prm;
-    double dv = P.dv_conc, dntp = P.dntp_conc;
-    if (dv == 0) dntp = 0;
-    if (dv < dntp) dv = dntp;
-    k.ln_salt = std::log((P.mv_conc + 120.0 * std::sqrt(dv - dntp)) / 1000.0);
-    k.ln_dna4 = std::log(P.dna_conc / 4000000000.0);
-    k.ln_dna1 = std::log(P.dna_conc / 1000000000.0);
-    k.dmso_term = P.dmso_conc * P.dmso_fact; k.formamide = P.formamide_conc;
+    std::vector<double> fterm;
+    fill_filter_constants(ctx->prm, k, fterm);
     int rc;
+    if ((rc = ensure(ctx, ctx->fterm, 33 * 33 * 8)) != PFB_OK) return rc;
     if ((rc = ensure(ctx, ctx->misc, 4096)) != PFB_OK) return rc;
+    k.fterm = (const double *)ctx->fterm.p;
+    CK(cudaMemcpyAsync(ctx->fterm.p, fterm.data(), 33 * 33 * 8, cudaMemcpyHostToDevice, ctx->stream));
     double *d = (double *)((uint8_t *)ctx->misc.p + 3072);
     k_oligo<<<1, 1, 0, ctx->stream>>>(k, h, (int)n, d);
     double hres[2];

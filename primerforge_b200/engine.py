@@ -132,8 +132,9 @@ class Engine:
     def sync(self):
         self._check(self._lib.pfb_sync(self._ctx))
 
-    def set_debug_counts(self, on: bool = True):
-        self._check(self._lib.pfb_set_debug_counts(self._ctx, int(on)))
+    def set_scan_mode(self, mode: int):
+        """0 auto, 1 plain L2 probe, 2 shared-memory filter (same results)"""
+        self._check(self._lib.pfb_set_scan_mode(self._ctx, int(mode)))
 
     def device_buffer(self, which: int):
         ptr, n = C.c_void_p(), C.c_uint64()
@@ -152,12 +153,6 @@ class Engine:
         t = _lib.PfbTiming()
         self._check(self._lib.pfb_timings(self._ctx, C.byref(t)))
         return {name: getattr(t, name) for name, _ in t._fields_}
-
-    def first_genome_allowed(self) -> np.ndarray:
-        nk = self.params.k_max - self.params.k_min + 1
-        out = np.zeros(nk, dtype=np.uint64)
-        self._check(self._lib.pfb_first_genome_allowed(self._ctx, out.ctypes.data, nk))
-        return out
 
     def records(self) -> np.ndarray:
         n, _ = self.counts()
