@@ -11,11 +11,11 @@
 //     contig word-aligned in one arena (k_encode);
 //   * genome 1's CANDIDATE windows (one end G/C, ACGT only, and -- with prefilter -- GC / repeat / Tm
 //     in range) are entered into a 2-bit-per-bin table (seen once / seen again) with L2-resident
-//     atomicOr (k_scan<CAND1>).  A candidate that is alone in its bin owns the bin, so (k, bin) is a
+//     atomicOr (k_cand1).  A candidate that is alone in its bin owns the bin, so (k, bin) is a
 //     perfect hash of the key set: a bitmap over bins + popcount ranks gives a dense slot id
-//     (k_candbits, k_scan_p*, k_scan<FILL1>) -- this replaces the string sets and the Aho-Corasick
+//     (k_candbits, k_scan_p*, k_walk1<FILL1>) -- this replaces the string sets and the Aho-Corasick
 //     automaton;
-//   * every genome, the first included, is then ONE pass (k_scan<SCAN> / k_scan_filtered):
+//   * every genome, the first included, is then ONE pass (k_scan_filtered / k_scan_plain):
 //     window -> bin -> bitmap probe; on a hit the 64-bit canonical word is compared with the slot's
 //     key: equal = an occurrence (position and orientation OR-ed into the genome's row, a second one
 //     raises DUP), different = a sketch collision in that genome (POLL); windows touching a '~'
@@ -24,7 +24,7 @@
 //     reference would have read.  The probe goes through a per-k Bloom-style filter held in shared
 //     memory (192 KB per CTA) so that only ~1 in 6 windows reaches L2;
 //   * survivors are emitted in the reference's dict order by an ordered compaction over genome 1
-//     (k_scan<EMIT_*>), filters are evaluated in fp64 with the reference's operation order, the
+//     (k_walk1<EMIT_*>), filters are evaluated in fp64 with the reference's operation order, the
 //     per-position "first k-mer that passes" pick is an atomicMin over a direct-mapped array.
 //
 // No tensor cores: nothing here is a contraction.
@@ -43,24 +43,25 @@
 namespace {
 
 // ------------------------------------------------------------------------------------------
-// row word layout (one uint32 per genome and slot)
-constexpr uint32_t ROW_POS_MASK = 0x03FFFFFFu;  // leftmost start, genome-local padded coordinate
-constexpr uint32_t ROW_ORI = 1u << 26;          // forward word is the canonical one (h <= r)
-constexpr uint32_t ROW_HAS = 1u << 27;          // one occurrence seen
-constexpr uint32_t ROW_DUP = 1u << 28;          // a second occurrence seen
-constexpr uint32_t ROW_POLL = 1u << 29;         // a different k-mer of this genome shares the bin
-constexpr uint32_t ROW_JF = 1u << 30;           // forward-string-only polluter ('~' or non-ACGT window)
-constexpr uint32_t ROW_JR = 1u << 31;           // reverse-string-only polluter
+// row word layout (one uint64 per genome and slot).  Every window of the genome that lands in the slot's bin
+// ADDs (1 << 32) | start: after the scan "count == 1" is khmer's get() == 1 for that bin and, only then, the
+// low word is the start of the single occupant, which k_alive compares with the slot's key.  A fire-and-forget
+// RED: the scan never waits for an atomic's return value.  Strand-specific polluters OR the two top bits.
+constexpr uint64_t ROW_POS_MASK = 0x03FFFFFFull;   // leftmost start, genome-local padded coordinate
+constexpr uint64_t ROW_ONE = 1ull << 32;           // occupancy count lives in bits 32..59
+constexpr uint64_t ROW_CNT_MASK = 0x0FFFFFFFull;
+constexpr uint64_t ROW_JF = 1ull << 62;            // forward-string-only polluter ('~' or non-ACGT window)
+constexpr uint64_t ROW_JR = 1ull << 63;            // reverse-string-only polluter
 constexpr uint32_t MAX_GENOME_WORDS = 1u << 21; // 2^26 padded bases
 
 constexpr uint32_t FILTER_BYTES = 192u * 1024u; // shared-memory filter of k_scan_filtered
 constexpr uint32_t FILTER_BITS = FILTER_BYTES * 8u;
 constexpr uint32_t FILTER_WORDS = FILTER_BYTES / 4u;
+constexpr uint32_t QCAP = 64;                   // per-warp queue of filter-positive windows (16 B items)
+constexpr uint32_t SCANF_SMEM = FILTER_BYTES + 32u * QCAP * 16u;
 constexpr int SCAN_TILE = 2048;                 // elements per block of the device-wide scans
 
-enum Mode { CAND1 = 0, FILL1 = 1, SCAN = 2, EMIT_COUNT = 3, EMIT_WRITE = 4 };
-
-struct K {  // kernel arguments (by value)
+struct K {  // kernel arguments (by value, __grid_constant__)
     int kmin, kmax, nk;
     uint32_t P, PW;           // table prime, words per 1-bit bitmap (the 2-bit table has 2 * PW words)
     uint64_t barrett;         // floor(2^64 / P)
@@ -80,15 +81,17 @@ struct K {  // kernel arguments (by value)
     const uint32_t *gWordStart, *gFirstContig, *gNumContigs, *gVirtLen;
     uint32_t nContigs, nGenomes, totalWords;
     // genome-1 candidate table + key table
-    uint32_t *sk, *bits, *rank, *filter;
-    uint32_t *passmask1;
+    uint32_t *sk;             // [nk][2*PW] 2 bits per bin: seen once (low half), seen again (high half)
+    uint2 *br;                // [nk][PW] .x = key bitmap word, .y = exclusive popcount prefix (slot id base)
+    uint32_t *filter;         // [nk][FILTER_WORDS]
+    uint32_t *passmask1;      // per genome-1 end position: bit per k = candidate window
     uint64_t *canon1;
     uint8_t *slotK;
-    uint32_t *rows;           // [nGenomes][nslots]
+    unsigned long long *rows; // [nGenomes][nslots]
     uint64_t nslots;
     uint8_t *alive;
     // output
-    uint32_t *emitCnt;        // per genome-1 word
+    uint32_t *emitCnt;        // per genome-1 end position
     pfb_record *rec;
     pfb_pos *pos;             // [nGenomes][nrec]
     uint32_t *minRank;        // [totalWords*32]
@@ -122,16 +125,12 @@ __device__ __forceinline__ uint32_t mod_p(uint64_t x, const K &p) {
 
 __device__ __forceinline__ int gc_count(uint64_t h) { return __popcll(h & 0xAAAAAAAAAAAAAAAAull); }
 
-// Tm of one k-mer given as forward word (first base most significant).  Operation order mirrors
-// primer3's oligotm() as restated in oracle/pf_oracle.c so that the doubles agree bit for bit
-// (explicit _rn intrinsics: no FMA contraction).  nn = 16-entry table in shared memory (bank =
-// index, so a warp's divergent lookups never conflict).
-__device__ __forceinline__ double oligo_tm(uint64_t h, int k, int gc, const K &p, const uint32_t *nn) {
+// Tm from the nearest-neighbour sums of a k-mer (acc = (sum S << 16) | sum H over its k-1 pairs).
+// Operation order mirrors primer3's oligotm() as restated in oracle/pf_oracle.c so that the doubles
+// agree bit for bit (explicit _rn intrinsics: no FMA contraction).
+__device__ __forceinline__ double tm_from_sums(uint32_t acc, uint64_t h, int k, int gc, const K &p) {
     uint64_t rc = rc64(h) >> (64 - 2 * k);
     bool sym = ((k & 1) == 0) && rc == h;
-    uint32_t acc = 0;
-#pragma unroll 4
-    for (int i = 0; i < k - 1; i++) acc += nn[(h >> (2 * i)) & 15];
     int dh = (int)(acc & 0xFFFF), ds = (int)(acc >> 16);
     if (sym) ds += 14;
     int first = (int)((h >> (2 * k - 2)) & 3), last = (int)(h & 3);
@@ -147,6 +146,14 @@ __device__ __forceinline__ double oligo_tm(uint64_t h, int k, int gc, const K &p
     return tm;
 }
 
+// nn = the 16-entry table in shared memory (bank = index: divergent lookups never conflict)
+__device__ __forceinline__ double oligo_tm(uint64_t h, int k, int gc, const K &p, const uint32_t *nn) {
+    uint32_t acc = 0;
+#pragma unroll 4
+    for (int i = 0; i < k - 1; i++) acc += nn[(h >> (2 * i)) & 15];
+    return tm_from_sums(acc, h, k, gc, p);
+}
+
 __device__ __forceinline__ bool has_long_repeat(uint64_t h, int k, int R) {
     if (R <= 1) return true;
     if (k < R) return false;
@@ -157,30 +164,23 @@ __device__ __forceinline__ bool has_long_repeat(uint64_t h, int k, int R) {
     return y != 0;
 }
 
-// the three sequence filters of __evaluateKmersAtOnePosition (:301-320), cheapest first
-__device__ __forceinline__ bool passes_filters(uint64_t h, int k, const K &p, const uint32_t *nn) {
-    int gc = gc_count(h);
-    if (!((p.gc_ok[k] >> gc) & 1ull)) return false;
-    if (has_long_repeat(h, k, p.max_repeat)) return false;
-    double tm = oligo_tm(h, k, gc, p, nn);
-    return tm >= p.min_tm && tm <= p.max_tm;
-}
-
 __device__ __forceinline__ uint32_t filter_flags(uint64_t h, int k, const K &p, const uint32_t *nn, double *tm_out) {
     uint32_t f = 0;
     int gc = gc_count(h);
-    if ((p.gc_ok[k] >> gc) & 1ull) f |= PFB_F_GC_OK;
-    if (!has_long_repeat(h, k, p.max_repeat)) f |= PFB_F_REP_OK;
+    if ((p.gc_ok[k] >> gc) & 1ull) f |= PFB_F_GC_OK;                      // getCandidateKmers.py:301-303
+    if (!has_long_repeat(h, k, p.max_repeat)) f |= PFB_F_REP_OK;          // :309-320
     double tm = oligo_tm(h, k, gc, p, nn);
-    if (tm >= p.min_tm && tm <= p.max_tm) f |= PFB_F_TM_OK;
+    if (tm >= p.min_tm && tm <= p.max_tm) f |= PFB_F_TM_OK;               // :305-307
     *tm_out = tm;
     return f;
 }
 
-// slot id of a set bit (rank is the exclusive popcount prefix over the concatenated per-k bitmaps)
-__device__ __forceinline__ uint32_t slot_of(const K &p, int ki, uint32_t bin, uint32_t word) {
-    return p.rank[(size_t)ki * p.PW + (bin >> 5)] + __popc(word & ((1u << (bin & 31)) - 1u));
+// key table probe: one 8-byte load gives the bitmap word and the slot id base
+__device__ __forceinline__ uint2 probe(const K &p, int ki, uint32_t bin) {
+    return __ldg(&p.br[(size_t)ki * p.PW + (bin >> 5)]);
 }
+__device__ __forceinline__ bool probe_hit(uint2 e, uint32_t bin) { return (e.x >> (bin & 31)) & 1u; }
+__device__ __forceinline__ uint32_t slot_of(uint2 e, uint32_t bin) { return e.y + __popc(e.x & ((1u << (bin & 31)) - 1u)); }
 
 // ------------------------------------------------------------------------------------------
 // k_encode: ASCII -> 2 bits / base (+ invalid mask); one thread per 32-base word.
@@ -230,26 +230,15 @@ __global__ void __launch_bounds__(256) k_encode(const __grid_constant__ K p, uin
 }
 
 // ------------------------------------------------------------------------------------------
-// bookkeeping of one probe hit; shared by the scan kernels and k_junction
-__device__ __forceinline__ void on_hit(const K &p, int ki, uint32_t g, uint32_t bin, uint32_t word, uint64_t canon,
-                                       bool h_is_canon, uint32_t start) {
-    uint32_t idx = slot_of(p, ki, bin, word);
-    uint32_t *row = &p.rows[(size_t)g * p.nslots + idx];
-    if (p.canon1[idx] == canon) {
-        uint32_t old = atomicOr(row, ROW_HAS | (h_is_canon ? ROW_ORI : 0u) | start);
-        if (old & ROW_HAS) atomicOr(row, ROW_DUP);
-    } else {
-        atomicOr(row, ROW_POLL);
-    }
+// bookkeeping of one probe hit (any window of genome g whose bin holds a key)
+__device__ __forceinline__ void on_hit(const K &p, uint32_t g, uint2 e, uint32_t bin, uint32_t start) {
+    atomicAdd(&p.rows[(size_t)g * p.nslots + slot_of(e, bin)], ROW_ONE | start);
 }
 
 __device__ __forceinline__ void pollute(const K &p, int ki, uint32_t g, uint64_t canon, bool rev_table) {
     uint32_t bin = mod_p(canon, p);
-    uint32_t word = p.bits[(size_t)ki * p.PW + (bin >> 5)];
-    if ((word >> (bin & 31)) & 1u) {
-        uint32_t idx = slot_of(p, ki, bin, word);
-        atomicOr(&p.rows[(size_t)g * p.nslots + idx], rev_table ? ROW_JR : ROW_JF);
-    }
+    uint2 e = probe(p, ki, bin);
+    if (probe_hit(e, bin)) atomicOr(&p.rows[(size_t)g * p.nslots + slot_of(e, bin)], rev_table ? ROW_JR : ROW_JF);
 }
 
 // window with >= 1 non-ACGT byte: a strand-specific polluter.  The forward string hashes the byte as
@@ -265,20 +254,139 @@ __device__ __noinline__ void pollute_invalid_window(const K &p, int ki, int k, u
 }
 
 // ------------------------------------------------------------------------------------------
-// k_scan: one thread per 32-base word = 32 window end positions x nk lengths.
-//   CAND1    genome 1: candidate windows -> 2-bit table (the part of fkh.consume + the set
-//            comprehension of getCandidateKmers.py:46-55 that can matter for the result)
-//   FILL1    genome 1: key of every slot
-//   SCAN     all genomes: sketch membership (:54-55), strand algebra (:58-63), the per-k intersection
-//            (:127-142) and the relocation (:160-187) in one probe (plain L2 version)
-//   EMIT_*   ordered compaction of the surviving slots in the reference's dict order
-template <int MODE>
-__global__ void __launch_bounds__(256) k_scan(const __grid_constant__ K p, uint32_t w0, uint32_t w1) {
+// genome-1 kernels: one thread per window END position (coalesced, 32x the parallelism of a
+// per-word walk; genome 1 is a single genome, so parallelism matters more than rolling reuse)
+struct PosState {
+    uint64_t hf, hr;   // last 32 bases ending here: forward word (newest base lowest), rc word (top aligned)
+    uint64_t nmw;      // invalid-base bits, bit t = base of age t
+    uint32_t g, gpos;  // genome, genome-local padded coordinate of this end base
+    int n;             // bases of the contig up to and including this one
+};
+
+__device__ __forceinline__ bool load_pos(const K &p, uint32_t b, PosState &s) {
+    uint32_t w = b >> 5, j = b & 31;
+    uint32_t c = p.wordContig[w];
+    uint32_t i = w - p.cWordStart[c];
+    uint32_t q = 32u * i + j;
+    if (q >= p.cLen[c]) return false;
+    uint64_t cur = p.seq2[w], prev = i ? p.seq2[w - 1] : 0ull;
+    s.hf = j == 31 ? cur : ((prev << (2 * (j + 1))) | (cur >> (62 - 2 * j)));
+    s.hr = rc64(s.hf);
+    uint64_t nm = ((uint64_t)(i ? p.nmask[w - 1] : 0u) << 32) | p.nmask[w];
+    s.nmw = nm >> (31 - j);
+    s.g = p.cGenome[c];
+    s.gpos = b - 32u * p.gWordStart[s.g];
+    s.n = (int)q + 1;
+    return true;
+}
+
+// k_cand1: candidate windows of genome 1 -> 2-bit table.  Candidate = a k-mer the reference could
+// keep: no '~' / non-ACGT (:40-43), one end G/C (:29-33) and, with prefilter, GC / repeat / Tm in
+// range (:301-320; legal because the per-position pick takes the FIRST k-mer that passes, so k-mers
+// that fail can be dropped up front).  The sketch's "count == 1" is decided later by the scan, which
+// sees every window of genome 1, candidates or not.
+__global__ void __launch_bounds__(256) k_cand1(const __grid_constant__ K p, uint32_t nbases) {
     __shared__ uint32_t s_nn[16];
-    if (MODE == CAND1 || MODE == EMIT_WRITE) {
+    if (threadIdx.x < 16) s_nn[threadIdx.x] = c_nn[threadIdx.x];
+    __syncthreads();
+    uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= nbases) return;
+    PosState s;
+    uint32_t cm = 0;
+    if (load_pos(p, b, s)) {
+        int khi = min(p.kmax, s.n);
+        for (int k = p.kmin; k <= khi; k++) {
+            if (s.nmw & kmask1(k)) continue;
+            uint64_t h = s.hf & kmask2(k);
+            if (((h >> (2 * k - 2)) & 3) < 2 && (h & 3) < 2) continue;
+            if (p.prefilter) {
+                if (!((p.gc_ok[k] >> gc_count(h)) & 1ull)) continue;
+                if (has_long_repeat(h, k, p.max_repeat)) continue;
+            }
+            cm |= 1u << (k - p.kmin);
+        }
+        if (p.prefilter && cm) {
+            // one pass over the pairs serves every k: window k is complete after pair k-2
+            uint32_t acc = 0;
+            for (int i = 0; i + 2 <= khi; i++) {
+                acc += s_nn[(s.hf >> (2 * i)) & 15];
+                int k = i + 2, ki = k - p.kmin;
+                if (ki >= 0 && ((cm >> ki) & 1u)) {
+                    uint64_t h = s.hf & kmask2(k);
+                    double tm = tm_from_sums(acc, h, k, gc_count(h), p);
+                    if (!(tm >= p.min_tm && tm <= p.max_tm)) cm &= ~(1u << ki);
+                }
+            }
+        }
+        for (uint32_t m = cm; m; m &= m - 1) {
+            int ki = __ffs(m) - 1, k = p.kmin + ki;
+            uint64_t h = s.hf & kmask2(k), r = s.hr >> (64 - 2 * k);
+            uint32_t bin = mod_p(h < r ? h : r, p);
+            uint32_t *cell = &p.sk[(size_t)ki * 2 * p.PW + (bin >> 4)];
+            uint32_t bb = bin & 15u;
+            uint32_t old = atomicOr(cell, 1u << bb);
+            if ((old >> bb) & 1u) atomicOr(cell, 1u << (16 + bb));
+        }
+    }
+    p.passmask1[b] = cm;
+}
+
+// k_fill1 / k_emit: walk genome 1's candidate positions; FILL writes the key of every slot, EMIT
+// compacts the surviving slots in the reference's dict order (end position ascending, longest
+// first: getCandidateKmers.py:171-187 + pyahocorasick's emission order)
+enum { FILL1 = 0, EMIT_COUNT = 1, EMIT_WRITE = 2 };
+template <int MODE>
+__global__ void __launch_bounds__(256) k_walk1(const __grid_constant__ K p, uint32_t nbases) {
+    __shared__ uint32_t s_nn[16];
+    if (MODE == EMIT_WRITE) {
         if (threadIdx.x < 16) s_nn[threadIdx.x] = c_nn[threadIdx.x];
         __syncthreads();
     }
+    uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= nbases) return;
+    uint32_t pm = p.passmask1[b];
+    uint32_t emitted = 0, emit_at = 0;
+    if (pm) {
+        PosState s;
+        load_pos(p, b, s);
+        if (MODE == EMIT_WRITE) emit_at = p.emitCnt[b];
+        for (int ki = p.nk - 1; ki >= 0; ki--) {
+            if (!((pm >> ki) & 1u)) continue;
+            int k = p.kmin + ki;
+            uint64_t h = s.hf & kmask2(k), r = s.hr >> (64 - 2 * k);
+            uint64_t canon = h < r ? h : r;
+            uint32_t bin = mod_p(canon, p);
+            uint2 e = probe(p, ki, bin);
+            if (!probe_hit(e, bin)) continue;     // the candidate was not alone in its bin
+            uint32_t idx = slot_of(e, bin);
+            if (MODE == FILL1) {
+                p.canon1[idx] = canon;
+                p.slotK[idx] = (uint8_t)k;
+                continue;
+            }
+            if (!p.alive[idx]) continue;
+            if (MODE == EMIT_WRITE) {
+                pfb_record rec;
+                double tm;
+                uint32_t f = filter_flags(h, k, p, s_nn, &tm);
+                if (h == r) f |= PFB_F_PALIN;
+                rec.word = h; rec.tm = tm; rec.slot = idx; rec.gc_count = (uint16_t)gc_count(h);
+                rec.k = (uint8_t)k; rec.flags = (uint8_t)f;
+                p.rec[emit_at + emitted] = rec;
+            }
+            emitted++;
+        }
+    }
+    if (MODE == EMIT_COUNT) p.emitCnt[b] = emitted;
+}
+
+// ------------------------------------------------------------------------------------------
+// k_scan_plain: every window of every genome against the key table, probing the bitmap in L2
+// directly.  Used when the key set is too dense for the filter (prefilter = 0) and on tiny inputs.
+// One thread per 32-base word = 32 end positions x nk lengths with rolling words.
+// Implements sketch membership (:54-55), the strand algebra (:58-63), the per-k intersection
+// (:127-142) and the relocation (:160-187) in one probe.
+__global__ void __launch_bounds__(256) k_scan_plain(const __grid_constant__ K p, uint32_t w0, uint32_t w1) {
     uint32_t w = w0 + blockIdx.x * blockDim.x + threadIdx.x;
     if (w >= w1) return;
     uint32_t c = p.wordContig[w];
@@ -289,87 +397,48 @@ __global__ void __launch_bounds__(256) k_scan(const __grid_constant__ K p, uint3
     uint64_t hf = prev, hr = rc64(prev);
     uint32_t qbase = 32u * i;
     int nj = (int)min(32u, clen - qbase);
-    uint32_t gpos0 = 32u * (w - p.gWordStart[g]);   // genome-local padded coordinate of base j = 0
-    uint32_t emitted = 0, emit_at = 0;
-    if (MODE == EMIT_WRITE) emit_at = p.emitCnt[w - w0];
-
+    uint32_t gpos0 = 32u * (w - p.gWordStart[g]);
     for (int j = 0; j < nj; j++) {
         uint32_t code = (uint32_t)(cur >> (62 - 2 * j)) & 3u;
         hf = (hf << 2) | code;
         hr = (hr >> 2) | ((uint64_t)(code ^ 1u) << 62);
-        int n = (int)qbase + j + 1;                 // bases of this contig up to and including j
-        int khi = min(p.kmax, n);
-        uint32_t pm = 0;
-        if (MODE == FILL1 || MODE == EMIT_COUNT || MODE == EMIT_WRITE) {
-            pm = p.passmask1[gpos0 + j];
-            if (!pm) continue;
-            // longest first at one end position (pyahocorasick emission order)
-            for (int k = khi; k >= p.kmin; k--) {
-                int ki = k - p.kmin;
-                if (!((pm >> ki) & 1u)) continue;
-                uint64_t h = hf & kmask2(k), r = hr >> (64 - 2 * k);
-                uint64_t canon = h < r ? h : r;
-                uint32_t bin = mod_p(canon, p);
-                uint32_t word = p.bits[(size_t)ki * p.PW + (bin >> 5)];
-                if (!((word >> (bin & 31)) & 1u)) continue;     // candidate was not alone in its bin
-                uint32_t idx = slot_of(p, ki, bin, word);
-                if (MODE == FILL1) {
-                    p.canon1[idx] = canon;
-                    p.slotK[idx] = (uint8_t)k;
-                } else {
-                    if (!p.alive[idx]) continue;
-                    if (MODE == EMIT_WRITE) {
-                        pfb_record rec;
-                        double tm;
-                        uint32_t f = filter_flags(h, k, p, s_nn, &tm);
-                        if (h == r) f |= PFB_F_PALIN;
-                        rec.word = h; rec.tm = tm; rec.slot = idx; rec.gc_count = (uint16_t)gc_count(h);
-                        rec.k = (uint8_t)k; rec.flags = (uint8_t)f;
-                        p.rec[emit_at + emitted] = rec;
-                    }
-                    emitted++;
-                }
-            }
-            continue;
-        }
-
+        int khi = min(p.kmax, (int)qbase + j + 1);
         const uint64_t nmw = nm >> (31 - j);
         for (int k = p.kmin; k <= khi; k++) {
             int ki = k - p.kmin;
             uint64_t h = hf & kmask2(k), r = hr >> (64 - 2 * k);
-            uint32_t wn = (uint32_t)(nmw & kmask1(k));      // invalid bases inside the window (bit t = age t)
-            if (MODE == CAND1) {
-                if (wn) continue;                                                  // not a k-mer (:40-43 / non-ACGT)
-                if (((h >> (2 * k - 2)) & 3) < 2 && (h & 3) < 2) continue;          // isOneEndGc (:29-33)
-                if (p.prefilter && !passes_filters(h, k, p, s_nn)) continue;
-                uint64_t canon = h < r ? h : r;
-                uint32_t bin = mod_p(canon, p);
-                uint32_t *cell = &p.sk[(size_t)ki * 2 * p.PW + (bin >> 4)];
-                uint32_t b = bin & 15u;
-                uint32_t old = atomicOr(cell, 1u << b);
-                if ((old >> b) & 1u) atomicOr(cell, 1u << (16 + b));
-                pm |= 1u << ki;
-            } else {  // SCAN
-                if (wn) { pollute_invalid_window(p, ki, k, g, h, r, wn); continue; }
-                uint64_t canon = h < r ? h : r;
-                uint32_t bin = mod_p(canon, p);
-                uint32_t word = __ldg(&p.bits[(size_t)ki * p.PW + (bin >> 5)]);
-                if ((word >> (bin & 31)) & 1u) on_hit(p, ki, g, bin, word, canon, h <= r, gpos0 + j - k + 1);
-            }
+            uint32_t wn = (uint32_t)(nmw & kmask1(k));
+            if (wn) { pollute_invalid_window(p, ki, k, g, h, r, wn); continue; }
+            uint64_t canon = h < r ? h : r;
+            uint32_t bin = mod_p(canon, p);
+            uint2 e = probe(p, ki, bin);
+            if (probe_hit(e, bin)) on_hit(p, g, e, bin, gpos0 + j - k + 1);
         }
-        if (MODE == CAND1) p.passmask1[gpos0 + j] = pm;
     }
-    if (MODE == EMIT_COUNT) p.emitCnt[w - w0] = emitted;
 }
 
 // ------------------------------------------------------------------------------------------
-// k_scan_filtered: the SCAN pass with the probe staged through shared memory.  One persistent CTA
-// per SM; for each k a CTA copies that k's 192 KB filter (1 bit per ~6.4 bins, set when any bin of
-// the range holds a key) into shared memory and walks its share of the arena: only windows whose
-// filter bit is set go on to the exact bitmap in L2.
+// k_scan_filtered: the hot kernel.  One persistent 1024-thread CTA per SM.  For each k the CTA
+// copies that k's 192 KB filter (1 bit per ~6.4 bins, set when a bin of the range holds a key) into
+// shared memory and walks its share of the arena with rolling 2-bit words.  A window whose filter
+// bit is clear is done after one shared-memory load (~4 of 5 windows).  The others are NOT probed
+// in place: they are appended to a per-warp queue in shared memory, and whenever 32 are waiting the
+// whole warp drains them together: the L2 probe (bitmap + rank word) is paid once per 32 windows with
+// every lane busy, and a hit ends in one fire-and-forget RED on the genome's row.
+__device__ __forceinline__ void drain_queue(const K &p, int ki, const uint4 *q, uint32_t head, uint32_t n, uint32_t lane) {
+    if (lane < n) {
+        uint4 it = q[(head + lane) & (QCAP - 1)];   // x = bin, y = start, z = genome
+        uint2 e = probe(p, ki, it.x);
+        if (probe_hit(e, it.x)) on_hit(p, it.z, e, it.x, it.y);
+    }
+}
+
 __global__ void __launch_bounds__(1024, 1) k_scan_filtered(const __grid_constant__ K p, uint32_t w0, uint32_t w1) {
     extern __shared__ uint32_t s_filter[];
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint4 *queue = (uint4 *)(s_filter + FILTER_WORDS) + warp * QCAP;
     const uint32_t stride = gridDim.x * blockDim.x;
+    const uint32_t lt_mask = (1u << lane) - 1u;
     for (int ki = 0; ki < p.nk; ki++) {
         const int k = p.kmin + ki;
         __syncthreads();
@@ -382,39 +451,60 @@ __global__ void __launch_bounds__(1024, 1) k_scan_filtered(const __grid_constant
         const uint64_t km2 = kmask2(k);
         const uint64_t km1 = kmask1(k);
         const int rsh = 64 - 2 * k;
-        for (uint32_t w = w0 + blockIdx.x * blockDim.x + threadIdx.x; w < w1; w += stride) {
-            uint32_t c = p.wordContig[w];
-            uint32_t cws = p.cWordStart[c], clen = p.cLen[c];
-            uint32_t i = w - cws;
-            uint32_t qbase = 32u * i;
-            int nj = (int)min(32u, clen - qbase);
-            int jlo = (int)qbase + 1 >= k ? 0 : k - 1 - (int)qbase;   // first end position with a full window
-            if (jlo >= nj) continue;
-            uint32_t g = p.cGenome[c];
-            uint64_t cur = p.seq2[w], prev = i ? p.seq2[w - 1] : 0ull;
-            uint64_t nm = ((uint64_t)(i ? p.nmask[w - 1] : 0u) << 32) | p.nmask[w];
-            uint32_t gpos0 = 32u * (w - p.gWordStart[g]);
-            // state after base jlo - 1
-            uint64_t hf = jlo ? ((prev << (2 * jlo)) | (cur >> (64 - 2 * jlo))) : prev;
+        uint32_t qhead = 0, qn = 0;   // warp-uniform
+        for (uint32_t wb = w0 + blockIdx.x * blockDim.x + warp * 32; wb < w1; wb += stride) {
+            const uint32_t w = wb + lane;
+            int jlo = 32, nj = 0;
+            uint32_t g = 0, gpos0 = 0;
+            uint64_t cur = 0, nm = 0, hf = 0;
+            if (w < w1) {
+                uint32_t c = p.wordContig[w];
+                uint32_t i = w - p.cWordStart[c];
+                uint32_t qbase = 32u * i;
+                nj = (int)min(32u, p.cLen[c] - qbase);
+                jlo = (int)qbase + 1 >= k ? 0 : k - 1 - (int)qbase;     // first end position with a full window
+                g = p.cGenome[c];
+                cur = p.seq2[w];
+                hf = i ? p.seq2[w - 1] : 0ull;
+                nm = ((uint64_t)(i ? p.nmask[w - 1] : 0u) << 32) | p.nmask[w];
+                gpos0 = 32u * (w - p.gWordStart[g]);
+            }
             uint64_t hr = rc64(hf);
-#pragma unroll 4
-            for (int j = jlo; j < nj; j++) {
+            const bool any_n = __any_sync(0xFFFFFFFFu, nm != 0);
+#pragma unroll 2
+            for (int j = 0; j < 32; j++) {
                 uint32_t code = (uint32_t)(cur >> (62 - 2 * j)) & 3u;
                 hf = (hf << 2) | code;
                 hr = (hr >> 2) | ((uint64_t)(code ^ 1u) << 62);
                 uint64_t h = hf & km2, r = hr >> rsh;
-                if (nm) {
+                bool valid = j >= jlo && j < nj;
+                if (any_n && valid) {
                     uint32_t wn = (uint32_t)((nm >> (31 - j)) & km1);
-                    if (wn) { pollute_invalid_window(p, ki, k, g, h, r, wn); continue; }
+                    if (wn) { pollute_invalid_window(p, ki, k, g, h, r, wn); valid = false; }
                 }
                 uint64_t canon = h < r ? h : r;
                 uint32_t bin = mod_p(canon, p);
                 uint32_t fb = __umulhi(bin, p.fscale);
-                if (!((s_filter[fb >> 5] >> (fb & 31)) & 1u)) continue;
-                uint32_t word = __ldg(&p.bits[(size_t)ki * p.PW + (bin >> 5)]);
-                if ((word >> (bin & 31)) & 1u) on_hit(p, ki, g, bin, word, canon, h <= r, gpos0 + j - k + 1);
+                bool pred = valid && ((s_filter[fb >> 5] >> (fb & 31)) & 1u);
+                uint32_t m = __ballot_sync(0xFFFFFFFFu, pred);
+                if (m) {
+                    if (pred) {
+                        uint32_t at = (qhead + qn + __popc(m & lt_mask)) & (QCAP - 1);
+                        queue[at] = make_uint4(bin, gpos0 + j - k + 1, g, 0u);
+                    }
+                    qn += __popc(m);
+                    __syncwarp();
+                    if (qn >= 32) {
+                        drain_queue(p, ki, queue, qhead, 32, lane);
+                        qhead = (qhead + 32) & (QCAP - 1);
+                        qn -= 32;
+                        __syncwarp();
+                    }
+                }
             }
         }
+        drain_queue(p, ki, queue, qhead, qn, lane);
+        __syncwarp();
     }
 }
 
@@ -422,7 +512,7 @@ __global__ void __launch_bounds__(1024, 1) k_scan_filtered(const __grid_constant
 __global__ void __launch_bounds__(256) k_build_filter(const __grid_constant__ K p) {
     uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= (uint32_t)p.nk * p.PW) return;
-    uint32_t word = p.bits[t];
+    uint32_t word = p.br[t].x;
     if (!word) return;
     uint32_t ki = t / p.PW, wi = t - ki * p.PW;
     uint32_t *f = p.filter + (size_t)ki * FILTER_WORDS;
@@ -482,18 +572,20 @@ __global__ void __launch_bounds__(256) k_candbits(const __grid_constant__ K p) {
     uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= (uint32_t)p.nk * p.PW) return;
     uint32_t lo = p.sk[2 * (size_t)t], hi = p.sk[2 * (size_t)t + 1];
-    p.bits[t] = ((lo & ~(lo >> 16)) & 0xFFFFu) | ((hi & ~(hi >> 16)) << 16);
+    p.br[t].x = ((lo & ~(lo >> 16)) & 0xFFFFu) | ((hi & ~(hi >> 16)) << 16);
 }
 
 // device-wide exclusive scan in three launches; POPC: the value of an element is its popcount
-template <bool POPC>
+// element x of the input lives at in[x * S] and its prefix goes to out[x * S] (S = 2 for the
+// interleaved bitmap / rank table)
+template <bool POPC, int S>
 __global__ void __launch_bounds__(256) k_scan_p1(const uint32_t *in, uint32_t n, uint32_t *blockSums) {
     __shared__ uint32_t sm[8];
     uint32_t base = blockIdx.x * SCAN_TILE;
     uint32_t s = 0;
     for (int t = 0; t < SCAN_TILE / 256; t++) {
         uint32_t x = base + t * 256 + threadIdx.x;
-        if (x < n) s += POPC ? __popc(in[x]) : in[x];
+        if (x < n) s += POPC ? __popc(in[(size_t)x * S]) : in[(size_t)x * S];
     }
     for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xFFFFFFFFu, s, o);
     if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = s;
@@ -520,7 +612,7 @@ __global__ void __launch_bounds__(1024) k_scan_p2(uint32_t *blockSums, uint32_t 
     if (threadIdx.x == 1023) *total = sm[1023];
 }
 
-template <bool POPC>
+template <bool POPC, int S>
 __global__ void __launch_bounds__(256) k_scan_p3(const uint32_t *in, uint32_t *out, uint32_t n, const uint32_t *blockSums) {
     __shared__ uint32_t sm[8];
     uint32_t base = blockIdx.x * SCAN_TILE + threadIdx.x * (SCAN_TILE / 256);
@@ -529,7 +621,7 @@ __global__ void __launch_bounds__(256) k_scan_p3(const uint32_t *in, uint32_t *o
 #pragma unroll
     for (int t = 0; t < SCAN_TILE / 256; t++) {
         uint32_t x = base + t;
-        v[t] = x < n ? (POPC ? __popc(in[x]) : in[x]) : 0;
+        v[t] = x < n ? (POPC ? __popc(in[(size_t)x * S]) : in[(size_t)x * S]) : 0;
         s += v[t];
     }
     uint32_t incl = s;
@@ -545,35 +637,54 @@ __global__ void __launch_bounds__(256) k_scan_p3(const uint32_t *in, uint32_t *o
 #pragma unroll
     for (int t = 0; t < SCAN_TILE / 256; t++) {
         uint32_t x = base + t;
-        if (x < n) out[x] = run;
+        if (x < n) out[(size_t)x * S] = run;
         run += v[t];
     }
 }
 
 // ------------------------------------------------------------------------------------------
 // k_alive: per slot, the reference's rules for every genome on this context.
+//   the bin must hold exactly one window of the genome (khmer get() == 1, :35-38) and that window
+//   must be the key itself (read back from the packed genome at the recorded start);
 //   occurrence on the forward string ('+'): needs count == 1 in fkh  -> no JF polluter
 //   occurrence on the rc string ('-')     : needs count == 1 in rkh  -> no JR polluter
 //   palindrome, other genomes: in F ^ R  <=>  exactly one of the two tables reads 1 (:62-63)
 //   palindrome, first genome : in F - R  <=>  fkh reads 1 and rkh does not      (:58-59)
-__device__ __forceinline__ bool row_ok(uint32_t v, bool ori1, bool pal, bool first) {
-    if (!(v & ROW_HAS) || (v & (ROW_DUP | ROW_POLL))) return false;
+__device__ __forceinline__ uint64_t window_at(const K &p, uint32_t g, uint32_t lp, int k) {
+    uint32_t w = p.gWordStart[g] + (lp >> 5), o = lp & 31;
+    uint64_t a = p.seq2[w];
+    uint64_t x = o ? ((a << (2 * o)) | (p.seq2[w + 1] >> (64 - 2 * o))) : a;   // k <= 32 bases from offset o
+    return x >> (64 - 2 * k);
+}
+
+// returns 0 dead, 1 alive on '+', 2 alive on '-'
+__device__ __forceinline__ int row_state(const K &p, uint32_t g, unsigned long long v, uint64_t key_fwd, uint64_t key_rc,
+                                         int k, bool pal, bool first) {
+    if (((v >> 32) & ROW_CNT_MASK) != 1) return 0;
+    uint64_t h = window_at(p, g, (uint32_t)(v & ROW_POS_MASK), k);
     bool jf = (v & ROW_JF) != 0, jr = (v & ROW_JR) != 0;
-    if (pal) return first ? (!jf && jr) : (jf != jr);
-    bool minus = ((v & ROW_ORI) != 0) != ori1;
-    return minus ? !jr : !jf;
+    if (pal) return (h == key_fwd && (first ? (!jf && jr) : (jf != jr))) ? 2 : 0;   // later '-' match overwrites (:181-187)
+    if (h == key_fwd) return jf ? 0 : 1;
+    if (h == key_rc) return jr ? 0 : 2;
+    return 0;   // the single occupant is a different k-mer: a sketch collision with the key absent
 }
 
 __global__ void __launch_bounds__(256) k_alive(const __grid_constant__ K p) {
     uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= p.nslots) return;
-    uint64_t canon = p.canon1[idx];
     int k = p.slotK[idx];
-    bool pal = (rc64(canon) >> (64 - 2 * k)) == canon;
-    uint32_t v0 = p.rows[idx];
-    bool ori1 = (v0 & ROW_ORI) != 0;
-    bool ok = row_ok(v0, ori1, pal, true);
-    for (uint32_t g = 1; g < p.nGenomes && ok; g++) ok = row_ok(p.rows[(size_t)g * p.nslots + idx], ori1, pal, false);
+    // the key as it reads on genome 1's (+) strand
+    unsigned long long v0 = p.rows[idx];
+    bool ok = ((v0 >> 32) & ROW_CNT_MASK) == 1;
+    if (ok) {
+        uint64_t key = window_at(p, 0, (uint32_t)(v0 & ROW_POS_MASK), k);
+        uint64_t rc = rc64(key) >> (64 - 2 * k);
+        uint64_t canon = key < rc ? key : rc;
+        bool pal = key == rc;
+        ok = canon == p.canon1[idx] && row_state(p, 0, v0, key, rc, k, pal, true) != 0 && (pal || !(v0 & ROW_JF));
+        for (uint32_t g = 1; g < p.nGenomes && ok; g++)
+            ok = row_state(p, g, p.rows[(size_t)g * p.nslots + idx], key, rc, k, pal, false) != 0;
+    }
     p.alive[idx] = ok ? 1 : 0;
 }
 
@@ -584,16 +695,16 @@ __global__ void __launch_bounds__(256) k_positions(const __grid_constant__ K p) 
     uint32_t g = blockIdx.y;
     if (r >= p.nrec) return;
     pfb_record rec = p.rec[r];
-    uint32_t v = p.rows[(size_t)g * p.nslots + rec.slot];
-    bool ori1 = (p.rows[rec.slot] & ROW_ORI) != 0;
-    bool pal = (rec.flags & PFB_F_PALIN) != 0;
-    uint32_t lp = v & ROW_POS_MASK;
+    unsigned long long v = p.rows[(size_t)g * p.nslots + rec.slot];
+    uint32_t lp = (uint32_t)(v & ROW_POS_MASK);
     uint32_t gw = p.gWordStart[g] + (lp >> 5);
     uint32_t c = p.wordContig[gw];
     pfb_pos o;
     o.contig = c - p.gFirstContig[g];
     o.start = lp - 32u * (p.cWordStart[c] - p.gWordStart[g]);
-    o.strand = pal ? 1u : ((((v & ROW_ORI) != 0) != ori1) ? 1u : 0u);   // later '-' match overwrites (:181-187)
+    // '+' when the genome reads the key itself at that place, '-' when it reads its reverse complement;
+    // a palindrome matches both scans and the later '-' match overwrites (:181-187)
+    o.strand = ((rec.flags & PFB_F_PALIN) || window_at(p, g, lp, rec.k) != rec.word) ? 1u : 0u;
     p.pos[(size_t)g * p.nrec + r] = o;
     if ((rec.flags & 7u) == 7u) atomicMin(&p.minRank[(size_t)p.gWordStart[g] * 32u + lp], (uint32_t)r);
 }
@@ -606,8 +717,7 @@ __global__ void __launch_bounds__(256) k_pick(const __grid_constant__ K p) {
     if (r >= p.nrec) return;
     pfb_record rec = p.rec[r];
     if ((rec.flags & 7u) != 7u) return;
-    uint32_t v = p.rows[(size_t)g * p.nslots + rec.slot];
-    uint32_t lp = v & ROW_POS_MASK;
+    uint32_t lp = (uint32_t)(p.rows[(size_t)g * p.nslots + rec.slot] & ROW_POS_MASK);
     if (p.minRank[(size_t)p.gWordStart[g] * 32u + lp] == (uint32_t)r) p.pick[r] = 1;
 }
 
@@ -658,7 +768,7 @@ struct pfb_ctx {
     bool uploaded = false, computed = false;
     int stage_done = -1;
     // device
-    DevBuf raw, seq2, nmask, wordContig, tabs32, tabs64, sk, bits, rank, filter, fterm, scanTmp, misc, passmask1, canon1,
+    DevBuf raw, seq2, nmask, wordContig, tabs32, tabs64, sk, br, filter, fterm, scanTmp, misc, passmask1, canon1,
         slotK, rows, alive, emitCnt, rec, pos, minRank, pick;
     K k{};
     uint64_t nslots = 0, nrec = 0, npick = 0;
@@ -771,16 +881,16 @@ int build_layout(pfb_ctx *ctx) {
 }
 
 // device-wide exclusive scan helper (out may alias in)
-template <bool POPC>
+template <bool POPC, int S>
 int device_exscan(pfb_ctx *ctx, const uint32_t *in, uint32_t *out, uint32_t n, uint32_t *total_dev) {
     cudaStream_t st = ctx->stream;
     uint32_t nb = (n + SCAN_TILE - 1) / SCAN_TILE;
     int rc = ensure(ctx, ctx->scanTmp, (size_t)(nb + 1) * 4);
     if (rc != PFB_OK) return rc;
     uint32_t *bs = (uint32_t *)ctx->scanTmp.p;
-    k_scan_p1<POPC><<<nb, 256, 0, st>>>(in, n, bs);
+    k_scan_p1<POPC, S><<<nb, 256, 0, st>>>(in, n, bs);
     k_scan_p2<<<1, 1024, 0, st>>>(bs, nb, total_dev);
-    k_scan_p3<POPC><<<nb, 256, 0, st>>>(in, out, n, bs);
+    k_scan_p3<POPC, S><<<nb, 256, 0, st>>>(in, out, n, bs);
     ctx->launches += 3;
     return PFB_OK;
 }
@@ -822,7 +932,7 @@ int pfb_create(pfb_ctx **out, int device, const pfb_params *params) {
     cudaDeviceGetAttribute(&ctx->num_sms, cudaDevAttrMultiProcessorCount, device);
     e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
     if (e == cudaSuccess)
-        e = cudaFuncSetAttribute(k_scan_filtered, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FILTER_BYTES);
+        e = cudaFuncSetAttribute(k_scan_filtered, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SCANF_SMEM);
     if (e != cudaSuccess) { std::string m = cudaGetErrorString(e); delete ctx; return fail(nullptr, PFB_ECUDA, m); }
     for (auto &ev : ctx->ev) cudaEventCreate(&ev);
     *out = ctx;
@@ -833,8 +943,8 @@ void pfb_destroy(pfb_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    DevBuf *all[] = {&ctx->raw, &ctx->seq2, &ctx->nmask, &ctx->wordContig, &ctx->tabs32, &ctx->tabs64, &ctx->sk, &ctx->bits,
-                     &ctx->rank, &ctx->filter, &ctx->fterm, &ctx->scanTmp, &ctx->misc, &ctx->passmask1, &ctx->canon1,
+    DevBuf *all[] = {&ctx->raw, &ctx->seq2, &ctx->nmask, &ctx->wordContig, &ctx->tabs32, &ctx->tabs64, &ctx->sk, &ctx->br,
+                     &ctx->filter, &ctx->fterm, &ctx->scanTmp, &ctx->misc, &ctx->passmask1, &ctx->canon1,
                      &ctx->slotK, &ctx->rows, &ctx->alive, &ctx->emitCnt, &ctx->rec, &ctx->pos, &ctx->minRank, &ctx->pick};
     for (auto *b : all) release(*b);
     for (auto &ev : ctx->ev) if (ev) cudaEventDestroy(ev);
@@ -937,19 +1047,18 @@ static int stage0(pfb_ctx *ctx) {
     const uint32_t NB = (uint32_t)nk * k.PW;                                // words of the concatenated bitmaps
     ctx->launches = 0;
     // buffers
-    if ((rc = ensure(ctx, ctx->seq2, (size_t)(W + 1) * 8)) != PFB_OK) return rc;
+    if ((rc = ensure(ctx, ctx->seq2, (size_t)(W + 2) * 8)) != PFB_OK) return rc;
     if ((rc = ensure(ctx, ctx->nmask, (size_t)(W + 1) * 4)) != PFB_OK) return rc;
     if ((rc = ensure(ctx, ctx->wordContig, (size_t)(W + 1) * 4)) != PFB_OK) return rc;
     if ((rc = ensure(ctx, ctx->sk, (size_t)NB * 2 * 4)) != PFB_OK) return rc;
-    if ((rc = ensure(ctx, ctx->bits, (size_t)NB * 4)) != PFB_OK) return rc;
-    if ((rc = ensure(ctx, ctx->rank, (size_t)NB * 4)) != PFB_OK) return rc;
+    if ((rc = ensure(ctx, ctx->br, (size_t)NB * 8)) != PFB_OK) return rc;
     if ((rc = ensure(ctx, ctx->filter, (size_t)nk * FILTER_BYTES)) != PFB_OK) return rc;
     if ((rc = ensure(ctx, ctx->fterm, 33 * 33 * 8)) != PFB_OK) return rc;
     if ((rc = ensure(ctx, ctx->misc, 4096)) != PFB_OK) return rc;
     if ((rc = ensure(ctx, ctx->passmask1, (size_t)W1 * 32 * 4 + 4)) != PFB_OK) return rc;
-    if ((rc = ensure(ctx, ctx->emitCnt, (size_t)(W1 + 1) * 4)) != PFB_OK) return rc;
+    if ((rc = ensure(ctx, ctx->emitCnt, (size_t)W1 * 32 * 4 + 4)) != PFB_OK) return rc;
     k.seq2 = (uint64_t *)ctx->seq2.p; k.nmask = (uint32_t *)ctx->nmask.p; k.wordContig = (uint32_t *)ctx->wordContig.p;
-    k.sk = (uint32_t *)ctx->sk.p; k.bits = (uint32_t *)ctx->bits.p; k.rank = (uint32_t *)ctx->rank.p;
+    k.sk = (uint32_t *)ctx->sk.p; k.br = (uint2 *)ctx->br.p;
     k.filter = (uint32_t *)ctx->filter.p; k.fterm = (const double *)ctx->fterm.p;
     uint32_t *misc = (uint32_t *)ctx->misc.p;   // [0] nslots, [1] nrec, [2..3] npick (u64)
     k.passmask1 = (uint32_t *)ctx->passmask1.p; k.emitCnt = (uint32_t *)ctx->emitCnt.p;
@@ -961,9 +1070,10 @@ static int stage0(pfb_ctx *ctx) {
     if (W) { k_encode<<<nblk(W, 256), 256, 0, st>>>(k, 0, W); ctx->launches++; }
     CK(cudaEventRecord(ctx->ev[3], st));
     // genome 1: candidates -> key table
-    if (W1) { k_scan<CAND1><<<nblk(W1, 256), 256, 0, st>>>(k, 0, W1); ctx->launches++; }
+    const uint32_t N1 = W1 * 32u;                                           // padded end positions of genome 1
+    if (W1) { k_cand1<<<nblk(N1, 256), 256, 0, st>>>(k, N1); ctx->launches++; }
     k_candbits<<<nblk(NB, 256), 256, 0, st>>>(k); ctx->launches++;
-    if ((rc = device_exscan<true>(ctx, k.bits, k.rank, NB, misc)) != PFB_OK) return rc;
+    if ((rc = device_exscan<true, 2>(ctx, (const uint32_t *)k.br, (uint32_t *)k.br + 1, NB, misc)) != PFB_OK) return rc;
     uint32_t ns = 0;
     CK(cudaMemcpyAsync(&ns, misc, 4, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));   // fterm (host vector) is also consumed by now
@@ -973,16 +1083,16 @@ static int stage0(pfb_ctx *ctx) {
     const size_t nG = ctx->genomes.size();
     if ((rc = ensure(ctx, ctx->canon1, NS * 8)) != PFB_OK) return rc;
     if ((rc = ensure(ctx, ctx->slotK, NS)) != PFB_OK) return rc;
-    if ((rc = ensure(ctx, ctx->rows, NS * nG * 4)) != PFB_OK) return rc;
+    if ((rc = ensure(ctx, ctx->rows, NS * nG * 8)) != PFB_OK) return rc;
     if ((rc = ensure(ctx, ctx->alive, NS)) != PFB_OK) return rc;
     k.canon1 = (uint64_t *)ctx->canon1.p; k.slotK = (uint8_t *)ctx->slotK.p;
-    k.rows = (uint32_t *)ctx->rows.p; k.alive = (uint8_t *)ctx->alive.p;
-    CK(cudaMemsetAsync(ctx->rows.p, 0, NS * nG * 4, st));
+    k.rows = (unsigned long long *)ctx->rows.p; k.alive = (uint8_t *)ctx->alive.p;
+    CK(cudaMemsetAsync(ctx->rows.p, 0, NS * nG * 8, st));
     // the filter pays off while it stays sparse: expected fill 1 - exp(-keys_per_k / FILTER_BITS)
     bool use_filter = ctx->scan_mode == 2 ||
                       (ctx->scan_mode == 0 && (double)ctx->nslots / nk < 0.35 * FILTER_BITS && W >= 4096);
     ctx->used_filter = use_filter;
-    if (W1 && ctx->nslots) { k_scan<FILL1><<<nblk(W1, 256), 256, 0, st>>>(k, 0, W1); ctx->launches++; }
+    if (W1 && ctx->nslots) { k_walk1<FILL1><<<nblk(N1, 256), 256, 0, st>>>(k, N1); ctx->launches++; }
     if (use_filter && ctx->nslots) {
         CK(cudaMemsetAsync(ctx->filter.p, 0, (size_t)nk * FILTER_BYTES, st));
         k_build_filter<<<nblk(NB, 256), 256, 0, st>>>(k); ctx->launches++;
@@ -990,8 +1100,8 @@ static int stage0(pfb_ctx *ctx) {
     CK(cudaEventRecord(ctx->ev[4], st));
     // every genome (the first included): one pass against the key table
     if (W && ctx->nslots) {
-        if (use_filter) k_scan_filtered<<<ctx->num_sms, 1024, FILTER_BYTES, st>>>(k, 0, W);
-        else k_scan<SCAN><<<nblk(W, 256), 256, 0, st>>>(k, 0, W);
+        if (use_filter) k_scan_filtered<<<ctx->num_sms, 1024, SCANF_SMEM, st>>>(k, 0, W);
+        else k_scan_plain<<<nblk(W, 256), 256, 0, st>>>(k, 0, W);
         ctx->launches++;
         if (ctx->cLen.size() > nG) {   // some genome has more than one contig
             uint64_t nthr = (uint64_t)ctx->cLen.size() * nk * 2 * (2 * P.k_max - 1);
@@ -1012,11 +1122,12 @@ static int stage1(pfb_ctx *ctx) {
     const uint32_t W = ctx->totalWords;
     const uint32_t W1 = ctx->genomes.size() > 1 ? ctx->gWordStart[1] : W;
     const size_t nG = ctx->genomes.size();
+    const uint32_t N1 = W1 * 32u;
     uint32_t *misc = (uint32_t *)ctx->misc.p;
     ctx->nrec = 0; ctx->npick = 0;
     if (ctx->nslots && W1) {
-        k_scan<EMIT_COUNT><<<nblk(W1, 256), 256, 0, st>>>(k, 0, W1); ctx->launches++;
-        if ((rc = device_exscan<false>(ctx, k.emitCnt, k.emitCnt, W1, misc + 1)) != PFB_OK) return rc;
+        k_walk1<EMIT_COUNT><<<nblk(N1, 256), 256, 0, st>>>(k, N1); ctx->launches++;
+        if ((rc = device_exscan<false, 1>(ctx, k.emitCnt, k.emitCnt, N1, misc + 1)) != PFB_OK) return rc;
         uint32_t n = 0;
         CK(cudaMemcpyAsync(&n, misc + 1, 4, cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
@@ -1033,7 +1144,7 @@ static int stage1(pfb_ctx *ctx) {
     CK(cudaMemsetAsync(ctx->pick.p, 0, NR, st));
     if (ctx->nrec) {
         CK(cudaMemsetAsync(ctx->minRank.p, 0xFF, (size_t)W * 32 * 4, st));
-        k_scan<EMIT_WRITE><<<nblk(W1, 256), 256, 0, st>>>(k, 0, W1); ctx->launches++;
+        k_walk1<EMIT_WRITE><<<nblk(N1, 256), 256, 0, st>>>(k, N1); ctx->launches++;
         dim3 grid(nblk(ctx->nrec, 256), (unsigned)nG);
         k_positions<<<grid, 256, 0, st>>>(k); ctx->launches++;
         k_pick<<<grid, 256, 0, st>>>(k); ctx->launches++;
