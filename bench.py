@@ -228,9 +228,8 @@ def main():
             eng.compute_stage(2)
 
     def fetch_results():
-        rec = eng.records()
-        pos = [eng.positions(g, picked_only=True) for g in range(eng.n_genomes)]
-        return rec, pos
+        rec, ss, ct = eng.result_picked()     # pinned host buffers, plain D2H copies
+        return rec, [ss] + ([ct] if ct is not None else [])
 
     # ---- device-resident leg
     eng.upload()

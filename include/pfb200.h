@@ -117,7 +117,7 @@ int  pfb_run(pfb_ctx *ctx);
  * PFB_BUF_ALIVE buffer over ranks, between stage 1 and 2 it max-reduces PFB_BUF_PICK. */
 int  pfb_compute_stage(pfb_ctx *ctx, int stage);
 #define PFB_BUF_ALIVE 0   /* uint8 [n_slots]: 1 while the slot's k-mer is unique in every genome seen */
-#define PFB_BUF_PICK  1   /* uint8 [n_records] */
+#define PFB_BUF_PICK  1   /* uint32 [n_records], 0 / 1 (reduce it as bytes or as words) */
 int  pfb_device_buffer(pfb_ctx *ctx, int which, void **dev_ptr, uint64_t *n_bytes);
 int  pfb_sync(pfb_ctx *ctx);
 
@@ -127,6 +127,15 @@ int  pfb_result_records(pfb_ctx *ctx, pfb_record *out, uint64_t cap);
 /* positions of every record (picked_only = 0) or of the picked records only, in record order, in
  * the genome that was added as number `genome_idx` on this context */
 int  pfb_result_positions(pfb_ctx *ctx, uint32_t genome_idx, int picked_only, pfb_pos *out, uint64_t cap);
+/* the hot output path -- what __buildOutput (getCandidateKmers.py:442-489) needs: the picked records
+ * (PFB_F_PICK) and, for every genome g of this context, start_strand_out[g * cap + i] = leftmost start
+ * | strand << 31 and contig_out[g * cap + i] = contig index of picked record i (contig_out may be NULL
+ * when every genome is a single contig).  cap >= n_picked is the row pitch of the two arrays.  Plain
+ * device -> host copies into the caller's buffers: allocate them with pfb_host_alloc (pinned) to get
+ * full PCIe bandwidth. */
+int  pfb_result_picked(pfb_ctx *ctx, pfb_record *rec_out, uint32_t *start_strand_out, uint32_t *contig_out, uint64_t cap);
+int  pfb_host_alloc(void **out, uint64_t n_bytes);    /* cudaHostAlloc */
+int  pfb_host_free(void *ptr);
 int  pfb_timings(pfb_ctx *ctx, pfb_timing *out);
 /* how the scan probes the key bitmap: 0 auto (default), 1 plain L2 probe (k_scan<SCAN>), 2 through the
  * 192 KB shared-memory filter (k_scan_filtered).  Results are identical; tests run both. */

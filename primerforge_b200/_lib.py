@@ -28,7 +28,7 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", 
 EXPORTS = ["pfb_create", "pfb_destroy", "pfb_last_error", "pfb_default_params", "pfb_add_genome",
            "pfb_clear_genomes", "pfb_upload", "pfb_compute", "pfb_run", "pfb_compute_stage",
            "pfb_device_buffer", "pfb_sync", "pfb_result_counts", "pfb_result_records",
-           "pfb_result_positions", "pfb_timings", "pfb_set_scan_mode", "pfb_oligo_tm"]
+           "pfb_result_positions", "pfb_result_picked", "pfb_host_alloc", "pfb_host_free", "pfb_timings", "pfb_set_scan_mode", "pfb_oligo_tm"]
 
 
 class PfbParams(C.Structure):
@@ -89,6 +89,9 @@ def load():
     lib.pfb_result_counts.argtypes = [vp, C.POINTER(u64), C.POINTER(u64)]
     lib.pfb_result_records.argtypes = [vp, vp, u64]
     lib.pfb_result_positions.argtypes = [vp, u32, i32, vp, u64]
+    lib.pfb_result_picked.argtypes = [vp, vp, vp, vp, u64]
+    lib.pfb_host_alloc.argtypes = [C.POINTER(vp), u64]
+    lib.pfb_host_free.argtypes = [vp]
     lib.pfb_timings.argtypes = [vp, C.POINTER(PfbTiming)]
     lib.pfb_set_scan_mode.argtypes = [vp, i32]
     lib.pfb_oligo_tm.argtypes = [vp, C.c_char_p, C.POINTER(C.c_double), C.POINTER(C.c_double)]

@@ -93,10 +93,16 @@ struct K {  // kernel arguments (by value, __grid_constant__)
     // output
     uint32_t *emitCnt;        // per genome-1 end position
     pfb_record *rec;
-    pfb_pos *pos;             // [nGenomes][nrec]
+    uint32_t *pos;            // [nGenomes][nrec] start within contig | strand << 31
+    uint32_t *posContig;      // [nGenomes][nrec] contig index (only when some genome has > 1 contig)
+    int multiContig;
     uint32_t *minRank;        // [totalWords*32]
-    uint8_t *pick;
-    uint64_t nrec;
+    uint32_t *pick;           // [nrec] 0 / 1, then (stage 2) its exclusive prefix in pickOff
+    uint32_t *pickOff;
+    pfb_record *outRec;       // picked records, compacted
+    uint32_t *outPos;         // [nGenomes][npick]
+    uint32_t *outContig;      // [nGenomes][npick]
+    uint64_t nrec, npick;
 };
 
 // SantaLucia (1998) nearest-neighbour table in oligotm's integer units; index = 4*first + second
@@ -699,13 +705,12 @@ __global__ void __launch_bounds__(256) k_positions(const __grid_constant__ K p) 
     uint32_t lp = (uint32_t)(v & ROW_POS_MASK);
     uint32_t gw = p.gWordStart[g] + (lp >> 5);
     uint32_t c = p.wordContig[gw];
-    pfb_pos o;
-    o.contig = c - p.gFirstContig[g];
-    o.start = lp - 32u * (p.cWordStart[c] - p.gWordStart[g]);
+    uint32_t start = lp - 32u * (p.cWordStart[c] - p.gWordStart[g]);
     // '+' when the genome reads the key itself at that place, '-' when it reads its reverse complement;
     // a palindrome matches both scans and the later '-' match overwrites (:181-187)
-    o.strand = ((rec.flags & PFB_F_PALIN) || window_at(p, g, lp, rec.k) != rec.word) ? 1u : 0u;
-    p.pos[(size_t)g * p.nrec + r] = o;
+    uint32_t minus = ((rec.flags & PFB_F_PALIN) || window_at(p, g, lp, rec.k) != rec.word) ? 1u : 0u;
+    p.pos[(size_t)g * p.nrec + r] = start | (minus << 31);
+    if (p.multiContig) p.posContig[(size_t)g * p.nrec + r] = c - p.gFirstContig[g];
     if ((rec.flags & 7u) == 7u) atomicMin(&p.minRank[(size_t)p.gWordStart[g] * 32u + lp], (uint32_t)r);
 }
 
@@ -721,12 +726,19 @@ __global__ void __launch_bounds__(256) k_pick(const __grid_constant__ K p) {
     if (p.minRank[(size_t)p.gWordStart[g] * 32u + lp] == (uint32_t)r) p.pick[r] = 1;
 }
 
-__global__ void k_apply_pick(const __grid_constant__ K p, unsigned long long *npick) {
+// k_compact: picked records and their coordinates in every genome, densely packed for the D2H copy
+__global__ void __launch_bounds__(256) k_compact(const __grid_constant__ K p) {
     uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    bool pk = r < p.nrec && p.pick[r];
-    if (pk) p.rec[r].flags |= PFB_F_PICK;
-    unsigned m = __ballot_sync(0xFFFFFFFFu, pk);
-    if ((threadIdx.x & 31) == 0 && m) atomicAdd(npick, (unsigned long long)__popc(m));
+    if (r >= p.nrec) return;
+    if (!p.pick[r]) return;
+    p.rec[r].flags |= PFB_F_PICK;
+    uint32_t o = p.pickOff[r];
+    pfb_record rec = p.rec[r];
+    p.outRec[o] = rec;
+    for (uint32_t g = 0; g < p.nGenomes; g++) {
+        p.outPos[(size_t)g * p.npick + o] = p.pos[(size_t)g * p.nrec + r];
+        if (p.multiContig) p.outContig[(size_t)g * p.npick + o] = p.posContig[(size_t)g * p.nrec + r];
+    }
 }
 
 __global__ void k_oligo(const __grid_constant__ K p, uint64_t h, int k, double *out) {
@@ -769,7 +781,7 @@ struct pfb_ctx {
     int stage_done = -1;
     // device
     DevBuf raw, seq2, nmask, wordContig, tabs32, tabs64, sk, br, filter, fterm, scanTmp, misc, passmask1, canon1,
-        slotK, rows, alive, emitCnt, rec, pos, minRank, pick;
+        slotK, rows, alive, emitCnt, rec, pos, posContig, minRank, pick, pickOff, outRec, outPos, outContig;
     K k{};
     uint64_t nslots = 0, nrec = 0, npick = 0;
     uint64_t launches = 0;
@@ -945,7 +957,8 @@ void pfb_destroy(pfb_ctx *ctx) {
     cudaStreamSynchronize(ctx->stream);
     DevBuf *all[] = {&ctx->raw, &ctx->seq2, &ctx->nmask, &ctx->wordContig, &ctx->tabs32, &ctx->tabs64, &ctx->sk, &ctx->br,
                      &ctx->filter, &ctx->fterm, &ctx->scanTmp, &ctx->misc, &ctx->passmask1, &ctx->canon1,
-                     &ctx->slotK, &ctx->rows, &ctx->alive, &ctx->emitCnt, &ctx->rec, &ctx->pos, &ctx->minRank, &ctx->pick};
+                     &ctx->slotK, &ctx->rows, &ctx->alive, &ctx->emitCnt, &ctx->rec, &ctx->pos, &ctx->posContig, &ctx->minRank, &ctx->pick,
+                     &ctx->pickOff, &ctx->outRec, &ctx->outPos, &ctx->outContig};
     for (auto *b : all) release(*b);
     for (auto &ev : ctx->ev) if (ev) cudaEventDestroy(ev);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -1060,7 +1073,7 @@ static int stage0(pfb_ctx *ctx) {
     k.seq2 = (uint64_t *)ctx->seq2.p; k.nmask = (uint32_t *)ctx->nmask.p; k.wordContig = (uint32_t *)ctx->wordContig.p;
     k.sk = (uint32_t *)ctx->sk.p; k.br = (uint2 *)ctx->br.p;
     k.filter = (uint32_t *)ctx->filter.p; k.fterm = (const double *)ctx->fterm.p;
-    uint32_t *misc = (uint32_t *)ctx->misc.p;   // [0] nslots, [1] nrec, [2..3] npick (u64)
+    uint32_t *misc = (uint32_t *)ctx->misc.p;   // [0] nslots, [1] nrec, [2] npick
     k.passmask1 = (uint32_t *)ctx->passmask1.p; k.emitCnt = (uint32_t *)ctx->emitCnt.p;
 
     CK(cudaEventRecord(ctx->ev[2], st));
@@ -1136,12 +1149,17 @@ static int stage1(pfb_ctx *ctx) {
     k.nrec = ctx->nrec;
     const size_t NR = ctx->nrec ? ctx->nrec : 1;
     if ((rc = ensure(ctx, ctx->rec, NR * sizeof(pfb_record))) != PFB_OK) return rc;
-    if ((rc = ensure(ctx, ctx->pos, NR * nG * sizeof(pfb_pos))) != PFB_OK) return rc;
-    if ((rc = ensure(ctx, ctx->pick, NR)) != PFB_OK) return rc;
+    const bool multi = ctx->cLen.size() > nG;
+    if ((rc = ensure(ctx, ctx->pos, NR * nG * 4)) != PFB_OK) return rc;
+    if ((rc = ensure(ctx, ctx->posContig, multi ? NR * nG * 4 : 4)) != PFB_OK) return rc;
+    if ((rc = ensure(ctx, ctx->pick, NR * 4)) != PFB_OK) return rc;
+    if ((rc = ensure(ctx, ctx->pickOff, NR * 4)) != PFB_OK) return rc;
     if ((rc = ensure(ctx, ctx->minRank, (size_t)W * 32 * 4 + 4)) != PFB_OK) return rc;
-    k.rec = (pfb_record *)ctx->rec.p; k.pos = (pfb_pos *)ctx->pos.p; k.pick = (uint8_t *)ctx->pick.p;
+    k.rec = (pfb_record *)ctx->rec.p; k.pos = (uint32_t *)ctx->pos.p; k.posContig = (uint32_t *)ctx->posContig.p;
+    k.multiContig = multi ? 1 : 0;
+    k.pick = (uint32_t *)ctx->pick.p; k.pickOff = (uint32_t *)ctx->pickOff.p;
     k.minRank = (uint32_t *)ctx->minRank.p;
-    CK(cudaMemsetAsync(ctx->pick.p, 0, NR, st));
+    CK(cudaMemsetAsync(ctx->pick.p, 0, NR * 4, st));
     if (ctx->nrec) {
         CK(cudaMemsetAsync(ctx->minRank.p, 0xFF, (size_t)W * 32 * 4, st));
         k_walk1<EMIT_WRITE><<<nblk(N1, 256), 256, 0, st>>>(k, N1); ctx->launches++;
@@ -1156,16 +1174,27 @@ static int stage1(pfb_ctx *ctx) {
 static int stage2(pfb_ctx *ctx) {
     cudaStream_t st = ctx->stream;
     K &k = ctx->k;
-    unsigned long long *npick = (unsigned long long *)((uint32_t *)ctx->misc.p + 2);
+    int rc;
+    uint32_t *misc = (uint32_t *)ctx->misc.p;
+    const size_t nG = ctx->genomes.size();
+    ctx->npick = 0;
     if (ctx->nrec) {
-        k_apply_pick<<<nblk(ctx->nrec, 256), 256, 0, st>>>(k, npick); ctx->launches++;
+        if ((rc = device_exscan<false, 1>(ctx, k.pick, k.pickOff, (uint32_t)ctx->nrec, misc + 2)) != PFB_OK) return rc;
+        uint32_t np = 0;
+        CK(cudaMemcpyAsync(&np, misc + 2, 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        ctx->npick = np;
     }
+    k.npick = ctx->npick;
+    const size_t NP = ctx->npick ? ctx->npick : 1;
+    if ((rc = ensure(ctx, ctx->outRec, NP * sizeof(pfb_record))) != PFB_OK) return rc;
+    if ((rc = ensure(ctx, ctx->outPos, NP * nG * 4)) != PFB_OK) return rc;
+    if ((rc = ensure(ctx, ctx->outContig, k.multiContig ? NP * nG * 4 : 4)) != PFB_OK) return rc;
+    k.outRec = (pfb_record *)ctx->outRec.p; k.outPos = (uint32_t *)ctx->outPos.p; k.outContig = (uint32_t *)ctx->outContig.p;
+    if (ctx->npick) { k_compact<<<nblk(ctx->nrec, 256), 256, 0, st>>>(k); ctx->launches++; }
     CK(cudaEventRecord(ctx->ev[6], st));
-    unsigned long long np = 0;
-    CK(cudaMemcpyAsync(&np, npick, 8, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     CK(cudaGetLastError());
-    ctx->npick = np;
     pfb_timing &t = ctx->tm;
     cudaEventElapsedTime(&t.ms_encode, ctx->ev[2], ctx->ev[3]);
     cudaEventElapsedTime(&t.ms_first, ctx->ev[3], ctx->ev[4]);
@@ -1218,7 +1247,7 @@ int pfb_device_buffer(pfb_ctx *ctx, int which, void **dev_ptr, uint64_t *n_bytes
         *dev_ptr = ctx->alive.p; *n_bytes = ctx->nslots;
     } else if (which == PFB_BUF_PICK) {
         if (ctx->stage_done < 1) return fail(ctx, PFB_ESTATE, "stage 1 has not run");
-        *dev_ptr = ctx->pick.p; *n_bytes = ctx->nrec;
+        *dev_ptr = ctx->pick.p; *n_bytes = ctx->nrec * 4;
     } else {
         return fail(ctx, PFB_EINVAL, "unknown buffer");
     }
@@ -1250,23 +1279,56 @@ int pfb_result_positions(pfb_ctx *ctx, uint32_t genome_idx, int picked_only, pfb
     if (!ctx->computed) return fail(ctx, PFB_ESTATE, "no completed run");
     if (genome_idx >= ctx->genomes.size()) return fail(ctx, PFB_EINVAL, "genome index out of range");
     CK(cudaSetDevice(ctx->device));
-    const uint64_t need = picked_only ? ctx->npick : ctx->nrec;
-    if (cap < need) return fail(ctx, PFB_EINVAL, "position buffer too small");
-    if (!ctx->nrec) return PFB_OK;
-    const pfb_pos *src = (const pfb_pos *)ctx->pos.p + (size_t)genome_idx * ctx->nrec;
-    if (!picked_only) {
-        CK(cudaMemcpyAsync(out, src, ctx->nrec * sizeof(pfb_pos), cudaMemcpyDeviceToHost, ctx->stream));
-        CK(cudaStreamSynchronize(ctx->stream));
-        return PFB_OK;
+    const uint64_t n = picked_only ? ctx->npick : ctx->nrec;
+    if (cap < n) return fail(ctx, PFB_EINVAL, "position buffer too small");
+    if (!n) return PFB_OK;
+    const uint32_t *ps = (picked_only ? (const uint32_t *)ctx->outPos.p : (const uint32_t *)ctx->pos.p) + (size_t)genome_idx * n;
+    const uint32_t *cs = (picked_only ? (const uint32_t *)ctx->outContig.p : (const uint32_t *)ctx->posContig.p) + (size_t)genome_idx * n;
+    std::vector<uint32_t> hp(n), hc;
+    CK(cudaMemcpyAsync(hp.data(), ps, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    if (ctx->k.multiContig) {
+        hc.resize(n);
+        CK(cudaMemcpyAsync(hc.data(), cs, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
     }
-    // picked only: copy all, compact on the host side of the ABI (the pick vector is tiny)
-    std::vector<pfb_pos> all(ctx->nrec);
-    std::vector<uint8_t> pk(ctx->nrec);
-    CK(cudaMemcpyAsync(all.data(), src, ctx->nrec * sizeof(pfb_pos), cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaMemcpyAsync(pk.data(), ctx->pick.p, ctx->nrec, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
-    uint64_t n = 0;
-    for (uint64_t r = 0; r < ctx->nrec; r++) if (pk[r]) out[n++] = all[r];
+    for (uint64_t r = 0; r < n; r++) {
+        out[r].contig = ctx->k.multiContig ? hc[r] : 0u;
+        out[r].start = hp[r] & 0x7FFFFFFFu;
+        out[r].strand = hp[r] >> 31;
+    }
+    return PFB_OK;
+}
+
+int pfb_result_picked(pfb_ctx *ctx, pfb_record *rec_out, uint32_t *start_strand_out, uint32_t *contig_out, uint64_t cap) {
+    if (!ctx) return PFB_EINVAL;
+    if (!ctx->computed) return fail(ctx, PFB_ESTATE, "no completed run");
+    if (cap < ctx->npick) return fail(ctx, PFB_EINVAL, "output buffers too small");
+    if (!ctx->npick) return PFB_OK;
+    if (!rec_out || !start_strand_out) return fail(ctx, PFB_EINVAL, "NULL output buffer");
+    CK(cudaSetDevice(ctx->device));
+    const size_t nG = ctx->genomes.size(), np = ctx->npick;
+    CK(cudaMemcpyAsync(rec_out, ctx->outRec.p, np * sizeof(pfb_record), cudaMemcpyDeviceToHost, ctx->stream));
+    // the caller's rows are `cap` apart, the device rows `npick` apart
+    CK(cudaMemcpy2DAsync(start_strand_out, cap * 4, ctx->outPos.p, np * 4, np * 4, nG, cudaMemcpyDeviceToHost, ctx->stream));
+    if (contig_out) {
+        if (ctx->k.multiContig)
+            CK(cudaMemcpy2DAsync(contig_out, cap * 4, ctx->outContig.p, np * 4, np * 4, nG, cudaMemcpyDeviceToHost, ctx->stream));
+        else
+            for (size_t g = 0; g < nG; g++) memset(contig_out + g * cap, 0, np * 4);
+    }
+    CK(cudaStreamSynchronize(ctx->stream));
+    return PFB_OK;
+}
+
+int pfb_host_alloc(void **out, uint64_t n_bytes) {
+    if (!out) return PFB_EINVAL;
+    *out = nullptr;
+    cudaError_t e = cudaHostAlloc(out, n_bytes ? n_bytes : 1, cudaHostAllocDefault);
+    return e == cudaSuccess ? PFB_OK : PFB_ECUDA;
+}
+
+int pfb_host_free(void *ptr) {
+    if (ptr && cudaFreeHost(ptr) != cudaSuccess) return PFB_ECUDA;
     return PFB_OK;
 }
 

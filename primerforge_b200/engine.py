@@ -67,6 +67,8 @@ class Engine:
             raise PfbError(rc, self._lib.pfb_last_error(None).decode())
         self._keep = []
         self.n_genomes = 0
+        self._multi_contig = False
+        self._pinned = {}
 
     # -- plumbing
     def _check(self, rc: int):
@@ -77,6 +79,26 @@ class Engine:
         if getattr(self, "_ctx", None) and self._ctx.value:
             self._lib.pfb_destroy(self._ctx)
             self._ctx = C.c_void_p()
+            for ptr, _cap in self._pinned.values():
+                self._lib.pfb_host_free(ptr)
+            self._pinned = {}
+
+    def _pinned_array(self, name: str, dtype, shape):
+        """grow-only pinned host buffer viewed as a numpy array (full PCIe bandwidth for the D2H copy)"""
+        nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        ptr, cap = self._pinned.get(name, (None, 0))
+        if cap < nbytes:
+            if ptr:
+                self._lib.pfb_host_free(ptr)
+            want = nbytes + nbytes // 4 + 4096
+            new = C.c_void_p()
+            rc = self._lib.pfb_host_alloc(C.byref(new), want)
+            if rc != _lib.PFB_OK:
+                raise PfbError(rc, "cudaHostAlloc failed")
+            ptr, cap = new, want
+            self._pinned[name] = (ptr, cap)
+        buf = (C.c_uint8 * nbytes).from_address(ptr.value)
+        return np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
 
     def __del__(self):
         try:
@@ -103,6 +125,7 @@ class Engine:
         self._keep.append((bases, offsets))
         self._check(self._lib.pfb_add_genome(self._ctx, bases.ctypes.data, bases.size, offsets.ctypes.data, offsets.size - 1))
         self.n_genomes += 1
+        self._multi_contig |= offsets.size > 2
 
     def add_genome_ptr(self, ptr: int, n_bases: int, offsets: np.ndarray):
         """bases already in (pinned) host memory at address `ptr`"""
@@ -110,11 +133,13 @@ class Engine:
         self._keep.append((None, offsets))
         self._check(self._lib.pfb_add_genome(self._ctx, ptr, n_bases, offsets.ctypes.data, offsets.size - 1))
         self.n_genomes += 1
+        self._multi_contig |= offsets.size > 2
 
     def clear(self):
         self._check(self._lib.pfb_clear_genomes(self._ctx))
         self._keep = []
         self.n_genomes = 0
+        self._multi_contig = False
 
     # -- run
     def upload(self):
@@ -173,6 +198,20 @@ class Engine:
             rec = rec[(rec["flags"] & _lib.F_PICK) != 0]
         pos = [self.positions(g, picked_only) for g in range(self.n_genomes)]
         return StageResult(records=rec, positions=pos, timing=self.timing())
+
+    def result_picked(self):
+        """the hot output path: (records of the picked k-mers, start|strand<<31 per genome [G, n],
+        contig index per genome [G, n] or None when every genome is a single contig); the arrays are
+        views of pinned buffers owned by the engine (valid until the next call / close)"""
+        _n, m = self.counts()
+        G = self.n_genomes
+        cap = max(m, 1)
+        rec = self._pinned_array("rec", _lib.RECORD_DTYPE, (cap,))
+        ss = self._pinned_array("ss", np.uint32, (G, cap))
+        ct = self._pinned_array("ct", np.uint32, (G, cap)) if self._multi_contig else None
+        self._check(self._lib.pfb_result_picked(self._ctx, rec.ctypes.data, ss.ctypes.data,
+                                                ct.ctypes.data if ct is not None else None, cap))
+        return rec[:m], ss[:, :m], (ct[:, :m] if ct is not None else None)
 
     def oligo_tm(self, seq: str):
         tm, gc = C.c_double(), C.c_double()

@@ -176,3 +176,27 @@ def test_empty_and_ragged_inputs():
     with Engine(device=0) as eng:
         with pytest.raises(PfbError):
             eng.run()                                   # no genome added
+
+
+def test_picked_output_path_matches_full_output():
+    from primerforge_b200 import synth
+    from primerforge_b200.engine import Engine
+    gens = synth.make_genomes(4, 50_000, seed=401, snp_rate=0.003, n_inversions=2, n_contigs=3)
+    for prefilter in (0, 1):
+        with Engine(device=0, prefilter=prefilter) as eng:
+            for g in gens:
+                eng.add_genome(g.contigs)
+            eng.run()
+            res = eng.result()
+            rec, ss, ct = eng.result_picked()
+            sel = res.picked
+            assert rec.size == int(sel.sum()) and ct is not None
+            assert np.array_equal(rec["word"], res.records["word"][sel])
+            assert np.all(rec["flags"] & 8)
+            for gi in range(len(gens)):
+                pos = res.positions[gi][sel]
+                assert np.array_equal(ss[gi] & 0x7FFFFFFF, pos["start"])
+                assert np.array_equal(ss[gi] >> 31, pos["strand"])
+                assert np.array_equal(ct[gi], pos["contig"])
+                pk = eng.positions(gi, picked_only=True)
+                assert np.array_equal(pk["start"], pos["start"]) and np.array_equal(pk["contig"], pos["contig"])
