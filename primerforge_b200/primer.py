@@ -78,7 +78,7 @@ def _calc_tm(seq: str) -> float:
         return oligo_tm(seq)
 
 
-class _LocalPrimer:
+class Primer:
     """mirror of bin.Primer.Primer (used when primerForge is not importable)"""
     PLUS = "+"
     MINUS = "-"
@@ -110,7 +110,7 @@ class _LocalPrimer:
     __repr__ = __str__
 
     def __eq__(self, other):
-        if isinstance(other, _LocalPrimer):
+        if isinstance(other, Primer):
             return self.seq == other.seq
         if isinstance(other, str):
             return self.seq == other
@@ -139,8 +139,7 @@ class _LocalPrimer:
         return min((text[i:i + lmerSize] for i in range(len(text) - lmerSize + 1)), key=str)
 
 
-_LocalPrimer.__name__ = "Primer"
-_LocalPrimer.__qualname__ = "Primer"
+_LocalPrimer = Primer
 
 
 def primer_class():

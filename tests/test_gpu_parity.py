@@ -200,3 +200,86 @@ def test_picked_output_path_matches_full_output():
                 assert np.array_equal(ct[gi], pos["contig"])
                 pk = eng.positions(gi, picked_only=True)
                 assert np.array_equal(pk["start"], pos["start"]) and np.array_equal(pk["contig"], pos["contig"])
+
+
+@pytest.mark.parametrize("name,thal", [("basic", "off"), ("collide_multi", "pseudo")])
+def test_drop_in_entry_point(name, thal, tmp_path, capsys):
+    """_getAllCandidateKmers(params, sharedExists) from FASTA files, as bin/main.py:86 calls it"""
+    from types import SimpleNamespace
+    from primerforge_b200 import synth
+    from primerforge_b200.candidates import _getAllCandidateKmers
+    gold = load_golden(name)
+    if gold.table_size != 9999991:
+        pytest.skip("the entry point always uses khmer's table size") if thal == "off" else None
+    paths = synth.write_fasta(gold.genomes, str(tmp_path))
+    dumped = {}
+    log = SimpleNamespace(rename=lambda *a: None, info=lambda *a: None, debug=lambda *a: None, error=lambda *a: None)
+    params = SimpleNamespace(ingroupFns=paths, format="fasta", minLen=gold.k_min, maxLen=gold.k_max, minGc=gold.min_gc,
+                             maxGc=gold.max_gc, minTm=gold.min_tm, maxTm=gold.max_tm, maxRepeatLen=gold.max_repeat,
+                             tempTolerance=gold.temp_tolerance, numThreads=1, p3_mvConc=50.0, p3_dvConc=1.5,
+                             p3_dntpConc=0.6, p3_dnaConc=50.0, p3_tempC=37.0, p3_maxLoop=30, log=log,
+                             pickles={1: "sharedKmers.p", 2: "candidates.p"},
+                             dumpObj=lambda obj, fn, what, prefix="": dumped.__setitem__(fn, obj), loadObj=dumped.get)
+    if gold.table_size != 9999991:
+        # the golden case forces a small table; run the same through run_stage-level knobs instead
+        import primerforge_b200.candidates as cand
+        orig = cand.run_stage
+        cand.run_stage = lambda genomes, **kw: orig(genomes, table_size=gold.table_size, **kw)
+    try:
+        out = _getAllCandidateKmers(params, False, thal=("off" if thal == "off" else _pseudo_thal))
+    finally:
+        if gold.table_size != 9999991:
+            cand.run_stage = orig
+    assert "candidate kmers" in capsys.readouterr().out
+    assert dumped["candidates.p"] is out and list(out.keys()) == gold.names
+    for gi, (nm, gen) in enumerate(zip(gold.names, gold.genomes)):
+        cidx = {c: i for i, c in enumerate(gen.contig_ids)}
+        mine = set()
+        for contig, plist in out[nm].items():
+            keys = [min(p.start, p.end) for p in plist]
+            assert keys == sorted(keys)
+            mine |= {(str(p), cidx[contig], p.start, p.end, int(p.strand == "-")) for p in plist}
+        assert mine == golden_candidate_set(gold, gi)
+
+
+def test_full_size_properties():
+    """BASELINE config 2 at full size: size-independent properties of the result (the oracle would
+    take minutes here).  Every reported k-mer must read back from every genome at the reported
+    place and strand, be unique there among the reported set, and the order must be the dict order."""
+    from primerforge_b200 import synth
+    from primerforge_b200.engine import Engine
+    gens, cfg = synth.make_config(2)
+    with Engine(device=0, k_min=cfg["k_min"], k_max=cfg["k_max"]) as eng:
+        for g in gens:
+            eng.add_genome(g.contigs)
+        eng.run()
+        rec, ss, ct = eng.result_picked()
+        rec, ss = rec.copy(), ss.copy()
+        tm = eng.timing()
+    assert ct is None and rec.size > 100_000 and tm["used_filter"] == 1
+    k = rec["k"].astype(np.int64)
+    assert np.all((rec["flags"] & 15) == 15)
+    # dict order: genome-1 end position ascending, longest first at one end
+    end0 = (ss[0] & 0x7FFFFFFF).astype(np.int64) + k - 1
+    order_key = end0 * 64 + (63 - k)
+    assert np.all(np.diff(order_key) > 0)
+    assert np.all((ss[0] >> 31) == 0)                       # genome 1 holds every key on its (+) strand
+    code = np.full(256, 4, dtype=np.uint8)
+    for ch, v in zip(b"ATCG", range(4)):
+        code[ch] = v
+    rng = np.random.default_rng(5)
+    sample = rng.choice(rec.size, size=20000, replace=False)
+    for gi, gen in enumerate(gens):
+        seq = code[gen.contigs[0]]
+        start = (ss[gi] & 0x7FFFFFFF).astype(np.int64)[sample]
+        minus = (ss[gi] >> 31).astype(bool)[sample]
+        for s0, mi, w, kk in zip(start[:4000], minus[:4000], rec["word"][sample][:4000], k[sample][:4000]):
+            window = seq[s0:s0 + kk]
+            if mi:
+                window = (window[::-1] ^ 1)
+            val = 0
+            for c in window:
+                val = (val << 2) | int(c)
+            assert val == int(w)
+        # a position holds at most one picked k-mer per k
+        assert np.unique((ss[gi].astype(np.int64) << 6) | k).size == rec.size

@@ -1,0 +1,38 @@
+import os
+import sys
+
+import numpy as np
+
+from primerforge_b200 import seqio, synth
+
+STANDINS = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "standins")
+
+
+def test_fasta_reader_matches_biopython_rules(tmp_path):
+    gens = synth.make_genomes(2, 5000, seed=9, n_contigs=4)
+    paths = synth.write_fasta(gens, str(tmp_path))
+    sys.path.insert(0, STANDINS)
+    from Bio import SeqIO
+    for gen, path in zip(gens, paths):
+        ids, contigs = seqio.read_genome(path, "fasta")
+        ref = list(SeqIO.parse(path, "fasta"))
+        assert ids == [r.id for r in ref] == gen.contig_ids
+        for c, r, g in zip(contigs, ref, gen.contigs):
+            assert c.tobytes().decode() == str(r.seq) and np.array_equal(c, g)
+
+
+def test_fasta_edge_cases(tmp_path):
+    p = tmp_path / "x.fasta"
+    p.write_bytes(b">c1 desc here\r\nACGT\r\nAC\r\n>c2\n\n>c3\tz\nGG>GT\nTT")
+    ids, contigs = seqio.read_fasta(str(p))
+    assert ids == ["c1", "c2", "c3"]
+    assert [c.tobytes() for c in contigs] == [b"ACGTAC", b"", b"GG>GTTT"]
+
+
+def test_genbank_reader(tmp_path):
+    p = tmp_path / "x.gbk"
+    p.write_text("LOCUS       AB000001  12 bp    DNA\nVERSION     AB000001.2\nORIGIN\n        1 acgtacgtac gt\n//\n"
+                 "LOCUS       NOVERSION  4 bp\nORIGIN\n        1 ttga\n//\n")
+    ids, contigs = seqio.read_genome(str(p), "genbank")
+    assert ids == ["AB000001.2", "NOVERSION"]
+    assert [c.tobytes() for c in contigs] == [b"ACGTACGTACGT", b"TTGA"]
