@@ -114,7 +114,7 @@ def cpu_sample_run(cfg_index: int, threads: int = 0):
                        f"oracle/pf_oracle.c (OpenMP), {dt:.2f} s, {o.n_shared} shared k-mers"), dt
 
 
-def run_reference_arm(args):
+def run_reference_arm(args, emit):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -132,7 +132,7 @@ def run_reference_arm(args):
             "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64",
             "data": "synthetic", "impl": "reference", "config": cfg, "cpu_baseline": last,
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
-    print(json.dumps(line))
+    emit(line)
 
 
 def workload_config(index: int, n_gpus: int) -> dict:
@@ -149,6 +149,15 @@ def workload_config(index: int, n_gpus: int) -> dict:
 
 
 def main():
+    # exactly ONE line may reach stdout (the driver parses it): libraries that print banners during
+    # initialisation (NCCL's version line) are diverted to stderr
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(obj):
+        sys.stdout.flush()
+        os.write(real_stdout, (json.dumps(obj) + "\n").encode())
+
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
@@ -162,7 +171,7 @@ def main():
     args.warmup = max(args.warmup, 0)
 
     if args.impl == "reference":
-        run_reference_arm(args)
+        run_reference_arm(args, emit)
         return
 
     import torch
@@ -313,7 +322,7 @@ def main():
             "wall_s_timed_loop": wall}
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"], _ = cpu_sample_run(args.config)
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
