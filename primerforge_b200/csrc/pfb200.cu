@@ -13,7 +13,7 @@
 //     in range) are entered into a 2-bit-per-bin table (seen once / seen again) with L2-resident
 //     atomicOr (k_cand1).  A candidate that is alone in its bin owns the bin, so (k, bin) is a
 //     perfect hash of the key set: a bitmap over bins + popcount ranks gives a dense slot id
-//     (k_candbits, k_scan_p*, k_walk1<FILL1>) -- this replaces the string sets and the Aho-Corasick
+//     (k_candbits, k_scan_p*) -- this replaces the string sets and the Aho-Corasick
 //     automaton;
 //   * every genome, the first included, is then ONE pass (k_scan_filtered / k_scan_plain):
 //     window -> bin -> bitmap probe; on a hit the 64-bit canonical word is compared with the slot's
@@ -24,7 +24,7 @@
 //     reference would have read.  The probe goes through a per-k Bloom-style filter held in shared
 //     memory (192 KB per CTA) so that only ~1 in 6 windows reaches L2;
 //   * survivors are emitted in the reference's dict order by an ordered compaction over genome 1
-//     (k_walk1<EMIT_*>), filters are evaluated in fp64 with the reference's operation order, the
+//     (k_emit_mark / k_emit_write), filters are evaluated in fp64 with the reference's operation order, the
 //     per-position "first k-mer that passes" pick is an atomicMin over a direct-mapped array.
 //
 // No tensor cores: nothing here is a contraction.
@@ -84,14 +84,12 @@ struct K {  // kernel arguments (by value, __grid_constant__)
     uint32_t *sk;             // [nk][2*PW] 2 bits per bin: seen once (low half), seen again (high half)
     uint2 *br;                // [nk][PW] .x = key bitmap word, .y = exclusive popcount prefix (slot id base)
     uint32_t *filter;         // [nk][FILTER_WORDS]
-    uint32_t *passmask1;      // per genome-1 end position: bit per k = candidate window
-    uint64_t *canon1;
-    uint8_t *slotK;
+    uint32_t *emitMask;       // per genome-1 end position: bit per k = surviving key ending there
+    uint32_t *emitOff;        // exclusive popcount prefix of emitMask = record index base
     unsigned long long *rows; // [nGenomes][nslots]
     uint64_t nslots;
     uint8_t *alive;
     // output
-    uint32_t *emitCnt;        // per genome-1 end position
     pfb_record *rec;
     uint32_t *pos;            // [nGenomes][nrec] start within contig | strand << 31
     uint32_t *posContig;      // [nGenomes][nrec] contig index (only when some genome has > 1 contig)
@@ -150,6 +148,25 @@ __device__ __forceinline__ double tm_from_sums(uint32_t acc, uint64_t h, int k, 
     tm = __dsub_rn(tm, p.dmso_term);
     tm = __dadd_rn(tm, p.fterm[k * 33 + gc]);
     return tm;
+}
+
+// minTm <= Tm <= maxTm (:305-307), decided in fp32 when the fp32 value is clear of both bounds by
+// more than 0.01 degC (its error is < 1e-3) and with the exact fp64 formula otherwise, so the decision
+// is always the one the fp64 formula makes
+__device__ __forceinline__ bool tm_in_range(uint32_t acc, uint64_t h, int k, int gc, const K &p) {
+    int first = (int)((h >> (2 * k - 2)) & 3), last = (int)(h & 3);
+    int dh = (int)(acc & 0xFFFF) + (first < 2 ? -23 : -1) + (last < 2 ? -23 : -1);
+    int ds = (int)(acc >> 16) + (first < 2 ? -41 : 28) + (last < 2 ? -41 : 28);
+    float denom = -0.1f * (float)ds + (0.368f * (float)(k - 1) * (float)p.ln_salt + 1.987f * (float)p.ln_dna4);
+    float tmf = __fdividef(-100.0f * (float)dh, denom) - 273.15f - (float)p.dmso_term + (float)p.fterm[k * 33 + gc];
+    float lo = (float)p.min_tm, hi = (float)p.max_tm;
+    bool palin_possible = (k & 1) == 0;          // self-complementary oligos use other constants: exact path
+    if (!palin_possible || (rc64(h) >> (64 - 2 * k)) != h) {
+        if (tmf < lo - 0.01f || tmf > hi + 0.01f) return false;
+        if (tmf > lo + 0.01f && tmf < hi - 0.01f) return true;
+    }
+    double tm = tm_from_sums(acc, h, k, gc, p);
+    return tm >= p.min_tm && tm <= p.max_tm;
 }
 
 // nn = the 16-entry table in shared memory (bank = index: divergent lookups never conflict)
@@ -319,8 +336,7 @@ __global__ void __launch_bounds__(256) k_cand1(const __grid_constant__ K p, uint
                 int k = i + 2, ki = k - p.kmin;
                 if (ki >= 0 && ((cm >> ki) & 1u)) {
                     uint64_t h = s.hf & kmask2(k);
-                    double tm = tm_from_sums(acc, h, k, gc_count(h), p);
-                    if (!(tm >= p.min_tm && tm <= p.max_tm)) cm &= ~(1u << ki);
+                    if (!tm_in_range(acc, h, k, gc_count(h), p)) cm &= ~(1u << ki);
                 }
             }
         }
@@ -334,56 +350,6 @@ __global__ void __launch_bounds__(256) k_cand1(const __grid_constant__ K p, uint
             if ((old >> bb) & 1u) atomicOr(cell, 1u << (16 + bb));
         }
     }
-    p.passmask1[b] = cm;
-}
-
-// k_fill1 / k_emit: walk genome 1's candidate positions; FILL writes the key of every slot, EMIT
-// compacts the surviving slots in the reference's dict order (end position ascending, longest
-// first: getCandidateKmers.py:171-187 + pyahocorasick's emission order)
-enum { FILL1 = 0, EMIT_COUNT = 1, EMIT_WRITE = 2 };
-template <int MODE>
-__global__ void __launch_bounds__(256) k_walk1(const __grid_constant__ K p, uint32_t nbases) {
-    __shared__ uint32_t s_nn[16];
-    if (MODE == EMIT_WRITE) {
-        if (threadIdx.x < 16) s_nn[threadIdx.x] = c_nn[threadIdx.x];
-        __syncthreads();
-    }
-    uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= nbases) return;
-    uint32_t pm = p.passmask1[b];
-    uint32_t emitted = 0, emit_at = 0;
-    if (pm) {
-        PosState s;
-        load_pos(p, b, s);
-        if (MODE == EMIT_WRITE) emit_at = p.emitCnt[b];
-        for (int ki = p.nk - 1; ki >= 0; ki--) {
-            if (!((pm >> ki) & 1u)) continue;
-            int k = p.kmin + ki;
-            uint64_t h = s.hf & kmask2(k), r = s.hr >> (64 - 2 * k);
-            uint64_t canon = h < r ? h : r;
-            uint32_t bin = mod_p(canon, p);
-            uint2 e = probe(p, ki, bin);
-            if (!probe_hit(e, bin)) continue;     // the candidate was not alone in its bin
-            uint32_t idx = slot_of(e, bin);
-            if (MODE == FILL1) {
-                p.canon1[idx] = canon;
-                p.slotK[idx] = (uint8_t)k;
-                continue;
-            }
-            if (!p.alive[idx]) continue;
-            if (MODE == EMIT_WRITE) {
-                pfb_record rec;
-                double tm;
-                uint32_t f = filter_flags(h, k, p, s_nn, &tm);
-                if (h == r) f |= PFB_F_PALIN;
-                rec.word = h; rec.tm = tm; rec.slot = idx; rec.gc_count = (uint16_t)gc_count(h);
-                rec.k = (uint8_t)k; rec.flags = (uint8_t)f;
-                p.rec[emit_at + emitted] = rec;
-            }
-            emitted++;
-        }
-    }
-    if (MODE == EMIT_COUNT) p.emitCnt[b] = emitted;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -675,23 +641,71 @@ __device__ __forceinline__ int row_state(const K &p, uint32_t g, unsigned long l
     return 0;   // the single occupant is a different k-mer: a sketch collision with the key absent
 }
 
+// length of the k-mer a slot holds: slots are numbered per k, in bin order
+__device__ __forceinline__ int slot_ki(const uint32_t *s_base, int nk, uint32_t idx) {
+    int ki = 0;
+    while (ki + 1 < nk && s_base[ki + 1] <= idx) ki++;
+    return ki;
+}
+
 __global__ void __launch_bounds__(256) k_alive(const __grid_constant__ K p) {
+    __shared__ uint32_t s_base[32];
+    if (threadIdx.x < (unsigned)p.nk) s_base[threadIdx.x] = p.br[(size_t)threadIdx.x * p.PW].y;
+    __syncthreads();
     uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= p.nslots) return;
-    int k = p.slotK[idx];
-    // the key as it reads on genome 1's (+) strand
+    int k = p.kmin + slot_ki(s_base, p.nk, (uint32_t)idx);
     unsigned long long v0 = p.rows[idx];
     bool ok = ((v0 >> 32) & ROW_CNT_MASK) == 1;
     if (ok) {
+        // the key as it reads on genome 1's (+) strand: the single occupant of its bin there
         uint64_t key = window_at(p, 0, (uint32_t)(v0 & ROW_POS_MASK), k);
         uint64_t rc = rc64(key) >> (64 - 2 * k);
-        uint64_t canon = key < rc ? key : rc;
         bool pal = key == rc;
-        ok = canon == p.canon1[idx] && row_state(p, 0, v0, key, rc, k, pal, true) != 0 && (pal || !(v0 & ROW_JF));
+        ok = row_state(p, 0, v0, key, rc, k, pal, true) == (pal ? 2 : 1);
         for (uint32_t g = 1; g < p.nGenomes && ok; g++)
             ok = row_state(p, g, p.rows[(size_t)g * p.nslots + idx], key, rc, k, pal, false) != 0;
     }
     p.alive[idx] = ok ? 1 : 0;
+}
+
+// ordered emission in the reference's dict order (genome-1 end position ascending, longest first:
+// getCandidateKmers.py:171-187 + pyahocorasick's emission order) without walking the genome again:
+// k_emit_mark scatters one bit per surviving key to (end position, k), a popcount scan over the end
+// positions gives every key its record index, k_emit_write writes the record.
+__global__ void __launch_bounds__(256) k_emit_mark(const __grid_constant__ K p) {
+    __shared__ uint32_t s_base[32];
+    if (threadIdx.x < (unsigned)p.nk) s_base[threadIdx.x] = p.br[(size_t)threadIdx.x * p.PW].y;
+    __syncthreads();
+    uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= p.nslots || !p.alive[idx]) return;
+    int ki = slot_ki(s_base, p.nk, (uint32_t)idx);
+    uint32_t end = (uint32_t)(p.rows[idx] & ROW_POS_MASK) + (uint32_t)(p.kmin + ki) - 1u;
+    atomicOr(&p.emitMask[end], 1u << ki);
+}
+
+__global__ void __launch_bounds__(256) k_emit_write(const __grid_constant__ K p) {
+    __shared__ uint32_t s_base[32];
+    __shared__ uint32_t s_nn[16];
+    if (threadIdx.x < (unsigned)p.nk) s_base[threadIdx.x] = p.br[(size_t)threadIdx.x * p.PW].y;
+    if (threadIdx.x >= 32 && threadIdx.x < 48) s_nn[threadIdx.x - 32] = c_nn[threadIdx.x - 32];
+    __syncthreads();
+    uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= p.nslots || !p.alive[idx]) return;
+    int ki = slot_ki(s_base, p.nk, (uint32_t)idx);
+    int k = p.kmin + ki;
+    uint32_t start = (uint32_t)(p.rows[idx] & ROW_POS_MASK);
+    uint32_t end = start + (uint32_t)k - 1u;
+    uint32_t m = p.emitMask[end];
+    uint32_t r = p.emitOff[end] + __popc(ki < 31 ? (m >> (ki + 1)) : 0u);      // longer k-mers ending here come first
+    uint64_t h = window_at(p, 0, start, k);
+    pfb_record rec;
+    double tm;
+    uint32_t f = filter_flags(h, k, p, s_nn, &tm);
+    if ((rc64(h) >> (64 - 2 * k)) == h) f |= PFB_F_PALIN;
+    rec.word = h; rec.tm = tm; rec.slot = (uint32_t)idx; rec.gc_count = (uint16_t)gc_count(h);
+    rec.k = (uint8_t)k; rec.flags = (uint8_t)f;
+    p.rec[r] = rec;
 }
 
 // k_positions: (contig, leftmost start, strand) of every record in every genome
@@ -780,8 +794,8 @@ struct pfb_ctx {
     bool uploaded = false, computed = false;
     int stage_done = -1;
     // device
-    DevBuf raw, seq2, nmask, wordContig, tabs32, tabs64, sk, br, filter, fterm, scanTmp, misc, passmask1, canon1,
-        slotK, rows, alive, emitCnt, rec, pos, posContig, minRank, pick, pickOff, outRec, outPos, outContig;
+    DevBuf raw, seq2, nmask, wordContig, tabs32, tabs64, sk, br, filter, fterm, scanTmp, misc, emitMask, emitOff,
+        rows, alive, rec, pos, posContig, minRank, pick, pickOff, outRec, outPos, outContig;
     K k{};
     uint64_t nslots = 0, nrec = 0, npick = 0;
     uint64_t launches = 0;
@@ -956,8 +970,8 @@ void pfb_destroy(pfb_ctx *ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     DevBuf *all[] = {&ctx->raw, &ctx->seq2, &ctx->nmask, &ctx->wordContig, &ctx->tabs32, &ctx->tabs64, &ctx->sk, &ctx->br,
-                     &ctx->filter, &ctx->fterm, &ctx->scanTmp, &ctx->misc, &ctx->passmask1, &ctx->canon1,
-                     &ctx->slotK, &ctx->rows, &ctx->alive, &ctx->emitCnt, &ctx->rec, &ctx->pos, &ctx->posContig, &ctx->minRank, &ctx->pick,
+                     &ctx->filter, &ctx->fterm, &ctx->scanTmp, &ctx->misc, &ctx->emitMask, &ctx->emitOff,
+                     &ctx->rows, &ctx->alive, &ctx->rec, &ctx->pos, &ctx->posContig, &ctx->minRank, &ctx->pick,
                      &ctx->pickOff, &ctx->outRec, &ctx->outPos, &ctx->outContig};
     for (auto *b : all) release(*b);
     for (auto &ev : ctx->ev) if (ev) cudaEventDestroy(ev);
@@ -1068,13 +1082,13 @@ static int stage0(pfb_ctx *ctx) {
     if ((rc = ensure(ctx, ctx->filter, (size_t)nk * FILTER_BYTES)) != PFB_OK) return rc;
     if ((rc = ensure(ctx, ctx->fterm, 33 * 33 * 8)) != PFB_OK) return rc;
     if ((rc = ensure(ctx, ctx->misc, 4096)) != PFB_OK) return rc;
-    if ((rc = ensure(ctx, ctx->passmask1, (size_t)W1 * 32 * 4 + 4)) != PFB_OK) return rc;
-    if ((rc = ensure(ctx, ctx->emitCnt, (size_t)W1 * 32 * 4 + 4)) != PFB_OK) return rc;
+    if ((rc = ensure(ctx, ctx->emitMask, (size_t)W1 * 32 * 4 + 4)) != PFB_OK) return rc;
+    if ((rc = ensure(ctx, ctx->emitOff, (size_t)W1 * 32 * 4 + 4)) != PFB_OK) return rc;
     k.seq2 = (uint64_t *)ctx->seq2.p; k.nmask = (uint32_t *)ctx->nmask.p; k.wordContig = (uint32_t *)ctx->wordContig.p;
     k.sk = (uint32_t *)ctx->sk.p; k.br = (uint2 *)ctx->br.p;
     k.filter = (uint32_t *)ctx->filter.p; k.fterm = (const double *)ctx->fterm.p;
     uint32_t *misc = (uint32_t *)ctx->misc.p;   // [0] nslots, [1] nrec, [2] npick
-    k.passmask1 = (uint32_t *)ctx->passmask1.p; k.emitCnt = (uint32_t *)ctx->emitCnt.p;
+    k.emitMask = (uint32_t *)ctx->emitMask.p; k.emitOff = (uint32_t *)ctx->emitOff.p;
 
     CK(cudaEventRecord(ctx->ev[2], st));
     CK(cudaMemcpyAsync(ctx->fterm.p, fterm.data(), 33 * 33 * 8, cudaMemcpyHostToDevice, st));
@@ -1094,18 +1108,14 @@ static int stage0(pfb_ctx *ctx) {
     k.nslots = ctx->nslots;
     const size_t NS = ctx->nslots ? ctx->nslots : 1;
     const size_t nG = ctx->genomes.size();
-    if ((rc = ensure(ctx, ctx->canon1, NS * 8)) != PFB_OK) return rc;
-    if ((rc = ensure(ctx, ctx->slotK, NS)) != PFB_OK) return rc;
     if ((rc = ensure(ctx, ctx->rows, NS * nG * 8)) != PFB_OK) return rc;
     if ((rc = ensure(ctx, ctx->alive, NS)) != PFB_OK) return rc;
-    k.canon1 = (uint64_t *)ctx->canon1.p; k.slotK = (uint8_t *)ctx->slotK.p;
     k.rows = (unsigned long long *)ctx->rows.p; k.alive = (uint8_t *)ctx->alive.p;
     CK(cudaMemsetAsync(ctx->rows.p, 0, NS * nG * 8, st));
     // the filter pays off while it stays sparse: expected fill 1 - exp(-keys_per_k / FILTER_BITS)
     bool use_filter = ctx->scan_mode == 2 ||
                       (ctx->scan_mode == 0 && (double)ctx->nslots / nk < 0.35 * FILTER_BITS && W >= 4096);
     ctx->used_filter = use_filter;
-    if (W1 && ctx->nslots) { k_walk1<FILL1><<<nblk(N1, 256), 256, 0, st>>>(k, N1); ctx->launches++; }
     if (use_filter && ctx->nslots) {
         CK(cudaMemsetAsync(ctx->filter.p, 0, (size_t)nk * FILTER_BYTES, st));
         k_build_filter<<<nblk(NB, 256), 256, 0, st>>>(k); ctx->launches++;
@@ -1139,8 +1149,9 @@ static int stage1(pfb_ctx *ctx) {
     uint32_t *misc = (uint32_t *)ctx->misc.p;
     ctx->nrec = 0; ctx->npick = 0;
     if (ctx->nslots && W1) {
-        k_walk1<EMIT_COUNT><<<nblk(N1, 256), 256, 0, st>>>(k, N1); ctx->launches++;
-        if ((rc = device_exscan<false, 1>(ctx, k.emitCnt, k.emitCnt, N1, misc + 1)) != PFB_OK) return rc;
+        CK(cudaMemsetAsync(ctx->emitMask.p, 0, (size_t)N1 * 4, st));
+        k_emit_mark<<<nblk(ctx->nslots, 256), 256, 0, st>>>(k); ctx->launches++;
+        if ((rc = device_exscan<true, 1>(ctx, k.emitMask, k.emitOff, N1, misc + 1)) != PFB_OK) return rc;
         uint32_t n = 0;
         CK(cudaMemcpyAsync(&n, misc + 1, 4, cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
@@ -1162,7 +1173,7 @@ static int stage1(pfb_ctx *ctx) {
     CK(cudaMemsetAsync(ctx->pick.p, 0, NR * 4, st));
     if (ctx->nrec) {
         CK(cudaMemsetAsync(ctx->minRank.p, 0xFF, (size_t)W * 32 * 4, st));
-        k_walk1<EMIT_WRITE><<<nblk(N1, 256), 256, 0, st>>>(k, N1); ctx->launches++;
+        k_emit_write<<<nblk(ctx->nslots, 256), 256, 0, st>>>(k); ctx->launches++;
         dim3 grid(nblk(ctx->nrec, 256), (unsigned)nG);
         k_positions<<<grid, 256, 0, st>>>(k); ctx->launches++;
         k_pick<<<grid, 256, 0, st>>>(k); ctx->launches++;
