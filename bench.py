@@ -272,8 +272,11 @@ def main():
         flush.zero_()
         barrier()
         t0 = time.perf_counter()
-        eng.upload()
-        compute_once()
+        if world == 1:
+            eng.run()                 # pfb_run: H2D copies overlapped with the key-table build and the scan
+        else:
+            eng.upload()
+            compute_once()
         rec, pos = fetch_results()
         eng.sync()
         dt = time.perf_counter() - t0

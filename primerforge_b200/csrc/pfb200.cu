@@ -784,6 +784,10 @@ struct pfb_ctx {
     pfb_params prm{};
     std::string err;
     cudaStream_t stream = nullptr;
+    cudaStream_t copyStream = nullptr;          // H2D copies of pfb_run run here, overlapped with compute
+    std::vector<cudaEvent_t> evCopy;            // one per genome: its bases have arrived
+    bool pipelined = false;
+    std::vector<uint32_t> t32host;              // contig / genome tables (kept alive for the async copy)
     cudaEvent_t ev[8]{};
     std::vector<HostGenome> genomes;
     // layout (host)
@@ -957,6 +961,7 @@ int pfb_create(pfb_ctx **out, int device, const pfb_params *params) {
     ctx->prm = *params;
     cudaDeviceGetAttribute(&ctx->num_sms, cudaDevAttrMultiProcessorCount, device);
     e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->copyStream, cudaStreamNonBlocking);
     if (e == cudaSuccess)
         e = cudaFuncSetAttribute(k_scan_filtered, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SCANF_SMEM);
     if (e != cudaSuccess) { std::string m = cudaGetErrorString(e); delete ctx; return fail(nullptr, PFB_ECUDA, m); }
@@ -975,6 +980,8 @@ void pfb_destroy(pfb_ctx *ctx) {
                      &ctx->pickOff, &ctx->outRec, &ctx->outPos, &ctx->outContig};
     for (auto *b : all) release(*b);
     for (auto &ev : ctx->ev) if (ev) cudaEventDestroy(ev);
+    for (auto &ev : ctx->evCopy) if (ev) cudaEventDestroy(ev);
+    if (ctx->copyStream) { cudaStreamSynchronize(ctx->copyStream); cudaStreamDestroy(ctx->copyStream); }
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -1014,23 +1021,24 @@ int pfb_set_scan_mode(pfb_ctx *ctx, int mode) {
     return PFB_OK;
 }
 
-int pfb_upload(pfb_ctx *ctx) {
+static int upload_impl(pfb_ctx *ctx, bool async) {
     if (!ctx) return PFB_EINVAL;
     if (ctx->genomes.empty()) return fail(ctx, PFB_ESTATE, "no genome added");
     CK(cudaSetDevice(ctx->device));
     int rc = build_layout(ctx);
     if (rc != PFB_OK) return rc;
     cudaStream_t st = ctx->stream;
+    cudaStream_t cs = async ? ctx->copyStream : ctx->stream;
     if ((rc = ensure(ctx, ctx->raw, ctx->totalRaw + 64)) != PFB_OK) return rc;
-    CK(cudaEventRecord(ctx->ev[0], st));
-    for (size_t g = 0; g < ctx->genomes.size(); g++) {
-        auto &hg = ctx->genomes[g];
-        if (hg.n_bases)
-            CK(cudaMemcpyAsync((uint8_t *)ctx->raw.p + ctx->gRawStart[g], hg.bases, hg.n_bases, cudaMemcpyHostToDevice, st));
+    size_t nC = ctx->cLen.size(), nG = ctx->genomes.size();
+    while (ctx->evCopy.size() < nG) {
+        cudaEvent_t e;
+        CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        ctx->evCopy.push_back(e);
     }
     // contig / genome tables
-    size_t nC = ctx->cLen.size(), nG = ctx->genomes.size();
-    std::vector<uint32_t> t32;
+    std::vector<uint32_t> &t32 = ctx->t32host;
+    t32.clear();
     auto put32 = [&](const std::vector<uint32_t> &v) { size_t o = t32.size(); t32.insert(t32.end(), v.begin(), v.end()); return o; };
     size_t o_cws = put32(ctx->cWordStart), o_cl = put32(ctx->cLen), o_cg = put32(ctx->cGenome), o_cv = put32(ctx->cVirt);
     size_t o_gws = put32(ctx->gWordStart), o_gfc = put32(ctx->gFirstContig), o_gnc = put32(ctx->gNumContigs), o_gvl = put32(ctx->gVirtLen);
@@ -1038,8 +1046,14 @@ int pfb_upload(pfb_ctx *ctx) {
     if ((rc = ensure(ctx, ctx->tabs64, nC * 8)) != PFB_OK) return rc;
     CK(cudaMemcpyAsync(ctx->tabs32.p, t32.data(), t32.size() * 4, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(ctx->tabs64.p, ctx->cRawStart.data(), nC * 8, cudaMemcpyHostToDevice, st));
-    CK(cudaEventRecord(ctx->ev[1], st));
-    CK(cudaStreamSynchronize(st));   // t32 / host genome buffers are borrowed only until here
+    CK(cudaEventRecord(ctx->ev[0], cs));
+    for (size_t g = 0; g < nG; g++) {
+        auto &hg = ctx->genomes[g];
+        if (hg.n_bases)
+            CK(cudaMemcpyAsync((uint8_t *)ctx->raw.p + ctx->gRawStart[g], hg.bases, hg.n_bases, cudaMemcpyHostToDevice, cs));
+        if (async) CK(cudaEventRecord(ctx->evCopy[g], cs));
+    }
+    CK(cudaEventRecord(ctx->ev[1], cs));
     const uint32_t *b32 = (const uint32_t *)ctx->tabs32.p;
     K &k = ctx->k;
     k.cWordStart = b32 + o_cws; k.cLen = b32 + o_cl; k.cGenome = b32 + o_cg; k.cVirt = b32 + o_cv;
@@ -1047,12 +1061,18 @@ int pfb_upload(pfb_ctx *ctx) {
     k.cRawStart = (const uint64_t *)ctx->tabs64.p;
     k.nContigs = (uint32_t)nC; k.nGenomes = (uint32_t)nG; k.totalWords = ctx->totalWords;
     k.raw = (const uint8_t *)ctx->raw.p;
-    float ms = 0;
-    cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]);
-    ctx->tm.ms_upload = ms;
+    ctx->pipelined = async;
+    if (!async) {
+        CK(cudaStreamSynchronize(st));   // host genome buffers are borrowed only until here
+        float ms = 0;
+        cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]);
+        ctx->tm.ms_upload = ms;
+    }
     ctx->uploaded = true; ctx->computed = false; ctx->stage_done = -1;
     return PFB_OK;
 }
+
+int pfb_upload(pfb_ctx *ctx) { return upload_impl(ctx, false); }
 
 static int stage0(pfb_ctx *ctx) {
     const pfb_params &P = ctx->prm;
@@ -1094,7 +1114,14 @@ static int stage0(pfb_ctx *ctx) {
     CK(cudaMemcpyAsync(ctx->fterm.p, fterm.data(), 33 * 33 * 8, cudaMemcpyHostToDevice, st));
     CK(cudaMemsetAsync(ctx->misc.p, 0, 4096, st));
     CK(cudaMemsetAsync(ctx->sk.p, 0, (size_t)NB * 2 * 4, st));
-    if (W) { k_encode<<<nblk(W, 256), 256, 0, st>>>(k, 0, W); ctx->launches++; }
+    const size_t nG = ctx->genomes.size();
+    const bool piped = ctx->pipelined;
+    if (piped) {   // only genome 1 has to be there before the key table can be built
+        CK(cudaStreamWaitEvent(st, ctx->evCopy[0], 0));
+        if (W1) { k_encode<<<nblk(W1, 256), 256, 0, st>>>(k, 0, W1); ctx->launches++; }
+    } else if (W) {
+        k_encode<<<nblk(W, 256), 256, 0, st>>>(k, 0, W); ctx->launches++;
+    }
     CK(cudaEventRecord(ctx->ev[3], st));
     // genome 1: candidates -> key table
     const uint32_t N1 = W1 * 32u;                                           // padded end positions of genome 1
@@ -1107,7 +1134,6 @@ static int stage0(pfb_ctx *ctx) {
     ctx->nslots = ns;
     k.nslots = ctx->nslots;
     const size_t NS = ctx->nslots ? ctx->nslots : 1;
-    const size_t nG = ctx->genomes.size();
     if ((rc = ensure(ctx, ctx->rows, NS * nG * 8)) != PFB_OK) return rc;
     if ((rc = ensure(ctx, ctx->alive, NS)) != PFB_OK) return rc;
     k.rows = (unsigned long long *)ctx->rows.p; k.alive = (uint8_t *)ctx->alive.p;
@@ -1122,15 +1148,40 @@ static int stage0(pfb_ctx *ctx) {
     }
     CK(cudaEventRecord(ctx->ev[4], st));
     // every genome (the first included): one pass against the key table
-    if (W && ctx->nslots) {
-        if (use_filter) k_scan_filtered<<<ctx->num_sms, 1024, SCANF_SMEM, st>>>(k, 0, W);
-        else k_scan_plain<<<nblk(W, 256), 256, 0, st>>>(k, 0, W);
-        ctx->launches++;
-        if (ctx->cLen.size() > nG) {   // some genome has more than one contig
-            uint64_t nthr = (uint64_t)ctx->cLen.size() * nk * 2 * (2 * P.k_max - 1);
-            k_junction<<<nblk(nthr, 128), 128, 0, st>>>(k, 0, (uint32_t)ctx->cLen.size());
+    auto scan_range = [&](uint32_t wa, uint32_t wb, uint32_t ca, uint32_t cb, uint32_t n_gen) {
+        if (wb > wa) {
+            if (use_filter) k_scan_filtered<<<ctx->num_sms, 1024, SCANF_SMEM, st>>>(k, wa, wb);
+            else k_scan_plain<<<nblk(wb - wa, 256), 256, 0, st>>>(k, wa, wb);
             ctx->launches++;
         }
+        if (cb - ca > n_gen) {   // some genome of the range has more than one contig
+            uint64_t nthr = (uint64_t)(cb - ca) * nk * 2 * (2 * P.k_max - 1);
+            k_junction<<<nblk(nthr, 128), 128, 0, st>>>(k, ca, cb);
+            ctx->launches++;
+        }
+    };
+    if (W && ctx->nslots) {
+        if (!piped) {
+            scan_range(0, W, 0, (uint32_t)ctx->cLen.size(), (uint32_t)nG);
+        } else {
+            // genome 1 is resident; the others are encoded and scanned in batches of ~16 MB as their
+            // H2D copies land (the copies run on their own stream, see upload_impl)
+            scan_range(0, W1, 0, ctx->gFirstContig[0] + ctx->gNumContigs[0], 1);
+            size_t g = 1;
+            while (g < nG) {
+                size_t g2 = g;
+                uint64_t bytes = 0;
+                while (g2 < nG && (g2 == g || bytes + ctx->genomes[g2].n_bases <= (16u << 20))) bytes += ctx->genomes[g2++].n_bases;
+                CK(cudaStreamWaitEvent(st, ctx->evCopy[g2 - 1], 0));
+                uint32_t wa = ctx->gWordStart[g], wb = g2 < nG ? ctx->gWordStart[g2] : W;
+                uint32_t ca = ctx->gFirstContig[g], cb = g2 < nG ? ctx->gFirstContig[g2] : (uint32_t)ctx->cLen.size();
+                if (wb > wa) { k_encode<<<nblk(wb - wa, 256), 256, 0, st>>>(k, wa, wb); ctx->launches++; }
+                scan_range(wa, wb, ca, cb, (uint32_t)(g2 - g));
+                g = g2;
+            }
+        }
+    } else if (piped) {
+        CK(cudaStreamWaitEvent(st, ctx->evCopy[nG - 1], 0));
     }
     CK(cudaEventRecord(ctx->ev[5], st));
     if (ctx->nslots) { k_alive<<<nblk(ctx->nslots, 256), 256, 0, st>>>(k); ctx->launches++; }
@@ -1246,9 +1297,18 @@ int pfb_compute(pfb_ctx *ctx) {
 }
 
 int pfb_run(pfb_ctx *ctx) {
-    int rc = pfb_upload(ctx);
+    // H2D of genome i+1.. overlaps the key-table build and the scan of the genomes already resident
+    int rc = upload_impl(ctx, true);
     if (rc != PFB_OK) return rc;
-    return pfb_compute(ctx);
+    rc = pfb_compute(ctx);
+    cudaStreamSynchronize(ctx->copyStream);     // the host buffers are borrowed until here, success or not
+    if (rc == PFB_OK) {
+        float ms = 0;
+        cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]);
+        ctx->tm.ms_upload = ms;
+    }
+    ctx->pipelined = false;
+    return rc;
 }
 
 int pfb_device_buffer(pfb_ctx *ctx, int which, void **dev_ptr, uint64_t *n_bytes) {

@@ -283,3 +283,20 @@ def test_full_size_properties():
             assert val == int(w)
         # a position holds at most one picked k-mer per k
         assert np.unique((ss[gi].astype(np.int64) << 6) | k).size == rec.size
+
+
+def test_pipelined_run_equals_upload_then_compute():
+    from primerforge_b200 import synth
+    from primerforge_b200.engine import Engine
+    gens = synth.make_genomes(9, 700_000, seed=402, snp_rate=0.003, n_inversions=2, n_contigs=2)   # several 16 MB batches
+    with Engine(device=0) as eng:
+        for g in gens:
+            eng.add_genome(g.contigs)
+        eng.run()
+        a = eng.result()
+        eng.upload()
+        eng.compute()
+        b = eng.result()
+    assert a.records.size > 0 and np.array_equal(a.records, b.records)
+    for pa, pb in zip(a.positions, b.positions):
+        assert np.array_equal(pa, pb)
