@@ -397,20 +397,111 @@ __global__ void __launch_bounds__(256) k_scan_plain(const __grid_constant__ K p,
 // in place: they are appended to a per-warp queue in shared memory, and whenever 32 are waiting the
 // whole warp drains them together: the L2 probe (bitmap + rank word) is paid once per 32 windows with
 // every lane busy, and a hit ends in one fire-and-forget RED on the genome's row.
-__device__ __forceinline__ void drain_queue(const K &p, int ki, const uint4 *q, uint32_t head, uint32_t n, uint32_t lane) {
+// shared-memory accesses of the hot loop through 32-bit shared-window addresses (no generic-address
+// conversion per access)
+__device__ __forceinline__ uint32_t lds32(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
+    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
+}
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+    return v;
+}
+
+__device__ __forceinline__ void drain_queue(const K &p, int ki, uint32_t q_addr, uint32_t head, uint32_t n, uint32_t lane) {
     if (lane < n) {
-        uint4 it = q[(head + lane) & (QCAP - 1)];   // x = bin, y = start, z = genome
+        uint4 it = lds128(q_addr + (((head + lane) & (QCAP - 1)) << 4));   // x = bin, y = start, z = genome
         uint2 e = probe(p, ki, it.x);
         if (probe_hit(e, it.x)) on_hit(p, it.z, e, it.x, it.y);
+    }
+}
+
+// 32-bit-word arithmetic of the hot loop.  For the word (prev : cur) = 64 bases, the window of k bases
+// ending at base j of cur is a funnel shift of the stream by 2 * (31 - j) bits, and its reverse
+// complement is the same funnel shift, to the left, of the stream rc(cur) : rc(prev) -- so neither
+// word has to be rolled base by base and every window of a thread is independent of the others.
+template <bool FASTMOD>
+__device__ __forceinline__ uint32_t window_bin(const K &p, uint32_t h_lo, uint32_t h_hi, uint32_t t_lo, uint32_t t_hi,
+                                               uint32_t mlo, uint32_t mhi, int rsh, uint32_t m32, uint32_t a32) {
+    h_lo &= mlo; h_hi &= mhi;
+    uint64_t r = (((uint64_t)t_hi << 32) | t_lo) >> rsh;
+    uint32_t r_lo = (uint32_t)r, r_hi = (uint32_t)(r >> 32);
+    bool lt = h_hi < r_hi || (h_hi == r_hi && h_lo < r_lo);            // uniqify_rc: min(h, r)
+    uint32_t c_lo = lt ? h_lo : r_lo, c_hi = lt ? h_hi : r_hi;
+    if (FASTMOD) {
+        // canon < 2^40 and P < 2^24: (c_hi * (2^32 mod P) + c_lo mod P) mod P in 32-bit multiply-adds
+        const uint32_t neg_p = 0u - p.P;
+        uint32_t r1 = __umulhi(c_lo, m32) * neg_p + c_lo;                // c_lo - q P < 2P
+        uint32_t s1 = c_hi * a32 + r1;                                   // < 257 P < 2^32
+        uint32_t r2 = __umulhi(s1, m32) * neg_p + s1;                    // < 2P
+        return min(r2, r2 + neg_p);                                      // unsigned: picks the reduced one
+    }
+    return mod_p(((uint64_t)c_hi << 32) | c_lo, p);
+}
+
+template <bool FASTMOD, bool HASN>
+__device__ __forceinline__ void scan_word(const K &p, int ki, int k, uint32_t f_addr, uint32_t q_addr,
+                                          uint32_t &qhead, uint32_t &qn, uint32_t lane, uint32_t lt_mask,
+                                          uint64_t prev, uint64_t cur, uint64_t nm, uint32_t vmask, uint32_t g, uint32_t gpos0,
+                                          uint32_t mlo, uint32_t mhi, int rsh, uint32_t m32, uint32_t a32, uint64_t km1) {
+    const uint32_t c_lo = (uint32_t)cur, c_hi = (uint32_t)(cur >> 32), p_lo = (uint32_t)prev, p_hi = (uint32_t)(prev >> 32);
+    const uint64_t rcc = rc64(cur), rcp = rc64(prev);
+    const uint32_t rc_lo = (uint32_t)rcc, rc_hi = (uint32_t)(rcc >> 32), rp_lo = (uint32_t)rcp, rp_hi = (uint32_t)(rcp >> 32);
+#pragma unroll 1
+    for (int half = 0; half < 2; half++) {
+        // half 0: j = 31..16 (stream shift 0..30 bits), half 1: j = 15..0 (shift 32..62 bits)
+        const uint32_t a0 = half ? c_hi : c_lo, a1 = half ? p_lo : c_hi, a2 = half ? p_hi : p_lo;      // forward stream words
+        const uint32_t b2 = half ? rc_lo : rc_hi, b1 = half ? rp_hi : rc_lo, b0 = half ? rp_lo : rp_hi; // rc stream words
+#pragma unroll 4
+        for (int o = 0; o < 16; o++) {
+            const int j = 31 - 16 * half - o;
+            const uint32_t sh = 2 * o;
+            uint32_t h_lo = __funnelshift_r(a0, a1, sh), h_hi = __funnelshift_r(a1, a2, sh);
+            uint32_t t_hi = __funnelshift_l(b1, b2, sh), t_lo = __funnelshift_l(b0, b1, sh);
+            uint32_t valid = (vmask >> j) & 1u;
+            if (HASN) {
+                uint32_t wn = (uint32_t)((nm >> (31 - j)) & km1);
+                if (valid && wn) {
+                    uint64_t h = (((uint64_t)(h_hi & mhi)) << 32) | (h_lo & mlo);
+                    uint64_t r = (((uint64_t)t_hi << 32) | t_lo) >> rsh;
+                    pollute_invalid_window(p, ki, k, g, h, r, wn);
+                    valid = 0;
+                }
+            }
+            uint32_t bin = window_bin<FASTMOD>(p, h_lo, h_hi, t_lo, t_hi, mlo, mhi, rsh, m32, a32);
+            uint32_t fb = __umulhi(bin, p.fscale);
+            // the filter word is read unconditionally (bin < P always): no branch in front of the LDS
+            bool pred = ((lds32(f_addr + ((fb >> 5) << 2)) >> (fb & 31)) & valid) != 0;
+            uint32_t m = __ballot_sync(0xFFFFFFFFu, pred);
+            if (m) {
+                if (pred) sts128(q_addr + (((qhead + qn + __popc(m & lt_mask)) & (QCAP - 1)) << 4), bin, gpos0 + j - k + 1, g, 0u);
+                qn += __popc(m);
+                __syncwarp();
+                if (qn >= 32) {
+                    drain_queue(p, ki, q_addr, qhead, 32, lane);
+                    qhead = (qhead + 32) & (QCAP - 1);
+                    qn -= 32;
+                    __syncwarp();
+                }
+            }
+        }
     }
 }
 
 __global__ void __launch_bounds__(1024, 1) k_scan_filtered(const __grid_constant__ K p, uint32_t w0, uint32_t w1) {
     extern __shared__ uint32_t s_filter[];
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    uint4 *queue = (uint4 *)(s_filter + FILTER_WORDS) + warp * QCAP;
+    const uint32_t f_addr = (uint32_t)__cvta_generic_to_shared(s_filter);
+    const uint32_t q_addr = f_addr + FILTER_BYTES + warp * QCAP * 16u;
     const uint32_t stride = gridDim.x * blockDim.x;
     const uint32_t lt_mask = (1u << lane) - 1u;
+    const uint32_t m32 = (uint32_t)(0x100000000ull / p.P);            // floor(2^32 / P)
+    const uint32_t a32 = (uint32_t)(0x100000000ull % p.P);            // 2^32 mod P
     for (int ki = 0; ki < p.nk; ki++) {
         const int k = p.kmin + ki;
         __syncthreads();
@@ -422,60 +513,37 @@ __global__ void __launch_bounds__(1024, 1) k_scan_filtered(const __grid_constant
         __syncthreads();
         const uint64_t km2 = kmask2(k);
         const uint64_t km1 = kmask1(k);
+        const uint32_t mlo = (uint32_t)km2, mhi = (uint32_t)(km2 >> 32);
         const int rsh = 64 - 2 * k;
+        const bool fastmod = k <= 20 && p.P < (1u << 24);
         uint32_t qhead = 0, qn = 0;   // warp-uniform
         for (uint32_t wb = w0 + blockIdx.x * blockDim.x + warp * 32; wb < w1; wb += stride) {
             const uint32_t w = wb + lane;
-            int jlo = 32, nj = 0;
-            uint32_t g = 0, gpos0 = 0;
-            uint64_t cur = 0, nm = 0, hf = 0;
+            uint32_t vmask = 0, g = 0, gpos0 = 0;
+            uint64_t cur = 0, prev = 0, nm = 0;
             if (w < w1) {
                 uint32_t c = p.wordContig[w];
                 uint32_t i = w - p.cWordStart[c];
                 uint32_t qbase = 32u * i;
-                nj = (int)min(32u, p.cLen[c] - qbase);
-                jlo = (int)qbase + 1 >= k ? 0 : k - 1 - (int)qbase;     // first end position with a full window
+                uint32_t nj = min(32u, p.cLen[c] - qbase);
+                uint32_t jlo = qbase + 1 >= (uint32_t)k ? 0u : (uint32_t)k - 1 - qbase;   // first end position with a full window
+                if (jlo < nj) vmask = (nj == 32 ? 0xFFFFFFFFu : ((1u << nj) - 1u)) & ~((1u << jlo) - 1u);
                 g = p.cGenome[c];
                 cur = p.seq2[w];
-                hf = i ? p.seq2[w - 1] : 0ull;
+                prev = i ? p.seq2[w - 1] : 0ull;
                 nm = ((uint64_t)(i ? p.nmask[w - 1] : 0u) << 32) | p.nmask[w];
                 gpos0 = 32u * (w - p.gWordStart[g]);
             }
-            uint64_t hr = rc64(hf);
             const bool any_n = __any_sync(0xFFFFFFFFu, nm != 0);
-#pragma unroll 2
-            for (int j = 0; j < 32; j++) {
-                uint32_t code = (uint32_t)(cur >> (62 - 2 * j)) & 3u;
-                hf = (hf << 2) | code;
-                hr = (hr >> 2) | ((uint64_t)(code ^ 1u) << 62);
-                uint64_t h = hf & km2, r = hr >> rsh;
-                bool valid = j >= jlo && j < nj;
-                if (any_n && valid) {
-                    uint32_t wn = (uint32_t)((nm >> (31 - j)) & km1);
-                    if (wn) { pollute_invalid_window(p, ki, k, g, h, r, wn); valid = false; }
-                }
-                uint64_t canon = h < r ? h : r;
-                uint32_t bin = mod_p(canon, p);
-                uint32_t fb = __umulhi(bin, p.fscale);
-                bool pred = valid && ((s_filter[fb >> 5] >> (fb & 31)) & 1u);
-                uint32_t m = __ballot_sync(0xFFFFFFFFu, pred);
-                if (m) {
-                    if (pred) {
-                        uint32_t at = (qhead + qn + __popc(m & lt_mask)) & (QCAP - 1);
-                        queue[at] = make_uint4(bin, gpos0 + j - k + 1, g, 0u);
-                    }
-                    qn += __popc(m);
-                    __syncwarp();
-                    if (qn >= 32) {
-                        drain_queue(p, ki, queue, qhead, 32, lane);
-                        qhead = (qhead + 32) & (QCAP - 1);
-                        qn -= 32;
-                        __syncwarp();
-                    }
-                }
+            if (any_n) {
+                if (fastmod) scan_word<true, true>(p, ki, k, f_addr, q_addr, qhead, qn, lane, lt_mask, prev, cur, nm, vmask, g, gpos0, mlo, mhi, rsh, m32, a32, km1);
+                else scan_word<false, true>(p, ki, k, f_addr, q_addr, qhead, qn, lane, lt_mask, prev, cur, nm, vmask, g, gpos0, mlo, mhi, rsh, m32, a32, km1);
+            } else {
+                if (fastmod) scan_word<true, false>(p, ki, k, f_addr, q_addr, qhead, qn, lane, lt_mask, prev, cur, nm, vmask, g, gpos0, mlo, mhi, rsh, m32, a32, km1);
+                else scan_word<false, false>(p, ki, k, f_addr, q_addr, qhead, qn, lane, lt_mask, prev, cur, nm, vmask, g, gpos0, mlo, mhi, rsh, m32, a32, km1);
             }
         }
-        drain_queue(p, ki, queue, qhead, qn, lane);
+        drain_queue(p, ki, q_addr, qhead, qn, lane);
         __syncwarp();
     }
 }
