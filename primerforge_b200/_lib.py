@@ -13,7 +13,7 @@ import subprocess
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libpfb200.so")
+LIB_PATH = os.environ.get("PFB200_LIB") or os.path.join(_HERE, "libpfb200.so")   # PFB200_LIB: A/B builds
 SRC_PATH = os.path.join(_HERE, "csrc", "pfb200.cu")
 INCLUDE_DIR = os.path.join(os.path.dirname(_HERE), "include")
 

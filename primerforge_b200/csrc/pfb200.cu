@@ -36,6 +36,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -401,11 +402,13 @@ __global__ void __launch_bounds__(256) k_scan_plain(const __grid_constant__ K p,
 // conversion per access)
 __device__ __forceinline__ uint32_t lds32(uint32_t addr) {
     uint32_t v;
-    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+    asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));   // the filter is read-only during a k pass
     return v;
 }
-__device__ __forceinline__ void sts128(uint32_t addr, uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
-    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
+// predicated store: no divergent branch (and so no convergence barrier) around the queue append
+__device__ __forceinline__ void sts128_if(uint32_t pred, uint32_t addr, uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
+    asm volatile("{ .reg .pred q; setp.ne.u32 q, %0, 0; @q st.shared.v4.u32 [%1], {%2, %3, %4, %5}; }"
+                 ::"r"(pred), "r"(addr), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
 }
 __device__ __forceinline__ uint4 lds128(uint32_t addr) {
     uint4 v;
@@ -413,12 +416,26 @@ __device__ __forceinline__ uint4 lds128(uint32_t addr) {
     return v;
 }
 
-__device__ __forceinline__ void drain_queue(const K &p, int ki, uint32_t q_addr, uint32_t head, uint32_t n, uint32_t lane) {
-    if (lane < n) {
-        uint4 it = lds128(q_addr + (((head + lane) & (QCAP - 1)) << 4));   // x = bin, y = start, z = genome
-        uint2 e = probe(p, ki, it.x);
-        if (probe_hit(e, it.x)) on_hit(p, it.z, e, it.x, it.y);
-    }
+// Drain = probe of 32 queued windows, software-pipelined: the probe loads of one batch are ISSUED when
+// the batch fills up and CONSUMED when the next batch fills up (or at the end of the k pass), so their L2
+// latency overlaps ~4 loop iterations of hashing instead of stalling the warp.
+struct Pending {
+    uint2 e;          // the probe word in flight: (bitmap word, rank)
+    uint32_t meta;    // start | (bin & 31) << 26
+    uint32_t g;
+};
+
+__device__ __forceinline__ void drain_issue(const K &p, int ki, uint32_t q_addr, uint32_t head, uint32_t lane, Pending &pd) {
+    uint4 it = lds128(q_addr + (((head + lane) & (QCAP - 1)) << 4));   // x = bin, y = start, z = genome
+    pd.e = probe(p, ki, it.x);
+    pd.meta = it.y | ((it.x & 31u) << 26);
+    pd.g = it.z;
+}
+
+__device__ __forceinline__ void drain_consume(const K &p, const Pending &pd) {
+    uint32_t b = pd.meta >> 26;
+    if ((pd.e.x >> b) & 1u)
+        atomicAdd(&p.rows[(size_t)pd.g * p.nslots + pd.e.y + __popc(pd.e.x & ((1u << b) - 1u))], ROW_ONE | (pd.meta & (uint32_t)ROW_POS_MASK));
 }
 
 // 32-bit-word arithmetic of the hot loop.  For the word (prev : cur) = 64 bases, the window of k bases
@@ -444,9 +461,13 @@ __device__ __forceinline__ uint32_t window_bin(const K &p, uint32_t h_lo, uint32
     return mod_p(((uint64_t)c_hi << 32) | c_lo, p);
 }
 
+#ifndef PFB_GROUP
+#define PFB_GROUP 2
+#endif
+constexpr int GROUP = PFB_GROUP;
 template <bool FASTMOD, bool HASN>
 __device__ __forceinline__ void scan_word(const K &p, int ki, int k, uint32_t f_addr, uint32_t q_addr,
-                                          uint32_t &qhead, uint32_t &qn, uint32_t lane, uint32_t lt_mask,
+                                          uint32_t &qhead, uint32_t &qn, bool &pend, Pending &pd, uint32_t lane, uint32_t lt_mask,
                                           uint64_t prev, uint64_t cur, uint64_t nm, uint32_t vmask, uint32_t g, uint32_t gpos0,
                                           uint32_t mlo, uint32_t mhi, int rsh, uint32_t m32, uint32_t a32, uint64_t km1) {
     const uint32_t c_lo = (uint32_t)cur, c_hi = (uint32_t)(cur >> 32), p_lo = (uint32_t)prev, p_hi = (uint32_t)(prev >> 32);
@@ -457,33 +478,45 @@ __device__ __forceinline__ void scan_word(const K &p, int ki, int k, uint32_t f_
         // half 0: j = 31..16 (stream shift 0..30 bits), half 1: j = 15..0 (shift 32..62 bits)
         const uint32_t a0 = half ? c_hi : c_lo, a1 = half ? p_lo : c_hi, a2 = half ? p_hi : p_lo;      // forward stream words
         const uint32_t b2 = half ? rc_lo : rc_hi, b1 = half ? rp_hi : rc_lo, b0 = half ? rp_lo : rp_hi; // rc stream words
-#pragma unroll 4
-        for (int o = 0; o < 16; o++) {
-            const int j = 31 - 16 * half - o;
-            const uint32_t sh = 2 * o;
-            uint32_t h_lo = __funnelshift_r(a0, a1, sh), h_hi = __funnelshift_r(a1, a2, sh);
-            uint32_t t_hi = __funnelshift_l(b1, b2, sh), t_lo = __funnelshift_l(b0, b1, sh);
-            uint32_t valid = (vmask >> j) & 1u;
-            if (HASN) {
-                uint32_t wn = (uint32_t)((nm >> (31 - j)) & km1);
-                if (valid && wn) {
-                    uint64_t h = (((uint64_t)(h_hi & mhi)) << 32) | (h_lo & mlo);
-                    uint64_t r = (((uint64_t)t_hi << 32) | t_lo) >> rsh;
-                    pollute_invalid_window(p, ki, k, g, h, r, wn);
-                    valid = 0;
+#pragma unroll 1
+        for (int o4 = 0; o4 < 16; o4 += GROUP) {
+            // GROUP independent windows: their hash chains and filter loads overlap (ILP), then the
+            // warp-wide bookkeeping runs once per window
+            uint32_t bin[GROUP], hit[GROUP];
+#pragma unroll
+            for (int u = 0; u < GROUP; u++) {
+                const int o = o4 + u, j = 31 - 16 * half - o;
+                const uint32_t sh = 2 * o;
+                uint32_t h_lo = __funnelshift_r(a0, a1, sh), h_hi = __funnelshift_r(a1, a2, sh);
+                uint32_t t_hi = __funnelshift_l(b1, b2, sh), t_lo = __funnelshift_l(b0, b1, sh);
+                uint32_t valid = (vmask >> j) & 1u;
+                if (HASN) {
+                    uint32_t wn = (uint32_t)((nm >> (31 - j)) & km1);
+                    if (valid && wn) {
+                        uint64_t h = (((uint64_t)(h_hi & mhi)) << 32) | (h_lo & mlo);
+                        uint64_t r = (((uint64_t)t_hi << 32) | t_lo) >> rsh;
+                        pollute_invalid_window(p, ki, k, g, h, r, wn);
+                        valid = 0;
+                    }
                 }
+                bin[u] = window_bin<FASTMOD>(p, h_lo, h_hi, t_lo, t_hi, mlo, mhi, rsh, m32, a32);
+                uint32_t fb = __umulhi(bin[u], p.fscale);
+                // the filter word is read unconditionally (bin < P always): no branch in front of the LDS
+                hit[u] = (lds32(f_addr + ((fb >> 5) << 2)) >> (fb & 31)) & valid;
             }
-            uint32_t bin = window_bin<FASTMOD>(p, h_lo, h_hi, t_lo, t_hi, mlo, mhi, rsh, m32, a32);
-            uint32_t fb = __umulhi(bin, p.fscale);
-            // the filter word is read unconditionally (bin < P always): no branch in front of the LDS
-            bool pred = ((lds32(f_addr + ((fb >> 5) << 2)) >> (fb & 31)) & valid) != 0;
-            uint32_t m = __ballot_sync(0xFFFFFFFFu, pred);
-            if (m) {
-                if (pred) sts128(q_addr + (((qhead + qn + __popc(m & lt_mask)) & (QCAP - 1)) << 4), bin, gpos0 + j - k + 1, g, 0u);
+#pragma unroll
+            for (int u = 0; u < GROUP; u++) {
+                const int j = 31 - 16 * half - (o4 + u);
+                // straight-line append: ballot, predicated store, uniform counters; the only branch is the
+                // (warp-uniform, rarely taken) drain
+                uint32_t m = __ballot_sync(0xFFFFFFFFu, hit[u] != 0);
+                sts128_if(hit[u], q_addr + (((qhead + qn + __popc(m & lt_mask)) & (QCAP - 1)) << 4), bin[u], gpos0 + j - k + 1, g, 0u);
                 qn += __popc(m);
-                __syncwarp();
                 if (qn >= 32) {
-                    drain_queue(p, ki, q_addr, qhead, 32, lane);
+                    __syncwarp();
+                    if (pend) drain_consume(p, pd);
+                    drain_issue(p, ki, q_addr, qhead, lane, pd);
+                    pend = true;
                     qhead = (qhead + 32) & (QCAP - 1);
                     qn -= 32;
                     __syncwarp();
@@ -505,10 +538,12 @@ __global__ void __launch_bounds__(1024, 1) k_scan_filtered(const __grid_constant
     for (int ki = 0; ki < p.nk; ki++) {
         const int k = p.kmin + ki;
         __syncthreads();
-        {
-            const uint4 *src = (const uint4 *)(p.filter + (size_t)ki * FILTER_WORDS);
-            uint4 *dst = (uint4 *)s_filter;
-            for (uint32_t t = threadIdx.x; t < FILTER_WORDS / 4; t += blockDim.x) dst[t] = __ldg(src + t);
+        {   // LDGSTS: every thread has all its 16 B pieces in flight at once, nothing goes through registers
+            const uint8_t *src = (const uint8_t *)(p.filter + (size_t)ki * FILTER_WORDS);
+            for (uint32_t t = threadIdx.x; t < FILTER_WORDS / 4; t += blockDim.x)
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(f_addr + t * 16u), "l"(src + (size_t)t * 16u) : "memory");
+            asm volatile("cp.async.commit_group;" ::: "memory");
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
         }
         __syncthreads();
         const uint64_t km2 = kmask2(k);
@@ -517,6 +552,9 @@ __global__ void __launch_bounds__(1024, 1) k_scan_filtered(const __grid_constant
         const int rsh = 64 - 2 * k;
         const bool fastmod = k <= 20 && p.P < (1u << 24);
         uint32_t qhead = 0, qn = 0;   // warp-uniform
+        bool pend = false;
+        Pending pd;
+        pd.e = make_uint2(0u, 0u); pd.meta = 0; pd.g = 0;
         for (uint32_t wb = w0 + blockIdx.x * blockDim.x + warp * 32; wb < w1; wb += stride) {
             const uint32_t w = wb + lane;
             uint32_t vmask = 0, g = 0, gpos0 = 0;
@@ -536,24 +574,38 @@ __global__ void __launch_bounds__(1024, 1) k_scan_filtered(const __grid_constant
             }
             const bool any_n = __any_sync(0xFFFFFFFFu, nm != 0);
             if (any_n) {
-                if (fastmod) scan_word<true, true>(p, ki, k, f_addr, q_addr, qhead, qn, lane, lt_mask, prev, cur, nm, vmask, g, gpos0, mlo, mhi, rsh, m32, a32, km1);
-                else scan_word<false, true>(p, ki, k, f_addr, q_addr, qhead, qn, lane, lt_mask, prev, cur, nm, vmask, g, gpos0, mlo, mhi, rsh, m32, a32, km1);
+                if (fastmod) scan_word<true, true>(p, ki, k, f_addr, q_addr, qhead, qn, pend, pd, lane, lt_mask, prev, cur, nm, vmask, g, gpos0, mlo, mhi, rsh, m32, a32, km1);
+                else scan_word<false, true>(p, ki, k, f_addr, q_addr, qhead, qn, pend, pd, lane, lt_mask, prev, cur, nm, vmask, g, gpos0, mlo, mhi, rsh, m32, a32, km1);
             } else {
-                if (fastmod) scan_word<true, false>(p, ki, k, f_addr, q_addr, qhead, qn, lane, lt_mask, prev, cur, nm, vmask, g, gpos0, mlo, mhi, rsh, m32, a32, km1);
-                else scan_word<false, false>(p, ki, k, f_addr, q_addr, qhead, qn, lane, lt_mask, prev, cur, nm, vmask, g, gpos0, mlo, mhi, rsh, m32, a32, km1);
+                if (fastmod) scan_word<true, false>(p, ki, k, f_addr, q_addr, qhead, qn, pend, pd, lane, lt_mask, prev, cur, nm, vmask, g, gpos0, mlo, mhi, rsh, m32, a32, km1);
+                else scan_word<false, false>(p, ki, k, f_addr, q_addr, qhead, qn, pend, pd, lane, lt_mask, prev, cur, nm, vmask, g, gpos0, mlo, mhi, rsh, m32, a32, km1);
             }
         }
-        drain_queue(p, ki, q_addr, qhead, qn, lane);
+        __syncwarp();
+        if (pend) drain_consume(p, pd);
+        if (lane < qn) {   // the remainder of the k pass
+            drain_issue(p, ki, q_addr, qhead, lane, pd);
+            drain_consume(p, pd);
+        }
         __syncwarp();
     }
 }
 
 // filter bit of every key bin
-__global__ void __launch_bounds__(256) k_build_filter(const __grid_constant__ K p) {
+__global__ void __launch_bounds__(256) k_build_filter(const __grid_constant__ K p, int only_alive) {
     uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= (uint32_t)p.nk * p.PW) return;
-    uint32_t word = p.br[t].x;
+    uint2 e = p.br[t];
+    uint32_t word = e.x;
     if (!word) return;
+    if (only_alive) {   // keys already dead (collisions inside genome 1) need no filter bit: fewer false drains
+        uint32_t keep = 0;
+        for (uint32_t m = word; m; m &= m - 1) {
+            int b = __ffs(m) - 1;
+            if (p.alive[e.y + __popc(word & ((1u << b) - 1u))]) keep |= 1u << b;
+        }
+        word = keep;
+    }
     uint32_t ki = t / p.PW, wi = t - ki * p.PW;
     uint32_t *f = p.filter + (size_t)ki * FILTER_WORDS;
     while (word) {
@@ -716,7 +768,7 @@ __device__ __forceinline__ int slot_ki(const uint32_t *s_base, int nk, uint32_t 
     return ki;
 }
 
-__global__ void __launch_bounds__(256) k_alive(const __grid_constant__ K p) {
+__global__ void __launch_bounds__(256) k_alive(const __grid_constant__ K p, uint32_t n_check) {
     __shared__ uint32_t s_base[32];
     if (threadIdx.x < (unsigned)p.nk) s_base[threadIdx.x] = p.br[(size_t)threadIdx.x * p.PW].y;
     __syncthreads();
@@ -731,7 +783,7 @@ __global__ void __launch_bounds__(256) k_alive(const __grid_constant__ K p) {
         uint64_t rc = rc64(key) >> (64 - 2 * k);
         bool pal = key == rc;
         ok = row_state(p, 0, v0, key, rc, k, pal, true) == (pal ? 2 : 1);
-        for (uint32_t g = 1; g < p.nGenomes && ok; g++)
+        for (uint32_t g = 1; g < n_check && ok; g++)
             ok = row_state(p, g, p.rows[(size_t)g * p.nslots + idx], key, rc, k, pal, false) != 0;
     }
     p.alive[idx] = ok ? 1 : 0;
@@ -1212,7 +1264,7 @@ static int stage0(pfb_ctx *ctx) {
     ctx->used_filter = use_filter;
     if (use_filter && ctx->nslots) {
         CK(cudaMemsetAsync(ctx->filter.p, 0, (size_t)nk * FILTER_BYTES, st));
-        k_build_filter<<<nblk(NB, 256), 256, 0, st>>>(k); ctx->launches++;
+        k_build_filter<<<nblk(NB, 256), 256, 0, st>>>(k, 0); ctx->launches++;
     }
     CK(cudaEventRecord(ctx->ev[4], st));
     // every genome (the first included): one pass against the key table
@@ -1229,12 +1281,20 @@ static int stage0(pfb_ctx *ctx) {
         }
     };
     if (W && ctx->nslots) {
+        // genome 1 first: the keys that collide inside genome 1 itself (~1 - exp(-L / P) of them) are dead
+        // already, and a filter rebuilt without them sends fewer windows of the other genomes to L2
+        const uint32_t C1 = ctx->gFirstContig[0] + ctx->gNumContigs[0];
+        scan_range(0, W1, 0, C1, 1);
+        if (use_filter && nG > 1) {
+            k_alive<<<nblk(ctx->nslots, 256), 256, 0, st>>>(k, 1u); ctx->launches++;
+            CK(cudaMemsetAsync(ctx->filter.p, 0, (size_t)nk * FILTER_BYTES, st));
+            k_build_filter<<<nblk(NB, 256), 256, 0, st>>>(k, 1); ctx->launches++;
+        }
         if (!piped) {
-            scan_range(0, W, 0, (uint32_t)ctx->cLen.size(), (uint32_t)nG);
+            if (nG > 1) scan_range(W1, W, C1, (uint32_t)ctx->cLen.size(), (uint32_t)nG - 1);
         } else {
-            // genome 1 is resident; the others are encoded and scanned in batches of ~16 MB as their
-            // H2D copies land (the copies run on their own stream, see upload_impl)
-            scan_range(0, W1, 0, ctx->gFirstContig[0] + ctx->gNumContigs[0], 1);
+            // the other genomes are encoded and scanned in batches of ~16 MB as their H2D copies land
+            // (the copies run on their own stream, see upload_impl)
             size_t g = 1;
             while (g < nG) {
                 size_t g2 = g;
@@ -1252,7 +1312,7 @@ static int stage0(pfb_ctx *ctx) {
         CK(cudaStreamWaitEvent(st, ctx->evCopy[nG - 1], 0));
     }
     CK(cudaEventRecord(ctx->ev[5], st));
-    if (ctx->nslots) { k_alive<<<nblk(ctx->nslots, 256), 256, 0, st>>>(k); ctx->launches++; }
+    if (ctx->nslots) { k_alive<<<nblk(ctx->nslots, 256), 256, 0, st>>>(k, (uint32_t)nG); ctx->launches++; }
     CK(cudaGetLastError());
     return PFB_OK;
 }
