@@ -66,7 +66,7 @@ struct K {  // kernel arguments (by value, __grid_constant__)
     int kmin, kmax, nk;
     uint32_t P, PW;           // table prime, words per 1-bit bitmap (the 2-bit table has 2 * PW words)
     uint64_t barrett;         // floor(2^64 / P)
-    uint32_t fscale;          // floor(FILTER_BITS * 2^32 / P): bin -> filter bit
+    uint32_t fscale;          // floor(FILTER_WORDS * 2^32 / P): bin -> filter word (the bit is bin & 31)
     int max_repeat, prefilter;
     double min_tm, max_tm;
     double ln_salt, ln_dna4, ln_dna1, dmso_term;
@@ -154,7 +154,7 @@ __device__ __forceinline__ double tm_from_sums(uint32_t acc, uint64_t h, int k, 
 // minTm <= Tm <= maxTm (:305-307), decided in fp32 when the fp32 value is clear of both bounds by
 // more than 0.01 degC (its error is < 1e-3) and with the exact fp64 formula otherwise, so the decision
 // is always the one the fp64 formula makes
-__device__ __forceinline__ bool tm_in_range(uint32_t acc, uint64_t h, int k, int gc, const K &p) {
+__device__ __noinline__ bool tm_in_range(uint32_t acc, uint64_t h, int k, int gc, const K &p) {
     int first = (int)((h >> (2 * k - 2)) & 3), last = (int)(h & 3);
     int dh = (int)(acc & 0xFFFF) + (first < 2 ? -23 : -1) + (last < 2 ? -23 : -1);
     int ds = (int)(acc >> 16) + (first < 2 ? -41 : 28) + (last < 2 ? -41 : 28);
@@ -316,40 +316,56 @@ __global__ void __launch_bounds__(256) k_cand1(const __grid_constant__ K p, uint
     uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= nbases) return;
     PosState s;
+    if (!load_pos(p, b, s)) return;
+    const int khi = min(p.kmax, s.n);
+    const uint64_t hf = s.hf;
+    // everything that does not depend on k is computed once: G/C bits, invalid bits, and "a homopolymer
+    // run of max_repeat starts at age i" bits (pair-equality bits AND-ed max_repeat - 1 times)
+    const uint64_t gcbits = hf & 0xAAAAAAAAAAAAAAAAull;
+    uint64_t runs = 0;
+    const int R = p.max_repeat;
+    if (R >= 2) {
+        uint64_t e = hf ^ (hf >> 2);
+        uint64_t z = ~(e | (e >> 1)) & 0x5555555555555555ull;
+        runs = z;
+        for (int t = 1; t < R - 1; t++) runs &= z >> (2 * t);
+    }
+    const bool last_gc = (hf & 2ull) != 0;
+    // warp-uniform control flow from here on (no break / continue: lanes that leave a loop early would
+    // make the warp run it several times)
     uint32_t cm = 0;
-    if (load_pos(p, b, s)) {
-        int khi = min(p.kmax, s.n);
-        for (int k = p.kmin; k <= khi; k++) {
-            if (s.nmw & kmask1(k)) continue;
-            uint64_t h = s.hf & kmask2(k);
-            if (((h >> (2 * k - 2)) & 3) < 2 && (h & 3) < 2) continue;
-            if (p.prefilter) {
-                if (!((p.gc_ok[k] >> gc_count(h)) & 1ull)) continue;
-                if (has_long_repeat(h, k, p.max_repeat)) continue;
-            }
-            cm |= 1u << (k - p.kmin);
-        }
-        if (p.prefilter && cm) {
-            // one pass over the pairs serves every k: window k is complete after pair k-2
-            uint32_t acc = 0;
-            for (int i = 0; i + 2 <= khi; i++) {
-                acc += s_nn[(s.hf >> (2 * i)) & 15];
-                int k = i + 2, ki = k - p.kmin;
-                if (ki >= 0 && ((cm >> ki) & 1u)) {
-                    uint64_t h = s.hf & kmask2(k);
-                    if (!tm_in_range(acc, h, k, gc_count(h), p)) cm &= ~(1u << ki);
-                }
+    for (int ki = 0; ki < p.nk; ki++) {
+        const int k = p.kmin + ki;
+        bool ok = k <= khi && !(s.nmw & kmask1(k))                                         // :40-43
+                  && (last_gc || ((hf >> (2 * k - 1)) & 1ull));                             // isOneEndGc (:29-33)
+        if (p.prefilter)
+            ok = ok && ((p.gc_ok[k] >> __popcll(gcbits & kmask2(k))) & 1ull)                // :301-303
+                 && R > 1 && !(k >= R && (runs & kmask2(k - R + 1)) != 0);                  // :309-320
+        cm |= (ok ? 1u : 0u) << ki;
+    }
+    if (p.prefilter) {
+        // the nearest-neighbour sum of window k is the sum over pairs 0 .. k-2: one tight loop for the
+        // pairs every length shares, then one more pair per length
+        uint32_t acc = 0;
+        for (int i = 0; i + 2 <= p.kmin; i++) acc += s_nn[(uint32_t)(hf >> (2 * i)) & 15u];
+        for (int ki = 0; ki < p.nk; ki++) {
+            const int k = p.kmin + ki;
+            if (ki) acc += s_nn[(uint32_t)(hf >> (2 * (k - 2))) & 15u];
+            if ((cm >> ki) & 1u) {
+                uint64_t h = hf & kmask2(k);
+                if (!tm_in_range(acc, h, k, __popcll(gcbits & kmask2(k)), p)) cm &= ~(1u << ki);
             }
         }
-        for (uint32_t m = cm; m; m &= m - 1) {
-            int ki = __ffs(m) - 1, k = p.kmin + ki;
-            uint64_t h = s.hf & kmask2(k), r = s.hr >> (64 - 2 * k);
-            uint32_t bin = mod_p(h < r ? h : r, p);
-            uint32_t *cell = &p.sk[(size_t)ki * 2 * p.PW + (bin >> 4)];
-            uint32_t bb = bin & 15u;
-            uint32_t old = atomicOr(cell, 1u << bb);
-            if ((old >> bb) & 1u) atomicOr(cell, 1u << (16 + bb));
-        }
+    }
+    for (int ki = 0; ki < p.nk; ki++) {
+        if (!((cm >> ki) & 1u)) continue;
+        const int k = p.kmin + ki;
+        uint64_t h = hf & kmask2(k), r = s.hr >> (64 - 2 * k);
+        uint32_t bin = mod_p(h < r ? h : r, p);
+        uint32_t *cell = &p.sk[(size_t)ki * 2 * p.PW + (bin >> 4)];
+        uint32_t bb = bin & 15u;
+        uint32_t old = atomicOr(cell, 1u << bb);
+        if ((old >> bb) & 1u) atomicOr(cell, 1u << (16 + bb));
     }
 }
 
@@ -438,154 +454,166 @@ __device__ __forceinline__ void drain_consume(const K &p, const Pending &pd) {
         atomicAdd(&p.rows[(size_t)pd.g * p.nslots + pd.e.y + __popc(pd.e.x & ((1u << b) - 1u))], ROW_ONE | (pd.meta & (uint32_t)ROW_POS_MASK));
 }
 
-// 32-bit-word arithmetic of the hot loop.  For the word (prev : cur) = 64 bases, the window of k bases
-// ending at base j of cur is a funnel shift of the stream by 2 * (31 - j) bits, and its reverse
-// complement is the same funnel shift, to the left, of the stream rc(cur) : rc(prev) -- so neither
-// word has to be rolled base by base and every window of a thread is independent of the others.
-template <bool FASTMOD>
-__device__ __forceinline__ uint32_t window_bin(const K &p, uint32_t h_lo, uint32_t h_hi, uint32_t t_lo, uint32_t t_hi,
-                                               uint32_t mlo, uint32_t mhi, int rsh, uint32_t m32, uint32_t a32) {
-    h_lo &= mlo; h_hi &= mhi;
-    uint64_t r = (((uint64_t)t_hi << 32) | t_lo) >> rsh;
-    uint32_t r_lo = (uint32_t)r, r_hi = (uint32_t)(r >> 32);
-    bool lt = h_hi < r_hi || (h_hi == r_hi && h_lo < r_lo);            // uniqify_rc: min(h, r)
-    uint32_t c_lo = lt ? h_lo : r_lo, c_hi = lt ? h_hi : r_hi;
+// 32-bit-word arithmetic of the hot loop.  A thread owns one packed word (32 window end positions) and
+// its predecessor: 64 bases = the 128-bit stream prev : cur.  The window of k bases ending at base j of
+// cur is bits [2o, 2o + 2k) of that stream (o = 31 - j) and its reverse complement is bits
+// [128 - 2k - 2o, 128 - 2o) of the stream rc(cur) : rc(prev): each is ONE funnel shift per 32-bit
+// half -- nothing is rolled base by base, every window is independent, and the shift amounts are the
+// same for all lanes (uniform registers).  The loop is bound by the INT32 ALU pipe (profiles/
+// r01_scan_ablation.md), so the code below is written to minimise ALU-pipe instructions: multiply-add
+// forms for the modular reduction and the filter address (FMA pipe), no per-window validity work on
+// words that are entirely inside a contig and free of non-ACGT bytes (CLEAN).
+template <bool FASTMOD, bool KBIG>
+__device__ __forceinline__ uint32_t canon_bin(const K &p, uint32_t h_lo, uint32_t h_hi, uint32_t r_lo, uint32_t r_hi,
+                                              uint32_t m32, uint32_t a32, uint32_t neg_p) {
+    uint32_t c_lo, c_hi;
+    if (KBIG) {
+        bool lt = ((((uint64_t)h_hi) << 32) | h_lo) < ((((uint64_t)r_hi) << 32) | r_lo);   // uniqify_rc: min(h, r)
+        c_lo = lt ? h_lo : r_lo; c_hi = lt ? h_hi : r_hi;
+    } else {
+        c_lo = min(h_lo, r_lo); c_hi = 0;
+    }
     if (FASTMOD) {
         // canon < 2^40 and P < 2^24: (c_hi * (2^32 mod P) + c_lo mod P) mod P in 32-bit multiply-adds
-        const uint32_t neg_p = 0u - p.P;
         uint32_t r1 = __umulhi(c_lo, m32) * neg_p + c_lo;                // c_lo - q P < 2P
-        uint32_t s1 = c_hi * a32 + r1;                                   // < 257 P < 2^32
-        uint32_t r2 = __umulhi(s1, m32) * neg_p + s1;                    // < 2P
+        uint32_t s1 = KBIG ? c_hi * a32 + r1 : r1;                       // < 257 P < 2^32
+        uint32_t r2 = KBIG ? __umulhi(s1, m32) * neg_p + s1 : s1;        // < 2P
         return min(r2, r2 + neg_p);                                      // unsigned: picks the reduced one
     }
     return mod_p(((uint64_t)c_hi << 32) | c_lo, p);
 }
 
-#ifndef PFB_GROUP
-#define PFB_GROUP 2
-#endif
-constexpr int GROUP = PFB_GROUP;
-template <bool FASTMOD, bool HASN>
-__device__ __forceinline__ void scan_word(const K &p, int ki, int k, uint32_t f_addr, uint32_t q_addr,
-                                          uint32_t &qhead, uint32_t &qn, bool &pend, Pending &pd, uint32_t lane, uint32_t lt_mask,
+struct ScanWarp {            // per-warp state of k_scan_filtered
+    uint32_t f_addr, q_addr; // shared-window addresses of the filter and of this warp's queue
+    uint32_t qhead, qn;      // warp-uniform ring state
+    bool pend;               // a batch of 32 probes is in flight
+    Pending pd;
+    uint32_t lane, lt_mask;
+};
+
+template <bool FASTMOD, bool KBIG, bool CLEAN>
+__device__ __forceinline__ void scan_word(const K &p, int ki, int k, ScanWarp &sw,
                                           uint64_t prev, uint64_t cur, uint64_t nm, uint32_t vmask, uint32_t g, uint32_t gpos0,
-                                          uint32_t mlo, uint32_t mhi, int rsh, uint32_t m32, uint32_t a32, uint64_t km1) {
-    const uint32_t c_lo = (uint32_t)cur, c_hi = (uint32_t)(cur >> 32), p_lo = (uint32_t)prev, p_hi = (uint32_t)(prev >> 32);
+                                          uint32_t mlo, uint32_t mhi, uint32_t m32, uint32_t a32, uint64_t km1) {
+    const uint32_t F0 = (uint32_t)cur, F1 = (uint32_t)(cur >> 32), F2 = (uint32_t)prev, F3 = (uint32_t)(prev >> 32);
     const uint64_t rcc = rc64(cur), rcp = rc64(prev);
-    const uint32_t rc_lo = (uint32_t)rcc, rc_hi = (uint32_t)(rcc >> 32), rp_lo = (uint32_t)rcp, rp_hi = (uint32_t)(rcp >> 32);
+    const uint32_t R0 = (uint32_t)rcp, R1 = (uint32_t)(rcp >> 32), R2 = (uint32_t)rcc, R3 = (uint32_t)(rcc >> 32);
+    const uint32_t neg_p = 0u - p.P;
+    const int C = 128 - 2 * k;
+    int o = 0;
 #pragma unroll 1
-    for (int half = 0; half < 2; half++) {
-        // half 0: j = 31..16 (stream shift 0..30 bits), half 1: j = 15..0 (shift 32..62 bits)
-        const uint32_t a0 = half ? c_hi : c_lo, a1 = half ? p_lo : c_hi, a2 = half ? p_hi : p_lo;      // forward stream words
-        const uint32_t b2 = half ? rc_lo : rc_hi, b1 = half ? rp_hi : rc_lo, b0 = half ? rp_lo : rp_hi; // rc stream words
-#pragma unroll 1
-        for (int o4 = 0; o4 < 16; o4 += GROUP) {
-            // GROUP independent windows: their hash chains and filter loads overlap (ILP), then the
-            // warp-wide bookkeeping runs once per window
-            uint32_t bin[GROUP], hit[GROUP];
-#pragma unroll
-            for (int u = 0; u < GROUP; u++) {
-                const int o = o4 + u, j = 31 - 16 * half - o;
-                const uint32_t sh = 2 * o;
-                uint32_t h_lo = __funnelshift_r(a0, a1, sh), h_hi = __funnelshift_r(a1, a2, sh);
-                uint32_t t_hi = __funnelshift_l(b1, b2, sh), t_lo = __funnelshift_l(b0, b1, sh);
-                uint32_t valid = (vmask >> j) & 1u;
-                if (HASN) {
-                    uint32_t wn = (uint32_t)((nm >> (31 - j)) & km1);
-                    if (valid && wn) {
-                        uint64_t h = (((uint64_t)(h_hi & mhi)) << 32) | (h_lo & mlo);
-                        uint64_t r = (((uint64_t)t_hi << 32) | t_lo) >> rsh;
-                        pollute_invalid_window(p, ki, k, g, h, r, wn);
-                        valid = 0;
-                    }
+    while (o < 32) {
+        // a segment = a run of o over which both extractions read the same three words
+        const int wf = o >> 4, ar = C - 2 * o, wr = ar >> 5;
+        const int o_end = min((wf + 1) << 4, o + ((ar & 31) >> 1) + 1);
+        const uint32_t a0 = wf ? F1 : F0, a1 = wf ? F2 : F1, a2 = wf ? F3 : F2;
+        const uint32_t b0 = wr == 0 ? R0 : wr == 1 ? R1 : wr == 2 ? R2 : R3;
+        const uint32_t b1 = wr == 0 ? R1 : wr == 1 ? R2 : wr == 2 ? R3 : 0u;
+        const uint32_t b2 = wr == 0 ? R2 : wr == 1 ? R3 : 0u;
+#pragma unroll 2
+        for (; o < o_end; o++) {
+            const uint32_t sf = (2 * o) & 31, sr = (uint32_t)(C - 2 * o) & 31;
+            const int j = 31 - o;
+            uint32_t h_lo = __funnelshift_r(a0, a1, sf), h_hi = 0, r_lo = __funnelshift_r(b0, b1, sr), r_hi = 0;
+            if (KBIG) { h_hi = __funnelshift_r(a1, a2, sf) & mhi; r_hi = __funnelshift_r(b1, b2, sr) & mhi; }
+            else { h_lo &= mlo; r_lo &= mlo; }
+            uint32_t valid = 1;
+            if (!CLEAN) {
+                valid = (vmask >> j) & 1u;
+                uint32_t wn = (uint32_t)((nm >> (31 - j)) & km1);
+                if (valid && wn) {
+                    pollute_invalid_window(p, ki, k, g, (((uint64_t)h_hi) << 32) | h_lo, (((uint64_t)r_hi) << 32) | r_lo, wn);
+                    valid = 0;
                 }
-                bin[u] = window_bin<FASTMOD>(p, h_lo, h_hi, t_lo, t_hi, mlo, mhi, rsh, m32, a32);
-                uint32_t fb = __umulhi(bin[u], p.fscale);
-                // the filter word is read unconditionally (bin < P always): no branch in front of the LDS
-                hit[u] = (lds32(f_addr + ((fb >> 5) << 2)) >> (fb & 31)) & valid;
             }
-#pragma unroll
-            for (int u = 0; u < GROUP; u++) {
-                const int j = 31 - 16 * half - (o4 + u);
-                // straight-line append: ballot, predicated store, uniform counters; the only branch is the
-                // (warp-uniform, rarely taken) drain
-                uint32_t m = __ballot_sync(0xFFFFFFFFu, hit[u] != 0);
-                sts128_if(hit[u], q_addr + (((qhead + qn + __popc(m & lt_mask)) & (QCAP - 1)) << 4), bin[u], gpos0 + j - k + 1, g, 0u);
-                qn += __popc(m);
-                if (qn >= 32) {
-                    __syncwarp();
-                    if (pend) drain_consume(p, pd);
-                    drain_issue(p, ki, q_addr, qhead, lane, pd);
-                    pend = true;
-                    qhead = (qhead + 32) & (QCAP - 1);
-                    qn -= 32;
-                    __syncwarp();
-                }
+            const uint32_t bin = canon_bin<FASTMOD, KBIG>(p, h_lo, h_hi, r_lo, r_hi, m32, a32, neg_p);
+            // filter bit = (word umulhi(bin, scale), bit bin & 31); read unconditionally: no branch before the LDS
+            uint32_t hit = (lds32(sw.f_addr + __umulhi(bin, p.fscale) * 4u) >> (bin & 31u)) & valid;
+            // straight-line append: ballot, predicated store, uniform counters; the only branch is the
+            // (warp-uniform, rarely taken) drain
+            const uint32_t m = __ballot_sync(0xFFFFFFFFu, hit != 0);
+            sts128_if(hit, sw.q_addr + (((sw.qhead + sw.qn + __popc(m & sw.lt_mask)) & (QCAP - 1)) << 4), bin, gpos0 + j - k + 1, g, 0u);
+            sw.qn += __popc(m);
+            if (sw.qn >= 32) {
+                __syncwarp();
+                if (sw.pend) drain_consume(p, sw.pd);
+                drain_issue(p, ki, sw.q_addr, sw.qhead, sw.lane, sw.pd);
+                sw.pend = true;
+                sw.qhead = (sw.qhead + 32) & (QCAP - 1);
+                sw.qn -= 32;
+                __syncwarp();
             }
         }
     }
 }
 
-__global__ void __launch_bounds__(1024, 1) k_scan_filtered(const __grid_constant__ K p, uint32_t w0, uint32_t w1) {
-    extern __shared__ uint32_t s_filter[];
-    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint32_t f_addr = (uint32_t)__cvta_generic_to_shared(s_filter);
-    const uint32_t q_addr = f_addr + FILTER_BYTES + warp * QCAP * 16u;
-    const uint32_t stride = gridDim.x * blockDim.x;
-    const uint32_t lt_mask = (1u << lane) - 1u;
+template <bool FASTMOD, bool KBIG>
+__device__ __forceinline__ void scan_pass(const K &p, int ki, int k, ScanWarp &sw, uint32_t w0, uint32_t w1, uint32_t stride,
+                                          uint32_t warp) {
+    const uint64_t km2 = kmask2(k);
+    const uint64_t km1 = kmask1(k);
+    const uint32_t mlo = (uint32_t)km2, mhi = (uint32_t)(km2 >> 32);
     const uint32_t m32 = (uint32_t)(0x100000000ull / p.P);            // floor(2^32 / P)
     const uint32_t a32 = (uint32_t)(0x100000000ull % p.P);            // 2^32 mod P
+    for (uint32_t wb = w0 + blockIdx.x * blockDim.x + warp * 32; wb < w1; wb += stride) {
+        const uint32_t w = wb + sw.lane;
+        uint32_t vmask = 0, g = 0, gpos0 = 0;
+        uint64_t cur = 0, prev = 0, nm = 0;
+        if (w < w1) {
+            uint32_t c = p.wordContig[w];
+            uint32_t i = w - p.cWordStart[c];
+            uint32_t qbase = 32u * i;
+            uint32_t nj = min(32u, p.cLen[c] - qbase);
+            uint32_t jlo = qbase + 1 >= (uint32_t)k ? 0u : (uint32_t)k - 1 - qbase;   // first end position with a full window
+            if (jlo < nj) vmask = (nj == 32 ? 0xFFFFFFFFu : ((1u << nj) - 1u)) & ~((1u << jlo) - 1u);
+            g = p.cGenome[c];
+            cur = p.seq2[w];
+            prev = i ? p.seq2[w - 1] : 0ull;
+            nm = ((uint64_t)(i ? p.nmask[w - 1] : 0u) << 32) | p.nmask[w];
+            gpos0 = 32u * (w - p.gWordStart[g]);
+        }
+        // every lane's word entirely inside a contig and free of non-ACGT bytes: no validity work at all
+        const bool clean = __all_sync(0xFFFFFFFFu, vmask == 0xFFFFFFFFu && nm == 0);
+        if (clean) scan_word<FASTMOD, KBIG, true>(p, ki, k, sw, prev, cur, nm, vmask, g, gpos0, mlo, mhi, m32, a32, km1);
+        else scan_word<FASTMOD, KBIG, false>(p, ki, k, sw, prev, cur, nm, vmask, g, gpos0, mlo, mhi, m32, a32, km1);
+    }
+}
+
+__global__ void __launch_bounds__(1024, 1) k_scan_filtered(const __grid_constant__ K p, uint32_t w0, uint32_t w1) {
+    extern __shared__ uint32_t s_filter[];
+    ScanWarp sw;
+    sw.lane = threadIdx.x & 31;
+    const uint32_t warp = threadIdx.x >> 5;
+    sw.f_addr = (uint32_t)__cvta_generic_to_shared(s_filter);
+    sw.q_addr = sw.f_addr + FILTER_BYTES + warp * QCAP * 16u;
+    sw.lt_mask = (1u << sw.lane) - 1u;
+    const uint32_t stride = gridDim.x * blockDim.x;
     for (int ki = 0; ki < p.nk; ki++) {
         const int k = p.kmin + ki;
         __syncthreads();
         {   // LDGSTS: every thread has all its 16 B pieces in flight at once, nothing goes through registers
             const uint8_t *src = (const uint8_t *)(p.filter + (size_t)ki * FILTER_WORDS);
             for (uint32_t t = threadIdx.x; t < FILTER_WORDS / 4; t += blockDim.x)
-                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(f_addr + t * 16u), "l"(src + (size_t)t * 16u) : "memory");
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sw.f_addr + t * 16u), "l"(src + (size_t)t * 16u) : "memory");
             asm volatile("cp.async.commit_group;" ::: "memory");
             asm volatile("cp.async.wait_group 0;" ::: "memory");
         }
         __syncthreads();
-        const uint64_t km2 = kmask2(k);
-        const uint64_t km1 = kmask1(k);
-        const uint32_t mlo = (uint32_t)km2, mhi = (uint32_t)(km2 >> 32);
-        const int rsh = 64 - 2 * k;
+        sw.qhead = 0; sw.qn = 0; sw.pend = false;
+        sw.pd.e = make_uint2(0u, 0u); sw.pd.meta = 0; sw.pd.g = 0;
         const bool fastmod = k <= 20 && p.P < (1u << 24);
-        uint32_t qhead = 0, qn = 0;   // warp-uniform
-        bool pend = false;
-        Pending pd;
-        pd.e = make_uint2(0u, 0u); pd.meta = 0; pd.g = 0;
-        for (uint32_t wb = w0 + blockIdx.x * blockDim.x + warp * 32; wb < w1; wb += stride) {
-            const uint32_t w = wb + lane;
-            uint32_t vmask = 0, g = 0, gpos0 = 0;
-            uint64_t cur = 0, prev = 0, nm = 0;
-            if (w < w1) {
-                uint32_t c = p.wordContig[w];
-                uint32_t i = w - p.cWordStart[c];
-                uint32_t qbase = 32u * i;
-                uint32_t nj = min(32u, p.cLen[c] - qbase);
-                uint32_t jlo = qbase + 1 >= (uint32_t)k ? 0u : (uint32_t)k - 1 - qbase;   // first end position with a full window
-                if (jlo < nj) vmask = (nj == 32 ? 0xFFFFFFFFu : ((1u << nj) - 1u)) & ~((1u << jlo) - 1u);
-                g = p.cGenome[c];
-                cur = p.seq2[w];
-                prev = i ? p.seq2[w - 1] : 0ull;
-                nm = ((uint64_t)(i ? p.nmask[w - 1] : 0u) << 32) | p.nmask[w];
-                gpos0 = 32u * (w - p.gWordStart[g]);
-            }
-            const bool any_n = __any_sync(0xFFFFFFFFu, nm != 0);
-            if (any_n) {
-                if (fastmod) scan_word<true, true>(p, ki, k, f_addr, q_addr, qhead, qn, pend, pd, lane, lt_mask, prev, cur, nm, vmask, g, gpos0, mlo, mhi, rsh, m32, a32, km1);
-                else scan_word<false, true>(p, ki, k, f_addr, q_addr, qhead, qn, pend, pd, lane, lt_mask, prev, cur, nm, vmask, g, gpos0, mlo, mhi, rsh, m32, a32, km1);
-            } else {
-                if (fastmod) scan_word<true, false>(p, ki, k, f_addr, q_addr, qhead, qn, pend, pd, lane, lt_mask, prev, cur, nm, vmask, g, gpos0, mlo, mhi, rsh, m32, a32, km1);
-                else scan_word<false, false>(p, ki, k, f_addr, q_addr, qhead, qn, pend, pd, lane, lt_mask, prev, cur, nm, vmask, g, gpos0, mlo, mhi, rsh, m32, a32, km1);
-            }
+        if (k > 16) {
+            if (fastmod) scan_pass<true, true>(p, ki, k, sw, w0, w1, stride, warp);
+            else scan_pass<false, true>(p, ki, k, sw, w0, w1, stride, warp);
+        } else {
+            if (p.P < (1u << 24)) scan_pass<true, false>(p, ki, k, sw, w0, w1, stride, warp);
+            else scan_pass<false, false>(p, ki, k, sw, w0, w1, stride, warp);
         }
         __syncwarp();
-        if (pend) drain_consume(p, pd);
-        if (lane < qn) {   // the remainder of the k pass
-            drain_issue(p, ki, q_addr, qhead, lane, pd);
-            drain_consume(p, pd);
+        if (sw.pend) drain_consume(p, sw.pd);
+        if (sw.lane < sw.qn) {   // the remainder of the k pass
+            drain_issue(p, ki, sw.q_addr, sw.qhead, sw.lane, sw.pd);
+            drain_consume(p, sw.pd);
         }
         __syncwarp();
     }
@@ -611,8 +639,8 @@ __global__ void __launch_bounds__(256) k_build_filter(const __grid_constant__ K 
     while (word) {
         int b = __ffs(word) - 1;
         word &= word - 1;
-        uint32_t fb = __umulhi(wi * 32u + b, p.fscale);
-        atomicOr(&f[fb >> 5], 1u << (fb & 31));
+        uint32_t bin = wi * 32u + b;
+        atomicOr(&f[__umulhi(bin, p.fscale)], 1u << (bin & 31u));
     }
 }
 
@@ -1203,9 +1231,9 @@ static int stage0(pfb_ctx *ctx) {
     k.kmin = P.k_min; k.kmax = P.k_max; k.nk = nk;
     k.P = P.table_size; k.PW = (P.table_size + 31) / 32;
     k.barrett = (uint64_t)((((unsigned __int128)1) << 64) / P.table_size);
-    k.fscale = (uint64_t)FILTER_BITS >= P.table_size
+    k.fscale = (uint64_t)FILTER_WORDS >= P.table_size
                    ? 0xFFFFFFFFu
-                   : (uint32_t)((((unsigned __int128)FILTER_BITS) << 32) / P.table_size);
+                   : (uint32_t)((((unsigned __int128)FILTER_WORDS) << 32) / P.table_size);
     k.max_repeat = P.max_repeat; k.prefilter = P.prefilter;
     std::vector<double> fterm;
     fill_filter_constants(P, k, fterm);
