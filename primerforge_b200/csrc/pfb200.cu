@@ -25,7 +25,7 @@
 //     memory (192 KB per CTA) so that only ~1 in 6 windows reaches L2;
 //   * survivors are emitted in the reference's dict order by an ordered compaction over genome 1
 //     (k_emit_mark / k_emit_write), filters are evaluated in fp64 with the reference's operation order, the
-//     per-position "first k-mer that passes" pick is an atomicMin over a direct-mapped array.
+//     per-position "first k-mer that passes" pick looks only at the few records that can share a position.
 //
 // No tensor cores: nothing here is a contraction.
 
@@ -95,7 +95,6 @@ struct K {  // kernel arguments (by value, __grid_constant__)
     uint32_t *pos;            // [nGenomes][nrec] start within contig | strand << 31
     uint32_t *posContig;      // [nGenomes][nrec] contig index (only when some genome has > 1 contig)
     int multiContig;
-    uint32_t *minRank;        // [totalWords*32]
     uint32_t *pick;           // [nrec] 0 / 1, then (stage 2) its exclusive prefix in pickOff
     uint32_t *pickOff;
     pfb_record *outRec;       // picked records, compacted
@@ -857,35 +856,95 @@ __global__ void __launch_bounds__(256) k_emit_write(const __grid_constant__ K p)
 }
 
 // k_positions: (contig, leftmost start, strand) of every record in every genome
-// (getCandidateKmers.py:173-187); also seeds the grouping array with the smallest passing rank
-__global__ void __launch_bounds__(256) k_positions(const __grid_constant__ K p) {
-    uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    uint32_t g = blockIdx.y;
-    if (r >= p.nrec) return;
-    pfb_record rec = p.rec[r];
-    unsigned long long v = p.rows[(size_t)g * p.nslots + rec.slot];
-    uint32_t lp = (uint32_t)(v & ROW_POS_MASK);
-    uint32_t gw = p.gWordStart[g] + (lp >> 5);
-    uint32_t c = p.wordContig[gw];
-    uint32_t start = lp - 32u * (p.cWordStart[c] - p.gWordStart[g]);
-    // '+' when the genome reads the key itself at that place, '-' when it reads its reverse complement;
-    // a palindrome matches both scans and the later '-' match overwrites (:181-187)
-    uint32_t minus = ((rec.flags & PFB_F_PALIN) || window_at(p, g, lp, rec.k) != rec.word) ? 1u : 0u;
-    p.pos[(size_t)g * p.nrec + r] = start | (minus << 31);
-    if (p.multiContig) p.posContig[(size_t)g * p.nrec + r] = c - p.gFirstContig[g];
-    if ((rec.flags & 7u) == 7u) atomicMin(&p.minRank[(size_t)p.gWordStart[g] * 32u + lp], (uint32_t)r);
+// (getCandidateKmers.py:173-187) and the per-position pick (:222-247, 376-388): a record is picked when,
+// in at least one genome, no earlier record that passes the filters sits at the same (contig, start).
+// Group mates need no sort and no per-position array: two shared k-mers that start at the same place of
+// some genome read the same sequence there, so one is a prefix of the other ('+' strand) or a suffix of it
+// ('-' strand), and as both are unique in genome 1 they share their START (resp. their END) in genome 1.
+// The only possible earlier mates of record (start1, k) are therefore the records (same end1, k' > k) and
+// (same start1, k' < k), which the emit bitmap locates directly; whether such a record really is a mate
+// in genome g is decided by comparing the two starts in g.  One thread per record, loop over genomes.
+__device__ __forceinline__ int mate_candidates(const K &p, uint32_t start1, int ki, uint32_t r, uint32_t *cand, int cap) {
+    int n = 0;
+    const uint32_t end1 = start1 + (uint32_t)(p.kmin + ki) - 1u;
+    uint32_t m = p.emitMask[end1];
+    uint32_t off = p.emitOff[end1];
+    for (uint32_t hi = ki < 31 ? (m >> (ki + 1)) : 0u, kj = ki + 1; hi; hi >>= 1, kj++)       // same end, longer
+        if (hi & 1u) { uint32_t rr = off + __popc(kj < 31 ? (m >> (kj + 1)) : 0u); if (n < cap) cand[n] = rr; n++; }
+    for (int kj = 0; kj < ki; kj++) {                                                           // same start, shorter
+        uint32_t e2 = start1 + (uint32_t)(p.kmin + kj) - 1u;
+        uint32_t m2 = p.emitMask[e2];
+        if ((m2 >> kj) & 1u) { uint32_t rr = p.emitOff[e2] + __popc(m2 >> (kj + 1)); if (n < cap) cand[n] = rr; n++; }
+    }
+    (void)r;
+    return n;
 }
 
-// k_pick: a record is picked when it is the first passing k-mer of its (contig, start) group in
-// some genome (getCandidateKmers.py:222-247, 376-388)
-__global__ void __launch_bounds__(256) k_pick(const __grid_constant__ K p) {
+// general path (more candidates than the register cache holds): re-enumerate them for one genome
+__device__ __noinline__ bool has_earlier_mate(const K &p, uint32_t g, uint32_t lp, uint32_t start1, int ki) {
+    const uint32_t end1 = start1 + (uint32_t)(p.kmin + ki) - 1u;
+    uint32_t m = p.emitMask[end1];
+    uint32_t off = p.emitOff[end1];
+    for (uint32_t hi = ki < 31 ? (m >> (ki + 1)) : 0u, kj = ki + 1; hi; hi >>= 1, kj++) {
+        if (!(hi & 1u)) continue;
+        const pfb_record o = p.rec[off + __popc(kj < 31 ? (m >> (kj + 1)) : 0u)];
+        if ((o.flags & 7u) == 7u && (uint32_t)(p.rows[(size_t)g * p.nslots + o.slot] & ROW_POS_MASK) == lp) return true;
+    }
+    for (int kj = 0; kj < ki; kj++) {
+        uint32_t e2 = start1 + (uint32_t)(p.kmin + kj) - 1u;
+        uint32_t m2 = p.emitMask[e2];
+        if (!((m2 >> kj) & 1u)) continue;
+        const pfb_record o = p.rec[p.emitOff[e2] + __popc(m2 >> (kj + 1))];
+        if ((o.flags & 7u) == 7u && (uint32_t)(p.rows[(size_t)g * p.nslots + o.slot] & ROW_POS_MASK) == lp) return true;
+    }
+    return false;
+}
+
+__global__ void __launch_bounds__(256) k_positions(const __grid_constant__ K p) {
     uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    uint32_t g = blockIdx.y;
     if (r >= p.nrec) return;
-    pfb_record rec = p.rec[r];
-    if ((rec.flags & 7u) != 7u) return;
-    uint32_t lp = (uint32_t)(p.rows[(size_t)g * p.nslots + rec.slot] & ROW_POS_MASK);
-    if (p.minRank[(size_t)p.gWordStart[g] * 32u + lp] == (uint32_t)r) p.pick[r] = 1;
+    const pfb_record rec = p.rec[r];
+    const bool pass = (rec.flags & 7u) == 7u;
+    // earlier records that could share a position with this one, filtered to those that pass the filters
+    constexpr int CAP = 8;
+    uint32_t cand[CAP];
+    uint32_t cslot[CAP];
+    int nc = 0;
+    bool overflow = false;
+    const uint32_t start1 = (uint32_t)(p.rows[rec.slot] & ROW_POS_MASK);
+    if (pass) {
+        int n = mate_candidates(p, start1, rec.k - p.kmin, (uint32_t)r, cand, CAP);
+        overflow = n > CAP;
+        if (overflow) n = 0;
+        for (int i = 0; i < n; i++) {
+            const pfb_record o = p.rec[cand[i]];
+            if ((o.flags & 7u) == 7u) cslot[nc++] = o.slot;
+        }
+    }
+    bool picked = false;
+    for (uint32_t g = 0; g < p.nGenomes; g++) {
+        const unsigned long long v = p.rows[(size_t)g * p.nslots + rec.slot];
+        const uint32_t lp = (uint32_t)(v & ROW_POS_MASK);
+        const uint32_t gw = p.gWordStart[g] + (lp >> 5);
+        const uint32_t c = p.wordContig[gw];
+        const uint32_t start = lp - 32u * (p.cWordStart[c] - p.gWordStart[g]);
+        // '+' when the genome reads the key itself at that place, '-' when it reads its reverse complement;
+        // a palindrome matches both scans and the later '-' match overwrites (:181-187)
+        const uint32_t minus = ((rec.flags & PFB_F_PALIN) || window_at(p, g, lp, rec.k) != rec.word) ? 1u : 0u;
+        p.pos[(size_t)g * p.nrec + r] = start | (minus << 31);
+        if (p.multiContig) p.posContig[(size_t)g * p.nrec + r] = c - p.gFirstContig[g];
+        if (pass && !picked) {
+            bool first = true;
+            if (overflow) {
+                first = !has_earlier_mate(p, g, lp, start1, rec.k - p.kmin);
+            } else {
+                for (int i = 0; i < nc; i++)
+                    if ((uint32_t)(p.rows[(size_t)g * p.nslots + cslot[i]] & ROW_POS_MASK) == lp) first = false;
+            }
+            picked = first;
+        }
+    }
+    if (picked) p.pick[r] = 1u;
 }
 
 // k_compact: picked records and their coordinates in every genome, densely packed for the D2H copy
@@ -947,7 +1006,7 @@ struct pfb_ctx {
     int stage_done = -1;
     // device
     DevBuf raw, seq2, nmask, wordContig, tabs32, tabs64, sk, br, filter, fterm, scanTmp, misc, emitMask, emitOff,
-        rows, alive, rec, pos, posContig, minRank, pick, pickOff, outRec, outPos, outContig;
+        rows, alive, rec, pos, posContig, pick, pickOff, outRec, outPos, outContig;
     K k{};
     uint64_t nslots = 0, nrec = 0, npick = 0;
     uint64_t launches = 0;
@@ -1124,7 +1183,7 @@ void pfb_destroy(pfb_ctx *ctx) {
     cudaStreamSynchronize(ctx->stream);
     DevBuf *all[] = {&ctx->raw, &ctx->seq2, &ctx->nmask, &ctx->wordContig, &ctx->tabs32, &ctx->tabs64, &ctx->sk, &ctx->br,
                      &ctx->filter, &ctx->fterm, &ctx->scanTmp, &ctx->misc, &ctx->emitMask, &ctx->emitOff,
-                     &ctx->rows, &ctx->alive, &ctx->rec, &ctx->pos, &ctx->posContig, &ctx->minRank, &ctx->pick,
+                     &ctx->rows, &ctx->alive, &ctx->rec, &ctx->pos, &ctx->posContig, &ctx->pick,
                      &ctx->pickOff, &ctx->outRec, &ctx->outPos, &ctx->outContig};
     for (auto *b : all) release(*b);
     for (auto &ev : ctx->ev) if (ev) cudaEventDestroy(ev);
@@ -1372,18 +1431,13 @@ static int stage1(pfb_ctx *ctx) {
     if ((rc = ensure(ctx, ctx->posContig, multi ? NR * nG * 4 : 4)) != PFB_OK) return rc;
     if ((rc = ensure(ctx, ctx->pick, NR * 4)) != PFB_OK) return rc;
     if ((rc = ensure(ctx, ctx->pickOff, NR * 4)) != PFB_OK) return rc;
-    if ((rc = ensure(ctx, ctx->minRank, (size_t)W * 32 * 4 + 4)) != PFB_OK) return rc;
     k.rec = (pfb_record *)ctx->rec.p; k.pos = (uint32_t *)ctx->pos.p; k.posContig = (uint32_t *)ctx->posContig.p;
     k.multiContig = multi ? 1 : 0;
     k.pick = (uint32_t *)ctx->pick.p; k.pickOff = (uint32_t *)ctx->pickOff.p;
-    k.minRank = (uint32_t *)ctx->minRank.p;
     CK(cudaMemsetAsync(ctx->pick.p, 0, NR * 4, st));
     if (ctx->nrec) {
-        CK(cudaMemsetAsync(ctx->minRank.p, 0xFF, (size_t)W * 32 * 4, st));
         k_emit_write<<<nblk(ctx->nslots, 256), 256, 0, st>>>(k); ctx->launches++;
-        dim3 grid(nblk(ctx->nrec, 256), (unsigned)nG);
-        k_positions<<<grid, 256, 0, st>>>(k); ctx->launches++;
-        k_pick<<<grid, 256, 0, st>>>(k); ctx->launches++;
+        k_positions<<<nblk(ctx->nrec, 256), 256, 0, st>>>(k); ctx->launches++;
     }
     CK(cudaGetLastError());
     return PFB_OK;
