@@ -88,6 +88,9 @@ typedef struct pfb_timing {
     uint64_t n_picked;
     uint64_t n_launches;       /* kernels launched by the last run */
     uint64_t used_filter;      /* 1: the scan probed through the shared-memory filter (k_scan_filtered) */
+    uint64_t scan_main_bases;  /* bases covered by the one scan launch over genomes 2..G (pfb_compute only) */
+    float    ms_scan_main;     /* CUDA-event duration of that launch: the roofline kernel of bench.py */
+    float    reserved;
 } pfb_timing;
 
 /* lifecycle ------------------------------------------------------------------------------ */

@@ -359,7 +359,11 @@ pfo_result *pfo_run(int32_t n_genomes, const uint8_t *const *bases, const int64_
     size_t *order = (size_t *)malloc((n_total ? n_total : 1) * sizeof(size_t));
     size_t n_ins = 0;
 
-    for (int g = 0; g < n_genomes && n_total; g++) {
+    /* genome 0 first and alone: it assigns the insertion ranks (every shared k-mer occurs on its (+)
+     * strand); the other genomes only fill their own rows and run in parallel */
+#pragma omp parallel for schedule(dynamic, 1)
+    for (int g = 0; g < n_genomes; g++) {
+        if (!n_total) continue;
         int C = n_contigs[g];
         for (int c = 0; c < C; c++) {
             int64_t a = contig_off[g][c], b = contig_off[g][c + 1], len = b - a;
@@ -377,7 +381,7 @@ pfo_result *pfo_run(int32_t n_genomes, const uint8_t *const *bases, const int64_
                         int64_t id = map_get(&maps[ki], w);
                         if (id < 0) continue;
                         size_t gi = base_idx[ki] + (size_t)id;
-                        if (rank_of[gi] < 0) { rank_of[gi] = (int64_t)n_ins; order[n_ins++] = gi; }
+                        if (g == 0 && rank_of[gi] < 0) { rank_of[gi] = (int64_t)n_ins; order[n_ins++] = gi; }
                         entry_t *en = &entries[(size_t)g * n_total + gi];
                         en->contig = c;
                         en->start = strand == 0 ? e - k + 1 : len - e - 1;   /* :173-178 */

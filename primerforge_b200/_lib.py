@@ -43,7 +43,8 @@ class PfbTiming(C.Structure):
     _fields_ = [("ms_upload", C.c_float), ("ms_encode", C.c_float), ("ms_first", C.c_float), ("ms_scan", C.c_float),
                 ("ms_finalize", C.c_float), ("ms_total", C.c_float), ("n_bases", C.c_uint64), ("n_windows", C.c_uint64),
                 ("n_slots", C.c_uint64), ("n_records", C.c_uint64), ("n_picked", C.c_uint64), ("n_launches", C.c_uint64),
-                ("used_filter", C.c_uint64)]
+                ("used_filter", C.c_uint64), ("scan_main_bases", C.c_uint64), ("ms_scan_main", C.c_float),
+                ("reserved", C.c_float)]
 
 
 RECORD_DTYPE = np.dtype([("word", "<u8"), ("tm", "<f8"), ("slot", "<u4"), ("gc_count", "<u2"), ("k", "u1"), ("flags", "u1")])

@@ -995,7 +995,7 @@ struct pfb_ctx {
     std::vector<cudaEvent_t> evCopy;            // one per genome: its bases have arrived
     bool pipelined = false;
     std::vector<uint32_t> t32host;              // contig / genome tables (kept alive for the async copy)
-    cudaEvent_t ev[8]{};
+    cudaEvent_t ev[10]{};
     std::vector<HostGenome> genomes;
     // layout (host)
     std::vector<uint32_t> cWordStart, cLen, cGenome, cVirt, gWordStart, gFirstContig, gNumContigs, gVirtLen;
@@ -1378,7 +1378,9 @@ static int stage0(pfb_ctx *ctx) {
             k_build_filter<<<nblk(NB, 256), 256, 0, st>>>(k, 1); ctx->launches++;
         }
         if (!piped) {
+            CK(cudaEventRecord(ctx->ev[7], st));
             if (nG > 1) scan_range(W1, W, C1, (uint32_t)ctx->cLen.size(), (uint32_t)nG - 1);
+            CK(cudaEventRecord(ctx->ev[8], st));
         } else {
             // the other genomes are encoded and scanned in batches of ~16 MB as their H2D copies land
             // (the copies run on their own stream, see upload_impl)
@@ -1472,6 +1474,14 @@ static int stage2(pfb_ctx *ctx) {
     cudaEventElapsedTime(&t.ms_first, ctx->ev[3], ctx->ev[4]);
     cudaEventElapsedTime(&t.ms_scan, ctx->ev[4], ctx->ev[5]);
     cudaEventElapsedTime(&t.ms_finalize, ctx->ev[5], ctx->ev[6]);
+    t.ms_scan_main = 0.f;
+    t.scan_main_bases = 0;
+    if (!ctx->pipelined && ctx->nslots && ctx->genomes.size() > 1 && cudaEventElapsedTime(&t.ms_scan_main, ctx->ev[7], ctx->ev[8]) == cudaSuccess) {
+        for (size_t g = 1; g < ctx->genomes.size(); g++) t.scan_main_bases += ctx->genomes[g].n_bases;
+    } else {
+        t.ms_scan_main = 0.f;
+        cudaGetLastError();
+    }
     cudaEventElapsedTime(&t.ms_total, ctx->ev[2], ctx->ev[6]);
     uint64_t nb = 0, nw = 0;
     for (auto &g : ctx->genomes) {
