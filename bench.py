@@ -183,7 +183,7 @@ def main():
     import torch
     import torch.distributed as dist
     from primerforge_b200 import _lib, synth
-    from primerforge_b200.dist import allreduce_stage_buffers
+    from primerforge_b200.dist import allreduce_stage_buffers, run_sharded
     from primerforge_b200.engine import Engine
 
     rank = int(os.environ.get("RANK", "0"))
@@ -286,8 +286,7 @@ def main():
         if world == 1:
             eng.run()                 # pfb_run: H2D copies overlapped with the key-table build and the scan
         else:
-            eng.upload()
-            compute_once()
+            run_sharded(eng, upload=True)
         rec, pos = fetch_results()
         eng.sync()
         dt = time.perf_counter() - t0

@@ -114,6 +114,11 @@ int  pfb_clear_genomes(pfb_ctx *ctx);
 int  pfb_upload(pfb_ctx *ctx);
 int  pfb_compute(pfb_ctx *ctx);
 int  pfb_run(pfb_ctx *ctx);
+/* the two halves of pfb_run's overlap for callers that drive the stages themselves (multi-GPU): the copies
+ * are queued on a second stream, pfb_compute_stage(0) consumes each genome as it lands, pfb_upload_wait
+ * returns when the host buffers may be reused */
+int  pfb_upload_async(pfb_ctx *ctx);
+int  pfb_upload_wait(pfb_ctx *ctx);
 
 /* multi-GPU (one context per rank; genome 0 is added on every rank, the other genomes are
  * sharded): pfb_compute == stage 0,1,2.  Between stage 0 and 1 the caller min-reduces the

@@ -26,7 +26,7 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", 
 
 # every symbol include/pfb200.h declares
 EXPORTS = ["pfb_create", "pfb_destroy", "pfb_last_error", "pfb_default_params", "pfb_add_genome",
-           "pfb_clear_genomes", "pfb_upload", "pfb_compute", "pfb_run", "pfb_compute_stage",
+           "pfb_clear_genomes", "pfb_upload", "pfb_upload_async", "pfb_upload_wait", "pfb_compute", "pfb_run", "pfb_compute_stage",
            "pfb_device_buffer", "pfb_sync", "pfb_result_counts", "pfb_result_records",
            "pfb_result_positions", "pfb_result_picked", "pfb_host_alloc", "pfb_host_free", "pfb_timings", "pfb_set_scan_mode", "pfb_oligo_tm"]
 
@@ -83,7 +83,7 @@ def load():
     lib.pfb_default_params.argtypes = [C.POINTER(PfbParams)]
     lib.pfb_add_genome.argtypes = [vp, vp, u64, vp, u32]
     lib.pfb_clear_genomes.argtypes = [vp]
-    for fn in ("pfb_upload", "pfb_compute", "pfb_run", "pfb_sync"):
+    for fn in ("pfb_upload", "pfb_upload_async", "pfb_upload_wait", "pfb_compute", "pfb_run", "pfb_sync"):
         getattr(lib, fn).argtypes = [vp]
     lib.pfb_compute_stage.argtypes = [vp, i32]
     lib.pfb_device_buffer.argtypes = [vp, i32, C.POINTER(vp), C.POINTER(u64)]

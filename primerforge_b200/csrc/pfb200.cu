@@ -1281,6 +1281,20 @@ static int upload_impl(pfb_ctx *ctx, bool async) {
 
 int pfb_upload(pfb_ctx *ctx) { return upload_impl(ctx, false); }
 
+int pfb_upload_async(pfb_ctx *ctx) { return upload_impl(ctx, true); }
+
+int pfb_upload_wait(pfb_ctx *ctx) {
+    if (!ctx) return PFB_EINVAL;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->copyStream));
+    if (ctx->pipelined) {
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]) == cudaSuccess) ctx->tm.ms_upload = ms; else cudaGetLastError();
+    }
+    ctx->pipelined = false;
+    return PFB_OK;
+}
+
 static int stage0(pfb_ctx *ctx) {
     const pfb_params &P = ctx->prm;
     cudaStream_t st = ctx->stream;
@@ -1521,14 +1535,8 @@ int pfb_run(pfb_ctx *ctx) {
     int rc = upload_impl(ctx, true);
     if (rc != PFB_OK) return rc;
     rc = pfb_compute(ctx);
-    cudaStreamSynchronize(ctx->copyStream);     // the host buffers are borrowed until here, success or not
-    if (rc == PFB_OK) {
-        float ms = 0;
-        cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]);
-        ctx->tm.ms_upload = ms;
-    }
-    ctx->pipelined = false;
-    return rc;
+    int rc2 = pfb_upload_wait(ctx);             // the host buffers are borrowed until here, success or not
+    return rc != PFB_OK ? rc : rc2;
 }
 
 int pfb_device_buffer(pfb_ctx *ctx, int which, void **dev_ptr, uint64_t *n_bytes) {

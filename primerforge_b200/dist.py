@@ -48,11 +48,16 @@ def allreduce_stage_buffers(eng, which: int, op: str):
     torch.cuda.current_stream().synchronize()
 
 
-def run_sharded(eng):
-    """the three compute stages with the two reductions in between"""
+def run_sharded(eng, upload: bool = False):
+    """the three compute stages with the two reductions in between; with upload=True the H2D copies of
+    the rank's genomes are queued first and overlap stage 0"""
     from . import _lib
+    if upload:
+        eng.upload_async()
     eng.compute_stage(0)
     allreduce_stage_buffers(eng, _lib.PFB_BUF_ALIVE, "min")
     eng.compute_stage(1)
     allreduce_stage_buffers(eng, _lib.PFB_BUF_PICK, "max")
     eng.compute_stage(2)
+    if upload:
+        eng.upload_wait()

@@ -145,6 +145,12 @@ class Engine:
     def upload(self):
         self._check(self._lib.pfb_upload(self._ctx))
 
+    def upload_async(self):
+        self._check(self._lib.pfb_upload_async(self._ctx))
+
+    def upload_wait(self):
+        self._check(self._lib.pfb_upload_wait(self._ctx))
+
     def compute(self):
         self._check(self._lib.pfb_compute(self._ctx))
 

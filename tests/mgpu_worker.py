@@ -24,8 +24,7 @@ def main():
     eng = Engine(device=local)
     for gi in mine:
         eng.add_genome(gens[gi].contigs)
-    eng.upload()
-    run_sharded(eng)
+    run_sharded(eng, upload=True)
     rec, ss, ct = eng.result_picked()
     rec, ss = rec.copy(), ss.copy()
     ct = None if ct is None else ct.copy()
