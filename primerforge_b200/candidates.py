@@ -17,7 +17,7 @@ import time
 import numpy as np
 
 from . import _lib, seqio
-from .engine import ERR_NO_CANDIDATES, ERR_NO_SHARED, Engine, PfbError, words_to_strings
+from .engine import ERR_NO_CANDIDATES, ERR_NO_SHARED, Engine, PfbError, StageResult, words_to_strings
 from .primer import make_primer, primer_class
 
 _GAP = " " * 4
@@ -107,8 +107,9 @@ def build_output(names, contig_ids, records, positions, kmers, thal_values=None)
 
 
 def run_stage(genomes, *, k_min=16, k_max=20, min_gc=40.0, max_gc=60.0, min_tm=55.0, max_tm=68.0, max_repeat=4,
-              table_size=9999991, prefilter=True, device=0, scan_mode=0):
-    """genomes: list of (contig id list, list of uint8 ASCII arrays).  Returns (StageResult, engine timing)."""
+              table_size=9999991, prefilter=True, device=0, scan_mode=0, picked_only=False):
+    """genomes: list of (contig id list, list of uint8 ASCII arrays).  Returns a StageResult; with
+    picked_only it holds just the picked records (the compact D2H path of pfb_result_picked)."""
     with Engine(device=device, k_min=k_min, k_max=k_max, min_gc=min_gc, max_gc=max_gc, min_tm=min_tm, max_tm=max_tm,
                 max_repeat=max_repeat, table_size=table_size, prefilter=int(bool(prefilter))) as eng:
         eng.set_scan_mode(scan_mode)
@@ -118,7 +119,20 @@ def run_stage(genomes, *, k_min=16, k_max=20, min_gc=40.0, max_gc=60.0, min_tm=5
         n, _ = eng.counts()
         if n == 0:
             raise RuntimeError(ERR_NO_SHARED)
-        return eng.result()
+        if not picked_only:
+            return eng.result()
+        rec, ss, ct = eng.result_picked()
+        positions = []
+        for g in range(eng.n_genomes):
+            pos = np.zeros(rec.size, dtype=_lib.POS_DTYPE)
+            pos["start"] = ss[g] & 0x7FFFFFFF
+            pos["strand"] = ss[g] >> 31
+            if ct is not None:
+                pos["contig"] = ct[g]
+            positions.append(pos)
+        res = StageResult(records=rec.copy(), positions=positions, timing=eng.timing())
+        res.timing["n_shared_reported"] = n
+        return res
 
 
 def _getAllCandidateKmers(params, sharedExists: bool, thal="auto", device: int | None = None):
@@ -145,7 +159,8 @@ def _getAllCandidateKmers(params, sharedExists: bool, thal="auto", device: int |
         genomes.append((ids, contigs))
     try:
         res = run_stage(genomes, k_min=params.minLen, k_max=params.maxLen, min_gc=params.minGc, max_gc=params.maxGc,
-                        min_tm=params.minTm, max_tm=params.maxTm, max_repeat=params.maxRepeatLen, device=device)
+                        min_tm=params.minTm, max_tm=params.maxTm, max_repeat=params.maxRepeatLen, device=device,
+                        picked_only=thal_fn is None)
     except RuntimeError as exc:
         if str(exc) == ERR_NO_SHARED:
             log.error(ERR_NO_SHARED)
@@ -153,7 +168,7 @@ def _getAllCandidateKmers(params, sharedExists: bool, thal="auto", device: int |
     print(f"done {time.time() - t0:.2f}s")
     log.info(f"{_GAP}done {time.time() - t0:.2f}s")
 
-    msg2 = f"{_GAP}evaluating {res.records.size} kmers"
+    msg2 = f"{_GAP}evaluating {res.timing.get('n_shared_reported', res.records.size)} kmers"
     log.info(msg2)
     print(msg2, end=" ... ", flush=True)
     t1 = time.time()

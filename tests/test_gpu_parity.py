@@ -300,3 +300,76 @@ def test_pipelined_run_equals_upload_then_compute():
     assert a.records.size > 0 and np.array_equal(a.records, b.records)
     for pa, pb in zip(a.positions, b.positions):
         assert np.array_equal(pa, pb)
+
+
+def _random_case(seed):
+    from primerforge_b200 import synth
+    rng = np.random.default_rng(seed)
+    n_g = int(rng.integers(1, 6))
+    length = int(rng.integers(2_000, 30_000))
+    n_contigs = int(rng.choice([1, 1, 2, 5, 12]))
+    k_min = int(rng.integers(8, 30))
+    k_max = int(min(32, k_min + rng.integers(0, 8)))
+    table = int(rng.choice([4093, 20011, 65521, 1000003, 9999991, 16777259]))     # the last one is > 2^24
+    kw = dict(k_min=k_min, k_max=k_max, max_repeat=int(rng.integers(2, 6)), table_size=table,
+              min_gc=float(rng.choice([30.0, 40.0])), max_gc=float(rng.choice([60.0, 70.0])),
+              min_tm=float(rng.choice([45.0, 55.0])), max_tm=float(rng.choice([68.0, 80.0])))
+    gens = synth.make_genomes(n_g, length, seed=1000 + seed, snp_rate=float(rng.choice([0.0, 0.002, 0.01])),
+                              n_inversions=int(rng.integers(0, 4)), n_contigs=n_contigs,
+                              n_frac=float(rng.choice([0.0, 0.0, 0.001])))
+    if rng.random() < 0.3 and n_g > 1:            # a genome with ragged tiny contigs
+        a = gens[-1].contigs[0]
+        cut = [0, 3, 3, 10, int(a.size // 2), int(a.size // 2) + k_min - 1, a.size]
+        pieces = [a[cut[i]:cut[i + 1]] for i in range(len(cut) - 1)] + gens[-1].contigs[1:]
+        gens[-1].contigs = [np.ascontiguousarray(x) for x in pieces]
+        gens[-1].contig_ids = [f"r{i}" for i in range(len(pieces))]
+    return gens, kw
+
+
+@pytest.mark.parametrize("seed", range(24))
+def test_randomised_differential(seed):
+    """random small configurations (lengths, contig counts, k ranges up to 32, table sizes on both sides
+    of 2^24, N bases, ragged contigs, duplicated genomes) against the oracle, both scan kernels"""
+    from oracle import pf_oracle as po
+    gens, kw = _random_case(seed)
+    o = po.run(gens, po.default_params(**kw))
+    for scan_mode in (1, 2):
+        for prefilter in (False, True):
+            try:
+                res, _ = _run(gens, kw, prefilter, scan_mode)
+            except Exception as exc:      # no shared k-mer at all: both sides must agree
+                assert o.n_shared == 0 or (prefilter and not ((o.flags & 7) == 7).any()), exc
+                continue
+            keep = np.ones(o.n_shared, bool) if not prefilter else (o.flags & 7) == 7
+            rec = res.records
+            assert rec.size == int(keep.sum())
+            assert np.array_equal(rec["word"], o.word[keep]) and np.array_equal(rec["k"], o.k[keep])
+            assert np.array_equal(rec["flags"] & 15, o.flags[keep])
+            assert np.array_equal(rec["tm"], o.tm[keep])
+            for gi in range(len(gens)):
+                pos = res.positions[gi]
+                assert np.array_equal(pos["contig"].astype(np.int32), o.contig[gi][keep])
+                assert np.array_equal(pos["start"].astype(np.int64), o.start[gi][keep])
+                assert np.array_equal(pos["strand"].astype(np.uint8), o.strand[gi][keep])
+
+
+def test_genome_too_large_is_refused():
+    from primerforge_b200 import _lib
+    from primerforge_b200.engine import Engine, PfbError
+    big = np.full((1 << 26) + 64, ord("A"), dtype=np.uint8)
+    with Engine(device=0) as eng:
+        eng.add_genome([big])
+        with pytest.raises(PfbError) as exc:
+            eng.upload()
+        assert exc.value.code == _lib.PFB_ETOOLARGE
+
+
+def test_identical_genomes_and_single_genome():
+    from oracle import pf_oracle as po
+    from primerforge_b200 import synth
+    g = synth.make_genomes(1, 30_000, seed=555)[0]
+    kw = dict(k_min=16, k_max=20, min_gc=40.0, max_gc=60.0, min_tm=55.0, max_tm=68.0, max_repeat=4, table_size=9999991)
+    for gens in ([g], [g, g, g]):
+        o = po.run(gens, po.default_params(**kw))
+        res, _ = _run(gens, kw, False)
+        assert np.array_equal(res.records["word"], o.word) and np.array_equal(res.records["flags"] & 15, o.flags)
