@@ -72,6 +72,7 @@ struct K {  // kernel arguments (by value, __grid_constant__)
     double ln_salt, ln_dna4, ln_dna1, dmso_term;
     uint64_t gc_ok[33];       // per k: bit c set <=> gc count c is inside [minGc, maxGc]
     const double *fterm;      // [33][33] formamide term per (k, gc count)
+    const float4 *tmb;        // [33][33] Tm window as two lines in (ds, dh): dh >= x*ds + y and dh <= z*ds + w
     // arena
     const uint8_t *raw;
     uint64_t *seq2;
@@ -150,20 +151,22 @@ __device__ __forceinline__ double tm_from_sums(uint32_t acc, uint64_t h, int k, 
     return tm;
 }
 
-// minTm <= Tm <= maxTm (:305-307), decided in fp32 when the fp32 value is clear of both bounds by
-// more than 0.01 degC (its error is < 1e-3) and with the exact fp64 formula otherwise, so the decision
-// is always the one the fp64 formula makes
-__device__ __noinline__ bool tm_in_range(uint32_t acc, uint64_t h, int k, int gc, const K &p) {
-    int first = (int)((h >> (2 * k - 2)) & 3), last = (int)(h & 3);
-    int dh = (int)(acc & 0xFFFF) + (first < 2 ? -23 : -1) + (last < 2 ? -23 : -1);
-    int ds = (int)(acc >> 16) + (first < 2 ? -41 : 28) + (last < 2 ? -41 : 28);
-    float denom = -0.1f * (float)ds + (0.368f * (float)(k - 1) * (float)p.ln_salt + 1.987f * (float)p.ln_dna4);
-    float tmf = __fdividef(-100.0f * (float)dh, denom) - 273.15f - (float)p.dmso_term + (float)p.fterm[k * 33 + gc];
-    float lo = (float)p.min_tm, hi = (float)p.max_tm;
-    bool palin_possible = (k & 1) == 0;          // self-complementary oligos use other constants: exact path
-    if (!palin_possible || (rc64(h) >> (64 - 2 * k)) != h) {
-        if (tmf < lo - 0.01f || tmf > hi + 0.01f) return false;
-        if (tmf > lo + 0.01f && tmf < hi - 0.01f) return true;
+// minTm <= Tm <= maxTm (:305-307).  For a fixed length and GC count, Tm >= t is the half plane
+// dh >= a * ds + b of the integer nearest-neighbour sums (the denominator of the formula is negative), so
+// the window test is two fused multiply-adds against a per-(k, gc) table.  dh is an integer: unless it is
+// within 0.02 of a bound the fp32 evaluation (error < 1e-3) decides; otherwise -- and for oligos that
+// could be self-complementary, which use another constant -- the exact fp64 formula does, so the
+// decision is always the one the fp64 formula makes.
+__device__ __forceinline__ bool tm_in_range(uint32_t acc, uint64_t h, int k, int gc, const K &p) {
+    const uint32_t first = (uint32_t)(h >> (2 * k - 2)) & 3u, last = (uint32_t)h & 3u;
+    const int dh = (int)(acc & 0xFFFF) + (first < 2 ? -23 : -1) + (last < 2 ? -23 : -1);
+    const int ds = (int)(acc >> 16) + (first < 2 ? -41 : 28) + (last < 2 ? -41 : 28);
+    if ((k & 1) || (first ^ last) != 1u) {        // ends not complementary: cannot be a palindrome
+        const float4 b = __ldg(&p.tmb[k * 33 + gc]);
+        const float x = (float)ds, d = (float)dh;
+        const float lo = fmaf(b.x, x, b.y), hi = fmaf(b.z, x, b.w);
+        if (d < lo - 0.02f || d > hi + 0.02f) return false;
+        if (d > lo + 0.02f && d < hi - 0.02f) return true;
     }
     double tm = tm_from_sums(acc, h, k, gc, p);
     return tm >= p.min_tm && tm <= p.max_tm;
@@ -1057,7 +1060,10 @@ int validate(const pfb_params *p, std::string &why) {
 
 // constants of oligotm() and the GC window, computed with the host libm / IEEE doubles exactly like
 // the reference's C and Python code does
+// fterm upload: 33*33 doubles, then (16-byte aligned) 33*33 float4 Tm window lines
+constexpr size_t TMB_OFF = 33 * 33 + 1, FTERM_DOUBLES = TMB_OFF + 33 * 33 * 2;
 void fill_filter_constants(const pfb_params &P, K &k, std::vector<double> &fterm) {
+    // fterm holds 33*33 doubles followed by 33*33 float4 (the Tm window lines), one upload
     double dv = P.dv_conc, dntp = P.dntp_conc;
     if (dv == 0) dntp = 0;
     if (dv < dntp) dv = dntp;
@@ -1067,13 +1073,21 @@ void fill_filter_constants(const pfb_params &P, K &k, std::vector<double> &fterm
     k.ln_dna1 = std::log(P.dna_conc / 1000000000.0);
     k.dmso_term = P.dmso_conc * P.dmso_fact;
     k.min_tm = P.min_tm; k.max_tm = P.max_tm;
-    fterm.assign(33 * 33, 0.0);
+    fterm.assign(FTERM_DOUBLES, 0.0);
+    float *tmb = reinterpret_cast<float *>(fterm.data() + TMB_OFF);
     for (int kk = 1; kk <= 32; kk++) {
         uint64_t ok = 0;
         for (int gc = 0; gc <= kk; gc++) {
             double per = (double)gc / kk * 100;                                   // Primer.py:100
             if (per >= P.min_gc && per <= P.max_gc) ok |= 1ull << gc;              // getCandidateKmers.py:303
             fterm[kk * 33 + gc] = (0.453 * ((double)gc / kk) - 2.88) * P.formamide_conc;
+            // Tm >= t  <=>  dh >= 0.001 T ds - T A / 100 with T = t + 273.15 + dmso - fterm, A = salt and DNA terms
+            const double A = 0.368 * (kk - 1) * k.ln_salt + 1.987 * k.ln_dna4;
+            const double c = 273.15 + k.dmso_term - fterm[kk * 33 + gc];
+            const double Tmin = P.min_tm + c, Tmax = P.max_tm + c;
+            float *o = tmb + (size_t)(kk * 33 + gc) * 4;
+            o[0] = (float)(0.001 * Tmin); o[1] = (float)(-Tmin * A / 100.0);
+            o[2] = (float)(0.001 * Tmax); o[3] = (float)(-Tmax * A / 100.0);
         }
         k.gc_ok[kk] = ok;
     }
@@ -1321,18 +1335,19 @@ static int stage0(pfb_ctx *ctx) {
     if ((rc = ensure(ctx, ctx->sk, (size_t)NB * 2 * 4)) != PFB_OK) return rc;
     if ((rc = ensure(ctx, ctx->br, (size_t)NB * 8)) != PFB_OK) return rc;
     if ((rc = ensure(ctx, ctx->filter, (size_t)nk * FILTER_BYTES)) != PFB_OK) return rc;
-    if ((rc = ensure(ctx, ctx->fterm, 33 * 33 * 8)) != PFB_OK) return rc;
+    if ((rc = ensure(ctx, ctx->fterm, FTERM_DOUBLES * 8)) != PFB_OK) return rc;
     if ((rc = ensure(ctx, ctx->misc, 4096)) != PFB_OK) return rc;
     if ((rc = ensure(ctx, ctx->emitMask, (size_t)W1 * 32 * 4 + 4)) != PFB_OK) return rc;
     if ((rc = ensure(ctx, ctx->emitOff, (size_t)W1 * 32 * 4 + 4)) != PFB_OK) return rc;
     k.seq2 = (uint64_t *)ctx->seq2.p; k.nmask = (uint32_t *)ctx->nmask.p; k.wordContig = (uint32_t *)ctx->wordContig.p;
     k.sk = (uint32_t *)ctx->sk.p; k.br = (uint2 *)ctx->br.p;
     k.filter = (uint32_t *)ctx->filter.p; k.fterm = (const double *)ctx->fterm.p;
+    k.tmb = (const float4 *)((const double *)ctx->fterm.p + TMB_OFF);
     uint32_t *misc = (uint32_t *)ctx->misc.p;   // [0] nslots, [1] nrec, [2] npick
     k.emitMask = (uint32_t *)ctx->emitMask.p; k.emitOff = (uint32_t *)ctx->emitOff.p;
 
     CK(cudaEventRecord(ctx->ev[2], st));
-    CK(cudaMemcpyAsync(ctx->fterm.p, fterm.data(), 33 * 33 * 8, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(ctx->fterm.p, fterm.data(), FTERM_DOUBLES * 8, cudaMemcpyHostToDevice, st));
     CK(cudaMemsetAsync(ctx->misc.p, 0, 4096, st));
     CK(cudaMemsetAsync(ctx->sk.p, 0, (size_t)NB * 2 * 4, st));
     const size_t nG = ctx->genomes.size();
@@ -1653,10 +1668,11 @@ int pfb_oligo_tm(pfb_ctx *ctx, const char *seq, double *tm, double *gc_percent) 
     std::vector<double> fterm;
     fill_filter_constants(ctx->prm, k, fterm);
     int rc;
-    if ((rc = ensure(ctx, ctx->fterm, 33 * 33 * 8)) != PFB_OK) return rc;
+    if ((rc = ensure(ctx, ctx->fterm, FTERM_DOUBLES * 8)) != PFB_OK) return rc;
     if ((rc = ensure(ctx, ctx->misc, 4096)) != PFB_OK) return rc;
     k.fterm = (const double *)ctx->fterm.p;
-    CK(cudaMemcpyAsync(ctx->fterm.p, fterm.data(), 33 * 33 * 8, cudaMemcpyHostToDevice, ctx->stream));
+    k.tmb = (const float4 *)((const double *)ctx->fterm.p + TMB_OFF);
+    CK(cudaMemcpyAsync(ctx->fterm.p, fterm.data(), FTERM_DOUBLES * 8, cudaMemcpyHostToDevice, ctx->stream));
     double *d = (double *)((uint8_t *)ctx->misc.p + 3072);
     k_oligo<<<1, 1, 0, ctx->stream>>>(k, h, (int)n, d);
     double hres[2];
