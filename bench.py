@@ -141,13 +141,20 @@ def run_reference_arm(args, emit):
     emit(line)
 
 
-def workload_config(index: int, n_gpus: int) -> dict:
+def workload_config(index: int, n_gpus: int, strong: bool = False) -> dict:
     from primerforge_b200 import synth
+    from primerforge_b200.dist import shard_genomes
     cfg = synth.CONFIGS[index]
-    per_rank = cfg["n_genomes"]
-    total = per_rank if n_gpus == 1 else 1 + (per_rank - 1) * n_gpus
-    return {"workload": f"BASELINE config {index}: {per_rank} synthetic {cfg['length'] / 1e6:g} Mbp ingroup genomes per GPU "
-                        f"({total} distinct genomes in the job), primer_len {cfg['k_min']},{cfg['k_max']}, default GC/Tm, "
+    if strong and n_gpus > 1:
+        total = cfg["n_genomes"]
+        per_rank = len(shard_genomes(total, n_gpus, 0))
+        shape = f"{total} synthetic {cfg['length'] / 1e6:g} Mbp ingroup genomes in total, genome 0 on every GPU + {per_rank - 1} others per GPU"
+    else:
+        per_rank = cfg["n_genomes"]
+        total = per_rank if n_gpus == 1 else 1 + (per_rank - 1) * n_gpus
+        shape = (f"{per_rank} synthetic {cfg['length'] / 1e6:g} Mbp ingroup genomes per GPU "
+                 f"({total} distinct genomes in the job)")
+    return {"workload": f"BASELINE config {index}: {shape}, primer_len {cfg['k_min']},{cfg['k_max']}, default GC/Tm, "
                         f"max_repeats {cfg['max_repeats']}, {cfg['n_contigs']} contig(s) per genome",
             "genomes_per_gpu": per_rank, "distinct_genomes": total, "genome_bp": cfg["length"], "k_min": cfg["k_min"],
             "k_max": cfg["k_max"], "table_size": 9999991, "prefilter": 1, "l2": "flushed between steps (256 MiB write)",
@@ -166,13 +173,16 @@ def main():
 
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=60)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--config", type=int, default=2)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--genomes", type=int, default=None, help="override genomes per GPU (debug)")
     ap.add_argument("--length", type=int, default=None, help="override genome length (debug)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak (default): the config's genome count PER GPU; strong: the config's genome count in total, "
+                         "genome 0 on every rank and the others dealt round-robin")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
 
@@ -201,12 +211,21 @@ def main():
         cfg["n_genomes"] = args.genomes
     if args.length:
         cfg["length"] = args.length
-    per_rank = cfg["n_genomes"]
-    n_distinct = per_rank if world == 1 else 1 + (per_rank - 1) * world
-    # the generator is sequential in the genome index: every rank generates the prefix it needs
-    last_needed = per_rank if world == 1 else 1 + (per_rank - 1) * (rank + 1)
-    gens = synth.make_genomes(last_needed, cfg["length"], seed=synth.BASE_SEED + args.config, n_contigs=cfg["n_contigs"])
-    mine = gens[:per_rank] if world == 1 else [gens[0]] + gens[1 + (per_rank - 1) * rank: 1 + (per_rank - 1) * (rank + 1)]
+    strong = args.scaling == "strong" and world > 1
+    if strong:
+        from primerforge_b200.dist import shard_genomes
+        n_distinct = cfg["n_genomes"]
+        idx = shard_genomes(n_distinct, world, rank)
+        per_rank = len(shard_genomes(n_distinct, world, 0))          # the largest shard
+        gens = synth.make_genomes(max(idx) + 1, cfg["length"], seed=synth.BASE_SEED + args.config, n_contigs=cfg["n_contigs"])
+        mine = [gens[i] for i in idx]
+    else:
+        per_rank = cfg["n_genomes"]
+        n_distinct = per_rank if world == 1 else 1 + (per_rank - 1) * world
+        # the generator is sequential in the genome index: every rank generates the prefix it needs
+        last_needed = per_rank if world == 1 else 1 + (per_rank - 1) * (rank + 1)
+        gens = synth.make_genomes(last_needed, cfg["length"], seed=synth.BASE_SEED + args.config, n_contigs=cfg["n_contigs"])
+        mine = gens[:per_rank] if world == 1 else [gens[0]] + gens[1 + (per_rank - 1) * rank: 1 + (per_rank - 1) * (rank + 1)]
     del gens
     distinct_bases = n_distinct * cfg["length"]
 
@@ -232,15 +251,28 @@ def main():
             dist.barrier()
             torch.cuda.synchronize()
 
+    xchg = {"ms": [], "bytes": 0}
+    if world > 1:
+        ext = torch.cuda.ExternalStream(eng.stream_handle(), device=torch.device("cuda", local))
+        xev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+
     def compute_once():
         if world == 1:
             eng.compute()
         else:
+            # the two reductions are enqueued on the library's stream between the stages (no host waits);
+            # CUDA events on that stream time them
             eng.compute_stage(0)
+            xev[0].record(ext)
             allreduce_stage_buffers(eng, _lib.PFB_BUF_ALIVE, "min")
+            xev[1].record(ext)
             eng.compute_stage(1)
+            xev[2].record(ext)
             allreduce_stage_buffers(eng, _lib.PFB_BUF_PICK, "max")
+            xev[3].record(ext)
             eng.compute_stage(2)
+            xchg["ms"].append(xev[0].elapsed_time(xev[1]) + xev[2].elapsed_time(xev[3]))
+            xchg["bytes"] = eng.device_buffer(_lib.PFB_BUF_ALIVE)[1] + eng.device_buffer(_lib.PFB_BUF_PICK)[1]
 
     def fetch_results():
         rec, ss, ct = eng.result_picked()     # pinned host buffers, plain D2H copies
@@ -335,14 +367,24 @@ def main():
                                    "windows_per_s_G": windows / (ms_scan / 1e3) / 1e9 if ms_scan > 0 else 0.0,
                                    "evidence": "profiles/r01_scan_ablation.md, profiles/r01_v8_scan_filtered_ncu_raw.csv"}}
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64",
-            "data": "synthetic", "config": workload_config(args.config, world) | ({"genomes_per_gpu": per_rank, "genome_bp": cfg["length"]}),
+            "ms_per_step": step_ms, "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": "u64",
+            "data": "synthetic", "config": workload_config(args.config, world, strong) | ({"genomes_per_gpu": per_rank, "genome_bp": cfg["length"]}),
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_ms},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
             "phases_ms": {"ms_encode": float(np.mean(enc_ms)), "ms_first": float(np.mean(first_ms)), "ms_scan": float(np.mean(scan_ms)),
                           "ms_finalize": float(np.mean(fin_ms)), "ms_total": step_ms},
             "counts": dev_counts,
             "wall_s_timed_loop": wall}
+    if world > 1 and xchg["ms"]:
+        # ring all-reduce: every rank sends and receives 2 (N - 1) / N of the buffer per direction
+        ms_x = float(np.mean(xchg["ms"][-args.steps:]))
+        wire = 2.0 * (world - 1) / world * xchg["bytes"]
+        line["exchange"] = {"what": "MIN all-reduce of the per-key alive bytes + MAX all-reduce of the pick words (NCCL, on the library's stream)",
+                            "bytes_reduced_per_rank": int(xchg["bytes"]), "ms_per_step": ms_x,
+                            "wire_GBs_per_direction": wire / (ms_x / 1e3) / 1e9 if ms_x > 0 else None,
+                            "nvlink_peak_GBs_per_direction": 900.0,
+                            "frac_of_nvlink": wire / (ms_x / 1e3) / 1e9 / 900.0 if ms_x > 0 else None,
+                            "note": "latency-bound: ~6 MB per step; no k-mer crosses NVLink (DESIGN.md section 5)"}
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"], _ = cpu_sample_run(args.config)
     emit(line)

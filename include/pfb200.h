@@ -128,6 +128,10 @@ int  pfb_compute_stage(pfb_ctx *ctx, int stage);
 #define PFB_BUF_PICK  1   /* uint32 [n_records], 0 / 1 (reduce it as bytes or as words) */
 int  pfb_device_buffer(pfb_ctx *ctx, int which, void **dev_ptr, uint64_t *n_bytes);
 int  pfb_sync(pfb_ctx *ctx);
+/* the CUDA stream (cudaStream_t) every kernel of this context is launched on: a caller that enqueues its
+ * reductions on this stream (NCCL, or torch.cuda.ExternalStream) needs no host synchronisation between the
+ * stages */
+int  pfb_stream(pfb_ctx *ctx, void **stream_out);
 
 /* output ---------------------------------------------------------------------------------- */
 int  pfb_result_counts(pfb_ctx *ctx, uint64_t *n_records, uint64_t *n_picked);

@@ -27,7 +27,7 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", 
 # every symbol include/pfb200.h declares
 EXPORTS = ["pfb_create", "pfb_destroy", "pfb_last_error", "pfb_default_params", "pfb_add_genome",
            "pfb_clear_genomes", "pfb_upload", "pfb_upload_async", "pfb_upload_wait", "pfb_compute", "pfb_run", "pfb_compute_stage",
-           "pfb_device_buffer", "pfb_sync", "pfb_result_counts", "pfb_result_records",
+           "pfb_device_buffer", "pfb_sync", "pfb_stream", "pfb_result_counts", "pfb_result_records",
            "pfb_result_positions", "pfb_result_picked", "pfb_host_alloc", "pfb_host_free", "pfb_timings", "pfb_set_scan_mode", "pfb_oligo_tm"]
 
 
@@ -87,6 +87,7 @@ def load():
         getattr(lib, fn).argtypes = [vp]
     lib.pfb_compute_stage.argtypes = [vp, i32]
     lib.pfb_device_buffer.argtypes = [vp, i32, C.POINTER(vp), C.POINTER(u64)]
+    lib.pfb_stream.argtypes = [vp, C.POINTER(vp)]
     lib.pfb_result_counts.argtypes = [vp, C.POINTER(u64), C.POINTER(u64)]
     lib.pfb_result_records.argtypes = [vp, vp, u64]
     lib.pfb_result_positions.argtypes = [vp, u32, i32, vp, u64]

@@ -51,6 +51,7 @@ namespace {
 constexpr uint64_t ROW_POS_MASK = 0x03FFFFFFull;   // leftmost start, genome-local padded coordinate
 constexpr uint64_t ROW_ONE = 1ull << 32;           // occupancy count lives in bits 32..59
 constexpr uint64_t ROW_CNT_MASK = 0x0FFFFFFFull;
+constexpr uint64_t ROW_MINUS = 1ull << 61;         // set by k_alive: the single occupant reads as the key's reverse complement
 constexpr uint64_t ROW_JF = 1ull << 62;            // forward-string-only polluter ('~' or non-ACGT window)
 constexpr uint64_t ROW_JR = 1ull << 63;            // reverse-string-only polluter
 constexpr uint32_t MAX_GENOME_WORDS = 1u << 21; // 2^26 padded bases
@@ -813,8 +814,14 @@ __global__ void __launch_bounds__(256) k_alive(const __grid_constant__ K p, uint
         uint64_t rc = rc64(key) >> (64 - 2 * k);
         bool pal = key == rc;
         ok = row_state(p, 0, v0, key, rc, k, pal, true) == (pal ? 2 : 1);
-        for (uint32_t g = 1; g < n_check && ok; g++)
-            ok = row_state(p, g, p.rows[(size_t)g * p.nslots + idx], key, rc, k, pal, false) != 0;
+        if (ok && pal) p.rows[idx] = v0 | ROW_MINUS;
+        for (uint32_t g = 1; g < n_check && ok; g++) {
+            unsigned long long *row = &p.rows[(size_t)g * p.nslots + idx];
+            const unsigned long long v = *row;
+            const int st = row_state(p, g, v, key, rc, k, pal, false);
+            ok = st != 0;
+            if (st == 2 && !(v & ROW_MINUS)) *row = v | ROW_MINUS;   // k_positions reads the strand from here
+        }
     }
     p.alive[idx] = ok ? 1 : 0;
 }
@@ -928,14 +935,17 @@ __global__ void __launch_bounds__(256) k_positions(const __grid_constant__ K p) 
     for (uint32_t g = 0; g < p.nGenomes; g++) {
         const unsigned long long v = p.rows[(size_t)g * p.nslots + rec.slot];
         const uint32_t lp = (uint32_t)(v & ROW_POS_MASK);
-        const uint32_t gw = p.gWordStart[g] + (lp >> 5);
-        const uint32_t c = p.wordContig[gw];
-        const uint32_t start = lp - 32u * (p.cWordStart[c] - p.gWordStart[g]);
         // '+' when the genome reads the key itself at that place, '-' when it reads its reverse complement;
-        // a palindrome matches both scans and the later '-' match overwrites (:181-187)
-        const uint32_t minus = ((rec.flags & PFB_F_PALIN) || window_at(p, g, lp, rec.k) != rec.word) ? 1u : 0u;
+        // a palindrome matches both scans and the later '-' match overwrites (:181-187): k_alive left the
+        // answer in the row
+        const uint32_t minus = (uint32_t)(v >> 61) & 1u;
+        uint32_t start = lp;                       // single-contig genomes: the padded coordinate is the start
+        if (p.multiContig) {
+            const uint32_t c = p.wordContig[p.gWordStart[g] + (lp >> 5)];
+            start = lp - 32u * (p.cWordStart[c] - p.gWordStart[g]);
+            p.posContig[(size_t)g * p.nrec + r] = c - p.gFirstContig[g];
+        }
         p.pos[(size_t)g * p.nrec + r] = start | (minus << 31);
-        if (p.multiContig) p.posContig[(size_t)g * p.nrec + r] = c - p.gFirstContig[g];
         if (pass && !picked) {
             bool first = true;
             if (overflow) {
@@ -1232,6 +1242,12 @@ int pfb_sync(pfb_ctx *ctx) {
     if (!ctx) return PFB_EINVAL;
     CK(cudaSetDevice(ctx->device));
     CK(cudaStreamSynchronize(ctx->stream));
+    return PFB_OK;
+}
+
+int pfb_stream(pfb_ctx *ctx, void **stream_out) {
+    if (!ctx || !stream_out) return PFB_EINVAL;
+    *stream_out = (void *)ctx->stream;
     return PFB_OK;
 }
 

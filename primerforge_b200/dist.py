@@ -37,15 +37,21 @@ def reduce_bytes(t, op: str):
 
 
 def allreduce_stage_buffers(eng, which: int, op: str):
-    """all-reduce one of the engine's per-key / per-record byte vectors in place (NCCL on device memory)"""
+    """all-reduce one of the engine's per-key / per-record byte vectors in place (NCCL on device memory).
+    The reduction is enqueued behind the stage's kernels on the engine's own stream (ExternalStream), so
+    the host never waits between the stages."""
     import torch
     ptr, n = eng.device_buffer(which)
     if n == 0:
         return
-    eng.sync()
-    t = torch.as_tensor(_DeviceBytes(ptr, n), device=torch.device("cuda", torch.cuda.current_device()))
-    reduce_bytes(t, op)
-    torch.cuda.current_stream().synchronize()
+    dev = torch.device("cuda", torch.cuda.current_device())
+    ext = getattr(eng, "_torch_stream", None)
+    if ext is None:
+        ext = torch.cuda.ExternalStream(eng.stream_handle(), device=dev)
+        eng._torch_stream = ext
+    t = torch.as_tensor(_DeviceBytes(ptr, n), device=dev)
+    with torch.cuda.stream(ext):
+        reduce_bytes(t, op)
 
 
 def run_sharded(eng, upload: bool = False):

@@ -172,6 +172,12 @@ class Engine:
         self._check(self._lib.pfb_device_buffer(self._ctx, which, C.byref(ptr), C.byref(n)))
         return ptr.value or 0, int(n.value)
 
+    def stream_handle(self) -> int:
+        """cudaStream_t of the context (for stream-ordered reductions between the stages)"""
+        ptr = C.c_void_p()
+        self._check(self._lib.pfb_stream(self._ctx, C.byref(ptr)))
+        return ptr.value or 0
+
     # -- output
     def counts(self):
         n, m = C.c_uint64(), C.c_uint64()
