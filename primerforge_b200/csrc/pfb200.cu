@@ -55,6 +55,7 @@ constexpr uint64_t ROW_MINUS = 1ull << 61;         // set by k_alive: the single
 constexpr uint64_t ROW_JF = 1ull << 62;            // forward-string-only polluter ('~' or non-ACGT window)
 constexpr uint64_t ROW_JR = 1ull << 63;            // reverse-string-only polluter
 constexpr uint32_t MAX_GENOME_WORDS = 1u << 21; // 2^26 padded bases
+constexpr uint32_t ID_NONE = 0xFFFFFFFFu;
 
 constexpr uint32_t FILTER_BYTES = 192u * 1024u; // shared-memory filter of k_scan_filtered
 constexpr uint32_t FILTER_BITS = FILTER_BYTES * 8u;
@@ -89,9 +90,23 @@ struct K {  // kernel arguments (by value, __grid_constant__)
     uint32_t *filter;         // [nk][FILTER_WORDS]
     uint32_t *emitMask;       // per genome-1 end position: bit per k = surviving key ending there
     uint32_t *emitOff;        // exclusive popcount prefix of emitMask = record index base
-    unsigned long long *rows; // [nGenomes][nslots]
-    uint64_t nslots;
-    uint8_t *alive;
+    // rows: genome 1's row is indexed by slot (bin order); after its scan the slots that are still unique
+    // there get an ID in the reference's dict order (genome-1 end position, longest first), and the rows of
+    // every other genome, the records and the coordinates are indexed by id: everything after the scan
+    // streams through memory in order
+    unsigned long long *rows0; // [nslots]
+    unsigned long long *rows;  // [nGenomes - 1][nids]
+    uint32_t *remap;           // [nslots] slot -> id, ID_NONE = not unique in genome 1
+    uint2 *at;                 // [nk][PW16] key table of the other genomes: per 16 bins (bitmap16 | id0:24 | id1:24)
+    uint32_t *ovf;             // [n][16] ids of the words that do not fit that format
+    uint32_t *ovfCount;
+    uint32_t PW16, ovfCap;
+    int first_pass;            // 1 while genome 1 itself is scanned (hits go to rows0[slot])
+    uint64_t nslots, nids;
+    uint64_t *key1;            // [nids] the k-mer as it reads on genome 1's (+) strand
+    uint32_t *idMeta;          // [nids] genome-1 start | (k - kmin) << 26
+    uint8_t *alive;            // [nids] 1 while unique in every genome checked so far
+    uint32_t *recIdx;          // [nids] exclusive prefix of alive = record index
     // output
     pfb_record *rec;
     uint32_t *pos;            // [nGenomes][nrec] start within contig | strand << 31
@@ -258,14 +273,39 @@ __global__ void __launch_bounds__(256) k_encode(const __grid_constant__ K p, uin
 
 // ------------------------------------------------------------------------------------------
 // bookkeeping of one probe hit (any window of genome g whose bin holds a key)
-__device__ __forceinline__ void on_hit(const K &p, uint32_t g, uint2 e, uint32_t bin, uint32_t start) {
-    atomicAdd(&p.rows[(size_t)g * p.nslots + slot_of(e, bin)], ROW_ONE | start);
+// Key lookup.  Genome 1 is scanned against `br` (bitmap word + popcount rank -> slot, rows0[slot]).  The other
+// genomes are scanned against `at`, built after genome 1's scan from the keys that are still alive: one
+// 8-byte word per 16 bins holding the bitmap of the alive keys and, inline, the ids of the first two of them
+// (ids follow the reference's dict order, not the bin order, so they cannot be a popcount rank).  With keys in
+// ~2 % of the bins more than two per 16 bins is rare (< 1 % of the words); those words carry AT_SLOW and the
+// index of a 16-entry id list.  One load, no dependent second load on the hot path.
+constexpr uint32_t AT_SLOW = 0xFFFFFFu;           // id0 field: "the ids are in ovf[e.y >> 8]"
+
+__device__ __forceinline__ uint2 probe2(const K &p, int ki, uint32_t bin) {
+    return __ldg(&p.at[(size_t)ki * p.PW16 + (bin >> 4)]);
+}
+
+// id of the alive key in bin (b16 = bin & 15) given its probe word, ID_NONE when the bin holds none
+__device__ __forceinline__ uint32_t id_of(const K &p, uint2 e, uint32_t b16) {
+    if (!((e.x >> b16) & 1u)) return ID_NONE;
+    const uint32_t id0 = (e.x >> 16) | ((e.y & 0xFFu) << 16);
+    if (id0 == AT_SLOW) return __ldg(&p.ovf[(size_t)(e.y >> 8) * 16u + b16]);
+    return (e.x & ((1u << b16) - 1u)) ? (e.y >> 8) : id0;
+}
+
+// the row a window of genome g in `bin` counts into (nullptr: no key there)
+__device__ __forceinline__ unsigned long long *row_of_bin(const K &p, int ki, uint32_t g, uint32_t bin) {
+    if (p.first_pass) {
+        const uint2 e = probe(p, ki, bin);
+        return probe_hit(e, bin) ? &p.rows0[slot_of(e, bin)] : nullptr;
+    }
+    const uint32_t id = id_of(p, probe2(p, ki, bin), bin & 15u);
+    return id == ID_NONE ? nullptr : &p.rows[(size_t)(g - 1) * p.nids + id];
 }
 
 __device__ __forceinline__ void pollute(const K &p, int ki, uint32_t g, uint64_t canon, bool rev_table) {
-    uint32_t bin = mod_p(canon, p);
-    uint2 e = probe(p, ki, bin);
-    if (probe_hit(e, bin)) atomicOr(&p.rows[(size_t)g * p.nslots + slot_of(e, bin)], rev_table ? ROW_JR : ROW_JF);
+    unsigned long long *row = row_of_bin(p, ki, g, mod_p(canon, p));
+    if (row) atomicOr(row, rev_table ? ROW_JR : ROW_JF);
 }
 
 // window with >= 1 non-ACGT byte: a strand-specific polluter.  The forward string hashes the byte as
@@ -403,8 +443,8 @@ __global__ void __launch_bounds__(256) k_scan_plain(const __grid_constant__ K p,
             if (wn) { pollute_invalid_window(p, ki, k, g, h, r, wn); continue; }
             uint64_t canon = h < r ? h : r;
             uint32_t bin = mod_p(canon, p);
-            uint2 e = probe(p, ki, bin);
-            if (probe_hit(e, bin)) on_hit(p, g, e, bin, gpos0 + j - k + 1);
+            unsigned long long *row = row_of_bin(p, ki, g, bin);
+            if (row) atomicAdd(row, ROW_ONE | (gpos0 + j - k + 1));
         }
     }
 }
@@ -446,15 +486,20 @@ struct Pending {
 
 __device__ __forceinline__ void drain_issue(const K &p, int ki, uint32_t q_addr, uint32_t head, uint32_t lane, Pending &pd) {
     uint4 it = lds128(q_addr + (((head + lane) & (QCAP - 1)) << 4));   // x = bin, y = start, z = genome
-    pd.e = probe(p, ki, it.x);
+    pd.e = p.first_pass ? probe(p, ki, it.x) : probe2(p, ki, it.x);
     pd.meta = it.y | ((it.x & 31u) << 26);
     pd.g = it.z;
 }
 
 __device__ __forceinline__ void drain_consume(const K &p, const Pending &pd) {
-    uint32_t b = pd.meta >> 26;
-    if ((pd.e.x >> b) & 1u)
-        atomicAdd(&p.rows[(size_t)pd.g * p.nslots + pd.e.y + __popc(pd.e.x & ((1u << b) - 1u))], ROW_ONE | (pd.meta & (uint32_t)ROW_POS_MASK));
+    const uint32_t b = pd.meta >> 26;          // bin & 31: all the two tables need of the bin besides the probe word
+    const unsigned long long add = ROW_ONE | (pd.meta & (uint32_t)ROW_POS_MASK);
+    if (p.first_pass) {
+        if ((pd.e.x >> b) & 1u) atomicAdd(&p.rows0[pd.e.y + __popc(pd.e.x & ((1u << b) - 1u))], add);
+    } else {
+        const uint32_t id = id_of(p, pd.e, b & 15u);
+        if (id != ID_NONE) atomicAdd(&p.rows[(size_t)(pd.g - 1) * p.nids + id], add);
+    }
 }
 
 // 32-bit-word arithmetic of the hot loop.  A thread owns one packed word (32 window end positions) and
@@ -622,21 +667,12 @@ __global__ void __launch_bounds__(1024, 1) k_scan_filtered(const __grid_constant
     }
 }
 
-// filter bit of every key bin
-__global__ void __launch_bounds__(256) k_build_filter(const __grid_constant__ K p, int only_alive) {
+// filter bit of every key bin (genome 1's pass: all keys)
+__global__ void __launch_bounds__(256) k_build_filter(const __grid_constant__ K p) {
     uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= (uint32_t)p.nk * p.PW) return;
-    uint2 e = p.br[t];
-    uint32_t word = e.x;
+    uint32_t word = p.br[t].x;
     if (!word) return;
-    if (only_alive) {   // keys already dead (collisions inside genome 1) need no filter bit: fewer false drains
-        uint32_t keep = 0;
-        for (uint32_t m = word; m; m &= m - 1) {
-            int b = __ffs(m) - 1;
-            if (p.alive[e.y + __popc(word & ((1u << b) - 1u))]) keep |= 1u << b;
-        }
-        word = keep;
-    }
     uint32_t ki = t / p.PW, wi = t - ki * p.PW;
     uint32_t *f = p.filter + (size_t)ki * FILTER_WORDS;
     while (word) {
@@ -645,6 +681,50 @@ __global__ void __launch_bounds__(256) k_build_filter(const __grid_constant__ K 
         uint32_t bin = wi * 32u + b;
         atomicOr(&f[__umulhi(bin, p.fscale)], 1u << (bin & 31u));
     }
+}
+
+// k_build_at: the key table of genomes 2..G (see id_of) from the keys that survived genome 1, and -- keys that
+// are dead already need no filter bit: fewer false drains -- the filter of the alive keys.  One thread per
+// 16 bins.
+__global__ void __launch_bounds__(256) k_build_at(const __grid_constant__ K p, int with_filter) {
+    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (uint32_t)p.nk * p.PW16) return;
+    const uint32_t ki = t / p.PW16, wi = t - ki * p.PW16;
+    uint2 out = make_uint2(0u, 0u);
+    if ((wi >> 1) < p.PW) {
+        const uint2 e = p.br[(size_t)ki * p.PW + (wi >> 1)];
+        const uint32_t half = (wi & 1u) ? (e.x >> 16) : (e.x & 0xFFFFu);
+        if (half) {
+            uint32_t slot = e.y + ((wi & 1u) ? __popc(e.x & 0xFFFFu) : 0u);
+            uint32_t bm = 0, n = 0, id0 = 0, id1 = 0;
+            bool wide = false;
+            for (uint32_t m = half; m; m &= m - 1, slot++) {
+                const uint32_t id = p.remap[slot];
+                if (id == ID_NONE) continue;
+                bm |= 1u << (__ffs(m) - 1);
+                if (n == 0) id0 = id; else if (n == 1) id1 = id;
+                wide |= id >= AT_SLOW;
+                n++;
+            }
+            if (n > 2 || wide) {
+                const uint32_t idx = atomicAdd(p.ovfCount, 1u);
+                if (idx < p.ovfCap) {
+                    slot = e.y + ((wi & 1u) ? __popc(e.x & 0xFFFFu) : 0u);
+                    for (uint32_t m = half; m; m &= m - 1, slot++) p.ovf[(size_t)idx * 16u + (__ffs(m) - 1)] = p.remap[slot];
+                }
+                id0 = AT_SLOW; id1 = idx;
+            }
+            if (n) out = make_uint2(bm | (id0 << 16), (id0 >> 16) | (id1 << 8));
+            if (with_filter) {
+                uint32_t *f = p.filter + (size_t)ki * FILTER_WORDS;
+                for (uint32_t m = bm; m; m &= m - 1) {
+                    const uint32_t bin = wi * 16u + (__ffs(m) - 1);
+                    atomicOr(&f[__umulhi(bin, p.fscale)], 1u << (bin & 31u));
+                }
+            }
+        }
+    }
+    p.at[t] = out;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -698,17 +778,25 @@ __global__ void __launch_bounds__(256) k_candbits(const __grid_constant__ K p) {
     p.br[t].x = ((lo & ~(lo >> 16)) & 0xFFFFu) | ((hi & ~(hi >> 16)) << 16);
 }
 
-// device-wide exclusive scan in three launches; POPC: the value of an element is its popcount
-// element x of the input lives at in[x * S] and its prefix goes to out[x * S] (S = 2 for the
-// interleaved bitmap / rank table)
-template <bool POPC, int S>
-__global__ void __launch_bounds__(256) k_scan_p1(const uint32_t *in, uint32_t n, uint32_t *blockSums) {
+// device-wide exclusive scan in three launches.  MODE: the value of element x is in[x * S] (SV_U32), its
+// popcount (SV_POPC) or the byte in[x] (SV_U8); the prefix goes to out[x * S] (S = 2 for the interleaved
+// bitmap / rank table)
+enum { SV_U32 = 0, SV_POPC = 1, SV_U8 = 2 };
+template <int MODE, int S>
+__device__ __forceinline__ uint32_t scan_val(const void *in, uint32_t x) {
+    if (MODE == SV_U8) return ((const uint8_t *)in)[x];
+    uint32_t v = ((const uint32_t *)in)[(size_t)x * S];
+    return MODE == SV_POPC ? __popc(v) : v;
+}
+
+template <int MODE, int S>
+__global__ void __launch_bounds__(256) k_scan_p1(const void *in, uint32_t n, uint32_t *blockSums) {
     __shared__ uint32_t sm[8];
     uint32_t base = blockIdx.x * SCAN_TILE;
     uint32_t s = 0;
     for (int t = 0; t < SCAN_TILE / 256; t++) {
         uint32_t x = base + t * 256 + threadIdx.x;
-        if (x < n) s += POPC ? __popc(in[(size_t)x * S]) : in[(size_t)x * S];
+        if (x < n) s += scan_val<MODE, S>(in, x);
     }
     for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xFFFFFFFFu, s, o);
     if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = s;
@@ -735,8 +823,8 @@ __global__ void __launch_bounds__(1024) k_scan_p2(uint32_t *blockSums, uint32_t 
     if (threadIdx.x == 1023) *total = sm[1023];
 }
 
-template <bool POPC, int S>
-__global__ void __launch_bounds__(256) k_scan_p3(const uint32_t *in, uint32_t *out, uint32_t n, const uint32_t *blockSums) {
+template <int MODE, int S>
+__global__ void __launch_bounds__(256) k_scan_p3(const void *in, uint32_t *out, uint32_t n, const uint32_t *blockSums) {
     __shared__ uint32_t sm[8];
     uint32_t base = blockIdx.x * SCAN_TILE + threadIdx.x * (SCAN_TILE / 256);
     uint32_t v[SCAN_TILE / 256];
@@ -744,7 +832,7 @@ __global__ void __launch_bounds__(256) k_scan_p3(const uint32_t *in, uint32_t *o
 #pragma unroll
     for (int t = 0; t < SCAN_TILE / 256; t++) {
         uint32_t x = base + t;
-        v[t] = x < n ? (POPC ? __popc(in[(size_t)x * S]) : in[(size_t)x * S]) : 0;
+        v[t] = x < n ? scan_val<MODE, S>(in, x) : 0;
         s += v[t];
     }
     uint32_t incl = s;
@@ -799,70 +887,83 @@ __device__ __forceinline__ int slot_ki(const uint32_t *s_base, int nk, uint32_t 
     return ki;
 }
 
-__global__ void __launch_bounds__(256) k_alive(const __grid_constant__ K p, uint32_t n_check) {
+// k_alive1: genome 1's verdict per slot (bin order); every survivor sets its bit at (end position, k), from
+// which a popcount scan over genome 1's end positions derives its id = its rank in the reference's dict
+// order (genome-1 end position ascending, longest first: getCandidateKmers.py:171-187 + pyahocorasick's
+// emission order)
+__global__ void __launch_bounds__(256) k_alive1(const __grid_constant__ K p) {
     __shared__ uint32_t s_base[32];
     if (threadIdx.x < (unsigned)p.nk) s_base[threadIdx.x] = p.br[(size_t)threadIdx.x * p.PW].y;
     __syncthreads();
     uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= p.nslots) return;
-    int k = p.kmin + slot_ki(s_base, p.nk, (uint32_t)idx);
-    unsigned long long v0 = p.rows[idx];
+    const int ki = slot_ki(s_base, p.nk, (uint32_t)idx);
+    const int k = p.kmin + ki;
+    unsigned long long v0 = p.rows0[idx];
     bool ok = ((v0 >> 32) & ROW_CNT_MASK) == 1;
     if (ok) {
         // the key as it reads on genome 1's (+) strand: the single occupant of its bin there
-        uint64_t key = window_at(p, 0, (uint32_t)(v0 & ROW_POS_MASK), k);
+        const uint32_t start = (uint32_t)(v0 & ROW_POS_MASK);
+        uint64_t key = window_at(p, 0, start, k);
         uint64_t rc = rc64(key) >> (64 - 2 * k);
         bool pal = key == rc;
         ok = row_state(p, 0, v0, key, rc, k, pal, true) == (pal ? 2 : 1);
-        if (ok && pal) p.rows[idx] = v0 | ROW_MINUS;
-        for (uint32_t g = 1; g < n_check && ok; g++) {
-            unsigned long long *row = &p.rows[(size_t)g * p.nslots + idx];
-            const unsigned long long v = *row;
-            const int st = row_state(p, g, v, key, rc, k, pal, false);
-            ok = st != 0;
-            if (st == 2 && !(v & ROW_MINUS)) *row = v | ROW_MINUS;   // k_positions reads the strand from here
-        }
+        if (ok) atomicOr(&p.emitMask[start + (uint32_t)k - 1u], 1u << ki);
     }
-    p.alive[idx] = ok ? 1 : 0;
+    p.remap[idx] = ok ? 0u : ID_NONE;
 }
 
-// ordered emission in the reference's dict order (genome-1 end position ascending, longest first:
-// getCandidateKmers.py:171-187 + pyahocorasick's emission order) without walking the genome again:
-// k_emit_mark scatters one bit per surviving key to (end position, k), a popcount scan over the end
-// positions gives every key its record index, k_emit_write writes the record.
-__global__ void __launch_bounds__(256) k_emit_mark(const __grid_constant__ K p) {
+// k_assign_ids: slot -> id for the survivors of genome 1, and what the id-ordered kernels need per id
+__global__ void __launch_bounds__(256) k_assign_ids(const __grid_constant__ K p) {
     __shared__ uint32_t s_base[32];
     if (threadIdx.x < (unsigned)p.nk) s_base[threadIdx.x] = p.br[(size_t)threadIdx.x * p.PW].y;
     __syncthreads();
     uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= p.nslots || !p.alive[idx]) return;
-    int ki = slot_ki(s_base, p.nk, (uint32_t)idx);
-    uint32_t end = (uint32_t)(p.rows[idx] & ROW_POS_MASK) + (uint32_t)(p.kmin + ki) - 1u;
-    atomicOr(&p.emitMask[end], 1u << ki);
+    if (idx >= p.nslots || p.remap[idx] == ID_NONE) return;
+    const int ki = slot_ki(s_base, p.nk, (uint32_t)idx);
+    const int k = p.kmin + ki;
+    const uint32_t start = (uint32_t)(p.rows0[idx] & ROW_POS_MASK);
+    const uint32_t end = start + (uint32_t)k - 1u;
+    const uint32_t m = p.emitMask[end];
+    const uint32_t id = p.emitOff[end] + __popc(ki < 31 ? (m >> (ki + 1)) : 0u);   // longer k-mers ending here come first
+    p.remap[idx] = id;
+    p.key1[id] = window_at(p, 0, start, k);
+    p.idMeta[id] = start | ((uint32_t)ki << 26);
+    p.alive[id] = 1;
 }
 
+// k_aliveN: the rules for one (id, genome >= 2) per thread; ids follow genome 1's coordinates, so the rows
+// stream and -- for genomes that are largely collinear with genome 1 -- so do the read-backs
+__global__ void __launch_bounds__(256) k_aliveN(const __grid_constant__ K p) {
+    const uint64_t id = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (id >= p.nids) return;
+    const uint32_t g = 1u + blockIdx.y;
+    const int k = p.kmin + (int)(p.idMeta[id] >> 26);
+    const uint64_t key = p.key1[id];
+    const uint64_t rc = rc64(key) >> (64 - 2 * k);
+    unsigned long long *row = &p.rows[(size_t)(g - 1) * p.nids + id];
+    const unsigned long long v = *row;
+    const int st = row_state(p, g, v, key, rc, k, key == rc, false);
+    if (st == 0) p.alive[id] = 0;
+    else if (st == 2) *row = v | ROW_MINUS;     // k_positions reads the strand from here
+}
+
+// k_emit_write: the record of every id that is unique in every genome, at its rank among those
 __global__ void __launch_bounds__(256) k_emit_write(const __grid_constant__ K p) {
-    __shared__ uint32_t s_base[32];
     __shared__ uint32_t s_nn[16];
-    if (threadIdx.x < (unsigned)p.nk) s_base[threadIdx.x] = p.br[(size_t)threadIdx.x * p.PW].y;
-    if (threadIdx.x >= 32 && threadIdx.x < 48) s_nn[threadIdx.x - 32] = c_nn[threadIdx.x - 32];
+    if (threadIdx.x < 16) s_nn[threadIdx.x] = c_nn[threadIdx.x];
     __syncthreads();
-    uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= p.nslots || !p.alive[idx]) return;
-    int ki = slot_ki(s_base, p.nk, (uint32_t)idx);
-    int k = p.kmin + ki;
-    uint32_t start = (uint32_t)(p.rows[idx] & ROW_POS_MASK);
-    uint32_t end = start + (uint32_t)k - 1u;
-    uint32_t m = p.emitMask[end];
-    uint32_t r = p.emitOff[end] + __popc(ki < 31 ? (m >> (ki + 1)) : 0u);      // longer k-mers ending here come first
-    uint64_t h = window_at(p, 0, start, k);
+    const uint64_t id = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (id >= p.nids || !p.alive[id]) return;
+    const int k = p.kmin + (int)(p.idMeta[id] >> 26);
+    const uint64_t h = p.key1[id];
     pfb_record rec;
     double tm;
     uint32_t f = filter_flags(h, k, p, s_nn, &tm);
     if ((rc64(h) >> (64 - 2 * k)) == h) f |= PFB_F_PALIN;
-    rec.word = h; rec.tm = tm; rec.slot = (uint32_t)idx; rec.gc_count = (uint16_t)gc_count(h);
+    rec.word = h; rec.tm = tm; rec.slot = (uint32_t)id; rec.gc_count = (uint16_t)gc_count(h);
     rec.k = (uint8_t)k; rec.flags = (uint8_t)f;
-    p.rec[r] = rec;
+    p.rec[p.recIdx[id]] = rec;
 }
 
 // k_positions: (contig, leftmost start, strand) of every record in every genome
@@ -873,73 +974,66 @@ __global__ void __launch_bounds__(256) k_emit_write(const __grid_constant__ K p)
 // ('-' strand), and as both are unique in genome 1 they share their START (resp. their END) in genome 1.
 // The only possible earlier mates of record (start1, k) are therefore the records (same end1, k' > k) and
 // (same start1, k' < k), which the emit bitmap locates directly; whether such a record really is a mate
-// in genome g is decided by comparing the two starts in g.  One thread per record, loop over genomes.
-__device__ __forceinline__ int mate_candidates(const K &p, uint32_t start1, int ki, uint32_t r, uint32_t *cand, int cap) {
-    int n = 0;
-    const uint32_t end1 = start1 + (uint32_t)(p.kmin + ki) - 1u;
-    uint32_t m = p.emitMask[end1];
-    uint32_t off = p.emitOff[end1];
-    for (uint32_t hi = ki < 31 ? (m >> (ki + 1)) : 0u, kj = ki + 1; hi; hi >>= 1, kj++)       // same end, longer
-        if (hi & 1u) { uint32_t rr = off + __popc(kj < 31 ? (m >> (kj + 1)) : 0u); if (n < cap) cand[n] = rr; n++; }
-    for (int kj = 0; kj < ki; kj++) {                                                           // same start, shorter
-        uint32_t e2 = start1 + (uint32_t)(p.kmin + kj) - 1u;
-        uint32_t m2 = p.emitMask[e2];
-        if ((m2 >> kj) & 1u) { uint32_t rr = p.emitOff[e2] + __popc(m2 >> (kj + 1)); if (n < cap) cand[n] = rr; n++; }
-    }
-    (void)r;
-    return n;
+// in genome g is decided by comparing the two starts in g.  One thread per id, loop over genomes: every
+// access of the loop is coalesced (rows, mates' rows and coordinates are all in id order).
+struct Mates {
+    static constexpr int CAP = 8;
+    uint32_t id[CAP];
+    uint32_t same_start;    // bit i: mate i shares the START in genome 1 (so it is a mate there)
+    int n;                  // > CAP: overflow, re-enumerate per genome
+};
+
+__device__ __forceinline__ bool mate_passes(const K &p, uint32_t mid) {
+    return p.alive[mid] && (p.rec[p.recIdx[mid]].flags & 7u) == 7u;
 }
 
-// general path (more candidates than the register cache holds): re-enumerate them for one genome
-__device__ __noinline__ bool has_earlier_mate(const K &p, uint32_t g, uint32_t lp, uint32_t start1, int ki) {
+// visits the earlier potential mates of (start1, ki); f(mate id, shares start) returns true to stop
+template <typename F>
+__device__ __forceinline__ bool for_each_mate(const K &p, uint32_t start1, int ki, F f) {
     const uint32_t end1 = start1 + (uint32_t)(p.kmin + ki) - 1u;
-    uint32_t m = p.emitMask[end1];
-    uint32_t off = p.emitOff[end1];
-    for (uint32_t hi = ki < 31 ? (m >> (ki + 1)) : 0u, kj = ki + 1; hi; hi >>= 1, kj++) {
-        if (!(hi & 1u)) continue;
-        const pfb_record o = p.rec[off + __popc(kj < 31 ? (m >> (kj + 1)) : 0u)];
-        if ((o.flags & 7u) == 7u && (uint32_t)(p.rows[(size_t)g * p.nslots + o.slot] & ROW_POS_MASK) == lp) return true;
-    }
-    for (int kj = 0; kj < ki; kj++) {
-        uint32_t e2 = start1 + (uint32_t)(p.kmin + kj) - 1u;
-        uint32_t m2 = p.emitMask[e2];
-        if (!((m2 >> kj) & 1u)) continue;
-        const pfb_record o = p.rec[p.emitOff[e2] + __popc(m2 >> (kj + 1))];
-        if ((o.flags & 7u) == 7u && (uint32_t)(p.rows[(size_t)g * p.nslots + o.slot] & ROW_POS_MASK) == lp) return true;
+    const uint32_t m = p.emitMask[end1], off = p.emitOff[end1];
+    for (uint32_t hi = ki < 31 ? (m >> (ki + 1)) : 0u, kj = ki + 1; hi; hi >>= 1, kj++)        // same end, longer
+        if ((hi & 1u) && f(off + __popc(kj < 31 ? (m >> (kj + 1)) : 0u), false)) return true;
+    for (int kj = 0; kj < ki; kj++) {                                                            // same start, shorter
+        const uint32_t e2 = start1 + (uint32_t)(p.kmin + kj) - 1u;
+        const uint32_t m2 = p.emitMask[e2];
+        if (((m2 >> kj) & 1u) && f(p.emitOff[e2] + __popc(m2 >> (kj + 1)), true)) return true;
     }
     return false;
 }
 
 __global__ void __launch_bounds__(256) k_positions(const __grid_constant__ K p) {
-    uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= p.nrec) return;
-    const pfb_record rec = p.rec[r];
-    const bool pass = (rec.flags & 7u) == 7u;
-    // earlier records that could share a position with this one, filtered to those that pass the filters
-    constexpr int CAP = 8;
-    uint32_t cand[CAP];
-    uint32_t cslot[CAP];
-    int nc = 0;
-    bool overflow = false;
-    const uint32_t start1 = (uint32_t)(p.rows[rec.slot] & ROW_POS_MASK);
-    if (pass) {
-        int n = mate_candidates(p, start1, rec.k - p.kmin, (uint32_t)r, cand, CAP);
-        overflow = n > CAP;
-        if (overflow) n = 0;
-        for (int i = 0; i < n; i++) {
-            const pfb_record o = p.rec[cand[i]];
-            if ((o.flags & 7u) == 7u) cslot[nc++] = o.slot;
-        }
-    }
+    const uint64_t id = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (id >= p.nids || !p.alive[id]) return;
+    const uint32_t r = p.recIdx[id];
+    const uint32_t flags = p.rec[r].flags;
+    const bool pass = (flags & 7u) == 7u;
+    const uint32_t meta = p.idMeta[id];
+    const uint32_t start1 = meta & (uint32_t)ROW_POS_MASK;
+    const int ki = (int)(meta >> 26);
+    Mates mt;
+    mt.n = 0; mt.same_start = 0;
+    if (pass)
+        for_each_mate(p, start1, ki, [&](uint32_t mid, bool same_start) {
+            if (mate_passes(p, mid)) {
+                if (mt.n < Mates::CAP) { mt.id[mt.n] = mid; if (same_start) mt.same_start |= 1u << mt.n; }
+                mt.n++;
+            }
+            return false;
+        });
+    const bool overflow = mt.n > Mates::CAP;
     bool picked = false;
     for (uint32_t g = 0; g < p.nGenomes; g++) {
-        const unsigned long long v = p.rows[(size_t)g * p.nslots + rec.slot];
-        const uint32_t lp = (uint32_t)(v & ROW_POS_MASK);
-        // '+' when the genome reads the key itself at that place, '-' when it reads its reverse complement;
-        // a palindrome matches both scans and the later '-' match overwrites (:181-187): k_alive left the
-        // answer in the row
-        const uint32_t minus = (uint32_t)(v >> 61) & 1u;
-        uint32_t start = lp;                       // single-contig genomes: the padded coordinate is the start
+        uint32_t lp, minus;
+        if (g == 0) {
+            lp = start1;
+            minus = (flags & PFB_F_PALIN) ? 1u : 0u;    // a palindrome matches both scans, the later '-' match overwrites (:181-187)
+        } else {
+            const unsigned long long v = p.rows[(size_t)(g - 1) * p.nids + id];
+            lp = (uint32_t)(v & ROW_POS_MASK);
+            minus = (uint32_t)(v >> 61) & 1u;           // left there by k_aliveN
+        }
+        uint32_t start = lp;                            // single-contig genomes: the padded coordinate is the start
         if (p.multiContig) {
             const uint32_t c = p.wordContig[p.gWordStart[g] + (lp >> 5)];
             start = lp - 32u * (p.cWordStart[c] - p.gWordStart[g]);
@@ -949,10 +1043,15 @@ __global__ void __launch_bounds__(256) k_positions(const __grid_constant__ K p) 
         if (pass && !picked) {
             bool first = true;
             if (overflow) {
-                first = !has_earlier_mate(p, g, lp, start1, rec.k - p.kmin);
+                first = !for_each_mate(p, start1, ki, [&](uint32_t mid, bool same_start) {
+                    if (!mate_passes(p, mid)) return false;
+                    return g == 0 ? same_start : (uint32_t)(p.rows[(size_t)(g - 1) * p.nids + mid] & ROW_POS_MASK) == lp;
+                });
+            } else if (g == 0) {
+                first = mt.same_start == 0;
             } else {
-                for (int i = 0; i < nc; i++)
-                    if ((uint32_t)(p.rows[(size_t)g * p.nslots + cslot[i]] & ROW_POS_MASK) == lp) first = false;
+                for (int i = 0; i < mt.n; i++)
+                    if ((uint32_t)(p.rows[(size_t)(g - 1) * p.nids + mt.id[i]] & ROW_POS_MASK) == lp) first = false;
             }
             picked = first;
         }
@@ -1019,9 +1118,9 @@ struct pfb_ctx {
     int stage_done = -1;
     // device
     DevBuf raw, seq2, nmask, wordContig, tabs32, tabs64, sk, br, filter, fterm, scanTmp, misc, emitMask, emitOff,
-        rows, alive, rec, pos, posContig, pick, pickOff, outRec, outPos, outContig;
+        rows0, rows, remap, at, ovf, key1, idMeta, alive, recIdx, rec, pos, posContig, pick, pickOff, outRec, outPos, outContig;
     K k{};
-    uint64_t nslots = 0, nrec = 0, npick = 0;
+    uint64_t nslots = 0, nids = 0, nrec = 0, npick = 0;
     uint64_t launches = 0;
     bool used_filter = false;
     pfb_timing tm{};
@@ -1142,16 +1241,16 @@ int build_layout(pfb_ctx *ctx) {
 }
 
 // device-wide exclusive scan helper (out may alias in)
-template <bool POPC, int S>
-int device_exscan(pfb_ctx *ctx, const uint32_t *in, uint32_t *out, uint32_t n, uint32_t *total_dev) {
+template <int MODE, int S>
+int device_exscan(pfb_ctx *ctx, const void *in, uint32_t *out, uint32_t n, uint32_t *total_dev) {
     cudaStream_t st = ctx->stream;
     uint32_t nb = (n + SCAN_TILE - 1) / SCAN_TILE;
     int rc = ensure(ctx, ctx->scanTmp, (size_t)(nb + 1) * 4);
     if (rc != PFB_OK) return rc;
     uint32_t *bs = (uint32_t *)ctx->scanTmp.p;
-    k_scan_p1<POPC, S><<<nb, 256, 0, st>>>(in, n, bs);
+    k_scan_p1<MODE, S><<<nb, 256, 0, st>>>(in, n, bs);
     k_scan_p2<<<1, 1024, 0, st>>>(bs, nb, total_dev);
-    k_scan_p3<POPC, S><<<nb, 256, 0, st>>>(in, out, n, bs);
+    k_scan_p3<MODE, S><<<nb, 256, 0, st>>>(in, out, n, bs);
     ctx->launches += 3;
     return PFB_OK;
 }
@@ -1207,7 +1306,8 @@ void pfb_destroy(pfb_ctx *ctx) {
     cudaStreamSynchronize(ctx->stream);
     DevBuf *all[] = {&ctx->raw, &ctx->seq2, &ctx->nmask, &ctx->wordContig, &ctx->tabs32, &ctx->tabs64, &ctx->sk, &ctx->br,
                      &ctx->filter, &ctx->fterm, &ctx->scanTmp, &ctx->misc, &ctx->emitMask, &ctx->emitOff,
-                     &ctx->rows, &ctx->alive, &ctx->rec, &ctx->pos, &ctx->posContig, &ctx->pick,
+                     &ctx->rows0, &ctx->rows, &ctx->remap, &ctx->at, &ctx->ovf, &ctx->key1, &ctx->idMeta, &ctx->alive, &ctx->recIdx,
+                     &ctx->rec, &ctx->pos, &ctx->posContig, &ctx->pick,
                      &ctx->pickOff, &ctx->outRec, &ctx->outPos, &ctx->outContig};
     for (auto *b : all) release(*b);
     for (auto &ev : ctx->ev) if (ev) cudaEventDestroy(ev);
@@ -1359,7 +1459,7 @@ static int stage0(pfb_ctx *ctx) {
     k.sk = (uint32_t *)ctx->sk.p; k.br = (uint2 *)ctx->br.p;
     k.filter = (uint32_t *)ctx->filter.p; k.fterm = (const double *)ctx->fterm.p;
     k.tmb = (const float4 *)((const double *)ctx->fterm.p + TMB_OFF);
-    uint32_t *misc = (uint32_t *)ctx->misc.p;   // [0] nslots, [1] nrec, [2] npick
+    uint32_t *misc = (uint32_t *)ctx->misc.p;   // [0] nslots, [1] nids, [2] nrec, [3] npick, [4] id lists of k_build_at
     k.emitMask = (uint32_t *)ctx->emitMask.p; k.emitOff = (uint32_t *)ctx->emitOff.p;
 
     CK(cudaEventRecord(ctx->ev[2], st));
@@ -1379,24 +1479,25 @@ static int stage0(pfb_ctx *ctx) {
     const uint32_t N1 = W1 * 32u;                                           // padded end positions of genome 1
     if (W1) { k_cand1<<<nblk(N1, 256), 256, 0, st>>>(k, N1); ctx->launches++; }
     k_candbits<<<nblk(NB, 256), 256, 0, st>>>(k); ctx->launches++;
-    if ((rc = device_exscan<true, 2>(ctx, (const uint32_t *)k.br, (uint32_t *)k.br + 1, NB, misc)) != PFB_OK) return rc;
+    if ((rc = device_exscan<SV_POPC, 2>(ctx, k.br, (uint32_t *)k.br + 1, NB, misc)) != PFB_OK) return rc;
     uint32_t ns = 0;
     CK(cudaMemcpyAsync(&ns, misc, 4, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));   // fterm (host vector) is also consumed by now
     ctx->nslots = ns;
     k.nslots = ctx->nslots;
+    ctx->nids = 0; k.nids = 0;
     const size_t NS = ctx->nslots ? ctx->nslots : 1;
-    if ((rc = ensure(ctx, ctx->rows, NS * nG * 8)) != PFB_OK) return rc;
-    if ((rc = ensure(ctx, ctx->alive, NS)) != PFB_OK) return rc;
-    k.rows = (unsigned long long *)ctx->rows.p; k.alive = (uint8_t *)ctx->alive.p;
-    CK(cudaMemsetAsync(ctx->rows.p, 0, NS * nG * 8, st));
+    if ((rc = ensure(ctx, ctx->rows0, NS * 8)) != PFB_OK) return rc;
+    if ((rc = ensure(ctx, ctx->remap, NS * 4)) != PFB_OK) return rc;
+    k.rows0 = (unsigned long long *)ctx->rows0.p; k.remap = (uint32_t *)ctx->remap.p;
+    CK(cudaMemsetAsync(ctx->rows0.p, 0, NS * 8, st));
     // the filter pays off while it stays sparse: expected fill 1 - exp(-keys_per_k / FILTER_BITS)
     bool use_filter = ctx->scan_mode == 2 ||
                       (ctx->scan_mode == 0 && (double)ctx->nslots / nk < 0.35 * FILTER_BITS && W >= 4096);
     ctx->used_filter = use_filter;
     if (use_filter && ctx->nslots) {
         CK(cudaMemsetAsync(ctx->filter.p, 0, (size_t)nk * FILTER_BYTES, st));
-        k_build_filter<<<nblk(NB, 256), 256, 0, st>>>(k, 0); ctx->launches++;
+        k_build_filter<<<nblk(NB, 256), 256, 0, st>>>(k); ctx->launches++;
     }
     CK(cudaEventRecord(ctx->ev[4], st));
     // every genome (the first included): one pass against the key table
@@ -1413,18 +1514,53 @@ static int stage0(pfb_ctx *ctx) {
         }
     };
     if (W && ctx->nslots) {
-        // genome 1 first: the keys that collide inside genome 1 itself (~1 - exp(-L / P) of them) are dead
-        // already, and a filter rebuilt without them sends fewer windows of the other genomes to L2
+        // genome 1 first: its rows are indexed by slot.  The keys that collide inside genome 1 itself
+        // (~1 - exp(-L / P) of them) are dead already; the survivors get an id in the reference's dict order,
+        // the rows of every other genome are indexed by id, and a filter rebuilt without the dead keys sends
+        // fewer windows of the other genomes to L2
         const uint32_t C1 = ctx->gFirstContig[0] + ctx->gNumContigs[0];
+        k.first_pass = 1;
         scan_range(0, W1, 0, C1, 1);
-        if (use_filter && nG > 1) {
-            k_alive<<<nblk(ctx->nslots, 256), 256, 0, st>>>(k, 1u); ctx->launches++;
-            CK(cudaMemsetAsync(ctx->filter.p, 0, (size_t)nk * FILTER_BYTES, st));
-            k_build_filter<<<nblk(NB, 256), 256, 0, st>>>(k, 1); ctx->launches++;
+        k.first_pass = 0;
+        CK(cudaMemsetAsync(ctx->emitMask.p, 0, (size_t)N1 * 4 + 4, st));
+        k_alive1<<<nblk(ctx->nslots, 256), 256, 0, st>>>(k); ctx->launches++;
+        if ((rc = device_exscan<SV_POPC, 1>(ctx, k.emitMask, k.emitOff, N1, misc + 1)) != PFB_OK) return rc;
+        uint32_t ni = 0;
+        CK(cudaMemcpyAsync(&ni, misc + 1, 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        ctx->nids = ni; k.nids = ni;
+    }
+    {
+        const size_t NI = ctx->nids ? ctx->nids : 1;
+        const size_t nOther = nG > 1 ? nG - 1 : 1;
+        if ((rc = ensure(ctx, ctx->rows, NI * nOther * 8)) != PFB_OK) return rc;
+        if ((rc = ensure(ctx, ctx->key1, NI * 8)) != PFB_OK) return rc;
+        if ((rc = ensure(ctx, ctx->idMeta, NI * 4)) != PFB_OK) return rc;
+        if ((rc = ensure(ctx, ctx->alive, NI)) != PFB_OK) return rc;
+        if ((rc = ensure(ctx, ctx->recIdx, NI * 4)) != PFB_OK) return rc;
+        k.rows = (unsigned long long *)ctx->rows.p; k.key1 = (uint64_t *)ctx->key1.p; k.idMeta = (uint32_t *)ctx->idMeta.p;
+        k.alive = (uint8_t *)ctx->alive.p; k.recIdx = (uint32_t *)ctx->recIdx.p;
+    }
+    if (ctx->nids) {
+        if (nG > 1) CK(cudaMemsetAsync(ctx->rows.p, 0, (size_t)ctx->nids * (nG - 1) * 8, st));
+        k_assign_ids<<<nblk(ctx->nslots, 256), 256, 0, st>>>(k); ctx->launches++;
+        if (nG > 1) {
+            // key table of the other genomes (alive keys only, ids inline) and their filter
+            k.PW16 = (P.table_size + 15) / 16;
+            const size_t NA = (size_t)nk * k.PW16;
+            const size_t cap = ctx->nids / 3 + (ctx->nids > AT_SLOW ? ctx->nids - AT_SLOW : 0) + 16;
+            if (cap >= (1u << 24)) return fail(ctx, PFB_ETOOLARGE, "too many keys share 16-bin words for the inline id table");
+            if ((rc = ensure(ctx, ctx->at, NA * 8)) != PFB_OK) return rc;
+            if ((rc = ensure(ctx, ctx->ovf, cap * 64)) != PFB_OK) return rc;
+            k.at = (uint2 *)ctx->at.p; k.ovf = (uint32_t *)ctx->ovf.p; k.ovfCount = misc + 4; k.ovfCap = (uint32_t)cap;
+            if (use_filter) CK(cudaMemsetAsync(ctx->filter.p, 0, (size_t)nk * FILTER_BYTES, st));
+            k_build_at<<<nblk(NA, 256), 256, 0, st>>>(k, use_filter ? 1 : 0); ctx->launches++;
         }
+    }
+    if (ctx->nids && nG > 1) {
         if (!piped) {
             CK(cudaEventRecord(ctx->ev[7], st));
-            if (nG > 1) scan_range(W1, W, C1, (uint32_t)ctx->cLen.size(), (uint32_t)nG - 1);
+            scan_range(W1, W, ctx->gFirstContig[0] + ctx->gNumContigs[0], (uint32_t)ctx->cLen.size(), (uint32_t)nG - 1);
             CK(cudaEventRecord(ctx->ev[8], st));
         } else {
             // the other genomes are encoded and scanned in batches of ~16 MB as their H2D copies land
@@ -1446,7 +1582,9 @@ static int stage0(pfb_ctx *ctx) {
         CK(cudaStreamWaitEvent(st, ctx->evCopy[nG - 1], 0));
     }
     CK(cudaEventRecord(ctx->ev[5], st));
-    if (ctx->nslots) { k_alive<<<nblk(ctx->nslots, 256), 256, 0, st>>>(k, (uint32_t)nG); ctx->launches++; }
+    if (ctx->nids && nG > 1) {
+        k_aliveN<<<dim3(nblk(ctx->nids, 256), (unsigned)(nG - 1)), 256, 0, st>>>(k); ctx->launches++;
+    }
     CK(cudaGetLastError());
     return PFB_OK;
 }
@@ -1455,18 +1593,14 @@ static int stage1(pfb_ctx *ctx) {
     cudaStream_t st = ctx->stream;
     K &k = ctx->k;
     int rc;
-    const uint32_t W = ctx->totalWords;
-    const uint32_t W1 = ctx->genomes.size() > 1 ? ctx->gWordStart[1] : W;
     const size_t nG = ctx->genomes.size();
-    const uint32_t N1 = W1 * 32u;
     uint32_t *misc = (uint32_t *)ctx->misc.p;
     ctx->nrec = 0; ctx->npick = 0;
-    if (ctx->nslots && W1) {
-        CK(cudaMemsetAsync(ctx->emitMask.p, 0, (size_t)N1 * 4, st));
-        k_emit_mark<<<nblk(ctx->nslots, 256), 256, 0, st>>>(k); ctx->launches++;
-        if ((rc = device_exscan<true, 1>(ctx, k.emitMask, k.emitOff, N1, misc + 1)) != PFB_OK) return rc;
+    if (ctx->nids) {
+        // ids are in dict order already: the record index is the rank among the ids that survived every genome
+        if ((rc = device_exscan<SV_U8, 1>(ctx, k.alive, k.recIdx, (uint32_t)ctx->nids, misc + 2)) != PFB_OK) return rc;
         uint32_t n = 0;
-        CK(cudaMemcpyAsync(&n, misc + 1, 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(&n, misc + 2, 4, cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
         ctx->nrec = n;
     }
@@ -1483,8 +1617,8 @@ static int stage1(pfb_ctx *ctx) {
     k.pick = (uint32_t *)ctx->pick.p; k.pickOff = (uint32_t *)ctx->pickOff.p;
     CK(cudaMemsetAsync(ctx->pick.p, 0, NR * 4, st));
     if (ctx->nrec) {
-        k_emit_write<<<nblk(ctx->nslots, 256), 256, 0, st>>>(k); ctx->launches++;
-        k_positions<<<nblk(ctx->nrec, 256), 256, 0, st>>>(k); ctx->launches++;
+        k_emit_write<<<nblk(ctx->nids, 256), 256, 0, st>>>(k); ctx->launches++;
+        k_positions<<<nblk(ctx->nids, 256), 256, 0, st>>>(k); ctx->launches++;
     }
     CK(cudaGetLastError());
     return PFB_OK;
@@ -1498,9 +1632,9 @@ static int stage2(pfb_ctx *ctx) {
     const size_t nG = ctx->genomes.size();
     ctx->npick = 0;
     if (ctx->nrec) {
-        if ((rc = device_exscan<false, 1>(ctx, k.pick, k.pickOff, (uint32_t)ctx->nrec, misc + 2)) != PFB_OK) return rc;
+        if ((rc = device_exscan<SV_U32, 1>(ctx, k.pick, k.pickOff, (uint32_t)ctx->nrec, misc + 3)) != PFB_OK) return rc;
         uint32_t np = 0;
-        CK(cudaMemcpyAsync(&np, misc + 2, 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(&np, misc + 3, 4, cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
         ctx->npick = np;
     }
@@ -1521,7 +1655,7 @@ static int stage2(pfb_ctx *ctx) {
     cudaEventElapsedTime(&t.ms_finalize, ctx->ev[5], ctx->ev[6]);
     t.ms_scan_main = 0.f;
     t.scan_main_bases = 0;
-    if (!ctx->pipelined && ctx->nslots && ctx->genomes.size() > 1 && cudaEventElapsedTime(&t.ms_scan_main, ctx->ev[7], ctx->ev[8]) == cudaSuccess) {
+    if (!ctx->pipelined && ctx->nids && ctx->genomes.size() > 1 && cudaEventElapsedTime(&t.ms_scan_main, ctx->ev[7], ctx->ev[8]) == cudaSuccess) {
         for (size_t g = 1; g < ctx->genomes.size(); g++) t.scan_main_bases += ctx->genomes[g].n_bases;
     } else {
         t.ms_scan_main = 0.f;
@@ -1574,7 +1708,7 @@ int pfb_device_buffer(pfb_ctx *ctx, int which, void **dev_ptr, uint64_t *n_bytes
     if (!ctx || !dev_ptr || !n_bytes) return PFB_EINVAL;
     if (which == PFB_BUF_ALIVE) {
         if (ctx->stage_done < 0) return fail(ctx, PFB_ESTATE, "stage 0 has not run");
-        *dev_ptr = ctx->alive.p; *n_bytes = ctx->nslots;
+        *dev_ptr = ctx->alive.p; *n_bytes = ctx->nids;
     } else if (which == PFB_BUF_PICK) {
         if (ctx->stage_done < 1) return fail(ctx, PFB_ESTATE, "stage 1 has not run");
         *dev_ptr = ctx->pick.p; *n_bytes = ctx->nrec * 4;

@@ -1,0 +1,201 @@
+// pfb_fasta.cuh -- FASTA file bytes -> contigs, on the device (included by pfb200.cu).
+//
+// Replaces Bio.SeqIO.parse(fn, "fasta") at /root/reference/bin/getCandidateKmers.py:93,212 (biopython's
+// SimpleFastaParser): text before the first line that starts with '>' is skipped; a line that starts with
+// '>' opens a record (its id is the title up to the first whitespace -- extracted by the host from the
+// header offset reported here); every other line contributes its bytes minus '\n', '\r' and ' '.  Case is
+// preserved (only upper-case A C G T are nucleotides for the stage, like on the pfb_add_genome path).
+//
+// The files of a batch sit in one staging buffer (each 256-byte aligned).  A TILE of 4096 bytes is walked
+// by one warp, 32 bytes per step: the line-start / header / newline masks of a step are warp ballots, i.e.
+// uniform values, and a lane owns one byte, so the compacted bases leave as coalesced byte stores.
+//   k_fa_mark   : per tile: position of its last line start, number of header lines, first header of the file
+//   k_fa_scan   : exclusive MAX scan of the last line starts (which line does a tile begin inside?) and
+//                 exclusive SUM scan of the header counts / of the kept-byte counts over the tiles
+//   k_fa_sweep<false> : kept bytes per tile;  k_fa_sweep<true> : compaction + one entry per record
+// Traffic: the file bytes are read three times (they fit L2 for bacterial genomes) and written once.
+#pragma once
+
+#include <cstdint>
+
+namespace fa {
+
+constexpr uint32_t TILE = 4096;        // bytes per warp
+constexpr uint32_t WARPS = 8;          // warps (= tiles) per CTA
+constexpr uint32_t NO_HDR = 0xFFFFFFFFu;
+
+struct Args {
+    const uint8_t *stage;       // staging buffer holding the files of the batch
+    const uint64_t *src;        // [nFiles] offset of the file in `stage`
+    const uint64_t *len;        // [nFiles] bytes
+    const uint32_t *tile0;      // [nFiles + 1] first tile of the file
+    const uint64_t *dst;        // [nFiles] offset of the file's bases in `out`
+    uint32_t nFiles, nTiles;
+    // per tile
+    uint64_t *tLast;            // (file << 32 | offset of the last line start + 1), 0 = no line start in the tile
+    uint64_t *inLast;           // exclusive max scan of tLast
+    uint32_t *tHdr, *hdrBase;   // header lines in the tile / before it (all files of the batch), [nTiles + 1]
+    uint32_t *tKept, *keptBase; // kept bytes in the tile / before it, [nTiles + 1]
+    uint32_t *firstHdr;         // [nFiles] offset of the file's first header line (NO_HDR: none)
+    // output
+    uint8_t *out;               // compacted bases (the raw arena)
+    uint32_t *recStart;         // [cap] offset of the record's first base in the file's compacted bases (host-mapped)
+    uint32_t *recHdr;           // [cap] offset of the record's '>' in the file (host-mapped)
+    uint32_t *fileTab;          // [2 * nFiles + 1] per file: index of its first record, then kept bytes; last: total records
+    uint32_t cap;
+};
+
+__device__ __forceinline__ uint32_t file_of_tile(const Args &a, uint32_t t) {
+    uint32_t lo = 0, hi = a.nFiles;
+    while (hi - lo > 1) {
+        uint32_t mid = (lo + hi) >> 1;
+        if (a.tile0[mid] <= t) lo = mid; else hi = mid;
+    }
+    // files without tiles (length 0) share their tile0 with the next one: take the last file that starts here
+    return lo;
+}
+
+// masks of one 32-byte step (bit i = byte i of the step); `c` is this lane's byte
+struct Step {
+    uint32_t valid, nl, drop, ls, hs;
+};
+
+__device__ __forceinline__ Step classify(uint8_t c, bool in_file, uint32_t &prev_nl) {
+    Step s;
+    s.valid = __ballot_sync(0xFFFFFFFFu, in_file);
+    s.nl = __ballot_sync(0xFFFFFFFFu, in_file && c == '\n');
+    s.drop = __ballot_sync(0xFFFFFFFFu, in_file && (c == '\r' || c == ' '));
+    const uint32_t gt = __ballot_sync(0xFFFFFFFFu, in_file && c == '>');
+    s.ls = ((s.nl << 1) | prev_nl) & s.valid;      // a line starts after every newline (and at offset 0 of the file)
+    s.hs = s.ls & gt;
+    prev_nl = s.nl >> 31;
+    return s;
+}
+
+// is the byte before `off` a newline (or off the start of the file)?
+__device__ __forceinline__ uint32_t starts_line(const uint8_t *f, uint64_t off) { return off == 0 || f[off - 1] == '\n'; }
+
+__global__ void __launch_bounds__(WARPS * 32) k_fa_mark(const Args a) {
+    const uint32_t t = blockIdx.x * WARPS + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (t >= a.nTiles) return;
+    const uint32_t fi = file_of_tile(a, t);
+    const uint8_t *f = a.stage + a.src[fi];
+    const uint64_t len = a.len[fi];
+    const uint64_t base = (uint64_t)(t - a.tile0[fi]) * TILE;
+    uint32_t prev_nl = starts_line(f, base);
+    uint32_t last = 0, nh = 0, first = NO_HDR;
+    for (uint32_t j = 0; j < TILE / 32; j++) {
+        const uint64_t off = base + j * 32 + lane;
+        const bool in_file = off < len;
+        const uint8_t c = in_file ? f[off] : 0;
+        const Step s = classify(c, in_file, prev_nl);
+        if (s.ls) last = (uint32_t)(base + j * 32) + (31 - __clz(s.ls)) + 1;
+        if (s.hs) {
+            if (first == NO_HDR) first = (uint32_t)(base + j * 32) + (__ffs(s.hs) - 1);
+            nh += __popc(s.hs);
+        }
+    }
+    if (lane == 0) {
+        a.tLast[t] = last ? (((uint64_t)fi << 32) | last) : 0ull;
+        a.tHdr[t] = nh;
+        if (first != NO_HDR) atomicMin(&a.firstHdr[fi], first);
+    }
+}
+
+// single CTA: exclusive scans over the tiles (n + 1 outputs for the sums)
+__global__ void __launch_bounds__(1024) k_fa_scan(const uint32_t *val, uint32_t *out, const uint64_t *mval, uint64_t *mout, uint32_t n) {
+    __shared__ uint32_t ssum[1024];
+    __shared__ uint64_t smax[1024];
+    const uint32_t per = (n + 1023) / 1024;
+    const uint32_t lo = min(n, threadIdx.x * per), hi = min(n, lo + per);
+    uint32_t s = 0;
+    uint64_t m = 0;
+    for (uint32_t x = lo; x < hi; x++) {
+        s += val[x];
+        if (mval) m = max(m, mval[x]);
+    }
+    ssum[threadIdx.x] = s; smax[threadIdx.x] = m;
+    __syncthreads();
+    for (int off = 1; off < 1024; off <<= 1) {
+        uint32_t v = threadIdx.x >= off ? ssum[threadIdx.x - off] : 0;
+        uint64_t w = threadIdx.x >= off ? smax[threadIdx.x - off] : 0;
+        __syncthreads();
+        ssum[threadIdx.x] += v; smax[threadIdx.x] = max(smax[threadIdx.x], w);
+        __syncthreads();
+    }
+    uint32_t run = ssum[threadIdx.x] - s;
+    uint64_t mrun = threadIdx.x ? smax[threadIdx.x - 1] : 0;
+    for (uint32_t x = lo; x < hi; x++) {
+        uint32_t v = val[x];
+        out[x] = run; run += v;
+        if (mval) { uint64_t w = mval[x]; mout[x] = mrun; mrun = max(mrun, w); }
+    }
+    if (threadIdx.x == 1023) out[n] = ssum[1023];
+}
+
+// GATHER = false: kept bytes per tile.  GATHER = true: compaction and the record table.
+template <bool GATHER>
+__global__ void __launch_bounds__(WARPS * 32) k_fa_sweep(const Args a) {
+    const uint32_t t = blockIdx.x * WARPS + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (t >= a.nTiles) return;
+    const uint32_t fi = file_of_tile(a, t);
+    const uint8_t *f = a.stage + a.src[fi];
+    const uint64_t len = a.len[fi];
+    const uint32_t t0 = a.tile0[fi];
+    const uint64_t base = (uint64_t)(t - t0) * TILE;
+    const uint32_t F = a.firstHdr[fi];
+    uint32_t prev_nl = starts_line(f, base);
+    // the tile begins inside the line that started at the last line start before it: a header line?
+    uint32_t in_hdr = 0;
+    if (!prev_nl) {
+        const uint64_t il = a.inLast[t];                 // same file by construction (offset 0 of a file starts a line)
+        in_hdr = f[(uint32_t)il - 1u] == '>';
+    }
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    uint32_t run = 0, hrun = 0;
+    uint8_t *out = nullptr;
+    if (GATHER) {
+        run = a.keptBase[t] - a.keptBase[t0];            // offset in the file's compacted bases
+        hrun = a.hdrBase[t];
+        out = a.out + a.dst[fi];
+        if (t == t0 && lane == 0) {
+            a.fileTab[2 * fi] = a.hdrBase[t0];
+            a.fileTab[2 * fi + 1] = a.keptBase[a.tile0[fi + 1]] - a.keptBase[t0];
+            if (fi == 0) a.fileTab[2 * a.nFiles] = a.hdrBase[a.nTiles];
+        }
+    }
+    for (uint32_t j = 0; j < TILE / 32; j++) {
+        const uint64_t sb = base + j * 32;
+        const uint64_t off = sb + lane;
+        const bool in_file = off < len;
+        const uint8_t c = in_file ? f[off] : 0;
+        const Step s = classify(c, in_file, prev_nl);
+        // header mask: a line keeps the status decided at its start
+        uint32_t hdr = 0, prev = 0;
+        for (uint32_t m = s.ls; m; m &= m - 1) {
+            const uint32_t b = __ffs(m) - 1;
+            if (in_hdr && b > prev) hdr |= (0xFFFFFFFFu >> (32 - (b - prev))) << prev;
+            in_hdr = (s.hs >> b) & 1u;
+            prev = b;
+        }
+        if (in_hdr) hdr |= 0xFFFFFFFFu << prev;
+        // bytes before the first header line of the file are not part of any record
+        uint32_t junk = 0;
+        if (F == NO_HDR || sb + 32 <= F) junk = 0xFFFFFFFFu;
+        else if (sb < F) junk = 0xFFFFFFFFu >> (32 - (uint32_t)(F - sb));
+        const uint32_t keep = s.valid & ~hdr & ~s.nl & ~s.drop & ~junk;
+        if (GATHER) {
+            const uint32_t pos = run + __popc(keep & lt_mask);
+            if ((keep >> lane) & 1u) out[pos] = c;
+            if ((s.hs >> lane) & 1u) {
+                const uint32_t e = hrun + __popc(s.hs & lt_mask);
+                if (e < a.cap) { a.recStart[e] = pos; a.recHdr[e] = (uint32_t)off; }
+            }
+            hrun += __popc(s.hs);
+        }
+        run += __popc(keep);
+    }
+    if (!GATHER && lane == 0) a.tKept[t] = run;
+}
+
+}  // namespace fa
