@@ -180,6 +180,7 @@ def main():
     ap.add_argument("--genomes", type=int, default=None, help="override genomes per GPU (debug)")
     ap.add_argument("--length", type=int, default=None, help="override genome length (debug)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-fasta-leg", action="store_true")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="weak (default): the config's genome count PER GPU; strong: the config's genome count in total, "
                          "genome 0 on every rank and the others dealt round-robin")
@@ -327,6 +328,50 @@ def main():
             d2h = rec.nbytes + sum(p.nbytes for p in pos)
     clocks = sampler.stop() if rank == 0 else None
 
+    # ---- end-to-end from the FASTA FILE IMAGES (80-column, pinned host memory): the records are found and
+    # compacted on the device (pfb_add_fasta), everything else as above.  Single GPU only.
+    fasta_leg = None
+    if world == 1 and not args.no_fasta_leg:
+        images = []
+        for (t, off), gi in zip(pinned, range(len(pinned))):
+            parts = []
+            arr = t.numpy()
+            for c in range(len(off) - 1):
+                seq = arr[int(off[c]):int(off[c + 1])]
+                parts.append(np.frombuffer(f">g{gi:03d}_c{c:03d} synthetic\n".encode(), dtype=np.uint8))
+                full = (seq.size // 80) * 80
+                if full:
+                    body = np.empty((seq.size // 80, 81), dtype=np.uint8)
+                    body[:, :80] = seq[:full].reshape(-1, 80)
+                    body[:, 80] = 10
+                    parts.append(body.reshape(-1))
+                if seq.size > full:
+                    parts.append(seq[full:])
+                    parts.append(np.frombuffer(b"\n", dtype=np.uint8))
+            img = np.concatenate(parts)
+            pt = torch.empty(img.size, dtype=torch.uint8).pin_memory()
+            pt.numpy()[:] = img
+            images.append(pt)
+        eng_f = Engine(device=local, k_min=cfg["k_min"], k_max=cfg["k_max"], max_repeat=cfg["max_repeats"], prefilter=1)
+        for pt in images:
+            eng_f.add_fasta(ptr=pt.data_ptr(), n_bytes=pt.numel())
+        fa_s = []
+        for i in range(2 + min(args.steps, 50)):
+            flush.zero_()
+            barrier()
+            t0 = time.perf_counter()
+            eng_f.run()
+            rec_f, ss_f, ct_f = eng_f.result_picked()
+            eng_f.sync()
+            if i >= 2:
+                fa_s.append(time.perf_counter() - t0)
+        fa_ms = float(np.mean(fa_s) * 1e3)
+        fasta_leg = {"value": distinct_bases / 1e6 / (fa_ms / 1e3), "unit": UNIT, "ms_per_step": fa_ms,
+                     "h2d_bytes_per_step": int(sum(pt.numel() for pt in images)),
+                     "d2h_bytes_per_step": int(rec_f.nbytes + ss_f.nbytes + (ct_f.nbytes if ct_f is not None else 0)),
+                     "n_picked": int(rec_f.size), "input": "80-column FASTA file images in pinned host memory, parsed on the device"}
+        eng_f.close()
+
     step_ms = float(np.mean(dev_ms))
     e2e_ms = float(np.mean(e2e_s) * 1e3)
     if world > 1:
@@ -385,6 +430,8 @@ def main():
                             "nvlink_peak_GBs_per_direction": 900.0,
                             "frac_of_nvlink": wire / (ms_x / 1e3) / 1e9 / 900.0 if ms_x > 0 else None,
                             "note": "latency-bound: ~6 MB per step; no k-mer crosses NVLink (DESIGN.md section 5)"}
+    if fasta_leg is not None:
+        line["e2e_fasta"] = fasta_leg
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"], _ = cpu_sample_run(args.config)
     emit(line)

@@ -106,6 +106,16 @@ int  pfb_default_params(pfb_params *p);           /* bin/Parameters.py:30-52 + p
  * until pfb_run / pfb_upload returns (pinned memory makes the copy asynchronous). */
 int  pfb_add_genome(pfb_ctx *ctx, const uint8_t *bases, uint64_t n_bases,
                     const uint64_t *contig_off, uint32_t n_contigs);
+/* the same from the FASTA file itself: `file_bytes` is the file image (host pointer, borrowed like above); the
+ * records are found and their sequence lines compacted ON THE DEVICE, with Bio.SeqIO.parse(fn, "fasta")'s
+ * rules (getCandidateKmers.py:93,212; biopython's SimpleFastaParser): text before the first line starting
+ * with '>' is skipped, '\n' '\r' and ' ' never belong to a sequence, case is preserved.  All genomes of a
+ * context must be added the same way.  After pfb_upload / pfb_run, pfb_genome_info and pfb_contig_table
+ * report what was found: per record the offset of its '>' in the file (the id is the title up to the first
+ * whitespace, SeqRecord.id) and its length. */
+int  pfb_add_fasta(pfb_ctx *ctx, const uint8_t *file_bytes, uint64_t n_bytes);
+int  pfb_genome_info(pfb_ctx *ctx, uint32_t genome_idx, uint32_t *n_contigs, uint64_t *n_bases);
+int  pfb_contig_table(pfb_ctx *ctx, uint32_t genome_idx, uint64_t *header_off, uint64_t *length, uint32_t cap);
 int  pfb_clear_genomes(pfb_ctx *ctx);
 
 /* run: pfb_run == pfb_upload + pfb_compute.  pfb_compute can be repeated on resident inputs.

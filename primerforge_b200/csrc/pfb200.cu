@@ -30,6 +30,7 @@
 // No tensor cores: nothing here is a contraction.
 
 #include "../../include/pfb200.h"
+#include "pfb_fasta.cuh"
 
 #include <cuda_runtime.h>
 
@@ -1089,9 +1090,21 @@ struct DevBuf {
 };
 
 struct HostGenome {
-    const uint8_t *bases;
-    uint64_t n_bases;
+    const uint8_t *bases;        // contigs concatenated (pfb_add_genome) or the FASTA file image (pfb_add_fasta)
+    uint64_t n_bases;            // bases; for a FASTA genome known once the device has parsed it
     std::vector<uint64_t> off;   // n_contigs + 1
+    bool fasta = false;
+    uint64_t file_bytes = 0;
+    std::vector<uint64_t> hdr_off;   // FASTA: offset of every record's '>' in the file
+};
+
+// one batch of FASTA files being parsed on the device
+struct FaBatch {
+    size_t g0 = 0, g1 = 0;       // genomes [g0, g1)
+    uint32_t nTiles = 0, cap = 0;
+    fa::Args args{};
+    cudaEvent_t done = nullptr;
+    bool pending = false;
 };
 
 }  // namespace
@@ -1106,7 +1119,19 @@ struct pfb_ctx {
     cudaStream_t copyStream = nullptr;          // H2D copies of pfb_run run here, overlapped with compute
     std::vector<cudaEvent_t> evCopy;            // one per genome: its bases have arrived
     bool pipelined = false;
-    std::vector<uint32_t> t32host;              // contig / genome tables (kept alive for the async copy)
+    // FASTA ingest: file images are staged in `fa`, parsed on parseStream, record tables land in mapped host memory
+    cudaStream_t parseStream = nullptr;
+    bool any_fasta = false;
+    size_t laid_out = 0;                        // genomes covered by the current layout (FASTA: 1, then all)
+    std::vector<uint64_t> faStart;
+    FaBatch faBatch[2];
+    void *faHost[2] = {nullptr, nullptr};       // cudaHostAlloc(Mapped)
+    size_t faHostCap[2] = {0, 0};
+    std::vector<uint64_t> fa64host[2];
+    std::vector<uint32_t> fa32host[2];
+    std::vector<uint32_t> t32host, t32hostb;    // contig / genome tables (kept alive for the async copy)
+    std::vector<uint64_t> t64host, t64hostb;
+    uint64_t totalFa = 0, fa_launches = 0;
     cudaEvent_t ev[10]{};
     std::vector<HostGenome> genomes;
     // layout (host)
@@ -1117,7 +1142,7 @@ struct pfb_ctx {
     bool uploaded = false, computed = false;
     int stage_done = -1;
     // device
-    DevBuf raw, seq2, nmask, wordContig, tabs32, tabs64, sk, br, filter, fterm, scanTmp, misc, emitMask, emitOff,
+    DevBuf raw, fa, faWork[2], tabs32b, tabs64b, seq2, nmask, wordContig, tabs32, tabs64, sk, br, filter, fterm, scanTmp, misc, emitMask, emitOff,
         rows0, rows, remap, at, ovf, key1, idMeta, alive, recIdx, rec, pos, posContig, pick, pickOff, outRec, outPos, outContig;
     K k{};
     uint64_t nslots = 0, nids = 0, nrec = 0, npick = 0;
@@ -1149,6 +1174,21 @@ int ensure(pfb_ctx *ctx, DevBuf &b, size_t bytes) {
     size_t want = bytes + bytes / 8 + 256;
     CK(cudaMalloc(&b.p, want));
     b.cap = want;
+    return PFB_OK;
+}
+
+// grow a buffer keeping its first `keep` bytes
+int ensure_keep(pfb_ctx *ctx, DevBuf &b, size_t bytes, size_t keep) {
+    if (bytes <= b.cap && b.p) return PFB_OK;
+    DevBuf old = b;
+    b.p = nullptr; b.cap = 0;
+    int rc = ensure(ctx, b, bytes);
+    if (rc != PFB_OK) return rc;
+    if (old.p) {
+        CK(cudaStreamSynchronize(ctx->stream));
+        if (keep) CK(cudaMemcpy(b.p, old.p, std::min(keep, old.cap), cudaMemcpyDeviceToDevice));
+        CK(cudaFree(old.p));
+    }
     return PFB_OK;
 }
 
@@ -1203,16 +1243,31 @@ void fill_filter_constants(const pfb_params &P, K &k, std::vector<double> &fterm
     k.gc_ok[0] = 0;
 }
 
-// layout of the arena from the host-side genome list
-int build_layout(pfb_ctx *ctx) {
+// where every genome's bases start in the raw arena (FASTA genomes: the file size bounds the bases)
+void raw_starts(pfb_ctx *ctx) {
+    ctx->gRawStart.clear();
+    ctx->faStart.clear();
+    uint64_t raw = 0, fa = 0;
+    for (auto &g : ctx->genomes) {
+        raw = (raw + 255) & ~255ull;
+        fa = (fa + 255) & ~255ull;
+        ctx->gRawStart.push_back(raw);
+        ctx->faStart.push_back(fa);
+        raw += g.fasta ? g.file_bytes : g.n_bases;
+        if (g.fasta) fa += g.file_bytes;
+    }
+    ctx->totalRaw = raw;
+    ctx->totalFa = fa;
+}
+
+// layout of the arena for the first n genomes of the host-side genome list
+int build_layout(pfb_ctx *ctx, size_t n) {
     auto &G = ctx->genomes;
     ctx->cWordStart.clear(); ctx->cLen.clear(); ctx->cGenome.clear(); ctx->cVirt.clear(); ctx->cRawStart.clear();
-    ctx->gWordStart.clear(); ctx->gFirstContig.clear(); ctx->gNumContigs.clear(); ctx->gVirtLen.clear(); ctx->gRawStart.clear();
-    uint64_t raw = 0;
+    ctx->gWordStart.clear(); ctx->gFirstContig.clear(); ctx->gNumContigs.clear(); ctx->gVirtLen.clear();
     uint64_t words = 0;
-    for (size_t g = 0; g < G.size(); g++) {
-        raw = (raw + 255) & ~255ull;
-        ctx->gRawStart.push_back(raw);
+    for (size_t g = 0; g < n; g++) {
+        const uint64_t raw = ctx->gRawStart[g];
         ctx->gWordStart.push_back((uint32_t)words);
         ctx->gFirstContig.push_back((uint32_t)ctx->cLen.size());
         uint32_t nc = (uint32_t)G[g].off.size() - 1;
@@ -1232,11 +1287,154 @@ int build_layout(pfb_ctx *ctx) {
             return fail(ctx, PFB_ETOOLARGE, "genome " + std::to_string(g) + " exceeds 2^26 padded bases");
         ctx->gVirtLen.push_back((uint32_t)virt);
         words += gwords;
-        raw += G[g].n_bases;
         if (words >= (1ull << 31)) return fail(ctx, PFB_ETOOLARGE, "more than 2^36 bases on one context");
     }
-    ctx->totalRaw = raw;
     ctx->totalWords = (uint32_t)words;
+    ctx->laid_out = n;
+    return PFB_OK;
+}
+
+// contig / genome tables of the current layout -> device; `second` uses the other pair of buffers so that
+// kernels already launched with the first tables keep reading valid memory
+int upload_tables(pfb_ctx *ctx, bool second) {
+    cudaStream_t st = ctx->stream;
+    DevBuf &d32 = second ? ctx->tabs32b : ctx->tabs32;
+    DevBuf &d64 = second ? ctx->tabs64b : ctx->tabs64;
+    std::vector<uint32_t> &t32 = second ? ctx->t32hostb : ctx->t32host;
+    const size_t nC = ctx->cLen.size(), nG = ctx->laid_out;
+    t32.clear();
+    auto put32 = [&](const std::vector<uint32_t> &v) { size_t o = t32.size(); t32.insert(t32.end(), v.begin(), v.end()); return o; };
+    size_t o_cws = put32(ctx->cWordStart), o_cl = put32(ctx->cLen), o_cg = put32(ctx->cGenome), o_cv = put32(ctx->cVirt);
+    size_t o_gws = put32(ctx->gWordStart), o_gfc = put32(ctx->gFirstContig), o_gnc = put32(ctx->gNumContigs), o_gvl = put32(ctx->gVirtLen);
+    int rc;
+    if ((rc = ensure(ctx, d32, t32.size() * 4 + 4)) != PFB_OK) return rc;
+    if ((rc = ensure(ctx, d64, nC * 8 + 8)) != PFB_OK) return rc;
+    std::vector<uint64_t> &t64 = second ? ctx->t64hostb : ctx->t64host;
+    t64 = ctx->cRawStart;
+    if (!t32.empty()) CK(cudaMemcpyAsync(d32.p, t32.data(), t32.size() * 4, cudaMemcpyHostToDevice, st));
+    if (nC) CK(cudaMemcpyAsync(d64.p, t64.data(), nC * 8, cudaMemcpyHostToDevice, st));
+    const uint32_t *b32 = (const uint32_t *)d32.p;
+    K &k = ctx->k;
+    k.cWordStart = b32 + o_cws; k.cLen = b32 + o_cl; k.cGenome = b32 + o_cg; k.cVirt = b32 + o_cv;
+    k.gWordStart = b32 + o_gws; k.gFirstContig = b32 + o_gfc; k.gNumContigs = b32 + o_gnc; k.gVirtLen = b32 + o_gvl;
+    k.cRawStart = (const uint64_t *)d64.p;
+    k.nContigs = (uint32_t)nC; k.nGenomes = (uint32_t)nG; k.totalWords = ctx->totalWords;
+    k.raw = (const uint8_t *)ctx->raw.p;
+    return PFB_OK;
+}
+
+// ---- FASTA ingest (pfb_fasta.cuh): the files of genomes [g0, g1) are parsed on `ps` once their copies landed
+int fasta_enqueue(pfb_ctx *ctx, int b, size_t g0, size_t g1, cudaStream_t ps) {
+    FaBatch &B = ctx->faBatch[b];
+    B.g0 = g0; B.g1 = g1; B.pending = false;
+    const uint32_t nF = (uint32_t)(g1 - g0);
+    if (!nF) return PFB_OK;
+    std::vector<uint64_t> &h64 = ctx->fa64host[b];
+    std::vector<uint32_t> &h32 = ctx->fa32host[b];
+    h64.assign(3 * (size_t)nF, 0);
+    h32.assign(nF + 1, 0);
+    uint64_t bytes = 0;
+    uint32_t nT = 0;
+    for (uint32_t f = 0; f < nF; f++) {
+        const HostGenome &hg = ctx->genomes[g0 + f];
+        h64[f] = ctx->faStart[g0 + f];
+        h64[nF + f] = hg.file_bytes;
+        h64[2 * nF + f] = ctx->gRawStart[g0 + f];
+        h32[f] = nT;
+        nT += (uint32_t)((hg.file_bytes + fa::TILE - 1) / fa::TILE);
+        bytes += hg.file_bytes;
+    }
+    h32[nF] = nT;
+    B.nTiles = nT;
+    if (B.cap == 0) B.cap = (uint32_t)std::min<uint64_t>(1u << 26, 65536 + bytes / 256);
+    // device work area
+    size_t o = 0;
+    auto carve = [&](size_t n) { size_t at = o; o += (n + 255) & ~(size_t)255; return at; };
+    const size_t o64 = carve(3 * (size_t)nF * 8), o32 = carve((nF + 1) * 4), oFirst = carve(nF * 4);
+    const size_t oTLast = carve((size_t)nT * 8), oInLast = carve((size_t)nT * 8);
+    const size_t oTHdr = carve((size_t)(nT + 1) * 4), oHdrBase = carve((size_t)(nT + 1) * 4);
+    const size_t oTKept = carve((size_t)(nT + 1) * 4), oKeptBase = carve((size_t)(nT + 1) * 4);
+    int rc;
+    if ((rc = ensure(ctx, ctx->faWork[b], o)) != PFB_OK) return rc;
+    // host-mapped output: per-file table, then record starts, then header offsets
+    const size_t hostBytes = ((size_t)(2 * nF + 1) + 2 * (size_t)B.cap) * 4;
+    if (ctx->faHostCap[b] < hostBytes) {
+        if (ctx->faHost[b]) cudaFreeHost(ctx->faHost[b]);
+        ctx->faHost[b] = nullptr; ctx->faHostCap[b] = 0;
+        CK(cudaHostAlloc(&ctx->faHost[b], hostBytes, cudaHostAllocMapped));
+        ctx->faHostCap[b] = hostBytes;
+    }
+    uint8_t *w = (uint8_t *)ctx->faWork[b].p;
+    fa::Args &A = B.args;
+    A.stage = (const uint8_t *)ctx->fa.p;
+    A.src = (const uint64_t *)(w + o64); A.len = A.src + nF; A.dst = A.src + 2 * nF;
+    A.tile0 = (const uint32_t *)(w + o32);
+    A.nFiles = nF; A.nTiles = nT;
+    A.tLast = (uint64_t *)(w + oTLast); A.inLast = (uint64_t *)(w + oInLast);
+    A.tHdr = (uint32_t *)(w + oTHdr); A.hdrBase = (uint32_t *)(w + oHdrBase);
+    A.tKept = (uint32_t *)(w + oTKept); A.keptBase = (uint32_t *)(w + oKeptBase);
+    A.firstHdr = (uint32_t *)(w + oFirst);
+    A.out = (uint8_t *)ctx->raw.p;
+    uint32_t *hm = nullptr;
+    CK(cudaHostGetDevicePointer((void **)&hm, ctx->faHost[b], 0));
+    A.fileTab = hm; A.recStart = hm + (2 * nF + 1); A.recHdr = A.recStart + B.cap;
+    A.cap = B.cap;
+    memset(ctx->faHost[b], 0, (size_t)(2 * nF + 1) * 4);
+    if (!B.done) CK(cudaEventCreateWithFlags(&B.done, cudaEventDisableTiming));
+    CK(cudaMemcpyAsync(w + o64, h64.data(), h64.size() * 8, cudaMemcpyHostToDevice, ps));
+    CK(cudaMemcpyAsync(w + o32, h32.data(), h32.size() * 4, cudaMemcpyHostToDevice, ps));
+    CK(cudaMemsetAsync(w + oFirst, 0xFF, nF * 4, ps));
+    if (nT) {
+        const unsigned nb = nblk(nT, fa::WARPS);
+        fa::k_fa_mark<<<nb, fa::WARPS * 32, 0, ps>>>(A);
+        fa::k_fa_scan<<<1, 1024, 0, ps>>>(A.tHdr, A.hdrBase, A.tLast, A.inLast, nT);
+        fa::k_fa_sweep<false><<<nb, fa::WARPS * 32, 0, ps>>>(A);
+        fa::k_fa_scan<<<1, 1024, 0, ps>>>(A.tKept, A.keptBase, nullptr, nullptr, nT);
+        fa::k_fa_sweep<true><<<nb, fa::WARPS * 32, 0, ps>>>(A);
+        ctx->fa_launches += 5;
+    }
+    CK(cudaEventRecord(B.done, ps));
+    B.pending = true;
+    return PFB_OK;
+}
+
+// wait for a batch and turn its record table into contig offsets of the genomes
+int fasta_collect(pfb_ctx *ctx, int b) {
+    FaBatch &B = ctx->faBatch[b];
+    if (!B.pending) return PFB_OK;
+    B.pending = false;
+    CK(cudaEventSynchronize(B.done));
+    const uint32_t nF = B.args.nFiles;
+    const uint32_t *tab = (const uint32_t *)ctx->faHost[b];
+    const uint32_t total = tab[2 * nF];
+    if (total > B.cap) {
+        // more records than the table holds: grow it and repeat the gather pass (the scans are still valid)
+        B.cap = total + total / 4 + 16;
+        const size_t hostBytes = ((size_t)(2 * nF + 1) + 2 * (size_t)B.cap) * 4;
+        cudaFreeHost(ctx->faHost[b]);
+        ctx->faHost[b] = nullptr; ctx->faHostCap[b] = 0;
+        CK(cudaHostAlloc(&ctx->faHost[b], hostBytes, cudaHostAllocMapped));
+        ctx->faHostCap[b] = hostBytes;
+        uint32_t *hm = nullptr;
+        CK(cudaHostGetDevicePointer((void **)&hm, ctx->faHost[b], 0));
+        B.args.fileTab = hm; B.args.recStart = hm + (2 * nF + 1); B.args.recHdr = B.args.recStart + B.cap;
+        B.args.cap = B.cap;
+        fa::k_fa_sweep<true><<<nblk(B.nTiles, fa::WARPS), fa::WARPS * 32, 0, ctx->parseStream>>>(B.args);
+        ctx->fa_launches++;
+        CK(cudaStreamSynchronize(ctx->parseStream));
+        tab = (const uint32_t *)ctx->faHost[b];
+    }
+    const uint32_t *recStart = tab + (2 * nF + 1), *recHdr = recStart + B.cap;
+    for (uint32_t f = 0; f < nF; f++) {
+        HostGenome &hg = ctx->genomes[B.g0 + f];
+        const uint32_t r0 = tab[2 * f], kept = tab[2 * f + 1];
+        const uint32_t r1 = f + 1 < nF ? tab[2 * (f + 1)] : total;
+        if (r1 <= r0) return fail(ctx, PFB_EINVAL, "genome " + std::to_string(B.g0 + f) + ": no FASTA record (no line starts with '>')");
+        hg.off.clear(); hg.hdr_off.clear();
+        for (uint32_t r = r0; r < r1; r++) { hg.off.push_back(recStart[r]); hg.hdr_off.push_back(recHdr[r]); }
+        hg.off.push_back(kept);
+        hg.n_bases = kept;
+    }
     return PFB_OK;
 }
 
@@ -1292,6 +1490,7 @@ int pfb_create(pfb_ctx **out, int device, const pfb_params *params) {
     cudaDeviceGetAttribute(&ctx->num_sms, cudaDevAttrMultiProcessorCount, device);
     e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->copyStream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->parseStream, cudaStreamNonBlocking);
     if (e == cudaSuccess)
         e = cudaFuncSetAttribute(k_scan_filtered, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SCANF_SMEM);
     if (e != cudaSuccess) { std::string m = cudaGetErrorString(e); delete ctx; return fail(nullptr, PFB_ECUDA, m); }
@@ -1313,6 +1512,13 @@ void pfb_destroy(pfb_ctx *ctx) {
     for (auto &ev : ctx->ev) if (ev) cudaEventDestroy(ev);
     for (auto &ev : ctx->evCopy) if (ev) cudaEventDestroy(ev);
     if (ctx->copyStream) { cudaStreamSynchronize(ctx->copyStream); cudaStreamDestroy(ctx->copyStream); }
+    if (ctx->parseStream) { cudaStreamSynchronize(ctx->parseStream); cudaStreamDestroy(ctx->parseStream); }
+    for (int b = 0; b < 2; b++) {
+        release(ctx->faWork[b]);
+        if (ctx->faHost[b]) cudaFreeHost(ctx->faHost[b]);
+        if (ctx->faBatch[b].done) cudaEventDestroy(ctx->faBatch[b].done);
+    }
+    release(ctx->fa); release(ctx->tabs32b); release(ctx->tabs64b);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -1328,6 +1534,41 @@ int pfb_add_genome(pfb_ctx *ctx, const uint8_t *bases, uint64_t n_bases, const u
     g.off.assign(contig_off, contig_off + n_contigs + 1);
     ctx->genomes.push_back(std::move(g));
     ctx->uploaded = false; ctx->computed = false; ctx->stage_done = -1;
+    return PFB_OK;
+}
+
+int pfb_add_fasta(pfb_ctx *ctx, const uint8_t *file_bytes, uint64_t n_bytes) {
+    if (!ctx) return PFB_EINVAL;
+    if (!file_bytes || n_bytes == 0) return fail(ctx, PFB_EINVAL, "empty FASTA file");
+    if (n_bytes >= (1ull << 31)) return fail(ctx, PFB_ETOOLARGE, "FASTA file of 2 GiB or more");
+    HostGenome g;
+    g.bases = file_bytes; g.n_bases = 0; g.fasta = true; g.file_bytes = n_bytes;
+    ctx->genomes.push_back(std::move(g));
+    ctx->uploaded = false; ctx->computed = false; ctx->stage_done = -1;
+    return PFB_OK;
+}
+
+int pfb_genome_info(pfb_ctx *ctx, uint32_t genome_idx, uint32_t *n_contigs, uint64_t *n_bases) {
+    if (!ctx) return PFB_EINVAL;
+    if (genome_idx >= ctx->genomes.size()) return fail(ctx, PFB_EINVAL, "genome index out of range");
+    const HostGenome &g = ctx->genomes[genome_idx];
+    if (g.off.empty()) return fail(ctx, PFB_ESTATE, "the genome has not been parsed yet (pfb_upload / pfb_run)");
+    if (n_contigs) *n_contigs = (uint32_t)g.off.size() - 1;
+    if (n_bases) *n_bases = g.n_bases;
+    return PFB_OK;
+}
+
+int pfb_contig_table(pfb_ctx *ctx, uint32_t genome_idx, uint64_t *header_off, uint64_t *length, uint32_t cap) {
+    if (!ctx) return PFB_EINVAL;
+    if (genome_idx >= ctx->genomes.size()) return fail(ctx, PFB_EINVAL, "genome index out of range");
+    const HostGenome &g = ctx->genomes[genome_idx];
+    if (g.off.empty()) return fail(ctx, PFB_ESTATE, "the genome has not been parsed yet (pfb_upload / pfb_run)");
+    const uint32_t nc = (uint32_t)g.off.size() - 1;
+    if (cap < nc) return fail(ctx, PFB_EINVAL, "contig table too small");
+    for (uint32_t c = 0; c < nc; c++) {
+        if (header_off) header_off[c] = g.fasta ? g.hdr_off[c] : 0;
+        if (length) length[c] = g.off[c + 1] - g.off[c];
+    }
     return PFB_OK;
 }
 
@@ -1362,43 +1603,58 @@ static int upload_impl(pfb_ctx *ctx, bool async) {
     if (!ctx) return PFB_EINVAL;
     if (ctx->genomes.empty()) return fail(ctx, PFB_ESTATE, "no genome added");
     CK(cudaSetDevice(ctx->device));
-    int rc = build_layout(ctx);
-    if (rc != PFB_OK) return rc;
+    const size_t nG = ctx->genomes.size();
+    size_t nFasta = 0;
+    for (auto &g : ctx->genomes) nFasta += g.fasta ? 1 : 0;
+    if (nFasta && nFasta != nG) return fail(ctx, PFB_EINVAL, "pfb_add_genome and pfb_add_fasta cannot be mixed on one context");
+    ctx->any_fasta = nFasta != 0;
+    raw_starts(ctx);
+    int rc;
     cudaStream_t st = ctx->stream;
     cudaStream_t cs = async ? ctx->copyStream : ctx->stream;
     if ((rc = ensure(ctx, ctx->raw, ctx->totalRaw + 64)) != PFB_OK) return rc;
-    size_t nC = ctx->cLen.size(), nG = ctx->genomes.size();
+    if (ctx->any_fasta && (rc = ensure(ctx, ctx->fa, ctx->totalFa + 256)) != PFB_OK) return rc;
     while (ctx->evCopy.size() < nG) {
         cudaEvent_t e;
         CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         ctx->evCopy.push_back(e);
     }
-    // contig / genome tables
-    std::vector<uint32_t> &t32 = ctx->t32host;
-    t32.clear();
-    auto put32 = [&](const std::vector<uint32_t> &v) { size_t o = t32.size(); t32.insert(t32.end(), v.begin(), v.end()); return o; };
-    size_t o_cws = put32(ctx->cWordStart), o_cl = put32(ctx->cLen), o_cg = put32(ctx->cGenome), o_cv = put32(ctx->cVirt);
-    size_t o_gws = put32(ctx->gWordStart), o_gfc = put32(ctx->gFirstContig), o_gnc = put32(ctx->gNumContigs), o_gvl = put32(ctx->gVirtLen);
-    if ((rc = ensure(ctx, ctx->tabs32, t32.size() * 4)) != PFB_OK) return rc;
-    if ((rc = ensure(ctx, ctx->tabs64, nC * 8)) != PFB_OK) return rc;
-    CK(cudaMemcpyAsync(ctx->tabs32.p, t32.data(), t32.size() * 4, cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(ctx->tabs64.p, ctx->cRawStart.data(), nC * 8, cudaMemcpyHostToDevice, st));
+    ctx->fa_launches = 0;
     CK(cudaEventRecord(ctx->ev[0], cs));
     for (size_t g = 0; g < nG; g++) {
         auto &hg = ctx->genomes[g];
-        if (hg.n_bases)
+        if (hg.fasta) {
+            CK(cudaMemcpyAsync((uint8_t *)ctx->fa.p + ctx->faStart[g], hg.bases, hg.file_bytes, cudaMemcpyHostToDevice, cs));
+        } else if (hg.n_bases) {
             CK(cudaMemcpyAsync((uint8_t *)ctx->raw.p + ctx->gRawStart[g], hg.bases, hg.n_bases, cudaMemcpyHostToDevice, cs));
+        }
         if (async) CK(cudaEventRecord(ctx->evCopy[g], cs));
     }
     CK(cudaEventRecord(ctx->ev[1], cs));
-    const uint32_t *b32 = (const uint32_t *)ctx->tabs32.p;
-    K &k = ctx->k;
-    k.cWordStart = b32 + o_cws; k.cLen = b32 + o_cl; k.cGenome = b32 + o_cg; k.cVirt = b32 + o_cv;
-    k.gWordStart = b32 + o_gws; k.gFirstContig = b32 + o_gfc; k.gNumContigs = b32 + o_gnc; k.gVirtLen = b32 + o_gvl;
-    k.cRawStart = (const uint64_t *)ctx->tabs64.p;
-    k.nContigs = (uint32_t)nC; k.nGenomes = (uint32_t)nG; k.totalWords = ctx->totalWords;
-    k.raw = (const uint8_t *)ctx->raw.p;
     ctx->pipelined = async;
+    if (!ctx->any_fasta) {
+        if ((rc = build_layout(ctx, nG)) != PFB_OK) return rc;
+        if ((rc = upload_tables(ctx, false)) != PFB_OK) return rc;
+    } else if (!async) {
+        // every file is parsed on the device before the layout is made
+        if ((rc = fasta_enqueue(ctx, 0, 0, nG, st)) != PFB_OK) return rc;
+        if ((rc = fasta_collect(ctx, 0)) != PFB_OK) return rc;
+        if ((rc = build_layout(ctx, nG)) != PFB_OK) return rc;
+        if ((rc = upload_tables(ctx, false)) != PFB_OK) return rc;
+    } else {
+        // genome 1's file is parsed as soon as it has landed and the key table is built from it while the
+        // other files are still in flight; they are parsed behind their copies and join the layout just
+        // before they are scanned (stage0 -> fasta_finish)
+        CK(cudaStreamWaitEvent(ctx->parseStream, ctx->evCopy[0], 0));
+        if ((rc = fasta_enqueue(ctx, 0, 0, 1, ctx->parseStream)) != PFB_OK) return rc;
+        if (nG > 1) {
+            CK(cudaStreamWaitEvent(ctx->parseStream, ctx->evCopy[nG - 1], 0));
+            if ((rc = fasta_enqueue(ctx, 1, 1, nG, ctx->parseStream)) != PFB_OK) return rc;
+        }
+        if ((rc = fasta_collect(ctx, 0)) != PFB_OK) return rc;
+        if ((rc = build_layout(ctx, 1)) != PFB_OK) return rc;
+        if ((rc = upload_tables(ctx, false)) != PFB_OK) return rc;
+    }
     if (!async) {
         CK(cudaStreamSynchronize(st));   // host genome buffers are borrowed only until here
         float ms = 0;
@@ -1407,6 +1663,16 @@ static int upload_impl(pfb_ctx *ctx, bool async) {
     }
     ctx->uploaded = true; ctx->computed = false; ctx->stage_done = -1;
     return PFB_OK;
+}
+
+// FASTA, pipelined: the files of genomes 2..G have been parsed by now (or are about to be): complete the layout
+static int fasta_finish(pfb_ctx *ctx) {
+    int rc;
+    const size_t nG = ctx->genomes.size();
+    if (ctx->laid_out == nG) return PFB_OK;
+    if ((rc = fasta_collect(ctx, 1)) != PFB_OK) return rc;
+    if ((rc = build_layout(ctx, nG)) != PFB_OK) return rc;
+    return upload_tables(ctx, true);
 }
 
 int pfb_upload(pfb_ctx *ctx) { return upload_impl(ctx, false); }
@@ -1440,14 +1706,21 @@ static int stage0(pfb_ctx *ctx) {
     k.max_repeat = P.max_repeat; k.prefilter = P.prefilter;
     std::vector<double> fterm;
     fill_filter_constants(P, k, fterm);
-    const uint32_t W = ctx->totalWords;
-    const uint32_t W1 = ctx->genomes.size() > 1 ? ctx->gWordStart[1] : W;   // genome 1 = words [0, W1)
+    uint32_t W = ctx->totalWords;
+    const uint32_t W1 = ctx->laid_out > 1 ? ctx->gWordStart[1] : W;         // genome 1 = words [0, W1)
     const uint32_t NB = (uint32_t)nk * k.PW;                                // words of the concatenated bitmaps
     ctx->launches = 0;
+    // FASTA genomes still being parsed (pipelined run): the layout covers genome 1 only, the word arrays are
+    // sized by an estimate of the rest (re-checked in fasta_finish)
+    const bool partial = ctx->laid_out < ctx->genomes.size();
+    uint64_t W_alloc = W;
+    if (partial)
+        for (size_t g = ctx->laid_out; g < ctx->genomes.size(); g++)
+            W_alloc += ctx->genomes[g].file_bytes / 32 + ctx->genomes[g].file_bytes / 1024 + 4096;
     // buffers
-    if ((rc = ensure(ctx, ctx->seq2, (size_t)(W + 2) * 8)) != PFB_OK) return rc;
-    if ((rc = ensure(ctx, ctx->nmask, (size_t)(W + 1) * 4)) != PFB_OK) return rc;
-    if ((rc = ensure(ctx, ctx->wordContig, (size_t)(W + 1) * 4)) != PFB_OK) return rc;
+    if ((rc = ensure(ctx, ctx->seq2, (size_t)(W_alloc + 2) * 8)) != PFB_OK) return rc;
+    if ((rc = ensure(ctx, ctx->nmask, (size_t)(W_alloc + 1) * 4)) != PFB_OK) return rc;
+    if ((rc = ensure(ctx, ctx->wordContig, (size_t)(W_alloc + 1) * 4)) != PFB_OK) return rc;
     if ((rc = ensure(ctx, ctx->sk, (size_t)NB * 2 * 4)) != PFB_OK) return rc;
     if ((rc = ensure(ctx, ctx->br, (size_t)NB * 8)) != PFB_OK) return rc;
     if ((rc = ensure(ctx, ctx->filter, (size_t)nk * FILTER_BYTES)) != PFB_OK) return rc;
@@ -1493,7 +1766,7 @@ static int stage0(pfb_ctx *ctx) {
     CK(cudaMemsetAsync(ctx->rows0.p, 0, NS * 8, st));
     // the filter pays off while it stays sparse: expected fill 1 - exp(-keys_per_k / FILTER_BITS)
     bool use_filter = ctx->scan_mode == 2 ||
-                      (ctx->scan_mode == 0 && (double)ctx->nslots / nk < 0.35 * FILTER_BITS && W >= 4096);
+                      (ctx->scan_mode == 0 && (double)ctx->nslots / nk < 0.35 * FILTER_BITS && W_alloc >= 4096);
     ctx->used_filter = use_filter;
     if (use_filter && ctx->nslots) {
         CK(cudaMemsetAsync(ctx->filter.p, 0, (size_t)nk * FILTER_BYTES, st));
@@ -1556,6 +1829,15 @@ static int stage0(pfb_ctx *ctx) {
             if (use_filter) CK(cudaMemsetAsync(ctx->filter.p, 0, (size_t)nk * FILTER_BYTES, st));
             k_build_at<<<nblk(NA, 256), 256, 0, st>>>(k, use_filter ? 1 : 0); ctx->launches++;
         }
+    }
+    if (partial) {
+        // the other FASTA files have been parsed behind their copies: complete the layout
+        if ((rc = fasta_finish(ctx)) != PFB_OK) return rc;
+        W = ctx->totalWords;
+        if ((rc = ensure_keep(ctx, ctx->seq2, (size_t)(W + 2) * 8, (size_t)(W1 + 2) * 8)) != PFB_OK) return rc;
+        if ((rc = ensure_keep(ctx, ctx->nmask, (size_t)(W + 1) * 4, (size_t)(W1 + 1) * 4)) != PFB_OK) return rc;
+        if ((rc = ensure_keep(ctx, ctx->wordContig, (size_t)(W + 1) * 4, (size_t)(W1 + 1) * 4)) != PFB_OK) return rc;
+        k.seq2 = (uint64_t *)ctx->seq2.p; k.nmask = (uint32_t *)ctx->nmask.p; k.wordContig = (uint32_t *)ctx->wordContig.p;
     }
     if (ctx->nids && nG > 1) {
         if (!piped) {
@@ -1671,7 +1953,7 @@ static int stage2(pfb_ctx *ctx) {
         }
     }
     t.n_bases = nb; t.n_windows = nw; t.n_slots = ctx->nslots; t.n_records = ctx->nrec; t.n_picked = ctx->npick;
-    t.n_launches = ctx->launches;
+    t.n_launches = ctx->launches + ctx->fa_launches;
     t.used_filter = ctx->used_filter ? 1 : 0;
     ctx->computed = true;
     return PFB_OK;

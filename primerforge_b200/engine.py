@@ -135,6 +135,30 @@ class Engine:
         self.n_genomes += 1
         self._multi_contig |= offsets.size > 2
 
+    def add_fasta(self, data: np.ndarray | None = None, ptr: int | None = None, n_bytes: int | None = None):
+        """a genome given as its FASTA file image (uint8 array, or a raw host pointer e.g. into pinned memory);
+        the records are found and compacted on the device -- see contig_table() after run()"""
+        if data is not None:
+            data = np.ascontiguousarray(data, dtype=np.uint8)
+            ptr, n_bytes = data.ctypes.data, data.size
+        self._keep.append((data, None))
+        self._check(self._lib.pfb_add_fasta(self._ctx, ptr, int(n_bytes)))
+        self.n_genomes += 1
+        self._multi_contig = None       # known after the device has parsed the files
+
+    def genome_info(self, genome_idx: int):
+        nc, nb = C.c_uint32(), C.c_uint64()
+        self._check(self._lib.pfb_genome_info(self._ctx, genome_idx, C.byref(nc), C.byref(nb)))
+        return int(nc.value), int(nb.value)
+
+    def contig_table(self, genome_idx: int):
+        """(offset of each record's '>' in the FASTA file, length of each record)"""
+        nc, _ = self.genome_info(genome_idx)
+        hdr = np.zeros(nc, dtype=np.uint64)
+        ln = np.zeros(nc, dtype=np.uint64)
+        self._check(self._lib.pfb_contig_table(self._ctx, genome_idx, hdr.ctypes.data, ln.ctypes.data, nc))
+        return hdr, ln
+
     def clear(self):
         self._check(self._lib.pfb_clear_genomes(self._ctx))
         self._keep = []
@@ -218,6 +242,8 @@ class Engine:
         _n, m = self.counts()
         G = self.n_genomes
         cap = max(m, 1)
+        if self._multi_contig is None:
+            self._multi_contig = any(self.genome_info(g)[0] > 1 for g in range(G))
         rec = self._pinned_array("rec", _lib.RECORD_DTYPE, (cap,))
         ss = self._pinned_array("ss", np.uint32, (G, cap))
         ct = self._pinned_array("ct", np.uint32, (G, cap)) if self._multi_contig else None

@@ -69,3 +69,21 @@ def read_genome(path: str, fmt: str):
     if fmt in ("genbank", "gb"):
         return read_genbank(path)
     raise ValueError(f"unsupported ingroup format {fmt!r}")
+
+
+def fasta_ids(data: np.ndarray, header_off) -> list:
+    """record ids of a FASTA file image given the offsets of the '>' of its records (as found by the
+    device parser, pfb_contig_table): the title up to the first whitespace, like SeqRecord.id"""
+    ids = []
+    n = data.size
+    for st in header_off:
+        st = int(st)
+        chunk = data[st + 1:min(n, st + 1 + 4096)]
+        nl = np.flatnonzero(chunk == _NL)
+        if nl.size == 0 and st + 1 + 4096 < n:           # a very long title line
+            chunk = data[st + 1:]
+            nl = np.flatnonzero(chunk == _NL)
+        end = int(nl[0]) if nl.size else chunk.size
+        parts = chunk[:end].tobytes().decode("latin-1").strip("\r").split(None, 1)
+        ids.append(parts[0] if parts else "")
+    return ids

@@ -1,0 +1,148 @@
+"""Device FASTA ingest (pfb_add_fasta): the records the GPU parser finds and the stage results computed from
+them must equal what the host reader (primerforge_b200.seqio.read_fasta, Bio.SeqIO's FASTA rules) gives
+through pfb_add_genome -- for well-formed files and for every irregularity the rules cover."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _fasta_bytes(contigs, ids, width, rng=None, crlf=False, junk=b"", trailing_newline=True, spaces=False):
+    out = bytearray(junk)
+    nl = b"\r\n" if crlf else b"\n"
+    for cid, arr in zip(ids, contigs):
+        out += b">" + cid.encode() + b" some description > with a bracket" + nl
+        seq = arr.tobytes()
+        i = 0
+        while i < len(seq):
+            w = width if rng is None else int(rng.integers(1, 2 * width))
+            line = seq[i:i + w]
+            if spaces and len(line) > 4:
+                line = line[:3] + b" " + line[3:]
+            out += line + nl
+            i += w
+        if rng is not None and rng.random() < 0.3:
+            out += nl                                     # blank line between records
+    if not trailing_newline:
+        while out and out[-1:] in (b"\n", b"\r"):
+            out = out[:-1]
+    return np.frombuffer(bytes(out), dtype=np.uint8).copy()
+
+
+def _run(add, mode):
+    from primerforge_b200.engine import Engine
+    with Engine(device=0, prefilter=0) as eng:
+        add(eng)
+        if mode == "pipelined":
+            eng.run()
+        else:
+            eng.upload()
+            eng.compute()
+        res = eng.result()
+        tables = [eng.contig_table(g) for g in range(eng.n_genomes)]
+        info = [eng.genome_info(g) for g in range(eng.n_genomes)]
+    return res, tables, info
+
+
+def _compare(images, mode):
+    from primerforge_b200 import seqio
+    import os
+    import tempfile
+    host = []
+    with tempfile.TemporaryDirectory() as d:
+        for i, img in enumerate(images):
+            fn = os.path.join(d, f"g{i}.fasta")
+            img.tofile(fn)
+            host.append(seqio.read_fasta(fn))
+    res_f, tables, info = _run(lambda e: [e.add_fasta(img) for img in images], mode)
+    res_h, _, _ = _run(lambda e: [e.add_genome(c) for _ids, c in host], mode)
+    for g, (ids, contigs) in enumerate(host):
+        hdr, ln = tables[g]
+        assert info[g] == (len(contigs), sum(c.size for c in contigs))
+        assert ln.tolist() == [c.size for c in contigs]
+        assert seqio.fasta_ids(images[g], hdr) == ids
+        assert all(images[g][int(h)] == ord(">") for h in hdr)
+    assert res_f.records.size == res_h.records.size and res_f.records.size > 0
+    for f in ("word", "tm", "gc_count", "k", "flags"):
+        assert np.array_equal(res_f.records[f], res_h.records[f]), f
+    for pf, ph in zip(res_f.positions, res_h.positions):
+        assert np.array_equal(pf, ph)
+
+
+@pytest.mark.parametrize("mode", ["sync", "pipelined"])
+def test_regular_fasta(mode):
+    from primerforge_b200 import synth
+    gens = synth.make_genomes(4, 120_000, seed=77, snp_rate=0.003, n_inversions=2, n_contigs=4)
+    images = [_fasta_bytes(g.contigs, g.contig_ids, 80) for g in gens]
+    _compare(images, mode)
+
+
+@pytest.mark.parametrize("mode", ["sync", "pipelined"])
+@pytest.mark.parametrize("variant", ["crlf", "junk", "unwrapped", "ragged", "no_final_newline", "spaces", "long_title", "tiny_records"])
+def test_irregular_fasta(variant, mode):
+    from primerforge_b200 import synth
+    import zlib
+    rng = np.random.default_rng(zlib.crc32(variant.encode()) % 1000)
+    gens = synth.make_genomes(3, 60_000, seed=91, snp_rate=0.003, n_inversions=1, n_contigs=3)
+    images = []
+    for g in gens:
+        kw = {}
+        width = 70
+        ids = list(g.contig_ids)
+        contigs = list(g.contigs)
+        if variant == "crlf":
+            kw["crlf"] = True
+        elif variant == "junk":
+            kw["junk"] = b"; a comment line\n\nsome text before the first record\n"
+        elif variant == "unwrapped":
+            width = 10_000_000                            # one line per record: lines far longer than a tile
+        elif variant == "ragged":
+            kw["rng"] = rng
+        elif variant == "no_final_newline":
+            kw["trailing_newline"] = False
+        elif variant == "spaces":
+            kw["spaces"] = True
+        elif variant == "long_title":
+            ids = [cid + "_" + "x" * 9000 for cid in ids]  # a title line longer than two tiles
+        elif variant == "tiny_records":
+            extra = [np.frombuffer(b"ACGT", dtype=np.uint8), np.zeros(0, dtype=np.uint8), np.frombuffer(b"GGCCNNacgt", dtype=np.uint8)]
+            contigs = contigs[:1] + extra + contigs[1:]
+            ids = ids[:1] + ["t1", "empty", "t3"] + ids[1:]
+        images.append(_fasta_bytes(contigs, ids, width, **kw))
+    _compare(images, mode)
+
+
+def test_fasta_errors():
+    from primerforge_b200.engine import Engine, PfbError
+    from primerforge_b200 import synth
+    gens = synth.make_genomes(2, 20_000, seed=5)
+    with Engine(device=0) as eng:
+        eng.add_fasta(np.frombuffer(b"ACGTACGTACGT\nACGT\n", dtype=np.uint8).copy())     # no record at all
+        with pytest.raises(PfbError):
+            eng.run()
+    with Engine(device=0) as eng:                                                       # the two input kinds do not mix
+        eng.add_genome(gens[0].contigs)
+        eng.add_fasta(_fasta_bytes(gens[1].contigs, gens[1].contig_ids, 60))
+        with pytest.raises(PfbError):
+            eng.run()
+    with Engine(device=0) as eng:
+        with pytest.raises(PfbError):
+            eng.add_fasta(np.zeros(0, dtype=np.uint8))
+
+
+def test_many_records_grow_the_table():
+    """more records than the initial record table holds: the gather pass is repeated with a larger one"""
+    from primerforge_b200.engine import Engine
+    rng = np.random.default_rng(3)
+    n_rec = 70_000                                       # initial capacity is 65536 + bytes / 256
+    body = bytearray()
+    for i in range(n_rec):
+        body += b">r%d\n" % i + bytes(rng.choice(np.frombuffer(b"ACGT", dtype=np.uint8), size=2)) + b"\n"
+    img = np.frombuffer(bytes(body), dtype=np.uint8).copy()
+    with Engine(device=0) as eng:
+        eng.add_fasta(img)
+        eng.upload()
+        nc, nb = eng.genome_info(0)
+        hdr, ln = eng.contig_table(0)
+    assert nc == n_rec and nb == 2 * n_rec and np.all(ln == 2)
+    assert np.all(img[hdr.astype(np.int64)] == ord(">"))
