@@ -203,6 +203,18 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (there is no CPU path)")
     torch.cuda.set_device(local)
+    # pinned host buffers should live on the NUMA node next to this rank's GPU: bind the process to the CPUs
+    # NVML names for the device before anything is allocated (no-op where NVML refuses)
+    affinity = None
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        uuid = torch.cuda.get_device_properties(local).uuid
+        handle = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + str(uuid)).encode())
+        pynvml.nvmlDeviceSetCpuAffinity(handle)
+        affinity = len(os.sched_getaffinity(0))
+    except Exception as exc:      # noqa: BLE001
+        print(f"[bench] NUMA binding skipped: {exc}", file=sys.stderr)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -415,7 +427,7 @@ def main():
             "ms_per_step": step_ms, "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": "u64",
             "data": "synthetic", "config": workload_config(args.config, world, strong) | ({"genomes_per_gpu": per_rank, "genome_bp": cfg["length"]}),
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_ms},
-            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "host_cpus_bound": affinity,
             "phases_ms": {"ms_encode": float(np.mean(enc_ms)), "ms_first": float(np.mean(first_ms)), "ms_scan": float(np.mean(scan_ms)),
                           "ms_finalize": float(np.mean(fin_ms)), "ms_total": step_ms},
             "counts": dev_counts,
@@ -424,12 +436,12 @@ def main():
         # ring all-reduce: every rank sends and receives 2 (N - 1) / N of the buffer per direction
         ms_x = float(np.mean(xchg["ms"][-args.steps:]))
         wire = 2.0 * (world - 1) / world * xchg["bytes"]
-        line["exchange"] = {"what": "MIN all-reduce of the per-key alive bytes + MAX all-reduce of the pick words (NCCL, on the library's stream)",
+        line["exchange"] = {"what": "MIN all-reduce of the per-key alive bytes + MAX all-reduce of the pick bytes (NCCL, on the library's stream)",
                             "bytes_reduced_per_rank": int(xchg["bytes"]), "ms_per_step": ms_x,
                             "wire_GBs_per_direction": wire / (ms_x / 1e3) / 1e9 if ms_x > 0 else None,
                             "nvlink_peak_GBs_per_direction": 900.0,
                             "frac_of_nvlink": wire / (ms_x / 1e3) / 1e9 / 900.0 if ms_x > 0 else None,
-                            "note": "latency-bound: ~6 MB per step; no k-mer crosses NVLink (DESIGN.md section 5)"}
+                            "note": "latency-bound: ~2 MB per step; no k-mer crosses NVLink (DESIGN.md section 5)"}
     if fasta_leg is not None:
         line["e2e_fasta"] = fasta_leg
     if world == 1 and not args.no_cpu_baseline:

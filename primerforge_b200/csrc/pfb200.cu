@@ -113,7 +113,7 @@ struct K {  // kernel arguments (by value, __grid_constant__)
     uint32_t *pos;            // [nGenomes][nrec] start within contig | strand << 31
     uint32_t *posContig;      // [nGenomes][nrec] contig index (only when some genome has > 1 contig)
     int multiContig;
-    uint32_t *pick;           // [nrec] 0 / 1, then (stage 2) its exclusive prefix in pickOff
+    uint8_t *pick;            // [nrec] 0 / 1, then (stage 2) its exclusive prefix in pickOff
     uint32_t *pickOff;
     pfb_record *outRec;       // picked records, compacted
     uint32_t *outPos;         // [nGenomes][npick]
@@ -171,19 +171,19 @@ __device__ __forceinline__ double tm_from_sums(uint32_t acc, uint64_t h, int k, 
 // minTm <= Tm <= maxTm (:305-307).  For a fixed length and GC count, Tm >= t is the half plane
 // dh >= a * ds + b of the integer nearest-neighbour sums (the denominator of the formula is negative), so
 // the window test is two fused multiply-adds against a per-(k, gc) table.  dh is an integer: unless it is
-// within 0.02 of a bound the fp32 evaluation (error < 1e-3) decides; otherwise -- and for oligos that
-// could be self-complementary, which use another constant -- the exact fp64 formula does, so the
-// decision is always the one the fp64 formula makes.
-__device__ __forceinline__ bool tm_in_range(uint32_t acc, uint64_t h, int k, int gc, const K &p) {
+// within 0.004 of a bound the fp32 evaluation (error < 5e-4: |ds| < 9000, line slopes ~0.33, offsets ~180)
+// decides; otherwise -- and for self-complementary oligos, which use another constant -- the exact fp64
+// formula does, so the decision is always the one the fp64 formula makes.
+__device__ __forceinline__ bool tm_in_range(uint32_t acc, uint64_t h, int k, int gc, const K &p, bool self_compl) {
     const uint32_t first = (uint32_t)(h >> (2 * k - 2)) & 3u, last = (uint32_t)h & 3u;
     const int dh = (int)(acc & 0xFFFF) + (first < 2 ? -23 : -1) + (last < 2 ? -23 : -1);
     const int ds = (int)(acc >> 16) + (first < 2 ? -41 : 28) + (last < 2 ? -41 : 28);
-    if ((k & 1) || (first ^ last) != 1u) {        // ends not complementary: cannot be a palindrome
+    if (!self_compl) {
         const float4 b = __ldg(&p.tmb[k * 33 + gc]);
         const float x = (float)ds, d = (float)dh;
         const float lo = fmaf(b.x, x, b.y), hi = fmaf(b.z, x, b.w);
-        if (d < lo - 0.02f || d > hi + 0.02f) return false;
-        if (d > lo + 0.02f && d < hi - 0.02f) return true;
+        if (d < lo - 0.004f || d > hi + 0.004f) return false;
+        if (d > lo + 0.004f && d < hi - 0.004f) return true;
     }
     double tm = tm_from_sums(acc, h, k, gc, p);
     return tm >= p.min_tm && tm <= p.max_tm;
@@ -353,63 +353,105 @@ __device__ __forceinline__ bool load_pos(const K &p, uint32_t b, PosState &s) {
 // range (:301-320; legal because the per-position pick takes the FIRST k-mer that passes, so k-mers
 // that fail can be dropped up front).  The sketch's "count == 1" is decided later by the scan, which
 // sees every window of genome 1, candidates or not.
-__global__ void __launch_bounds__(256) k_cand1(const __grid_constant__ K p, uint32_t nbases) {
+//
+// A CTA covers CAND_POS consecutive end positions (one per thread) plus a 32-position halo warp.
+//   1. every thread looks up the nearest-neighbour value of the base pair ending at its position; a CTA-wide
+//      prefix sum P of those values turns the sum over ANY window into one subtraction, P[b] - P[b - k + 1]
+//      (both fields of the packed (S << 16 | H) value are differences of < 2^14, so the 32-bit wrap-around of
+//      the prefix is harmless);
+//   2. the cheap tests (ends, non-ACGT, GC window, homopolymers) run branch-free for every k;
+//   3. the (position, k) pairs that survive (~38 %) are compacted per warp, so that the Tm test, the
+//      canonical hash and the table update run with full warps instead of a few live lanes per k.
+constexpr int CAND_POS = 256;
+
+__global__ void __launch_bounds__(CAND_POS + 32) k_cand1(const __grid_constant__ K p, uint32_t nbases) {
     __shared__ uint32_t s_nn[16];
-    if (threadIdx.x < 16) s_nn[threadIdx.x] = c_nn[threadIdx.x];
+    __shared__ uint32_t s_P[CAND_POS + 32];
+    __shared__ uint32_t s_wsum[(CAND_POS + 32) / 32];
+    __shared__ uint64_t s_km2[32], s_gcok[32], s_run[32];
+    __shared__ uint32_t s_km1[32];
+    __shared__ uint16_t s_item[(CAND_POS + 32) / 32][32 * 32];
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid < 16) s_nn[tid] = c_nn[tid];
+    const int R = p.max_repeat;
+    if (tid >= 32 && tid < 32 + (uint32_t)p.nk) {
+        const int ki = tid - 32, k = p.kmin + ki;
+        s_km2[ki] = kmask2(k); s_km1[ki] = (uint32_t)kmask1(k); s_gcok[ki] = p.gc_ok[k];
+        s_run[ki] = (R >= 2 && k >= R) ? kmask2(k - R + 1) : 0ull;
+    }
     __syncthreads();
-    uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= nbases) return;
+    // thread t <-> end position b = first position of the CTA - 32 + t (warp 0 is the halo)
+    const long long bb = (long long)blockIdx.x * CAND_POS - 32 + tid;
     PosState s;
-    if (!load_pos(p, b, s)) return;
-    const int khi = min(p.kmax, s.n);
+    s.hf = 0; s.hr = 0; s.nmw = ~0ull; s.n = 0; s.g = 0; s.gpos = 0;
+    const bool have = bb >= 0 && bb < (long long)nbases && load_pos(p, (uint32_t)bb, s);
     const uint64_t hf = s.hf;
-    // everything that does not depend on k is computed once: G/C bits, invalid bits, and "a homopolymer
-    // run of max_repeat starts at age i" bits (pair-equality bits AND-ed max_repeat - 1 times)
+    // 1. prefix sums of the pair values
+    uint32_t incl = have ? s_nn[(uint32_t)hf & 15u] : 0u;
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t y = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+        if (lane >= (uint32_t)o) incl += y;
+    }
+    if (lane == 31) s_wsum[warp] = incl;
+    __syncthreads();
+    uint32_t woff = 0;
+    for (uint32_t i = 0; i < warp; i++) woff += s_wsum[i];
+    s_P[tid] = incl + woff;
+    __syncthreads();
+    if (warp == 0) return;                      // the halo only contributes its pair values
+    // 2. everything that does not depend on k once (G/C bits, "a homopolymer run of max_repeat starts at age i"
+    // bits: pair-equality bits AND-ed max_repeat - 1 times), then the cheap tests per k, branch-free
     const uint64_t gcbits = hf & 0xAAAAAAAAAAAAAAAAull;
     uint64_t runs = 0;
-    const int R = p.max_repeat;
     if (R >= 2) {
         uint64_t e = hf ^ (hf >> 2);
         uint64_t z = ~(e | (e >> 1)) & 0x5555555555555555ull;
         runs = z;
         for (int t = 1; t < R - 1; t++) runs &= z >> (2 * t);
     }
-    const bool last_gc = (hf & 2ull) != 0;
-    // warp-uniform control flow from here on (no break / continue: lanes that leave a loop early would
-    // make the warp run it several times)
+    const uint32_t last_gc = (uint32_t)(hf >> 1) & 1u;
+    const int khi = have ? min(p.kmax, s.n) : 0;
+    const bool pre = p.prefilter != 0;
     uint32_t cm = 0;
     for (int ki = 0; ki < p.nk; ki++) {
         const int k = p.kmin + ki;
-        bool ok = k <= khi && !(s.nmw & kmask1(k))                                         // :40-43
-                  && (last_gc || ((hf >> (2 * k - 1)) & 1ull));                             // isOneEndGc (:29-33)
-        if (p.prefilter)
-            ok = ok && ((p.gc_ok[k] >> __popcll(gcbits & kmask2(k))) & 1ull)                // :301-303
-                 && R > 1 && !(k >= R && (runs & kmask2(k - R + 1)) != 0);                  // :309-320
-        cm |= (ok ? 1u : 0u) << ki;
+        uint32_t ok = (k <= khi) & ((s.nmw & s_km1[ki]) == 0)                                         // :40-43
+                      & (last_gc | ((uint32_t)(hf >> (2 * k - 1)) & 1u));                              // isOneEndGc (:29-33)
+        if (pre)
+            ok &= (uint32_t)(s_gcok[ki] >> __popcll(gcbits & s_km2[ki])) & 1u                         // :301-303
+                  & (R > 1) & ((runs & s_run[ki]) == 0);                                               // :309-320
+        cm |= ok << ki;
     }
-    if (p.prefilter) {
-        // the nearest-neighbour sum of window k is the sum over pairs 0 .. k-2: one tight loop for the
-        // pairs every length shares, then one more pair per length
-        uint32_t acc = 0;
-        for (int i = 0; i + 2 <= p.kmin; i++) acc += s_nn[(uint32_t)(hf >> (2 * i)) & 15u];
-        for (int ki = 0; ki < p.nk; ki++) {
-            const int k = p.kmin + ki;
-            if (ki) acc += s_nn[(uint32_t)(hf >> (2 * (k - 2))) & 15u];
-            if ((cm >> ki) & 1u) {
-                uint64_t h = hf & kmask2(k);
-                if (!tm_in_range(acc, h, k, __popcll(gcbits & kmask2(k)), p)) cm &= ~(1u << ki);
-            }
-        }
-    }
+    // 3. compaction of the surviving (lane, k) pairs of the warp
+    uint16_t *items = s_item[warp];
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    uint32_t n_items = 0;
     for (int ki = 0; ki < p.nk; ki++) {
-        if (!((cm >> ki) & 1u)) continue;
-        const int k = p.kmin + ki;
-        uint64_t h = hf & kmask2(k), r = s.hr >> (64 - 2 * k);
-        uint32_t bin = mod_p(h < r ? h : r, p);
+        const uint32_t m = __ballot_sync(0xFFFFFFFFu, (cm >> ki) & 1u);
+        if ((cm >> ki) & 1u) items[n_items + __popc(m & lt_mask)] = (uint16_t)(lane | (ki << 5));
+        n_items += __popc(m);
+    }
+    __syncwarp();
+    const uint32_t hf_lo = (uint32_t)hf, hf_hi = (uint32_t)(hf >> 32);
+    for (uint32_t base = 0; base < n_items; base += 32) {
+        const bool live = base + lane < n_items;
+        const uint32_t it = live ? items[base + lane] : 0u;
+        const uint32_t src = it & 31u;
+        const int ki = (int)(it >> 5), k = p.kmin + ki;
+        const uint64_t w = ((uint64_t)__shfl_sync(0xFFFFFFFFu, hf_hi, src) << 32) | __shfl_sync(0xFFFFFFFFu, hf_lo, src);
+        if (!live) continue;
+        const uint64_t h = w & s_km2[ki];
+        const uint64_t r = rc64(h) >> (64 - 2 * k);
+        if (pre) {
+            const uint32_t pi = warp * 32 + src;
+            const uint32_t acc = s_P[pi] - s_P[pi - (uint32_t)(k - 1)];
+            if (!tm_in_range(acc, h, k, __popcll(h & 0xAAAAAAAAAAAAAAAAull), p, r == h)) continue;
+        }
+        const uint32_t bin = mod_p(h < r ? h : r, p);
         uint32_t *cell = &p.sk[(size_t)ki * 2 * p.PW + (bin >> 4)];
-        uint32_t bb = bin & 15u;
-        uint32_t old = atomicOr(cell, 1u << bb);
-        if ((old >> bb) & 1u) atomicOr(cell, 1u << (16 + bb));
+        const uint32_t bbit = bin & 15u;
+        const uint32_t old = atomicOr(cell, 1u << bbit);
+        if ((old >> bbit) & 1u) atomicOr(cell, 1u << (16 + bbit));
     }
 }
 
@@ -1057,7 +1099,7 @@ __global__ void __launch_bounds__(256) k_positions(const __grid_constant__ K p) 
             picked = first;
         }
     }
-    if (picked) p.pick[r] = 1u;
+    if (picked) p.pick[r] = 1;
 }
 
 // k_compact: picked records and their coordinates in every genome, densely packed for the D2H copy
@@ -1750,7 +1792,7 @@ static int stage0(pfb_ctx *ctx) {
     CK(cudaEventRecord(ctx->ev[3], st));
     // genome 1: candidates -> key table
     const uint32_t N1 = W1 * 32u;                                           // padded end positions of genome 1
-    if (W1) { k_cand1<<<nblk(N1, 256), 256, 0, st>>>(k, N1); ctx->launches++; }
+    if (W1) { k_cand1<<<nblk(N1, CAND_POS), CAND_POS + 32, 0, st>>>(k, N1); ctx->launches++; }
     k_candbits<<<nblk(NB, 256), 256, 0, st>>>(k); ctx->launches++;
     if ((rc = device_exscan<SV_POPC, 2>(ctx, k.br, (uint32_t *)k.br + 1, NB, misc)) != PFB_OK) return rc;
     uint32_t ns = 0;
@@ -1892,12 +1934,12 @@ static int stage1(pfb_ctx *ctx) {
     const bool multi = ctx->cLen.size() > nG;
     if ((rc = ensure(ctx, ctx->pos, NR * nG * 4)) != PFB_OK) return rc;
     if ((rc = ensure(ctx, ctx->posContig, multi ? NR * nG * 4 : 4)) != PFB_OK) return rc;
-    if ((rc = ensure(ctx, ctx->pick, NR * 4)) != PFB_OK) return rc;
+    if ((rc = ensure(ctx, ctx->pick, NR)) != PFB_OK) return rc;
     if ((rc = ensure(ctx, ctx->pickOff, NR * 4)) != PFB_OK) return rc;
     k.rec = (pfb_record *)ctx->rec.p; k.pos = (uint32_t *)ctx->pos.p; k.posContig = (uint32_t *)ctx->posContig.p;
     k.multiContig = multi ? 1 : 0;
-    k.pick = (uint32_t *)ctx->pick.p; k.pickOff = (uint32_t *)ctx->pickOff.p;
-    CK(cudaMemsetAsync(ctx->pick.p, 0, NR * 4, st));
+    k.pick = (uint8_t *)ctx->pick.p; k.pickOff = (uint32_t *)ctx->pickOff.p;
+    CK(cudaMemsetAsync(ctx->pick.p, 0, NR, st));
     if (ctx->nrec) {
         k_emit_write<<<nblk(ctx->nids, 256), 256, 0, st>>>(k); ctx->launches++;
         k_positions<<<nblk(ctx->nids, 256), 256, 0, st>>>(k); ctx->launches++;
@@ -1914,7 +1956,7 @@ static int stage2(pfb_ctx *ctx) {
     const size_t nG = ctx->genomes.size();
     ctx->npick = 0;
     if (ctx->nrec) {
-        if ((rc = device_exscan<SV_U32, 1>(ctx, k.pick, k.pickOff, (uint32_t)ctx->nrec, misc + 3)) != PFB_OK) return rc;
+        if ((rc = device_exscan<SV_U8, 1>(ctx, k.pick, k.pickOff, (uint32_t)ctx->nrec, misc + 3)) != PFB_OK) return rc;
         uint32_t np = 0;
         CK(cudaMemcpyAsync(&np, misc + 3, 4, cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
@@ -1993,7 +2035,7 @@ int pfb_device_buffer(pfb_ctx *ctx, int which, void **dev_ptr, uint64_t *n_bytes
         *dev_ptr = ctx->alive.p; *n_bytes = ctx->nids;
     } else if (which == PFB_BUF_PICK) {
         if (ctx->stage_done < 1) return fail(ctx, PFB_ESTATE, "stage 1 has not run");
-        *dev_ptr = ctx->pick.p; *n_bytes = ctx->nrec * 4;
+        *dev_ptr = ctx->pick.p; *n_bytes = ctx->nrec;
     } else {
         return fail(ctx, PFB_EINVAL, "unknown buffer");
     }
