@@ -528,9 +528,9 @@ struct Pending {
 };
 
 __device__ __forceinline__ void drain_issue(const K &p, int ki, uint32_t q_addr, uint32_t head, uint32_t lane, Pending &pd) {
-    uint4 it = lds128(q_addr + (((head + lane) & (QCAP - 1)) << 4));   // x = bin, y = start, z = genome
+    uint4 it = lds128(q_addr + (((head + lane) & (QCAP - 1)) << 4));   // x = bin, y = o, z = genome, w = start at o = 0
     pd.e = p.first_pass ? probe(p, ki, it.x) : probe2(p, ki, it.x);
-    pd.meta = it.y | ((it.x & 31u) << 26);
+    pd.meta = ((it.w - it.y) & (uint32_t)ROW_POS_MASK) | ((it.x & 31u) << 26);
     pd.g = it.z;
 }
 
@@ -591,6 +591,7 @@ __device__ __forceinline__ void scan_word(const K &p, int ki, int k, ScanWarp &s
     const uint32_t R0 = (uint32_t)rcp, R1 = (uint32_t)(rcp >> 32), R2 = (uint32_t)rcc, R3 = (uint32_t)(rcc >> 32);
     const uint32_t neg_p = 0u - p.P;
     const int C = 128 - 2 * k;
+    const uint32_t start31 = gpos0 + 31u - (uint32_t)k + 1u;     // start of the window ending at base 31 of the word (o = 0)
     int o = 0;
 #pragma unroll 1
     while (o < 32) {
@@ -601,9 +602,9 @@ __device__ __forceinline__ void scan_word(const K &p, int ki, int k, ScanWarp &s
         const uint32_t b0 = wr == 0 ? R0 : wr == 1 ? R1 : wr == 2 ? R2 : R3;
         const uint32_t b1 = wr == 0 ? R1 : wr == 1 ? R2 : wr == 2 ? R3 : 0u;
         const uint32_t b2 = wr == 0 ? R2 : wr == 1 ? R3 : 0u;
-#pragma unroll 2
+#pragma unroll 4
         for (; o < o_end; o++) {
-            const uint32_t sf = (2 * o) & 31, sr = (uint32_t)(C - 2 * o) & 31;
+            const uint32_t sf = 2u * (uint32_t)o, sr = (uint32_t)(C - 2 * o);   // the funnel shift takes the low 5 bits itself
             const int j = 31 - o;
             uint32_t h_lo = __funnelshift_r(a0, a1, sf), h_hi = 0, r_lo = __funnelshift_r(b0, b1, sr), r_hi = 0;
             if (KBIG) { h_hi = __funnelshift_r(a1, a2, sf) & mhi; r_hi = __funnelshift_r(b1, b2, sr) & mhi; }
@@ -619,11 +620,14 @@ __device__ __forceinline__ void scan_word(const K &p, int ki, int k, ScanWarp &s
             }
             const uint32_t bin = canon_bin<FASTMOD, KBIG>(p, h_lo, h_hi, r_lo, r_hi, m32, a32, neg_p);
             // filter bit = (word umulhi(bin, scale), bit bin & 31); read unconditionally: no branch before the LDS
-            uint32_t hit = (lds32(sw.f_addr + __umulhi(bin, p.fscale) * 4u) >> (bin & 31u)) & valid;
+            uint32_t hit = lds32(sw.f_addr + __umulhi(bin, p.fscale) * 4u) & __funnelshift_l(0u, 1u, bin);   // word & (1 << (bin & 31))
+            if (!CLEAN) hit = valid ? hit : 0u;
             // straight-line append: ballot, predicated store, uniform counters; the only branch is the
-            // (warp-uniform, rarely taken) drain
-            const uint32_t m = __ballot_sync(0xFFFFFFFFu, hit != 0);
-            sts128_if(hit, sw.q_addr + (((sw.qhead + sw.qn + __popc(m & sw.lt_mask)) & (QCAP - 1)) << 4), bin, gpos0 + j - k + 1, g, 0u);
+            // (warp-uniform, rarely taken) drain.  The item holds (bin, o, genome, start of the window at o = 0):
+            // the start itself is only needed for the ~22 % of the windows that are drained
+            uint32_t m;
+            asm volatile("{ .reg .pred q; setp.ne.u32 q, %1, 0; vote.sync.ballot.b32 %0, q, 0xffffffff; }" : "=r"(m) : "r"(hit));
+            sts128_if(hit, sw.q_addr + (((sw.qhead + sw.qn + __popc(m & sw.lt_mask)) & (QCAP - 1)) << 4), bin, (uint32_t)o, g, start31);
             sw.qn += __popc(m);
             if (sw.qn >= 32) {
                 __syncwarp();
