@@ -16,16 +16,21 @@
 //     (k_candbits, k_scan_p*) -- this replaces the string sets and the Aho-Corasick
 //     automaton;
 //   * every genome, the first included, is then ONE pass (k_scan_filtered / k_scan_plain):
-//     window -> bin -> bitmap probe; on a hit the 64-bit canonical word is compared with the slot's
-//     key: equal = an occurrence (position and orientation OR-ed into the genome's row, a second one
-//     raises DUP), different = a sketch collision in that genome (POLL); windows touching a '~'
-//     junction or a non-ACGT byte pollute only one strand's table (JF / JR; k_junction).  A slot is
-//     shared iff every genome has exactly one occurrence and a clean bin in the strand table the
-//     reference would have read.  The probe goes through a per-k Bloom-style filter held in shared
-//     memory (192 KB per CTA) so that only ~1 in 6 windows reaches L2;
-//   * survivors are emitted in the reference's dict order by an ordered compaction over genome 1
-//     (k_emit_mark / k_emit_write), filters are evaluated in fp64 with the reference's operation order, the
-//     per-position "first k-mer that passes" pick looks only at the few records that can share a position.
+//     window -> bin -> key-table probe; a window landing in a key's bin adds (1 << 32 | start) to the
+//     (genome, key) row with a fire-and-forget RED; windows touching a '~' junction or a non-ACGT byte
+//     pollute only one strand's table (two flag bits; k_junction).  After the pass "count == 1" is khmer's
+//     get() == 1 and the single occupant is read back and compared with the key (k_alive1 / k_aliveN): a
+//     key is shared iff every genome has exactly one occurrence and a clean bin in the strand table the
+//     reference would have read.  The probe goes through a per-k Bloom-style filter held in shared memory
+//     (192 KB per CTA) so that only ~1 in 5 windows reaches L2;
+//   * genome 1 is scanned first; its survivors get ids in the reference's dict order (genome-1 end
+//     position ascending, longest first) and everything downstream -- rows of the other genomes, verdicts,
+//     records, coordinates -- is indexed by id and streams through memory (k_alive1, k_assign_ids,
+//     k_build_at, k_aliveN, k_emit_write); filters are evaluated in fp64 with the reference's operation
+//     order, the per-position "first k-mer that passes" pick looks only at the few records that can share
+//     a position (k_positions);
+//   * FASTA files can be handed over as they are: records and sequence lines are found on the device
+//     (pfb_fasta.cuh).
 //
 // No tensor cores: nothing here is a contraction.
 
