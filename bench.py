@@ -321,7 +321,7 @@ def main():
     tm = eng.timing()
 
     # ---- end-to-end leg (host buffers -> host results through the C ABI)
-    e2e_s = []
+    e2e_s, e2e_parts = [], []
     h2d = sum(t.numel() for t, _ in pinned)
     d2h = 0
     for i in range(max(1, args.warmup // 2) + args.steps):
@@ -332,11 +332,13 @@ def main():
             eng.run()                 # pfb_run: H2D copies overlapped with the key-table build and the scan
         else:
             run_sharded(eng, upload=True)
+        t1 = time.perf_counter()
         rec, pos = fetch_results()
         eng.sync()
         dt = time.perf_counter() - t0
         if i >= max(1, args.warmup // 2):
             e2e_s.append(dt)
+            e2e_parts.append((t1 - t0, dt - (t1 - t0), eng.timing()["ms_total"]))
             d2h = rec.nbytes + sum(p.nbytes for p in pos)
     clocks = sampler.stop() if rank == 0 else None
 
@@ -426,7 +428,9 @@ def main():
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": step_ms, "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": "u64",
             "data": "synthetic", "config": workload_config(args.config, world, strong) | ({"genomes_per_gpu": per_rank, "genome_bp": cfg["length"]}),
-            "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_ms},
+            "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_ms,
+                    "ms_run_call": float(np.mean([a for a, _, _ in e2e_parts]) * 1e3), "ms_fetch_results": float(np.mean([b for _, b, _ in e2e_parts]) * 1e3),
+                    "ms_device_span_in_run": float(np.mean([c for _, _, c in e2e_parts]))},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "host_cpus_bound": affinity,
             "phases_ms": {"ms_encode": float(np.mean(enc_ms)), "ms_first": float(np.mean(first_ms)), "ms_scan": float(np.mean(scan_ms)),
                           "ms_finalize": float(np.mean(fin_ms)), "ms_total": step_ms},

@@ -135,7 +135,8 @@ int  pfb_upload_wait(pfb_ctx *ctx);
  * PFB_BUF_ALIVE buffer over ranks, between stage 1 and 2 it max-reduces PFB_BUF_PICK. */
 int  pfb_compute_stage(pfb_ctx *ctx, int stage);
 #define PFB_BUF_ALIVE 0   /* uint8 [n_slots]: 1 while the slot's k-mer is unique in every genome seen */
-#define PFB_BUF_PICK  1   /* uint8 [n_records], 0 / 1 */
+#define PFB_BUF_PICK  1   /* uint8, 0 / 1 per record; the buffer is padded with zeros (its length is the number of keys
+                             that survived genome 1, >= n_records) so that no stage has to wait for a count */
 int  pfb_device_buffer(pfb_ctx *ctx, int which, void **dev_ptr, uint64_t *n_bytes);
 int  pfb_sync(pfb_ctx *ctx);
 /* the CUDA stream (cudaStream_t) every kernel of this context is launched on: a caller that enqueues its

@@ -115,15 +115,14 @@ struct K {  // kernel arguments (by value, __grid_constant__)
     uint32_t *recIdx;          // [nids] exclusive prefix of alive = record index
     // output
     pfb_record *rec;
-    uint32_t *pos;            // [nGenomes][nrec] start within contig | strand << 31
-    uint32_t *posContig;      // [nGenomes][nrec] contig index (only when some genome has > 1 contig)
+    uint32_t *pos;            // [nGenomes][nids] (first nrec used) start within contig | strand << 31
+    uint32_t *posContig;      // [nGenomes][nids] contig index (only when some genome has > 1 contig)
     int multiContig;
     uint8_t *pick;            // [nrec] 0 / 1, then (stage 2) its exclusive prefix in pickOff
     uint32_t *pickOff;
     pfb_record *outRec;       // picked records, compacted
-    uint32_t *outPos;         // [nGenomes][npick]
-    uint32_t *outContig;      // [nGenomes][npick]
-    uint64_t nrec, npick;
+    uint32_t *outPos;         // [nGenomes][nids] (rows are nids apart: the host learns nrec / npick only at the end)
+    uint32_t *outContig;      // [nGenomes][nids]
 };
 
 // SantaLucia (1998) nearest-neighbour table in oligotm's integer units; index = 4*first + second
@@ -648,14 +647,14 @@ __device__ __forceinline__ void scan_word(const K &p, int ki, int k, ScanWarp &s
 }
 
 template <bool FASTMOD, bool KBIG>
-__device__ __forceinline__ void scan_pass(const K &p, int ki, int k, ScanWarp &sw, uint32_t w0, uint32_t w1, uint32_t stride,
+__device__ __forceinline__ void scan_pass(const K &p, int ki, int k, ScanWarp &sw, uint32_t first, uint32_t w1, uint32_t stride,
                                           uint32_t warp) {
     const uint64_t km2 = kmask2(k);
     const uint64_t km1 = kmask1(k);
     const uint32_t mlo = (uint32_t)km2, mhi = (uint32_t)(km2 >> 32);
     const uint32_t m32 = (uint32_t)(0x100000000ull / p.P);            // floor(2^32 / P)
     const uint32_t a32 = (uint32_t)(0x100000000ull % p.P);            // 2^32 mod P
-    for (uint32_t wb = w0 + blockIdx.x * blockDim.x + warp * 32; wb < w1; wb += stride) {
+    for (uint32_t wb = first + warp * 32; wb < w1; wb += stride) {
         const uint32_t w = wb + sw.lane;
         uint32_t vmask = 0, g = 0, gpos0 = 0;
         uint64_t cur = 0, prev = 0, nm = 0;
@@ -679,7 +678,9 @@ __device__ __forceinline__ void scan_pass(const K &p, int ki, int k, ScanWarp &s
     }
 }
 
-__global__ void __launch_bounds__(1024, 1) k_scan_filtered(const __grid_constant__ K p, uint32_t w0, uint32_t w1) {
+// (one length per CTA -- a single filter load -- was tried and is much slower: the CTAs of the nk lengths then
+// work on the same stretch of a genome at the same time and their REDs collide on the same row cache lines)
+__global__ void __launch_bounds__(1024, 1) k_scan_filtered(const __grid_constant__ K p, uint32_t w0_, uint32_t w1) {
     extern __shared__ uint32_t s_filter[];
     ScanWarp sw;
     sw.lane = threadIdx.x & 31;
@@ -688,6 +689,7 @@ __global__ void __launch_bounds__(1024, 1) k_scan_filtered(const __grid_constant
     sw.q_addr = sw.f_addr + FILTER_BYTES + warp * QCAP * 16u;
     sw.lt_mask = (1u << sw.lane) - 1u;
     const uint32_t stride = gridDim.x * blockDim.x;
+    const uint32_t w0 = w0_ + blockIdx.x * blockDim.x;
     for (int ki = 0; ki < p.nk; ki++) {
         const int k = p.kmin + ki;
         __syncthreads();
@@ -1089,9 +1091,9 @@ __global__ void __launch_bounds__(256) k_positions(const __grid_constant__ K p) 
         if (p.multiContig) {
             const uint32_t c = p.wordContig[p.gWordStart[g] + (lp >> 5)];
             start = lp - 32u * (p.cWordStart[c] - p.gWordStart[g]);
-            p.posContig[(size_t)g * p.nrec + r] = c - p.gFirstContig[g];
+            p.posContig[(size_t)g * p.nids + r] = c - p.gFirstContig[g];
         }
-        p.pos[(size_t)g * p.nrec + r] = start | (minus << 31);
+        p.pos[(size_t)g * p.nids + r] = start | (minus << 31);
         if (pass && !picked) {
             bool first = true;
             if (overflow) {
@@ -1114,15 +1116,15 @@ __global__ void __launch_bounds__(256) k_positions(const __grid_constant__ K p) 
 // k_compact: picked records and their coordinates in every genome, densely packed for the D2H copy
 __global__ void __launch_bounds__(256) k_compact(const __grid_constant__ K p) {
     uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= p.nrec) return;
+    if (r >= p.nids) return;                    // pick is 0 beyond the last record
     if (!p.pick[r]) return;
     p.rec[r].flags |= PFB_F_PICK;
     uint32_t o = p.pickOff[r];
     pfb_record rec = p.rec[r];
     p.outRec[o] = rec;
     for (uint32_t g = 0; g < p.nGenomes; g++) {
-        p.outPos[(size_t)g * p.npick + o] = p.pos[(size_t)g * p.nrec + r];
-        if (p.multiContig) p.outContig[(size_t)g * p.npick + o] = p.posContig[(size_t)g * p.nrec + r];
+        p.outPos[(size_t)g * p.nids + o] = p.pos[(size_t)g * p.nids + r];
+        if (p.multiContig) p.outContig[(size_t)g * p.nids + o] = p.posContig[(size_t)g * p.nids + r];
     }
 }
 
@@ -1896,17 +1898,29 @@ static int stage0(pfb_ctx *ctx) {
             scan_range(W1, W, ctx->gFirstContig[0] + ctx->gNumContigs[0], (uint32_t)ctx->cLen.size(), (uint32_t)nG - 1);
             CK(cudaEventRecord(ctx->ev[8], st));
         } else {
-            // the other genomes are encoded and scanned in batches of ~16 MB as their H2D copies land
-            // (the copies run on their own stream, see upload_impl)
+            // the other genomes are encoded and scanned in batches as their H2D copies land (the copies run on
+            // their own stream, see upload_impl): a batch = every genome that has arrived by the time the host
+            // gets here (at least 4 MB of them unless they are the last), so the batches adapt to how far the
+            // copies are ahead of the kernels
             size_t g = 1;
+            bool first_batch = true;
             while (g < nG) {
+                // decide the next batch when the GPU STARTS the previous one: the host stays one batch ahead,
+                // never idles the GPU, and the batch holds everything that landed meanwhile
+                if (!first_batch) CK(cudaEventSynchronize(ctx->ev[9]));
+                first_batch = false;
                 size_t g2 = g;
                 uint64_t bytes = 0;
-                while (g2 < nG && (g2 == g || bytes + ctx->genomes[g2].n_bases <= (16u << 20))) bytes += ctx->genomes[g2++].n_bases;
-                CK(cudaStreamWaitEvent(st, ctx->evCopy[g2 - 1], 0));
+                while (g2 < nG) {
+                    if (bytes >= (4u << 20) && cudaEventQuery(ctx->evCopy[g2]) != cudaSuccess) break;
+                    CK(cudaEventSynchronize(ctx->evCopy[g2]));
+                    bytes += ctx->genomes[g2++].n_bases;
+                }
+                cudaGetLastError();   // cudaErrorNotReady of the query is not an error
                 uint32_t wa = ctx->gWordStart[g], wb = g2 < nG ? ctx->gWordStart[g2] : W;
                 uint32_t ca = ctx->gFirstContig[g], cb = g2 < nG ? ctx->gFirstContig[g2] : (uint32_t)ctx->cLen.size();
                 if (wb > wa) { k_encode<<<nblk(wb - wa, 256), 256, 0, st>>>(k, wa, wb); ctx->launches++; }
+                CK(cudaEventRecord(ctx->ev[9], st));
                 scan_range(wa, wb, ca, cb, (uint32_t)(g2 - g));
                 g = g2;
             }
@@ -1922,6 +1936,8 @@ static int stage0(pfb_ctx *ctx) {
     return PFB_OK;
 }
 
+// stages 1 and 2 never wait for the device: every buffer is sized by the number of ids (>= records >= picked
+// records), rows are nids apart, and the counts are read back once at the very end
 static int stage1(pfb_ctx *ctx) {
     cudaStream_t st = ctx->stream;
     K &k = ctx->k;
@@ -1929,27 +1945,20 @@ static int stage1(pfb_ctx *ctx) {
     const size_t nG = ctx->genomes.size();
     uint32_t *misc = (uint32_t *)ctx->misc.p;
     ctx->nrec = 0; ctx->npick = 0;
-    if (ctx->nids) {
-        // ids are in dict order already: the record index is the rank among the ids that survived every genome
-        if ((rc = device_exscan<SV_U8, 1>(ctx, k.alive, k.recIdx, (uint32_t)ctx->nids, misc + 2)) != PFB_OK) return rc;
-        uint32_t n = 0;
-        CK(cudaMemcpyAsync(&n, misc + 2, 4, cudaMemcpyDeviceToHost, st));
-        CK(cudaStreamSynchronize(st));
-        ctx->nrec = n;
-    }
-    k.nrec = ctx->nrec;
-    const size_t NR = ctx->nrec ? ctx->nrec : 1;
-    if ((rc = ensure(ctx, ctx->rec, NR * sizeof(pfb_record))) != PFB_OK) return rc;
+    const size_t NI = ctx->nids ? ctx->nids : 1;
+    if ((rc = ensure(ctx, ctx->rec, NI * sizeof(pfb_record))) != PFB_OK) return rc;
     const bool multi = ctx->cLen.size() > nG;
-    if ((rc = ensure(ctx, ctx->pos, NR * nG * 4)) != PFB_OK) return rc;
-    if ((rc = ensure(ctx, ctx->posContig, multi ? NR * nG * 4 : 4)) != PFB_OK) return rc;
-    if ((rc = ensure(ctx, ctx->pick, NR)) != PFB_OK) return rc;
-    if ((rc = ensure(ctx, ctx->pickOff, NR * 4)) != PFB_OK) return rc;
+    if ((rc = ensure(ctx, ctx->pos, NI * nG * 4)) != PFB_OK) return rc;
+    if ((rc = ensure(ctx, ctx->posContig, multi ? NI * nG * 4 : 4)) != PFB_OK) return rc;
+    if ((rc = ensure(ctx, ctx->pick, NI)) != PFB_OK) return rc;
+    if ((rc = ensure(ctx, ctx->pickOff, NI * 4)) != PFB_OK) return rc;
     k.rec = (pfb_record *)ctx->rec.p; k.pos = (uint32_t *)ctx->pos.p; k.posContig = (uint32_t *)ctx->posContig.p;
     k.multiContig = multi ? 1 : 0;
     k.pick = (uint8_t *)ctx->pick.p; k.pickOff = (uint32_t *)ctx->pickOff.p;
-    CK(cudaMemsetAsync(ctx->pick.p, 0, NR, st));
-    if (ctx->nrec) {
+    CK(cudaMemsetAsync(ctx->pick.p, 0, NI, st));
+    if (ctx->nids) {
+        // ids are in dict order already: the record index is the rank among the ids that survived every genome
+        if ((rc = device_exscan<SV_U8, 1>(ctx, k.alive, k.recIdx, (uint32_t)ctx->nids, misc + 2)) != PFB_OK) return rc;
         k_emit_write<<<nblk(ctx->nids, 256), 256, 0, st>>>(k); ctx->launches++;
         k_positions<<<nblk(ctx->nids, 256), 256, 0, st>>>(k); ctx->launches++;
     }
@@ -1963,24 +1972,21 @@ static int stage2(pfb_ctx *ctx) {
     int rc;
     uint32_t *misc = (uint32_t *)ctx->misc.p;
     const size_t nG = ctx->genomes.size();
-    ctx->npick = 0;
-    if (ctx->nrec) {
-        if ((rc = device_exscan<SV_U8, 1>(ctx, k.pick, k.pickOff, (uint32_t)ctx->nrec, misc + 3)) != PFB_OK) return rc;
-        uint32_t np = 0;
-        CK(cudaMemcpyAsync(&np, misc + 3, 4, cudaMemcpyDeviceToHost, st));
-        CK(cudaStreamSynchronize(st));
-        ctx->npick = np;
-    }
-    k.npick = ctx->npick;
-    const size_t NP = ctx->npick ? ctx->npick : 1;
-    if ((rc = ensure(ctx, ctx->outRec, NP * sizeof(pfb_record))) != PFB_OK) return rc;
-    if ((rc = ensure(ctx, ctx->outPos, NP * nG * 4)) != PFB_OK) return rc;
-    if ((rc = ensure(ctx, ctx->outContig, k.multiContig ? NP * nG * 4 : 4)) != PFB_OK) return rc;
+    const size_t NI = ctx->nids ? ctx->nids : 1;
+    if ((rc = ensure(ctx, ctx->outRec, NI * sizeof(pfb_record))) != PFB_OK) return rc;
+    if ((rc = ensure(ctx, ctx->outPos, NI * nG * 4)) != PFB_OK) return rc;
+    if ((rc = ensure(ctx, ctx->outContig, k.multiContig ? NI * nG * 4 : 4)) != PFB_OK) return rc;
     k.outRec = (pfb_record *)ctx->outRec.p; k.outPos = (uint32_t *)ctx->outPos.p; k.outContig = (uint32_t *)ctx->outContig.p;
-    if (ctx->npick) { k_compact<<<nblk(ctx->nrec, 256), 256, 0, st>>>(k); ctx->launches++; }
+    uint32_t counts[2] = {0, 0};
+    if (ctx->nids) {
+        if ((rc = device_exscan<SV_U8, 1>(ctx, k.pick, k.pickOff, (uint32_t)ctx->nids, misc + 3)) != PFB_OK) return rc;
+        k_compact<<<nblk(ctx->nids, 256), 256, 0, st>>>(k); ctx->launches++;
+        CK(cudaMemcpyAsync(counts, misc + 2, 8, cudaMemcpyDeviceToHost, st));
+    }
     CK(cudaEventRecord(ctx->ev[6], st));
     CK(cudaStreamSynchronize(st));
     CK(cudaGetLastError());
+    ctx->nrec = counts[0]; ctx->npick = counts[1];
     pfb_timing &t = ctx->tm;
     cudaEventElapsedTime(&t.ms_encode, ctx->ev[2], ctx->ev[3]);
     cudaEventElapsedTime(&t.ms_first, ctx->ev[3], ctx->ev[4]);
@@ -2044,7 +2050,7 @@ int pfb_device_buffer(pfb_ctx *ctx, int which, void **dev_ptr, uint64_t *n_bytes
         *dev_ptr = ctx->alive.p; *n_bytes = ctx->nids;
     } else if (which == PFB_BUF_PICK) {
         if (ctx->stage_done < 1) return fail(ctx, PFB_ESTATE, "stage 1 has not run");
-        *dev_ptr = ctx->pick.p; *n_bytes = ctx->nrec;
+        *dev_ptr = ctx->pick.p; *n_bytes = ctx->nids;     // zero beyond the last record
     } else {
         return fail(ctx, PFB_EINVAL, "unknown buffer");
     }
@@ -2079,8 +2085,8 @@ int pfb_result_positions(pfb_ctx *ctx, uint32_t genome_idx, int picked_only, pfb
     const uint64_t n = picked_only ? ctx->npick : ctx->nrec;
     if (cap < n) return fail(ctx, PFB_EINVAL, "position buffer too small");
     if (!n) return PFB_OK;
-    const uint32_t *ps = (picked_only ? (const uint32_t *)ctx->outPos.p : (const uint32_t *)ctx->pos.p) + (size_t)genome_idx * n;
-    const uint32_t *cs = (picked_only ? (const uint32_t *)ctx->outContig.p : (const uint32_t *)ctx->posContig.p) + (size_t)genome_idx * n;
+    const uint32_t *ps = (picked_only ? (const uint32_t *)ctx->outPos.p : (const uint32_t *)ctx->pos.p) + (size_t)genome_idx * ctx->nids;
+    const uint32_t *cs = (picked_only ? (const uint32_t *)ctx->outContig.p : (const uint32_t *)ctx->posContig.p) + (size_t)genome_idx * ctx->nids;
     std::vector<uint32_t> hp(n), hc;
     CK(cudaMemcpyAsync(hp.data(), ps, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
     if (ctx->k.multiContig) {
@@ -2105,11 +2111,11 @@ int pfb_result_picked(pfb_ctx *ctx, pfb_record *rec_out, uint32_t *start_strand_
     CK(cudaSetDevice(ctx->device));
     const size_t nG = ctx->genomes.size(), np = ctx->npick;
     CK(cudaMemcpyAsync(rec_out, ctx->outRec.p, np * sizeof(pfb_record), cudaMemcpyDeviceToHost, ctx->stream));
-    // the caller's rows are `cap` apart, the device rows `npick` apart
-    CK(cudaMemcpy2DAsync(start_strand_out, cap * 4, ctx->outPos.p, np * 4, np * 4, nG, cudaMemcpyDeviceToHost, ctx->stream));
+    // the caller's rows are `cap` apart, the device rows `nids` apart
+    CK(cudaMemcpy2DAsync(start_strand_out, cap * 4, ctx->outPos.p, ctx->nids * 4, np * 4, nG, cudaMemcpyDeviceToHost, ctx->stream));
     if (contig_out) {
         if (ctx->k.multiContig)
-            CK(cudaMemcpy2DAsync(contig_out, cap * 4, ctx->outContig.p, np * 4, np * 4, nG, cudaMemcpyDeviceToHost, ctx->stream));
+            CK(cudaMemcpy2DAsync(contig_out, cap * 4, ctx->outContig.p, ctx->nids * 4, np * 4, nG, cudaMemcpyDeviceToHost, ctx->stream));
         else
             for (size_t g = 0; g < nG; g++) memset(contig_out + g * cap, 0, np * 4);
     }
