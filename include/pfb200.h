@@ -114,6 +114,11 @@ int  pfb_add_genome(pfb_ctx *ctx, const uint8_t *bases, uint64_t n_bases,
  * report what was found: per record the offset of its '>' in the file (the id is the title up to the first
  * whitespace, SeqRecord.id) and its length. */
 int  pfb_add_fasta(pfb_ctx *ctx, const uint8_t *file_bytes, uint64_t n_bytes);
+/* the same for a GenBank flat file (the reference's default --format, Bio.SeqIO.parse(fn, "genbank")): a line
+ * starting with LOCUS opens a record, the letters of the lines between its ORIGIN line and the next "//" are
+ * the sequence, upper-cased.  pfb_contig_table reports the offset of each LOCUS line (the host takes the id
+ * from the VERSION / LOCUS lines that follow) and the sequence length. */
+int  pfb_add_genbank(pfb_ctx *ctx, const uint8_t *file_bytes, uint64_t n_bytes);
 int  pfb_genome_info(pfb_ctx *ctx, uint32_t genome_idx, uint32_t *n_contigs, uint64_t *n_bases);
 int  pfb_contig_table(pfb_ctx *ctx, uint32_t genome_idx, uint64_t *header_off, uint64_t *length, uint32_t cap);
 int  pfb_clear_genomes(pfb_ctx *ctx);

@@ -26,7 +26,7 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", 
 
 # every symbol include/pfb200.h declares
 EXPORTS = ["pfb_create", "pfb_destroy", "pfb_last_error", "pfb_default_params", "pfb_add_genome",
-           "pfb_add_fasta", "pfb_genome_info", "pfb_contig_table",
+           "pfb_add_fasta", "pfb_add_genbank", "pfb_genome_info", "pfb_contig_table",
            "pfb_clear_genomes", "pfb_upload", "pfb_upload_async", "pfb_upload_wait", "pfb_compute", "pfb_run", "pfb_compute_stage",
            "pfb_device_buffer", "pfb_sync", "pfb_stream", "pfb_result_counts", "pfb_result_records",
            "pfb_result_positions", "pfb_result_picked", "pfb_host_alloc", "pfb_host_free", "pfb_timings", "pfb_set_scan_mode", "pfb_oligo_tm"]
@@ -84,6 +84,7 @@ def load():
     lib.pfb_default_params.argtypes = [C.POINTER(PfbParams)]
     lib.pfb_add_genome.argtypes = [vp, vp, u64, vp, u32]
     lib.pfb_add_fasta.argtypes = [vp, vp, u64]
+    lib.pfb_add_genbank.argtypes = [vp, vp, u64]
     lib.pfb_genome_info.argtypes = [vp, u32, C.POINTER(u32), C.POINTER(u64)]
     lib.pfb_contig_table.argtypes = [vp, u32, vp, vp, u32]
     lib.pfb_clear_genomes.argtypes = [vp]

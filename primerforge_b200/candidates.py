@@ -108,24 +108,24 @@ def build_output(names, contig_ids, records, positions, kmers, thal_values=None)
 
 def run_stage(genomes, *, k_min=16, k_max=20, min_gc=40.0, max_gc=60.0, min_tm=55.0, max_tm=68.0, max_repeat=4,
               table_size=9999991, prefilter=True, device=0, scan_mode=0, picked_only=False, fasta_images=None,
-              contig_ids_out=None):
-    """genomes: list of (contig id list, list of uint8 ASCII arrays), or -- fasta_images: list of uint8 FASTA
-    file images -- the files themselves, parsed on the device (their record ids are appended to
-    contig_ids_out).  Returns a StageResult; with picked_only it holds just the picked records (the compact
+              contig_ids_out=None, file_format="fasta"):
+    """genomes: list of (contig id list, list of uint8 ASCII arrays), or -- fasta_images: list of uint8 FASTA /
+    GenBank file images (file_format) -- the files themselves, parsed on the device (their record ids are
+    appended to contig_ids_out).  Returns a StageResult; with picked_only it holds just the picked records (the compact
     D2H path of pfb_result_picked)."""
     with Engine(device=device, k_min=k_min, k_max=k_max, min_gc=min_gc, max_gc=max_gc, min_tm=min_tm, max_tm=max_tm,
                 max_repeat=max_repeat, table_size=table_size, prefilter=int(bool(prefilter))) as eng:
         eng.set_scan_mode(scan_mode)
         if fasta_images is not None:
             for img in fasta_images:
-                eng.add_fasta(img)
+                eng.add_fasta(img, fmt=file_format)
         else:
             for _ids, contigs in genomes:
                 eng.add_genome(contigs)
         eng.run()
         if fasta_images is not None and contig_ids_out is not None:
             for g, img in enumerate(fasta_images):
-                contig_ids_out.append(seqio.fasta_ids(img, eng.contig_table(g)[0]))
+                contig_ids_out.append(seqio.file_ids(img, eng.contig_table(g)[0], file_format))
         n, _ = eng.counts()
         if n == 0:
             raise RuntimeError(ERR_NO_SHARED)
@@ -162,8 +162,11 @@ def _getAllCandidateKmers(params, sharedExists: bool, thal="auto", device: int |
     thal_fn = _thal_provider(params, os.environ.get("PFB200_THAL", thal) if thal == "auto" else thal)
 
     names, contig_ids, genomes, images = [], [], [], None
-    # FASTA files go to the GPU as they are (records found and compacted there); GenBank is read on the host
-    if str(params.format).lower() == "fasta" and os.environ.get("PFB200_HOST_PARSE", "0") != "1":
+    # the files go to the GPU as they are (records found and compacted there); PFB200_HOST_PARSE=1 reads them
+    # on the host instead
+    fmt = str(params.format).lower()
+    fmt = "genbank" if fmt == "gb" else fmt
+    if fmt in ("fasta", "genbank") and os.environ.get("PFB200_HOST_PARSE", "0") != "1":
         images = [np.fromfile(fn, dtype=np.uint8) for fn in params.ingroupFns]
         names = [os.path.basename(fn) for fn in params.ingroupFns]
     else:
@@ -175,7 +178,7 @@ def _getAllCandidateKmers(params, sharedExists: bool, thal="auto", device: int |
     try:
         res = run_stage(genomes, k_min=params.minLen, k_max=params.maxLen, min_gc=params.minGc, max_gc=params.maxGc,
                         min_tm=params.minTm, max_tm=params.maxTm, max_repeat=params.maxRepeatLen, device=device,
-                        picked_only=thal_fn is None, fasta_images=images, contig_ids_out=contig_ids)
+                        picked_only=thal_fn is None, fasta_images=images, contig_ids_out=contig_ids, file_format=fmt)
     except RuntimeError as exc:
         if str(exc) == ERR_NO_SHARED:
             log.error(ERR_NO_SHARED)

@@ -1146,9 +1146,9 @@ struct HostGenome {
     const uint8_t *bases;        // contigs concatenated (pfb_add_genome) or the FASTA file image (pfb_add_fasta)
     uint64_t n_bases;            // bases; for a FASTA genome known once the device has parsed it
     std::vector<uint64_t> off;   // n_contigs + 1
-    bool fasta = false;
+    int fasta = 0;               // 0: bases given, fa::FMT_FASTA / fa::FMT_GENBANK: file image, parsed on the device
     uint64_t file_bytes = 0;
-    std::vector<uint64_t> hdr_off;   // FASTA: offset of every record's '>' in the file
+    std::vector<uint64_t> hdr_off;   // file image: offset of every record's '>' / LOCUS line in the file
 };
 
 // one batch of FASTA files being parsed on the device
@@ -1405,6 +1405,7 @@ int fasta_enqueue(pfb_ctx *ctx, int b, size_t g0, size_t g1, cudaStream_t ps) {
     auto carve = [&](size_t n) { size_t at = o; o += (n + 255) & ~(size_t)255; return at; };
     const size_t o64 = carve(3 * (size_t)nF * 8), o32 = carve((nF + 1) * 4), oFirst = carve(nF * 4);
     const size_t oTLast = carve((size_t)nT * 8), oInLast = carve((size_t)nT * 8);
+    const size_t oTMark = carve((size_t)nT * 8), oInMark = carve((size_t)nT * 8);
     const size_t oTHdr = carve((size_t)(nT + 1) * 4), oHdrBase = carve((size_t)(nT + 1) * 4);
     const size_t oTKept = carve((size_t)(nT + 1) * 4), oKeptBase = carve((size_t)(nT + 1) * 4);
     int rc;
@@ -1423,7 +1424,9 @@ int fasta_enqueue(pfb_ctx *ctx, int b, size_t g0, size_t g1, cudaStream_t ps) {
     A.src = (const uint64_t *)(w + o64); A.len = A.src + nF; A.dst = A.src + 2 * nF;
     A.tile0 = (const uint32_t *)(w + o32);
     A.nFiles = nF; A.nTiles = nT;
+    A.format = ctx->genomes[g0].fasta;
     A.tLast = (uint64_t *)(w + oTLast); A.inLast = (uint64_t *)(w + oInLast);
+    A.tMark = (uint64_t *)(w + oTMark); A.inMark = (uint64_t *)(w + oInMark);
     A.tHdr = (uint32_t *)(w + oTHdr); A.hdrBase = (uint32_t *)(w + oHdrBase);
     A.tKept = (uint32_t *)(w + oTKept); A.keptBase = (uint32_t *)(w + oKeptBase);
     A.firstHdr = (uint32_t *)(w + oFirst);
@@ -1439,11 +1442,19 @@ int fasta_enqueue(pfb_ctx *ctx, int b, size_t g0, size_t g1, cudaStream_t ps) {
     CK(cudaMemsetAsync(w + oFirst, 0xFF, nF * 4, ps));
     if (nT) {
         const unsigned nb = nblk(nT, fa::WARPS);
-        fa::k_fa_mark<<<nb, fa::WARPS * 32, 0, ps>>>(A);
-        fa::k_fa_scan<<<1, 1024, 0, ps>>>(A.tHdr, A.hdrBase, A.tLast, A.inLast, nT);
-        fa::k_fa_sweep<false><<<nb, fa::WARPS * 32, 0, ps>>>(A);
-        fa::k_fa_scan<<<1, 1024, 0, ps>>>(A.tKept, A.keptBase, nullptr, nullptr, nT);
-        fa::k_fa_sweep<true><<<nb, fa::WARPS * 32, 0, ps>>>(A);
+        if (A.format == fa::FMT_FASTA) {
+            fa::k_fa_mark<fa::FMT_FASTA><<<nb, fa::WARPS * 32, 0, ps>>>(A);
+            fa::k_fa_scan<<<1, 1024, 0, ps>>>(A.tHdr, A.hdrBase, A.tLast, A.inLast, nullptr, nullptr, nT);
+            fa::k_fa_sweep<fa::FMT_FASTA, false><<<nb, fa::WARPS * 32, 0, ps>>>(A);
+            fa::k_fa_scan<<<1, 1024, 0, ps>>>(A.tKept, A.keptBase, nullptr, nullptr, nullptr, nullptr, nT);
+            fa::k_fa_sweep<fa::FMT_FASTA, true><<<nb, fa::WARPS * 32, 0, ps>>>(A);
+        } else {
+            fa::k_fa_mark<fa::FMT_GENBANK><<<nb, fa::WARPS * 32, 0, ps>>>(A);
+            fa::k_fa_scan<<<1, 1024, 0, ps>>>(A.tHdr, A.hdrBase, A.tLast, A.inLast, A.tMark, A.inMark, nT);
+            fa::k_fa_sweep<fa::FMT_GENBANK, false><<<nb, fa::WARPS * 32, 0, ps>>>(A);
+            fa::k_fa_scan<<<1, 1024, 0, ps>>>(A.tKept, A.keptBase, nullptr, nullptr, nullptr, nullptr, nT);
+            fa::k_fa_sweep<fa::FMT_GENBANK, true><<<nb, fa::WARPS * 32, 0, ps>>>(A);
+        }
         ctx->fa_launches += 5;
     }
     CK(cudaEventRecord(B.done, ps));
@@ -1472,7 +1483,8 @@ int fasta_collect(pfb_ctx *ctx, int b) {
         CK(cudaHostGetDevicePointer((void **)&hm, ctx->faHost[b], 0));
         B.args.fileTab = hm; B.args.recStart = hm + (2 * nF + 1); B.args.recHdr = B.args.recStart + B.cap;
         B.args.cap = B.cap;
-        fa::k_fa_sweep<true><<<nblk(B.nTiles, fa::WARPS), fa::WARPS * 32, 0, ctx->parseStream>>>(B.args);
+        if (B.args.format == fa::FMT_FASTA) fa::k_fa_sweep<fa::FMT_FASTA, true><<<nblk(B.nTiles, fa::WARPS), fa::WARPS * 32, 0, ctx->parseStream>>>(B.args);
+        else fa::k_fa_sweep<fa::FMT_GENBANK, true><<<nblk(B.nTiles, fa::WARPS), fa::WARPS * 32, 0, ctx->parseStream>>>(B.args);
         ctx->fa_launches++;
         CK(cudaStreamSynchronize(ctx->parseStream));
         tab = (const uint32_t *)ctx->faHost[b];
@@ -1482,7 +1494,7 @@ int fasta_collect(pfb_ctx *ctx, int b) {
         HostGenome &hg = ctx->genomes[B.g0 + f];
         const uint32_t r0 = tab[2 * f], kept = tab[2 * f + 1];
         const uint32_t r1 = f + 1 < nF ? tab[2 * (f + 1)] : total;
-        if (r1 <= r0) return fail(ctx, PFB_EINVAL, "genome " + std::to_string(B.g0 + f) + ": no FASTA record (no line starts with '>')");
+        if (r1 <= r0) return fail(ctx, PFB_EINVAL, "genome " + std::to_string(B.g0 + f) + ": no record (no line starts with '>' / LOCUS)");
         hg.off.clear(); hg.hdr_off.clear();
         for (uint32_t r = r0; r < r1; r++) { hg.off.push_back(recStart[r]); hg.hdr_off.push_back(recHdr[r]); }
         hg.off.push_back(kept);
@@ -1590,16 +1602,20 @@ int pfb_add_genome(pfb_ctx *ctx, const uint8_t *bases, uint64_t n_bases, const u
     return PFB_OK;
 }
 
-int pfb_add_fasta(pfb_ctx *ctx, const uint8_t *file_bytes, uint64_t n_bytes) {
+static int add_file(pfb_ctx *ctx, const uint8_t *file_bytes, uint64_t n_bytes, int format) {
     if (!ctx) return PFB_EINVAL;
-    if (!file_bytes || n_bytes == 0) return fail(ctx, PFB_EINVAL, "empty FASTA file");
-    if (n_bytes >= (1ull << 31)) return fail(ctx, PFB_ETOOLARGE, "FASTA file of 2 GiB or more");
+    if (!file_bytes || n_bytes == 0) return fail(ctx, PFB_EINVAL, "empty file");
+    if (n_bytes >= (1ull << 31)) return fail(ctx, PFB_ETOOLARGE, "file of 2 GiB or more");
     HostGenome g;
-    g.bases = file_bytes; g.n_bases = 0; g.fasta = true; g.file_bytes = n_bytes;
+    g.bases = file_bytes; g.n_bases = 0; g.fasta = format; g.file_bytes = n_bytes;
     ctx->genomes.push_back(std::move(g));
     ctx->uploaded = false; ctx->computed = false; ctx->stage_done = -1;
     return PFB_OK;
 }
+
+int pfb_add_fasta(pfb_ctx *ctx, const uint8_t *file_bytes, uint64_t n_bytes) { return add_file(ctx, file_bytes, n_bytes, fa::FMT_FASTA); }
+
+int pfb_add_genbank(pfb_ctx *ctx, const uint8_t *file_bytes, uint64_t n_bytes) { return add_file(ctx, file_bytes, n_bytes, fa::FMT_GENBANK); }
 
 int pfb_genome_info(pfb_ctx *ctx, uint32_t genome_idx, uint32_t *n_contigs, uint64_t *n_bases) {
     if (!ctx) return PFB_EINVAL;
@@ -1658,8 +1674,10 @@ static int upload_impl(pfb_ctx *ctx, bool async) {
     CK(cudaSetDevice(ctx->device));
     const size_t nG = ctx->genomes.size();
     size_t nFasta = 0;
-    for (auto &g : ctx->genomes) nFasta += g.fasta ? 1 : 0;
-    if (nFasta && nFasta != nG) return fail(ctx, PFB_EINVAL, "pfb_add_genome and pfb_add_fasta cannot be mixed on one context");
+    for (auto &g : ctx->genomes) nFasta += g.fasta == ctx->genomes[0].fasta && g.fasta ? 1 : 0;
+    for (auto &g : ctx->genomes)
+        if (g.fasta != ctx->genomes[0].fasta)
+            return fail(ctx, PFB_EINVAL, "pfb_add_genome, pfb_add_fasta and pfb_add_genbank cannot be mixed on one context");
     ctx->any_fasta = nFasta != 0;
     raw_starts(ctx);
     int rc;

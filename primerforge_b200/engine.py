@@ -135,16 +135,21 @@ class Engine:
         self.n_genomes += 1
         self._multi_contig |= offsets.size > 2
 
-    def add_fasta(self, data: np.ndarray | None = None, ptr: int | None = None, n_bytes: int | None = None):
-        """a genome given as its FASTA file image (uint8 array, or a raw host pointer e.g. into pinned memory);
-        the records are found and compacted on the device -- see contig_table() after run()"""
+    def add_fasta(self, data: np.ndarray | None = None, ptr: int | None = None, n_bytes: int | None = None, fmt: str = "fasta"):
+        """a genome given as its FASTA (or, fmt="genbank", GenBank) file image (uint8 array, or a raw host
+        pointer e.g. into pinned memory); the records are found and compacted on the device -- see
+        contig_table() after run()"""
         if data is not None:
             data = np.ascontiguousarray(data, dtype=np.uint8)
             ptr, n_bytes = data.ctypes.data, data.size
         self._keep.append((data, None))
-        self._check(self._lib.pfb_add_fasta(self._ctx, ptr, int(n_bytes)))
+        fn = self._lib.pfb_add_fasta if fmt == "fasta" else self._lib.pfb_add_genbank
+        self._check(fn(self._ctx, ptr, int(n_bytes)))
         self.n_genomes += 1
         self._multi_contig = None       # known after the device has parsed the files
+
+    def add_genbank(self, data: np.ndarray | None = None, ptr: int | None = None, n_bytes: int | None = None):
+        self.add_fasta(data, ptr, n_bytes, fmt="genbank")
 
     def genome_info(self, genome_idx: int):
         nc, nb = C.c_uint32(), C.c_uint64()

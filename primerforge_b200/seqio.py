@@ -87,3 +87,36 @@ def fasta_ids(data: np.ndarray, header_off) -> list:
         parts = chunk[:end].tobytes().decode("latin-1").strip("\r").split(None, 1)
         ids.append(parts[0] if parts else "")
     return ids
+
+
+def genbank_ids(data: np.ndarray, header_off) -> list:
+    """record ids of a GenBank file image given the offsets of its LOCUS lines (device parser): the VERSION
+    accession if the header has one, else the LOCUS name -- like SeqRecord.id"""
+    ids = []
+    n = data.size
+    for st in header_off:
+        st = int(st)
+        locus = version = None
+        pos = st
+        while pos < n:
+            chunk = data[pos:min(n, pos + 65536)]
+            nl = np.flatnonzero(chunk == _NL)
+            end = pos + (int(nl[0]) if nl.size else chunk.size)
+            line = data[pos:end].tobytes().decode("latin-1")
+            if line.startswith("LOCUS") and pos == st:
+                f = line.split()
+                locus = f[1] if len(f) > 1 else "<unknown id>"
+            elif line.startswith("VERSION"):
+                f = line.split()
+                version = f[1] if len(f) > 1 else None
+                break
+            elif line.startswith("ORIGIN") or line.startswith("//") or (line.startswith("LOCUS") and pos != st) \
+                    or line.startswith("FEATURES"):
+                break
+            pos = end + 1
+        ids.append(version or locus or "<unknown id>")
+    return ids
+
+
+def file_ids(data: np.ndarray, header_off, fmt: str) -> list:
+    return fasta_ids(data, header_off) if fmt.lower() == "fasta" else genbank_ids(data, header_off)

@@ -146,3 +146,116 @@ def test_many_records_grow_the_table():
         hdr, ln = eng.contig_table(0)
     assert nc == n_rec and nb == 2 * n_rec and np.all(ln == 2)
     assert np.all(img[hdr.astype(np.int64)] == ord(">"))
+
+
+# ---------------------------------------------------------------------------------------------- GenBank
+def _genbank_bytes(contigs, ids, version=True, crlf=False, junk=b"", upper=False, long_feature=False):
+    nl = "\r\n" if crlf else "\n"
+    out = [junk.decode()]
+    for cid, arr in zip(ids, contigs):
+        seq = arr.tobytes().decode()
+        seq = seq if upper else seq.lower()
+        out.append(f"LOCUS       {cid}  {len(seq)} bp    DNA     linear   BCT 01-JAN-2000{nl}")
+        out.append(f"DEFINITION  synthetic record, the word ORIGIN and // inside a line must not matter.{nl}")
+        out.append(f"ACCESSION   {cid}{nl}")
+        if version:
+            out.append(f"VERSION     {cid}.1{nl}")
+        out.append(f"FEATURES             Location/Qualifiers{nl}     source          1..{len(seq)}{nl}")
+        out.append(f"                     /organism=\"Synthetic acgt\"{nl}")
+        if long_feature:
+            out.append("                     /translation=\"" + "MKV" * 4000 + f"\"{nl}")     # a line longer than two tiles
+        out.append(f"ORIGIN      {nl}")
+        for i in range(0, len(seq), 60):
+            line = seq[i:i + 60]
+            groups = " ".join(line[j:j + 10] for j in range(0, len(line), 10))
+            out.append(f"{i + 1:9d} {groups}{nl}")
+        out.append(f"//{nl}")
+    return np.frombuffer("".join(out).encode(), dtype=np.uint8).copy()
+
+
+def _compare_genbank(images, mode):
+    from primerforge_b200 import seqio
+    import os
+    import tempfile
+    host = []
+    with tempfile.TemporaryDirectory() as d:
+        for i, img in enumerate(images):
+            fn = os.path.join(d, f"g{i}.gbk")
+            img.tofile(fn)
+            host.append(seqio.read_genbank(fn))
+    res_f, tables, info = _run(lambda e: [e.add_genbank(img) for img in images], mode)
+    res_h, _, _ = _run(lambda e: [e.add_genome(c) for _ids, c in host], mode)
+    for g, (ids, contigs) in enumerate(host):
+        hdr, ln = tables[g]
+        assert info[g] == (len(contigs), sum(c.size for c in contigs))
+        assert ln.tolist() == [c.size for c in contigs]
+        assert seqio.genbank_ids(images[g], hdr) == ids
+        assert all(images[g][int(h):int(h) + 5].tobytes() == b"LOCUS" for h in hdr)
+    assert res_f.records.size == res_h.records.size and res_f.records.size > 0
+    for f in ("word", "tm", "gc_count", "k", "flags"):
+        assert np.array_equal(res_f.records[f], res_h.records[f]), f
+    for pf, ph in zip(res_f.positions, res_h.positions):
+        assert np.array_equal(pf, ph)
+
+
+@pytest.mark.parametrize("mode", ["sync", "pipelined"])
+@pytest.mark.parametrize("variant", ["plain", "no_version", "crlf", "junk", "upper", "long_feature", "empty_records"])
+def test_genbank_device_parser(variant, mode):
+    from primerforge_b200 import synth
+    gens = synth.make_genomes(3, 60_000, seed=93, snp_rate=0.003, n_inversions=1, n_contigs=3)
+    images = []
+    for g in gens:
+        kw = {}
+        ids = list(g.contig_ids)
+        contigs = list(g.contigs)
+        if variant == "no_version":
+            kw["version"] = False
+        elif variant == "crlf":
+            kw["crlf"] = True
+        elif variant == "junk":
+            kw["junk"] = b"some text\nORIGIN\n        1 acgtacgt\n//\nmore text\n"     # sequence-looking text before any LOCUS
+        elif variant == "upper":
+            kw["upper"] = True
+        elif variant == "long_feature":
+            kw["long_feature"] = True
+        elif variant == "empty_records":
+            contigs = contigs[:1] + [np.zeros(0, dtype=np.uint8), np.frombuffer(b"ACGTNNACGT", dtype=np.uint8)] + contigs[1:]
+            ids = ids[:1] + ["empty", "tiny"] + ids[1:]
+        images.append(_genbank_bytes(contigs, ids, **kw))
+    _compare_genbank(images, mode)
+
+
+def test_drop_in_entry_point_genbank(tmp_path, capsys):
+    """_getAllCandidateKmers with params.format = 'genbank' (the reference's default): device ingest and host
+    reader give the same candidates"""
+    import os
+    from types import SimpleNamespace
+    from primerforge_b200 import synth
+    from primerforge_b200.candidates import _getAllCandidateKmers
+    gens = synth.make_genomes(3, 80_000, seed=17, snp_rate=0.003, n_inversions=2, n_contigs=2)
+    paths = []
+    for g in gens:
+        fn = str(tmp_path / g.name.replace(".fasta", ".gbk"))
+        _genbank_bytes(g.contigs, g.contig_ids).tofile(fn)
+        paths.append(fn)
+    log = SimpleNamespace(rename=lambda *a: None, info=lambda *a: None, debug=lambda *a: None, error=lambda *a: None)
+
+    def params():
+        return SimpleNamespace(ingroupFns=paths, format="genbank", minLen=16, maxLen=20, minGc=40.0, maxGc=60.0, minTm=55.0,
+                               maxTm=68.0, maxRepeatLen=4, tempTolerance=5.0, numThreads=1, p3_mvConc=50.0, p3_dvConc=1.5,
+                               p3_dntpConc=0.6, p3_dnaConc=50.0, p3_tempC=37.0, p3_maxLoop=30, log=log,
+                               pickles={1: "sharedKmers.p", 2: "candidates.p"}, dumpObj=lambda *a, **k: None, loadObj=lambda *a: None)
+    out_dev = _getAllCandidateKmers(params(), False, thal="off")
+    os.environ["PFB200_HOST_PARSE"] = "1"
+    try:
+        out_host = _getAllCandidateKmers(params(), False, thal="off")
+    finally:
+        del os.environ["PFB200_HOST_PARSE"]
+    capsys.readouterr()
+    assert list(out_dev.keys()) == list(out_host.keys()) == [os.path.basename(p) for p in paths]
+    for name in out_dev:
+        assert list(out_dev[name].keys()) == list(out_host[name].keys())
+        for contig in out_dev[name]:
+            a = [(str(p), p.start, p.end, p.strand, p.Tm, p.gcPer) for p in out_dev[name][contig]]
+            b = [(str(p), p.start, p.end, p.strand, p.Tm, p.gcPer) for p in out_host[name][contig]]
+            assert a == b and len(a) > 0

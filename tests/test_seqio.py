@@ -36,3 +36,15 @@ def test_genbank_reader(tmp_path):
     ids, contigs = seqio.read_genome(str(p), "genbank")
     assert ids == ["AB000001.2", "NOVERSION"]
     assert [c.tobytes() for c in contigs] == [b"ACGTACGTACGT", b"TTGA"]
+
+
+def test_ids_from_header_offsets():
+    """the host half of the device ingest: record ids from the offsets the GPU parser reports"""
+    fa = np.frombuffer(b"junk\n>c1 desc here\r\nACGT\n>c2\n\n>c3\tz\nGG", dtype=np.uint8)
+    assert seqio.fasta_ids(fa, [5, 25, 30]) == ["c1", "c2", "c3"]
+    gb = ("LOCUS       AB000001  12 bp    DNA\nDEFINITION  x\nVERSION     AB000001.2\nORIGIN\n        1 acgtacgtac gt\n//\n"
+          "LOCUS       NOVERSION  4 bp\nORIGIN\n        1 ttga\n//\n").encode()
+    arr = np.frombuffer(gb, dtype=np.uint8)
+    offs = [0, gb.index(b"LOCUS       NOVERSION")]
+    assert seqio.genbank_ids(arr, offs) == ["AB000001.2", "NOVERSION"]
+    assert seqio.file_ids(arr, offs, "genbank") == ["AB000001.2", "NOVERSION"]
