@@ -181,6 +181,7 @@ def main():
     ap.add_argument("--length", type=int, default=None, help="override genome length (debug)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-fasta-leg", action="store_true")
+    ap.add_argument("--scan-mode", type=int, default=0, help="0 auto, 1 plain L2 probe, 2 shared-memory filter (debug)")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="weak (default): the config's genome count PER GPU; strong: the config's genome count in total, "
                          "genome 0 on every rank and the others dealt round-robin")
@@ -254,6 +255,7 @@ def main():
     del mine
 
     eng = Engine(device=local, k_min=cfg["k_min"], k_max=cfg["k_max"], max_repeat=cfg["max_repeats"], prefilter=1)
+    eng.set_scan_mode(args.scan_mode)
     for t, off in pinned:
         eng.add_genome_ptr(t.data_ptr(), t.numel(), off)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")

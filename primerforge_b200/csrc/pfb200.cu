@@ -1897,6 +1897,11 @@ static int stage0(pfb_ctx *ctx) {
             if ((rc = ensure(ctx, ctx->at, NA * 8)) != PFB_OK) return rc;
             if ((rc = ensure(ctx, ctx->ovf, cap * 64)) != PFB_OK) return rc;
             k.at = (uint2 *)ctx->at.p; k.ovf = (uint32_t *)ctx->ovf.p; k.ovfCount = misc + 4; k.ovfCap = (uint32_t)cap;
+            // the other genomes only meet the keys that survived genome 1: decide again whether their filter
+            // stays sparse enough (long genomes lose most keys to collisions inside genome 1)
+            use_filter = ctx->scan_mode == 2 ||
+                         (ctx->scan_mode == 0 && (double)ctx->nids / nk < 0.35 * FILTER_BITS && W_alloc >= 4096);
+            ctx->used_filter = use_filter;
             if (use_filter) CK(cudaMemsetAsync(ctx->filter.p, 0, (size_t)nk * FILTER_BYTES, st));
             k_build_at<<<nblk(NA, 256), 256, 0, st>>>(k, use_filter ? 1 : 0); ctx->launches++;
         }
