@@ -922,7 +922,17 @@ __device__ __forceinline__ uint64_t window_at(const K &p, uint32_t g, uint32_t l
     return x >> (64 - 2 * k);
 }
 
-// returns 0 dead, 1 alive on '+', 2 alive on '-'
+// returns 0 dead, 1 alive on '+', 2 alive on '-'; h = the window the genome holds at the row's start (read by the
+// caller, and only when the row's count is 1: otherwise the start field is a sum of starts)
+__device__ __forceinline__ int row_state_h(unsigned long long v, uint64_t h, uint64_t key_fwd, uint64_t key_rc, bool pal, bool first) {
+    if (((v >> 32) & ROW_CNT_MASK) != 1) return 0;
+    bool jf = (v & ROW_JF) != 0, jr = (v & ROW_JR) != 0;
+    if (pal) return (h == key_fwd && (first ? (!jf && jr) : (jf != jr))) ? 2 : 0;   // later '-' match overwrites (:181-187)
+    if (h == key_fwd) return jf ? 0 : 1;
+    if (h == key_rc) return jr ? 0 : 2;
+    return 0;   // the single occupant is a different k-mer: a sketch collision with the key absent
+}
+
 __device__ __forceinline__ int row_state(const K &p, uint32_t g, unsigned long long v, uint64_t key_fwd, uint64_t key_rc,
                                          int k, bool pal, bool first) {
     if (((v >> 32) & ROW_CNT_MASK) != 1) return 0;
@@ -988,18 +998,29 @@ __global__ void __launch_bounds__(256) k_assign_ids(const __grid_constant__ K p)
 
 // k_aliveN: the rules for one (id, genome >= 2) per thread; ids follow genome 1's coordinates, so the rows
 // stream and -- for genomes that are largely collinear with genome 1 -- so do the read-backs
+constexpr uint32_t ALIVE_GPT = 2;   // genomes per thread: two independent row -> genome-word load chains in flight
+
 __global__ void __launch_bounds__(256) k_aliveN(const __grid_constant__ K p) {
     const uint64_t id = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (id >= p.nids) return;
-    const uint32_t g = 1u + blockIdx.y;
+    const uint32_t g0 = 1u + blockIdx.y * ALIVE_GPT;
     const int k = p.kmin + (int)(p.idMeta[id] >> 26);
     const uint64_t key = p.key1[id];
     const uint64_t rc = rc64(key) >> (64 - 2 * k);
-    unsigned long long *row = &p.rows[(size_t)(g - 1) * p.nids + id];
-    const unsigned long long v = *row;
-    const int st = row_state(p, g, v, key, rc, k, key == rc, false);
-    if (st == 0) p.alive[id] = 0;
-    else if (st == 2) *row = v | ROW_MINUS;     // k_positions reads the strand from here
+    unsigned long long v[ALIVE_GPT];
+    uint64_t h[ALIVE_GPT];
+#pragma unroll
+    for (uint32_t i = 0; i < ALIVE_GPT; i++) v[i] = g0 + i < p.nGenomes ? p.rows[(size_t)(g0 + i - 1) * p.nids + id] : 0ull;
+#pragma unroll
+    for (uint32_t i = 0; i < ALIVE_GPT; i++)
+        h[i] = ((v[i] >> 32) & ROW_CNT_MASK) == 1 ? window_at(p, g0 + i, (uint32_t)(v[i] & ROW_POS_MASK), k) : 0ull;
+#pragma unroll
+    for (uint32_t i = 0; i < ALIVE_GPT; i++) {
+        if (g0 + i >= p.nGenomes) break;
+        const int st = row_state_h(v[i], h[i], key, rc, key == rc, false);
+        if (st == 0) p.alive[id] = 0;
+        else if (st == 2) p.rows[(size_t)(g0 + i - 1) * p.nids + id] = v[i] | ROW_MINUS;     // k_positions reads the strand from here
+    }
 }
 
 // k_emit_write: the record of every id that is unique in every genome, at its rank among those
@@ -1077,13 +1098,12 @@ __global__ void __launch_bounds__(256) k_positions(const __grid_constant__ K p) 
         });
     const bool overflow = mt.n > Mates::CAP;
     bool picked = false;
-    for (uint32_t g = 0; g < p.nGenomes; g++) {
+    auto one_genome = [&](uint32_t g, unsigned long long v) {
         uint32_t lp, minus;
         if (g == 0) {
             lp = start1;
             minus = (flags & PFB_F_PALIN) ? 1u : 0u;    // a palindrome matches both scans, the later '-' match overwrites (:181-187)
         } else {
-            const unsigned long long v = p.rows[(size_t)(g - 1) * p.nids + id];
             lp = (uint32_t)(v & ROW_POS_MASK);
             minus = (uint32_t)(v >> 61) & 1u;           // left there by k_aliveN
         }
@@ -1109,6 +1129,16 @@ __global__ void __launch_bounds__(256) k_positions(const __grid_constant__ K p) 
             }
             picked = first;
         }
+    };
+    one_genome(0, 0ull);
+    // the rows of four genomes are requested before the first is used: four times the bytes in flight per thread
+    for (uint32_t g0 = 1; g0 < p.nGenomes; g0 += 4) {
+        unsigned long long v[4];
+#pragma unroll
+        for (uint32_t i = 0; i < 4; i++) v[i] = g0 + i < p.nGenomes ? p.rows[(size_t)(g0 + i - 1) * p.nids + id] : 0ull;
+#pragma unroll
+        for (uint32_t i = 0; i < 4; i++)
+            if (g0 + i < p.nGenomes) one_genome(g0 + i, v[i]);
     }
     if (picked) p.pick[r] = 1;
 }
@@ -1122,9 +1152,19 @@ __global__ void __launch_bounds__(256) k_compact(const __grid_constant__ K p) {
     uint32_t o = p.pickOff[r];
     pfb_record rec = p.rec[r];
     p.outRec[o] = rec;
-    for (uint32_t g = 0; g < p.nGenomes; g++) {
-        p.outPos[(size_t)g * p.nids + o] = p.pos[(size_t)g * p.nids + r];
-        if (p.multiContig) p.outContig[(size_t)g * p.nids + o] = p.posContig[(size_t)g * p.nids + r];
+    for (uint32_t g0 = 0; g0 < p.nGenomes; g0 += 4) {     // four loads in flight before the first store
+        uint32_t a[4], c[4];
+#pragma unroll
+        for (uint32_t i = 0; i < 4; i++) {
+            a[i] = g0 + i < p.nGenomes ? p.pos[(size_t)(g0 + i) * p.nids + r] : 0u;
+            c[i] = (p.multiContig && g0 + i < p.nGenomes) ? p.posContig[(size_t)(g0 + i) * p.nids + r] : 0u;
+        }
+#pragma unroll
+        for (uint32_t i = 0; i < 4; i++) {
+            if (g0 + i >= p.nGenomes) break;
+            p.outPos[(size_t)(g0 + i) * p.nids + o] = a[i];
+            if (p.multiContig) p.outContig[(size_t)(g0 + i) * p.nids + o] = c[i];
+        }
     }
 }
 
@@ -1952,8 +1992,9 @@ static int stage0(pfb_ctx *ctx) {
         CK(cudaStreamWaitEvent(st, ctx->evCopy[nG - 1], 0));
     }
     CK(cudaEventRecord(ctx->ev[5], st));
+    if (nG - 1 > 65535u * ALIVE_GPT) return fail(ctx, PFB_ETOOLARGE, "more than 131070 genomes on one context");
     if (ctx->nids && nG > 1) {
-        k_aliveN<<<dim3(nblk(ctx->nids, 256), (unsigned)(nG - 1)), 256, 0, st>>>(k); ctx->launches++;
+        k_aliveN<<<dim3(nblk(ctx->nids, 256), nblk(nG - 1, ALIVE_GPT)), 256, 0, st>>>(k); ctx->launches++;
     }
     CK(cudaGetLastError());
     return PFB_OK;
