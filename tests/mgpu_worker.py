@@ -19,11 +19,21 @@ def main():
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     n_genomes, length = int(sys.argv[1]), int(sys.argv[2])
     n_contigs = int(sys.argv[3]) if len(sys.argv) > 3 else 1
+    as_fasta = len(sys.argv) > 4 and sys.argv[4] == "fasta"       # hand the ranks FASTA file images (device ingest)
     gens = synth.make_genomes(n_genomes, length, seed=909, snp_rate=0.004, n_inversions=3, n_contigs=n_contigs)
     mine = shard_genomes(n_genomes, world, rank)
     eng = Engine(device=local)
     for gi in mine:
-        eng.add_genome(gens[gi].contigs)
+        if as_fasta:
+            img = bytearray()
+            for cid, arr in zip(gens[gi].contig_ids, gens[gi].contigs):
+                img += b">" + cid.encode() + b"\n"
+                raw = arr.tobytes()
+                for i in range(0, len(raw), 70):
+                    img += raw[i:i + 70] + b"\n"
+            eng.add_fasta(np.frombuffer(bytes(img), dtype=np.uint8).copy())
+        else:
+            eng.add_genome(gens[gi].contigs)
     run_sharded(eng, upload=True)
     rec, ss, ct = eng.result_picked()
     rec, ss = rec.copy(), ss.copy()

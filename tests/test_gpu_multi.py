@@ -8,15 +8,15 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-@pytest.mark.parametrize("n_contigs", [1, 5])
-def test_sharded_equals_single_gpu(n_contigs):
+@pytest.mark.parametrize("n_contigs,ingest", [(1, "bases"), (5, "bases"), (3, "fasta")])
+def test_sharded_equals_single_gpu(n_contigs, ingest):
     import torch
     n = torch.cuda.device_count()
     if n < 2:
         pytest.skip("needs >= 2 GPUs")
     world = 2 if n < 4 else 4
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
-           "--master-port", "29611", os.path.join(ROOT, "tests", "mgpu_worker.py"), "7", "300000", str(n_contigs)]
+           "--master-port", "29611", os.path.join(ROOT, "tests", "mgpu_worker.py"), "7", "300000", str(n_contigs), ingest]
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-4000:]
     assert "ok=True" in out.stdout
