@@ -235,11 +235,21 @@ __device__ __forceinline__ uint32_t slot_of(uint2 e, uint32_t bin) { return e.y 
 __global__ void __launch_bounds__(256) k_encode(const __grid_constant__ K p, uint32_t w0, uint32_t w1) {
     uint32_t w = w0 + blockIdx.x * blockDim.x + threadIdx.x;
     if (w >= w1) return;
-    // owning contig: last contig whose first word is <= w
+    // owning contig: last contig whose first word is <= w.  The 32 words of a warp nearly always lie in one
+    // contig: the search runs once for the warp's first word (the same loads in every lane) and again per
+    // lane only when the next contig starts inside the warp's span
+    const uint32_t w_first = w - (threadIdx.x & 31u);
     uint32_t lo = 0, hi = p.nContigs;
     while (hi - lo > 1) {
         uint32_t mid = (lo + hi) >> 1;
-        if (p.cWordStart[mid] <= w) lo = mid; else hi = mid;
+        if (p.cWordStart[mid] <= w_first) lo = mid; else hi = mid;
+    }
+    if (lo + 1 < p.nContigs && p.cWordStart[lo + 1] <= w) {
+        hi = p.nContigs;
+        while (hi - lo > 1) {
+            uint32_t mid = (lo + hi) >> 1;
+            if (p.cWordStart[mid] <= w) lo = mid; else hi = mid;
+        }
     }
     uint32_t c = lo;
     uint32_t i = w - p.cWordStart[c];

@@ -242,39 +242,55 @@ def test_drop_in_entry_point(name, thal, tmp_path, capsys):
         assert mine == golden_candidate_set(gold, gi)
 
 
-def test_full_size_properties():
-    """BASELINE config 2 at full size: size-independent properties of the result (the oracle would
+@pytest.mark.parametrize("config", [2, 5])
+def test_full_size_properties(config):
+    """BASELINE configs 2 and 5 at full size: size-independent properties of the result (the oracle would
     take minutes here).  Every reported k-mer must read back from every genome at the reported
-    place and strand, be unique there among the reported set, and the order must be the dict order."""
+    place and strand, be unique there among the reported set, and the order must be the dict order.
+    Config 5 adds 50 contigs per genome, 19 lengths (k 12-30, the 64-bit modular reduction) and max_repeats 3."""
     from primerforge_b200 import synth
     from primerforge_b200.engine import Engine
-    gens, cfg = synth.make_config(2)
-    with Engine(device=0, k_min=cfg["k_min"], k_max=cfg["k_max"]) as eng:
+    gens, cfg = synth.make_config(config)
+    with Engine(device=0, k_min=cfg["k_min"], k_max=cfg["k_max"], max_repeat=cfg["max_repeats"]) as eng:
         for g in gens:
             eng.add_genome(g.contigs)
         eng.run()
         rec, ss, ct = eng.result_picked()
         rec, ss = rec.copy(), ss.copy()
+        ct = None if ct is None else ct.copy()
         tm = eng.timing()
-    assert ct is None and rec.size > 100_000 and tm["used_filter"] == 1
+    multi = cfg["n_contigs"] > 1
+    assert (ct is not None) == multi and rec.size > 100_000 and tm["used_filter"] == 1
     k = rec["k"].astype(np.int64)
     assert np.all((rec["flags"] & 15) == 15)
-    # dict order: genome-1 end position ascending, longest first at one end
+    assert k.min() >= cfg["k_min"] and k.max() <= cfg["k_max"]
+    # dict order: genome-1 contig, end position ascending, longest first at one end
+    c0 = ct[0].astype(np.int64) if multi else np.zeros(rec.size, dtype=np.int64)
     end0 = (ss[0] & 0x7FFFFFFF).astype(np.int64) + k - 1
-    order_key = end0 * 64 + (63 - k)
+    order_key = (c0 << 40) + end0 * 64 + (63 - k)
     assert np.all(np.diff(order_key) > 0)
     assert np.all((ss[0] >> 31) == 0)                       # genome 1 holds every key on its (+) strand
     code = np.full(256, 4, dtype=np.uint8)
     for ch, v in zip(b"ATCG", range(4)):
         code[ch] = v
     rng = np.random.default_rng(5)
-    sample = rng.choice(rec.size, size=20000, replace=False)
+    sample = rng.choice(rec.size, size=3000, replace=False)
+    # no homopolymer of max_repeats or more in any candidate (checked on the 2-bit words of the sample)
+    for w, kk in zip(rec["word"][sample][:500], k[sample][:500]):
+        bases = [(int(w) >> (2 * (int(kk) - 1 - i))) & 3 for i in range(int(kk))]
+        run = best = 1
+        for i in range(1, len(bases)):
+            run = run + 1 if bases[i] == bases[i - 1] else 1
+            best = max(best, run)
+        assert best < cfg["max_repeats"]
     for gi, gen in enumerate(gens):
-        seq = code[gen.contigs[0]]
+        seqs = [code[c] for c in gen.contigs]
         start = (ss[gi] & 0x7FFFFFFF).astype(np.int64)[sample]
         minus = (ss[gi] >> 31).astype(bool)[sample]
-        for s0, mi, w, kk in zip(start[:4000], minus[:4000], rec["word"][sample][:4000], k[sample][:4000]):
-            window = seq[s0:s0 + kk]
+        contig = ct[gi][sample] if multi else np.zeros(sample.size, dtype=np.int64)
+        for s0, mi, ci, w, kk in zip(start, minus, contig, rec["word"][sample], k[sample]):
+            window = seqs[int(ci)][s0:s0 + kk]
+            assert window.size == kk
             if mi:
                 window = (window[::-1] ^ 1)
             val = 0
@@ -282,7 +298,8 @@ def test_full_size_properties():
                 val = (val << 2) | int(c)
             assert val == int(w)
         # a position holds at most one picked k-mer per k
-        assert np.unique((ss[gi].astype(np.int64) << 6) | k).size == rec.size
+        cg = ct[gi].astype(np.int64) if multi else np.zeros(rec.size, dtype=np.int64)
+        assert np.unique((cg << 40) | (ss[gi].astype(np.int64) << 6) | k).size == rec.size
 
 
 def test_pipelined_run_equals_upload_then_compute():
