@@ -182,6 +182,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-fasta-leg", action="store_true")
     ap.add_argument("--scan-mode", type=int, default=0, help="0 auto, 1 plain L2 probe, 2 shared-memory filter (debug)")
+    ap.add_argument("--dropin-leg", action="store_true",
+                    help="also time the drop-in entry point _getAllCandidateKmers(params, False) from FASTA files on disk "
+                         "to the dict of Primer objects (SURVEY 8d T_e2e; dominated by building G x |S| Python objects)")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="weak (default): the config's genome count PER GPU; strong: the config's genome count in total, "
                          "genome 0 on every rank and the others dealt round-robin")
@@ -450,6 +453,27 @@ def main():
                             "note": "latency-bound: ~2 MB per step; no k-mer crosses NVLink (DESIGN.md section 5)"}
     if fasta_leg is not None:
         line["e2e_fasta"] = fasta_leg
+    if args.dropin_leg and world == 1:
+        import tempfile
+        from types import SimpleNamespace
+        from primerforge_b200.candidates import _getAllCandidateKmers
+        gens2 = synth.make_genomes(per_rank, cfg["length"], seed=synth.BASE_SEED + args.config, n_contigs=cfg["n_contigs"])
+        with tempfile.TemporaryDirectory() as tmpd:
+            paths = synth.write_fasta(gens2, tmpd)
+            del gens2
+            log = SimpleNamespace(rename=lambda *a: None, info=lambda *a: None, debug=lambda *a: None, error=lambda *a: None)
+            prm = SimpleNamespace(ingroupFns=paths, format="fasta", minLen=cfg["k_min"], maxLen=cfg["k_max"], minGc=40.0, maxGc=60.0,
+                                  minTm=55.0, maxTm=68.0, maxRepeatLen=cfg["max_repeats"], tempTolerance=5.0, numThreads=1,
+                                  p3_mvConc=50.0, p3_dvConc=1.5, p3_dntpConc=0.6, p3_dnaConc=50.0, p3_tempC=37.0, p3_maxLoop=30,
+                                  log=log, pickles={1: "sharedKmers.p", 2: "candidates.p"}, dumpObj=lambda *a, **k: None,
+                                  loadObj=lambda *a: None)
+            t0 = time.perf_counter()
+            out = _getAllCandidateKmers(prm, False, thal="off", device=local)
+            dt = time.perf_counter() - t0
+        n_obj = sum(len(v) for per in out.values() for v in per.values())
+        line["e2e_dropin"] = {"value": distinct_bases / 1e6 / dt, "unit": UNIT, "seconds": dt, "primer_objects": int(n_obj),
+                              "what": "_getAllCandidateKmers(params, False) from FASTA files on disk to dict[str, dict[str, list[Primer]]], "
+                                      "hairpin / homodimer screening off; the time is building the Python Primer objects"}
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"], _ = cpu_sample_run(args.config)
     emit(line)

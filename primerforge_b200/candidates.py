@@ -18,7 +18,7 @@ import numpy as np
 
 from . import _lib, seqio
 from .engine import ERR_NO_CANDIDATES, ERR_NO_SHARED, Engine, PfbError, StageResult, words_to_strings
-from .primer import make_primer, primer_class
+from .primer import primer_class
 
 _GAP = " " * 4
 _SHARED, _CAND = 1, 2        # bin/Parameters.py: pickles[_SHARED], pickles[_CAND]
@@ -84,24 +84,67 @@ def screen_groups(records, positions, kmers, thal_fn, limit: float):
 
 
 def build_output(names, contig_ids, records, positions, kmers, thal_values=None):
-    """__buildOutput (:442-489) + the per-contig sort (:598-602): genome -> contig -> list[Primer]"""
+    """__buildOutput (:442-489) + the per-contig sort (:598-602): genome -> contig -> list[Primer].
+
+    G x |S| Python objects are the expensive part of the whole stage once the arithmetic runs on the GPU, so
+    the records are created column-wise: plain Python lists of the fields, one instance dict per record and
+    no constructor call (the constructor would recompute GC and Tm, which come from the device)."""
+    import gc
+    gc_was_enabled = gc.isenabled()
+    gc.disable()        # millions of small containers: the cyclic collector's passes over them cost more than creating them
+    try:
+        return _build_output(names, contig_ids, records, positions, kmers, thal_values)
+    finally:
+        if gc_was_enabled:
+            gc.enable()
+
+
+def _build_output(names, contig_ids, records, positions, kmers, thal_values):
     cls = primer_class()
+    from .primer import Seq
     k = records["k"].astype(np.int64)
     gc_per = records["gc_count"] / records["k"] * 100
     tm = records["tm"]
+    seqs = [Seq(s) for s in kmers]
+    n = len(seqs)
+    new = cls.__new__
     out = {}
     for g, name in enumerate(names):
         pos = positions[g]
         order = np.lexsort((pos["strand"], k, pos["start"], pos["contig"]))
-        per_contig = {}
+        left = pos["start"][order].astype(np.int64)
+        kk = k[order]
+        minus = pos["strand"][order].astype(bool)
+        right = left + kk - 1
+        starts = np.where(minus, right, left).tolist()          # '-' records keep start > end (Primer.py:42-45)
+        ends = np.where(minus, left, right).tolist()
+        strands = np.where(minus, "-", "+").tolist()
+        order_l = order.tolist()
+        seq_o = [seqs[r] for r in order_l]
+        tm_o = tm[order].tolist()
+        gc_o = gc_per[order].tolist()
+        k_o = kk.tolist()
+        if thal_values is not None:
+            th_o = [thal_values.get(r) or (None, None, None, None) for r in order_l]
+        else:
+            th_o = None
+        contig_sorted = pos["contig"][order]
+        # contigs are contiguous runs of the sorted order
+        bounds = np.flatnonzero(np.r_[True, contig_sorted[1:] != contig_sorted[:-1], True]) if n else np.zeros(1, dtype=np.int64)
         ids = contig_ids[g]
-        for r in order:
-            r = int(r)
-            cname = ids[int(pos["contig"][r])]
-            th = thal_values.get(r) if thal_values is not None else None
-            per_contig.setdefault(cname, []).append(
-                make_primer(cls, kmers[r], cname, int(pos["start"][r]), int(k[r]), bool(pos["strand"][r]),
-                            float(tm[r]), float(gc_per[r]), th))
+        per_contig = {}
+        for a, b in zip(bounds[:-1].tolist(), bounds[1:].tolist()):
+            cname = ids[int(contig_sorted[a])]
+            plist = []
+            append = plist.append
+            for i in range(a, b):
+                p = new(cls)
+                th = th_o[i] if th_o is not None else (None, None, None, None)
+                p.__dict__ = {"seq": seq_o[i], "start": starts[i], "end": ends[i], "contig": cname, "strand": strands[i],
+                              "Tm": tm_o[i], "gcPer": gc_o[i], "hairpinTm": th[0], "rcHairpin": th[1],
+                              "homodimerTm": th[2], "rcHomodimer": th[3], "_Primer__length": k_o[i]}
+                append(p)
+            per_contig[cname] = plist
         out[name] = per_contig
     return out
 
