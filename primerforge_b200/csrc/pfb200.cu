@@ -487,6 +487,8 @@ __global__ void __launch_bounds__(256) k_scan_plain(const __grid_constant__ K p,
     uint32_t qbase = 32u * i;
     int nj = (int)min(32u, clen - qbase);
     uint32_t gpos0 = 32u * (w - p.gWordStart[g]);
+    // (probing four lengths at once with the 32-bit modular reduction was tried: slower, 0.280 vs 0.258 ms for
+    // one 5 Mbp genome -- the kernel lives on thread-level parallelism, the extra registers cost occupancy)
     for (int j = 0; j < nj; j++) {
         uint32_t code = (uint32_t)(cur >> (62 - 2 * j)) & 3u;
         hf = (hf << 2) | code;
@@ -1885,9 +1887,11 @@ static int stage0(pfb_ctx *ctx) {
     if ((rc = ensure(ctx, ctx->remap, NS * 4)) != PFB_OK) return rc;
     k.rows0 = (unsigned long long *)ctx->rows0.p; k.remap = (uint32_t *)ctx->remap.p;
     CK(cudaMemsetAsync(ctx->rows0.p, 0, NS * 8, st));
-    // the filter pays off while it stays sparse: expected fill 1 - exp(-keys_per_k / FILTER_BITS)
-    bool use_filter = ctx->scan_mode == 2 ||
-                      (ctx->scan_mode == 0 && (double)ctx->nslots / nk < 0.35 * FILTER_BITS && W_alloc >= 4096);
+    // the filter pays off while it stays sparse (expected fill 1 - exp(-keys_per_k / FILTER_BITS)) and the launch
+    // is long enough to amortise the nk filter loads.  Genome 1's own pass meets ALL its candidate keys (a dense
+    // filter) in one short launch: measured, the plain L2 probe is faster there at every genome size tried
+    // (5 Mbp: 0.14 vs 0.18 ms), so the filter is only used for it when forced (scan mode 2, tests)
+    bool use_filter = ctx->scan_mode == 2;
     ctx->used_filter = use_filter;
     if (use_filter && ctx->nslots) {
         CK(cudaMemsetAsync(ctx->filter.p, 0, (size_t)nk * FILTER_BYTES, st));
