@@ -836,6 +836,14 @@ __global__ void __launch_bounds__(128) k_junction(const __grid_constant__ K p, u
 }
 
 // ------------------------------------------------------------------------------------------
+// zero fill on the SMs.  cudaMemsetAsync may run on a copy engine, where it queues up behind the 5 MB H2D
+// chunks of a pipelined run (measured: up to 0.1 ms per memset); a kernel does not.
+__global__ void __launch_bounds__(256) k_zero(uint4 *p, size_t n16) {
+    const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (size_t)gridDim.x * blockDim.x) p[i] = z;
+}
+
+// ------------------------------------------------------------------------------------------
 // bits = seen once and not seen again
 __global__ void __launch_bounds__(256) k_candbits(const __grid_constant__ K p) {
     uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -870,7 +878,9 @@ __global__ void __launch_bounds__(256) k_scan_p1(const void *in, uint32_t n, uin
     if (threadIdx.x == 0) { uint32_t tot = 0; for (int i = 0; i < 8; i++) tot += sm[i]; blockSums[blockIdx.x] = tot; }
 }
 
-__global__ void __launch_bounds__(1024) k_scan_p2(uint32_t *blockSums, uint32_t nb, uint32_t *total) {
+// the total also goes to host-mapped memory: the host reads it after a stream synchronise, with no device -> host
+// copy that would queue up behind the H2D copies of a pipelined run
+__global__ void __launch_bounds__(1024) k_scan_p2(uint32_t *blockSums, uint32_t nb, uint32_t *total, uint32_t *total_host) {
     __shared__ uint32_t sm[1024];
     uint32_t per = (nb + 1023) / 1024;
     uint32_t lo = min(nb, threadIdx.x * per), hi = min(nb, lo + per);
@@ -886,7 +896,7 @@ __global__ void __launch_bounds__(1024) k_scan_p2(uint32_t *blockSums, uint32_t 
     }
     uint32_t run = sm[threadIdx.x] - s;
     for (uint32_t x = lo; x < hi; x++) { uint32_t v = blockSums[x]; blockSums[x] = run; run += v; }
-    if (threadIdx.x == 1023) *total = sm[1023];
+    if (threadIdx.x == 1023) { *total = sm[1023]; if (total_host) *total_host = sm[1023]; }
 }
 
 template <int MODE, int S>
@@ -1224,6 +1234,12 @@ struct pfb_ctx {
     cudaStream_t copyStream = nullptr;          // H2D copies of pfb_run run here, overlapped with compute
     std::vector<cudaEvent_t> evCopy;            // one per genome: its bases have arrived
     bool pipelined = false;
+    // PFB200_TRACE=1: timestamps (ms after the first H2D copy was queued) of the pipeline's milestones on stderr
+    volatile uint32_t *countsHost = nullptr;    // mapped pinned: [0] nslots, [1] nids, [2] nrec, [3] npick as written by the scans
+    uint32_t *countsDev = nullptr;              // the same memory as the device sees it
+    size_t encoded_upto = 0;                    // pipelined run: genomes [0, encoded_upto) are packed already
+    bool tracing = false;
+    std::vector<std::pair<std::string, cudaEvent_t>> trace;
     // FASTA ingest: file images are staged in `fa`, parsed on parseStream, record tables land in mapped host memory
     cudaStream_t parseStream = nullptr;
     bool any_fasta = false;
@@ -1259,6 +1275,25 @@ struct pfb_ctx {
 static std::string g_create_err;
 
 namespace {
+
+void trace_mark(pfb_ctx *ctx, cudaStream_t st, const std::string &label) {
+    if (!ctx->tracing) return;
+    cudaEvent_t e;
+    if (cudaEventCreate(&e) != cudaSuccess) return;
+    cudaEventRecord(e, st);
+    ctx->trace.emplace_back(label, e);
+}
+
+void trace_dump(pfb_ctx *ctx) {
+    if (!ctx->tracing) return;
+    for (auto &t : ctx->trace) {
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, ctx->ev[0], t.second) == cudaSuccess) fprintf(stderr, "[pfb trace] %8.3f ms  %s\n", ms, t.first.c_str());
+        cudaEventDestroy(t.second);
+    }
+    cudaGetLastError();
+    ctx->trace.clear();
+}
 
 int fail(pfb_ctx *c, int code, const std::string &msg) {
     if (c) c->err = msg; else g_create_err = msg;
@@ -1297,12 +1332,24 @@ int ensure_keep(pfb_ctx *ctx, DevBuf &b, size_t bytes, size_t keep) {
     return PFB_OK;
 }
 
+int zero_async(pfb_ctx *ctx, DevBuf &b, size_t bytes, cudaStream_t st) {
+    if (!bytes) return PFB_OK;
+    const size_t n16 = (bytes + 15) / 16;
+    if (n16 * 16 > b.cap) return fail(ctx, PFB_ECUDA, "zero_async beyond the buffer");
+    const unsigned blocks = (unsigned)std::min<size_t>((n16 + 255) / 256, (size_t)ctx->num_sms * 16);
+    k_zero<<<blocks, 256, 0, st>>>((uint4 *)b.p, n16);
+    return PFB_OK;
+}
+
 void release(DevBuf &b) {
     if (b.p) cudaFree(b.p);
     b.p = nullptr; b.cap = 0;
 }
 
 inline unsigned nblk(uint64_t n, unsigned bs) { return (unsigned)((n + bs - 1) / bs); }
+
+// zero the first `bytes` of a DevBuf (rounded up to 16: every buffer has that much slack, see ensure)
+int zero_async(pfb_ctx *ctx, DevBuf &b, size_t bytes, cudaStream_t st);
 
 int validate(const pfb_params *p, std::string &why) {
     if (!p) { why = "params is NULL"; return PFB_EINVAL; }
@@ -1557,14 +1604,14 @@ int fasta_collect(pfb_ctx *ctx, int b) {
 
 // device-wide exclusive scan helper (out may alias in)
 template <int MODE, int S>
-int device_exscan(pfb_ctx *ctx, const void *in, uint32_t *out, uint32_t n, uint32_t *total_dev) {
+int device_exscan(pfb_ctx *ctx, const void *in, uint32_t *out, uint32_t n, uint32_t *total_dev, uint32_t *total_host) {
     cudaStream_t st = ctx->stream;
     uint32_t nb = (n + SCAN_TILE - 1) / SCAN_TILE;
     int rc = ensure(ctx, ctx->scanTmp, (size_t)(nb + 1) * 4);
     if (rc != PFB_OK) return rc;
     uint32_t *bs = (uint32_t *)ctx->scanTmp.p;
     k_scan_p1<MODE, S><<<nb, 256, 0, st>>>(in, n, bs);
-    k_scan_p2<<<1, 1024, 0, st>>>(bs, nb, total_dev);
+    k_scan_p2<<<1, 1024, 0, st>>>(bs, nb, total_dev, total_host);
     k_scan_p3<MODE, S><<<nb, 256, 0, st>>>(in, out, n, bs);
     ctx->launches += 3;
     return PFB_OK;
@@ -1604,6 +1651,7 @@ int pfb_create(pfb_ctx **out, int device, const pfb_params *params) {
     ctx = new pfb_ctx();
     ctx->device = device;
     ctx->prm = *params;
+    { const char *tr = getenv("PFB200_TRACE"); ctx->tracing = tr && tr[0] == '1'; }
     cudaDeviceGetAttribute(&ctx->num_sms, cudaDevAttrMultiProcessorCount, device);
     e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->copyStream, cudaStreamNonBlocking);
@@ -1612,6 +1660,14 @@ int pfb_create(pfb_ctx **out, int device, const pfb_params *params) {
         e = cudaFuncSetAttribute(k_scan_filtered, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SCANF_SMEM);
     if (e != cudaSuccess) { std::string m = cudaGetErrorString(e); delete ctx; return fail(nullptr, PFB_ECUDA, m); }
     for (auto &ev : ctx->ev) cudaEventCreate(&ev);
+    {
+        void *h = nullptr, *d = nullptr;
+        if (cudaHostAlloc(&h, 64, cudaHostAllocMapped) != cudaSuccess || cudaHostGetDevicePointer(&d, h, 0) != cudaSuccess) {
+            std::string m = "cudaHostAlloc (mapped) failed"; pfb_destroy(ctx); return fail(nullptr, PFB_ECUDA, m);
+        }
+        memset(h, 0, 64);
+        ctx->countsHost = (volatile uint32_t *)h; ctx->countsDev = (uint32_t *)d;
+    }
     *out = ctx;
     return PFB_OK;
 }
@@ -1628,6 +1684,7 @@ void pfb_destroy(pfb_ctx *ctx) {
     for (auto *b : all) release(*b);
     for (auto &ev : ctx->ev) if (ev) cudaEventDestroy(ev);
     for (auto &ev : ctx->evCopy) if (ev) cudaEventDestroy(ev);
+    if (ctx->countsHost) cudaFreeHost((void *)ctx->countsHost);
     if (ctx->copyStream) { cudaStreamSynchronize(ctx->copyStream); cudaStreamDestroy(ctx->copyStream); }
     if (ctx->parseStream) { cudaStreamSynchronize(ctx->parseStream); cudaStreamDestroy(ctx->parseStream); }
     for (int b = 0; b < 2; b++) {
@@ -1752,6 +1809,7 @@ static int upload_impl(pfb_ctx *ctx, bool async) {
             CK(cudaMemcpyAsync((uint8_t *)ctx->raw.p + ctx->gRawStart[g], hg.bases, hg.n_bases, cudaMemcpyHostToDevice, cs));
         }
         if (async) CK(cudaEventRecord(ctx->evCopy[g], cs));
+        trace_mark(ctx, cs, "copy landed: genome " + std::to_string(g));
     }
     CK(cudaEventRecord(ctx->ev[1], cs));
     ctx->pipelined = async;
@@ -1860,33 +1918,50 @@ static int stage0(pfb_ctx *ctx) {
 
     CK(cudaEventRecord(ctx->ev[2], st));
     CK(cudaMemcpyAsync(ctx->fterm.p, fterm.data(), FTERM_DOUBLES * 8, cudaMemcpyHostToDevice, st));
-    CK(cudaMemsetAsync(ctx->misc.p, 0, 4096, st));
-    CK(cudaMemsetAsync(ctx->sk.p, 0, (size_t)NB * 2 * 4, st));
+    if ((rc = zero_async(ctx, ctx->misc, 4096, st)) != PFB_OK) return rc;
+    if ((rc = zero_async(ctx, ctx->sk, (size_t)NB * 2 * 4, st)) != PFB_OK) return rc;
     const size_t nG = ctx->genomes.size();
     const bool piped = ctx->pipelined;
     if (piped) {   // only genome 1 has to be there before the key table can be built
         CK(cudaStreamWaitEvent(st, ctx->evCopy[0], 0));
         if (W1) { k_encode<<<nblk(W1, 256), 256, 0, st>>>(k, 0, W1); ctx->launches++; }
+        ctx->encoded_upto = 1;
     } else if (W) {
         k_encode<<<nblk(W, 256), 256, 0, st>>>(k, 0, W); ctx->launches++;
     }
+    // pipelined run: pack whatever has landed meanwhile.  Called just before the host waits for a count, so
+    // that the GPU has something to do during the round trip.
+    auto encode_landed = [&]() -> int {
+        if (!piped || partial) return PFB_OK;
+        size_t g2 = ctx->encoded_upto;
+        while (g2 < nG && cudaEventQuery(ctx->evCopy[g2]) == cudaSuccess) g2++;
+        cudaGetLastError();
+        if (g2 > ctx->encoded_upto) {
+            const uint32_t wa = ctx->gWordStart[ctx->encoded_upto], wb = g2 < nG ? ctx->gWordStart[g2] : ctx->totalWords;
+            if (wb > wa) { k_encode<<<nblk(wb - wa, 256), 256, 0, st>>>(k, wa, wb); ctx->launches++; }
+            ctx->encoded_upto = g2;
+        }
+        return PFB_OK;
+    };
     CK(cudaEventRecord(ctx->ev[3], st));
+    trace_mark(ctx, st, "genome 1 encoded");
     // genome 1: candidates -> key table
     const uint32_t N1 = W1 * 32u;                                           // padded end positions of genome 1
     if (W1) { k_cand1<<<nblk(N1, CAND_POS), CAND_POS + 32, 0, st>>>(k, N1); ctx->launches++; }
     k_candbits<<<nblk(NB, 256), 256, 0, st>>>(k); ctx->launches++;
-    if ((rc = device_exscan<SV_POPC, 2>(ctx, k.br, (uint32_t *)k.br + 1, NB, misc)) != PFB_OK) return rc;
-    uint32_t ns = 0;
-    CK(cudaMemcpyAsync(&ns, misc, 4, cudaMemcpyDeviceToHost, st));
+    if ((rc = device_exscan<SV_POPC, 2>(ctx, k.br, (uint32_t *)k.br + 1, NB, misc, ctx->countsDev)) != PFB_OK) return rc;
+    trace_mark(ctx, st, "slots counted (host waits for the count after this)");
+    if ((rc = encode_landed()) != PFB_OK) return rc;
     CK(cudaStreamSynchronize(st));   // fterm (host vector) is also consumed by now
-    ctx->nslots = ns;
+    trace_mark(ctx, st, "host has the slot count");
+    ctx->nslots = ctx->countsHost[0];
     k.nslots = ctx->nslots;
     ctx->nids = 0; k.nids = 0;
     const size_t NS = ctx->nslots ? ctx->nslots : 1;
     if ((rc = ensure(ctx, ctx->rows0, NS * 8)) != PFB_OK) return rc;
     if ((rc = ensure(ctx, ctx->remap, NS * 4)) != PFB_OK) return rc;
     k.rows0 = (unsigned long long *)ctx->rows0.p; k.remap = (uint32_t *)ctx->remap.p;
-    CK(cudaMemsetAsync(ctx->rows0.p, 0, NS * 8, st));
+    if ((rc = zero_async(ctx, ctx->rows0, NS * 8, st)) != PFB_OK) return rc;
     // the filter pays off while it stays sparse (expected fill 1 - exp(-keys_per_k / FILTER_BITS)) and the launch
     // is long enough to amortise the nk filter loads.  Genome 1's own pass meets ALL its candidate keys (a dense
     // filter) in one short launch: measured, the plain L2 probe is faster there at every genome size tried
@@ -1894,10 +1969,11 @@ static int stage0(pfb_ctx *ctx) {
     bool use_filter = ctx->scan_mode == 2;
     ctx->used_filter = use_filter;
     if (use_filter && ctx->nslots) {
-        CK(cudaMemsetAsync(ctx->filter.p, 0, (size_t)nk * FILTER_BYTES, st));
+        if ((rc = zero_async(ctx, ctx->filter, (size_t)nk * FILTER_BYTES, st)) != PFB_OK) return rc;
         k_build_filter<<<nblk(NB, 256), 256, 0, st>>>(k); ctx->launches++;
     }
     CK(cudaEventRecord(ctx->ev[4], st));
+    trace_mark(ctx, st, "key table built");
     // every genome (the first included): one pass against the key table
     auto scan_range = [&](uint32_t wa, uint32_t wb, uint32_t ca, uint32_t cb, uint32_t n_gen) {
         if (wb > wa) {
@@ -1920,12 +1996,15 @@ static int stage0(pfb_ctx *ctx) {
         k.first_pass = 1;
         scan_range(0, W1, 0, C1, 1);
         k.first_pass = 0;
-        CK(cudaMemsetAsync(ctx->emitMask.p, 0, (size_t)N1 * 4 + 4, st));
+        trace_mark(ctx, st, "genome 1 scanned");
+        if ((rc = zero_async(ctx, ctx->emitMask, (size_t)N1 * 4 + 4, st)) != PFB_OK) return rc;
         k_alive1<<<nblk(ctx->nslots, 256), 256, 0, st>>>(k); ctx->launches++;
-        if ((rc = device_exscan<SV_POPC, 1>(ctx, k.emitMask, k.emitOff, N1, misc + 1)) != PFB_OK) return rc;
-        uint32_t ni = 0;
-        CK(cudaMemcpyAsync(&ni, misc + 1, 4, cudaMemcpyDeviceToHost, st));
+        if ((rc = device_exscan<SV_POPC, 1>(ctx, k.emitMask, k.emitOff, N1, misc + 1, ctx->countsDev + 1)) != PFB_OK) return rc;
+        trace_mark(ctx, st, "ids counted (host waits for the count after this)");
+        if ((rc = encode_landed()) != PFB_OK) return rc;
         CK(cudaStreamSynchronize(st));
+        trace_mark(ctx, st, "host has the id count");
+        const uint32_t ni = ctx->countsHost[1];
         ctx->nids = ni; k.nids = ni;
     }
     {
@@ -1940,7 +2019,7 @@ static int stage0(pfb_ctx *ctx) {
         k.alive = (uint8_t *)ctx->alive.p; k.recIdx = (uint32_t *)ctx->recIdx.p;
     }
     if (ctx->nids) {
-        if (nG > 1) CK(cudaMemsetAsync(ctx->rows.p, 0, (size_t)ctx->nids * (nG - 1) * 8, st));
+        if (nG > 1 && (rc = zero_async(ctx, ctx->rows, (size_t)ctx->nids * (nG - 1) * 8, st)) != PFB_OK) return rc;
         k_assign_ids<<<nblk(ctx->nslots, 256), 256, 0, st>>>(k); ctx->launches++;
         if (nG > 1) {
             // key table of the other genomes (alive keys only, ids inline) and their filter
@@ -1956,8 +2035,9 @@ static int stage0(pfb_ctx *ctx) {
             use_filter = ctx->scan_mode == 2 ||
                          (ctx->scan_mode == 0 && (double)ctx->nids / nk < 0.35 * FILTER_BITS && W_alloc >= 4096);
             ctx->used_filter = use_filter;
-            if (use_filter) CK(cudaMemsetAsync(ctx->filter.p, 0, (size_t)nk * FILTER_BYTES, st));
+            if (use_filter && (rc = zero_async(ctx, ctx->filter, (size_t)nk * FILTER_BYTES, st)) != PFB_OK) return rc;
             k_build_at<<<nblk(NA, 256), 256, 0, st>>>(k, use_filter ? 1 : 0); ctx->launches++;
+            trace_mark(ctx, st, "key table of the other genomes built");
         }
     }
     if (partial) {
@@ -1981,24 +2061,45 @@ static int stage0(pfb_ctx *ctx) {
             // copies are ahead of the kernels
             size_t g = 1;
             bool first_batch = true;
+            uint64_t prev_bytes = 0;
             while (g < nG) {
-                // decide the next batch when the GPU STARTS the previous one: the host stays one batch ahead,
-                // never idles the GPU, and the batch holds everything that landed meanwhile
+                // decide the next batch when the GPU STARTS the previous one: the host stays one batch ahead and
+                // never idles the GPU.  Copies land about as fast as genomes are scanned, so the batch waits for
+                // as many bytes as will land while the previous batch runs (60 % of its size; at least 4 MB):
+                // few large launches instead of a tail of one-genome launches
                 if (!first_batch) CK(cudaEventSynchronize(ctx->ev[9]));
+                uint64_t want = first_batch ? (4u << 20) : std::max<uint64_t>(4u << 20, prev_bytes * 6 / 10);
+                {   // when what is still in flight is small next to what is ready, one launch over everything beats
+                    // a second short launch: wait for the stragglers
+                    uint64_t ready = 0, flying = 0;
+                    size_t gq = g;
+                    while (gq < nG && (gq < ctx->encoded_upto || cudaEventQuery(ctx->evCopy[gq]) == cudaSuccess)) ready += ctx->genomes[gq++].n_bases;
+                    for (; gq < nG; gq++) flying += ctx->genomes[gq].n_bases;
+                    cudaGetLastError();
+                    if (flying * 10 <= ready * 3) want = ~0ull;
+                }
                 first_batch = false;
                 size_t g2 = g;
                 uint64_t bytes = 0;
                 while (g2 < nG) {
-                    if (bytes >= (4u << 20) && cudaEventQuery(ctx->evCopy[g2]) != cudaSuccess) break;
-                    CK(cudaEventSynchronize(ctx->evCopy[g2]));
+                    if (g2 >= ctx->encoded_upto) {       // (packed genomes have landed: no need to ask)
+                        if (bytes >= want && cudaEventQuery(ctx->evCopy[g2]) != cudaSuccess) break;
+                        CK(cudaEventSynchronize(ctx->evCopy[g2]));
+                    }
                     bytes += ctx->genomes[g2++].n_bases;
                 }
                 cudaGetLastError();   // cudaErrorNotReady of the query is not an error
+                prev_bytes = bytes;
+                const size_t ge = std::max(g, std::min(ctx->encoded_upto, g2));      // [g, ge) is packed already
                 uint32_t wa = ctx->gWordStart[g], wb = g2 < nG ? ctx->gWordStart[g2] : W;
+                uint32_t we = ge < nG ? ctx->gWordStart[ge] : W;
                 uint32_t ca = ctx->gFirstContig[g], cb = g2 < nG ? ctx->gFirstContig[g2] : (uint32_t)ctx->cLen.size();
-                if (wb > wa) { k_encode<<<nblk(wb - wa, 256), 256, 0, st>>>(k, wa, wb); ctx->launches++; }
+                if (wb > we) { k_encode<<<nblk(wb - we, 256), 256, 0, st>>>(k, we, wb); ctx->launches++; }
+                ctx->encoded_upto = std::max(ctx->encoded_upto, g2);
                 CK(cudaEventRecord(ctx->ev[9], st));
+                trace_mark(ctx, st, "scan starts: genomes " + std::to_string(g) + ".." + std::to_string(g2 - 1));
                 scan_range(wa, wb, ca, cb, (uint32_t)(g2 - g));
+                trace_mark(ctx, st, "scan done:   genomes " + std::to_string(g) + ".." + std::to_string(g2 - 1));
                 g = g2;
             }
         }
@@ -2006,6 +2107,7 @@ static int stage0(pfb_ctx *ctx) {
         CK(cudaStreamWaitEvent(st, ctx->evCopy[nG - 1], 0));
     }
     CK(cudaEventRecord(ctx->ev[5], st));
+    trace_mark(ctx, st, "ids assigned / all scans queued behind");
     if (nG - 1 > 65535u * ALIVE_GPT) return fail(ctx, PFB_ETOOLARGE, "more than 131070 genomes on one context");
     if (ctx->nids && nG > 1) {
         k_aliveN<<<dim3(nblk(ctx->nids, 256), nblk(nG - 1, ALIVE_GPT)), 256, 0, st>>>(k); ctx->launches++;
@@ -2033,10 +2135,10 @@ static int stage1(pfb_ctx *ctx) {
     k.rec = (pfb_record *)ctx->rec.p; k.pos = (uint32_t *)ctx->pos.p; k.posContig = (uint32_t *)ctx->posContig.p;
     k.multiContig = multi ? 1 : 0;
     k.pick = (uint8_t *)ctx->pick.p; k.pickOff = (uint32_t *)ctx->pickOff.p;
-    CK(cudaMemsetAsync(ctx->pick.p, 0, NI, st));
+    if ((rc = zero_async(ctx, ctx->pick, NI, st)) != PFB_OK) return rc;
     if (ctx->nids) {
         // ids are in dict order already: the record index is the rank among the ids that survived every genome
-        if ((rc = device_exscan<SV_U8, 1>(ctx, k.alive, k.recIdx, (uint32_t)ctx->nids, misc + 2)) != PFB_OK) return rc;
+        if ((rc = device_exscan<SV_U8, 1>(ctx, k.alive, k.recIdx, (uint32_t)ctx->nids, misc + 2, ctx->countsDev + 2)) != PFB_OK) return rc;
         k_emit_write<<<nblk(ctx->nids, 256), 256, 0, st>>>(k); ctx->launches++;
         k_positions<<<nblk(ctx->nids, 256), 256, 0, st>>>(k); ctx->launches++;
     }
@@ -2055,16 +2157,19 @@ static int stage2(pfb_ctx *ctx) {
     if ((rc = ensure(ctx, ctx->outPos, NI * nG * 4)) != PFB_OK) return rc;
     if ((rc = ensure(ctx, ctx->outContig, k.multiContig ? NI * nG * 4 : 4)) != PFB_OK) return rc;
     k.outRec = (pfb_record *)ctx->outRec.p; k.outPos = (uint32_t *)ctx->outPos.p; k.outContig = (uint32_t *)ctx->outContig.p;
-    uint32_t counts[2] = {0, 0};
     if (ctx->nids) {
-        if ((rc = device_exscan<SV_U8, 1>(ctx, k.pick, k.pickOff, (uint32_t)ctx->nids, misc + 3)) != PFB_OK) return rc;
+        if ((rc = device_exscan<SV_U8, 1>(ctx, k.pick, k.pickOff, (uint32_t)ctx->nids, misc + 3, ctx->countsDev + 3)) != PFB_OK) return rc;
         k_compact<<<nblk(ctx->nids, 256), 256, 0, st>>>(k); ctx->launches++;
-        CK(cudaMemcpyAsync(counts, misc + 2, 8, cudaMemcpyDeviceToHost, st));
     }
     CK(cudaEventRecord(ctx->ev[6], st));
     CK(cudaStreamSynchronize(st));
     CK(cudaGetLastError());
-    ctx->nrec = counts[0]; ctx->npick = counts[1];
+    ctx->nrec = ctx->nids ? ctx->countsHost[2] : 0; ctx->npick = ctx->nids ? ctx->countsHost[3] : 0;
+    if (ctx->tracing) {
+        trace_mark(ctx, st, "results compacted (end of the stage)");
+        CK(cudaStreamSynchronize(st));
+        trace_dump(ctx);
+    }
     pfb_timing &t = ctx->tm;
     cudaEventElapsedTime(&t.ms_encode, ctx->ev[2], ctx->ev[3]);
     cudaEventElapsedTime(&t.ms_first, ctx->ev[3], ctx->ev[4]);
