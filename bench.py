@@ -429,7 +429,7 @@ def main():
                 "ms_per_launch": ms_scan, "share_of_step": ms_scan / step_ms if step_ms else None,
                 "actual_limiter": {"kind": "INT32 ALU pipe issue (hash + filter + queue append per window); DRAM traffic is ~6% of the modelled bytes",
                                    "windows_per_s_G": windows / (ms_scan / 1e3) / 1e9 if ms_scan > 0 else 0.0,
-                                   "evidence": "profiles/r01_scan_ablation.md, profiles/r01_v13_ncu_summary.json"}}
+                                   "evidence": "profiles/r01_scan_ablation.md, profiles/r01_v14_ncu_summary.json"}}
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": step_ms, "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": "u64",
             "data": "synthetic", "config": workload_config(args.config, world, strong) | ({"genomes_per_gpu": per_rank, "genome_bp": cfg["length"]}),
