@@ -102,6 +102,12 @@ def cpu_sample_run(cfg_index: int, threads: int = 0, length: int = 1_000_000):
     from primerforge_b200 import synth
     cfg = synth.CONFIGS[cfg_index]
     n_g = 3
+    if not threads:
+        # every host thread the process may use, whatever OMP_NUM_THREADS says (torchrun sets it to 1 per rank)
+        try:
+            threads = len(os.sched_getaffinity(0))
+        except AttributeError:
+            threads = os.cpu_count() or 1
     gens = synth.make_genomes(n_g, length, seed=synth.BASE_SEED + cfg_index, n_contigs=cfg["n_contigs"])
     par = po.default_params(k_min=cfg["k_min"], k_max=cfg["k_max"], max_repeat=cfg["max_repeats"], n_threads=threads)
     t0 = time.perf_counter()
