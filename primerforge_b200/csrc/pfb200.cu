@@ -752,6 +752,25 @@ __global__ void __launch_bounds__(256) k_build_filter(const __grid_constant__ K 
 // k_build_at: the key table of genomes 2..G (see id_of) from the keys that survived genome 1, and -- keys that
 // are dead already need no filter bit: fewer false drains -- the filter of the alive keys.  One thread per
 // 16 bins.
+__device__ __forceinline__ uint64_t window_at(const K &p, uint32_t g, uint32_t lp, int k);   // defined with k_alive1 below
+
+// slot -> id of one key that survived genome 1 (its rank in dict order: longer k-mers ending at the same place come
+// first), and what the id-ordered kernels need per id
+__device__ __forceinline__ uint32_t assign_id(const K &p, uint32_t slot, int ki) {
+    const int k = p.kmin + ki;
+    const uint32_t start = (uint32_t)(p.rows0[slot] & ROW_POS_MASK);
+    const uint32_t end = start + (uint32_t)k - 1u;
+    const uint32_t m = p.emitMask[end];
+    const uint32_t id = p.emitOff[end] + __popc(ki < 31 ? (m >> (ki + 1)) : 0u);
+    p.remap[slot] = id;
+    p.key1[id] = window_at(p, 0, start, k);
+    p.idMeta[id] = start | ((uint32_t)ki << 26);
+    p.alive[id] = 1;
+    return id;
+}
+
+// (with more than one genome the ids are assigned here as well -- every slot lies in exactly one 16-bin word --
+// instead of in a separate k_assign_ids pass)
 __global__ void __launch_bounds__(256) k_build_at(const __grid_constant__ K p, int with_filter) {
     uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= (uint32_t)p.nk * p.PW16) return;
@@ -765,8 +784,8 @@ __global__ void __launch_bounds__(256) k_build_at(const __grid_constant__ K p, i
             uint32_t bm = 0, n = 0, id0 = 0, id1 = 0;
             bool wide = false;
             for (uint32_t m = half; m; m &= m - 1, slot++) {
-                const uint32_t id = p.remap[slot];
-                if (id == ID_NONE) continue;
+                if (p.remap[slot] == ID_NONE) continue;         // k_alive1: not unique in genome 1
+                const uint32_t id = assign_id(p, slot, (int)ki);
                 bm |= 1u << (__ffs(m) - 1);
                 if (n == 0) id0 = id; else if (n == 1) id1 = id;
                 wide |= id >= AT_SLOW;
@@ -1006,16 +1025,7 @@ __global__ void __launch_bounds__(256) k_assign_ids(const __grid_constant__ K p)
     __syncthreads();
     uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= p.nslots || p.remap[idx] == ID_NONE) return;
-    const int ki = slot_ki(s_base, p.nk, (uint32_t)idx);
-    const int k = p.kmin + ki;
-    const uint32_t start = (uint32_t)(p.rows0[idx] & ROW_POS_MASK);
-    const uint32_t end = start + (uint32_t)k - 1u;
-    const uint32_t m = p.emitMask[end];
-    const uint32_t id = p.emitOff[end] + __popc(ki < 31 ? (m >> (ki + 1)) : 0u);   // longer k-mers ending here come first
-    p.remap[idx] = id;
-    p.key1[id] = window_at(p, 0, start, k);
-    p.idMeta[id] = start | ((uint32_t)ki << 26);
-    p.alive[id] = 1;
+    assign_id(p, (uint32_t)idx, slot_ki(s_base, p.nk, (uint32_t)idx));
 }
 
 // k_aliveN: the rules for one (id, genome >= 2) per thread; ids follow genome 1's coordinates, so the rows
@@ -2020,7 +2030,7 @@ static int stage0(pfb_ctx *ctx) {
     }
     if (ctx->nids) {
         if (nG > 1 && (rc = zero_async(ctx, ctx->rows, (size_t)ctx->nids * (nG - 1) * 8, st)) != PFB_OK) return rc;
-        k_assign_ids<<<nblk(ctx->nslots, 256), 256, 0, st>>>(k); ctx->launches++;
+        if (nG == 1) { k_assign_ids<<<nblk(ctx->nslots, 256), 256, 0, st>>>(k); ctx->launches++; }   // else: inside k_build_at
         if (nG > 1) {
             // key table of the other genomes (alive keys only, ids inline) and their filter
             k.PW16 = (P.table_size + 15) / 16;
