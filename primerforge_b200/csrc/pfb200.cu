@@ -107,6 +107,7 @@ struct K {  // kernel arguments (by value, __grid_constant__)
     uint32_t *ovf;             // [n][16] ids of the words that do not fit that format
     uint32_t *ovfCount;
     uint32_t PW16, ovfCap;
+    uint32_t atWide;           // ids from here on do not fit the inline format (AT_SLOW; lowered by tests)
     int first_pass;            // 1 while genome 1 itself is scanned (hits go to rows0[slot])
     uint64_t nslots, nids;
     uint64_t *key1;            // [nids] the k-mer as it reads on genome 1's (+) strand
@@ -788,7 +789,7 @@ __global__ void __launch_bounds__(256) k_build_at(const __grid_constant__ K p, i
                 const uint32_t id = assign_id(p, slot, (int)ki);
                 bm |= 1u << (__ffs(m) - 1);
                 if (n == 0) id0 = id; else if (n == 1) id1 = id;
-                wide |= id >= AT_SLOW;
+                wide |= id >= p.atWide;
                 n++;
             }
             if (n > 2 || wide) {
@@ -1247,6 +1248,7 @@ struct pfb_ctx {
     // PFB200_TRACE=1: timestamps (ms after the first H2D copy was queued) of the pipeline's milestones on stderr
     volatile uint32_t *countsHost = nullptr;    // mapped pinned: [0] nslots, [1] nids, [2] nrec, [3] npick as written by the scans
     uint32_t *countsDev = nullptr;              // the same memory as the device sees it
+    uint32_t at_wide = 0xFFFFFFu;               // PFB200_AT_WIDE lowers it so that tests reach the id-list path
     size_t encoded_upto = 0;                    // pipelined run: genomes [0, encoded_upto) are packed already
     bool tracing = false;
     std::vector<std::pair<std::string, cudaEvent_t>> trace;
@@ -1662,6 +1664,7 @@ int pfb_create(pfb_ctx **out, int device, const pfb_params *params) {
     ctx->device = device;
     ctx->prm = *params;
     { const char *tr = getenv("PFB200_TRACE"); ctx->tracing = tr && tr[0] == '1'; }
+    { const char *aw = getenv("PFB200_AT_WIDE"); if (aw && atoi(aw) > 0) ctx->at_wide = std::min<uint32_t>(AT_SLOW, (uint32_t)atoi(aw)); }
     cudaDeviceGetAttribute(&ctx->num_sms, cudaDevAttrMultiProcessorCount, device);
     e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->copyStream, cudaStreamNonBlocking);
@@ -2035,7 +2038,8 @@ static int stage0(pfb_ctx *ctx) {
             // key table of the other genomes (alive keys only, ids inline) and their filter
             k.PW16 = (P.table_size + 15) / 16;
             const size_t NA = (size_t)nk * k.PW16;
-            const size_t cap = ctx->nids / 3 + (ctx->nids > AT_SLOW ? ctx->nids - AT_SLOW : 0) + 16;
+            const size_t cap = ctx->nids / 3 + (ctx->nids > ctx->at_wide ? ctx->nids - ctx->at_wide : 0) + 16;
+            k.atWide = ctx->at_wide;
             if (cap >= (1u << 24)) return fail(ctx, PFB_ETOOLARGE, "too many keys share 16-bin words for the inline id table");
             if ((rc = ensure(ctx, ctx->at, NA * 8)) != PFB_OK) return rc;
             if ((rc = ensure(ctx, ctx->ovf, cap * 64)) != PFB_OK) return rc;

@@ -259,3 +259,21 @@ def test_drop_in_entry_point_genbank(tmp_path, capsys):
             a = [(str(p), p.start, p.end, p.strand, p.Tm, p.gcPer) for p in out_dev[name][contig]]
             b = [(str(p), p.start, p.end, p.strand, p.Tm, p.gcPer) for p in out_host[name][contig]]
             assert a == b and len(a) > 0
+
+
+def test_many_tiny_records_outgrow_the_word_estimate():
+    """pipelined run: the word arrays are sized from the file sizes before genomes 2..G are parsed; thousands
+    of records shorter than a word break that estimate and the arrays must grow without losing genome 1"""
+    from primerforge_b200 import synth
+    gens = synth.make_genomes(3, 60_000, seed=29, snp_rate=0.003, n_inversions=1, n_contigs=2)
+    rng = np.random.default_rng(8)
+    images = []
+    for gi, g in enumerate(gens):
+        contigs, ids = list(g.contigs), list(g.contig_ids)
+        if gi:
+            for i in range(20_000):
+                contigs.append(rng.choice(np.frombuffer(b"ACGT", dtype=np.uint8), size=8))
+                ids.append(f"t{i}")
+        images.append(_fasta_bytes(contigs, ids, 70))
+    _compare(images, "pipelined")
+    _compare(images, "sync")

@@ -390,3 +390,27 @@ def test_identical_genomes_and_single_genome():
         o = po.run(gens, po.default_params(**kw))
         res, _ = _run(gens, kw, False)
         assert np.array_equal(res.records["word"], o.word) and np.array_equal(res.records["flags"] & 15, o.flags)
+
+
+def test_id_list_path_of_the_key_table(monkeypatch):
+    """ids that do not fit the 24-bit inline format of the genomes-2..G key table go through the per-word id
+    lists (normally only beyond 16.7 M keys); PFB200_AT_WIDE lowers the limit so that most keys take that path"""
+    from primerforge_b200 import synth
+    from primerforge_b200.engine import Engine
+    gens = synth.make_genomes(4, 150_000, seed=23, snp_rate=0.003, n_inversions=2, n_contigs=2)
+
+    def run():
+        with Engine(device=0, prefilter=1) as eng:
+            for g in gens:
+                eng.add_genome(g.contigs)
+            eng.run()
+            res = eng.result()
+            return res.records.copy(), [p.copy() for p in res.positions]
+    rec_a, pos_a = run()
+    monkeypatch.setenv("PFB200_AT_WIDE", "500")
+    rec_b, pos_b = run()
+    assert rec_a.size > 5000
+    for f in ("word", "tm", "k", "flags", "gc_count"):
+        assert np.array_equal(rec_a[f], rec_b[f])
+    for a, b in zip(pos_a, pos_b):
+        assert np.array_equal(a, b)
