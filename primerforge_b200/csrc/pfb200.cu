@@ -25,7 +25,7 @@
 //     (192 KB per CTA) so that only ~1 in 5 windows reaches L2;
 //   * genome 1 is scanned first; its survivors get ids in the reference's dict order (genome-1 end
 //     position ascending, longest first) and everything downstream -- rows of the other genomes, verdicts,
-//     records, coordinates -- is indexed by id and streams through memory (k_alive1, k_assign_ids,
+//     records, coordinates -- is indexed by id and streams through memory (k_alive1,
 //     k_build_at, k_aliveN, k_emit_write); filters are evaluated in fp64 with the reference's operation
 //     order, the per-position "first k-mer that passes" pick looks only at the few records that can share
 //     a position (k_positions);
