@@ -1350,6 +1350,7 @@ int zero_async(pfb_ctx *ctx, DevBuf &b, size_t bytes, cudaStream_t st) {
     if (n16 * 16 > b.cap) return fail(ctx, PFB_ECUDA, "zero_async beyond the buffer");
     const unsigned blocks = (unsigned)std::min<size_t>((n16 + 255) / 256, (size_t)ctx->num_sms * 16);
     k_zero<<<blocks, 256, 0, st>>>((uint4 *)b.p, n16);
+    ctx->launches++;
     return PFB_OK;
 }
 
