@@ -872,7 +872,7 @@ __global__ void __launch_bounds__(256) k_candbits(const __grid_constant__ K p) {
     p.br[t].x = ((lo & ~(lo >> 16)) & 0xFFFFu) | ((hi & ~(hi >> 16)) << 16);
 }
 
-// device-wide exclusive scan in three launches.  MODE: the value of element x is in[x * S] (SV_U32), its
+// device-wide exclusive scan in two launches (tile sums, then every tile sums the tile sums before it).  MODE: the value of element x is in[x * S] (SV_U32), its
 // popcount (SV_POPC) or the byte in[x] (SV_U8); the prefix goes to out[x * S] (S = 2 for the interleaved
 // bitmap / rank table)
 enum { SV_U32 = 0, SV_POPC = 1, SV_U8 = 2 };
@@ -898,30 +898,17 @@ __global__ void __launch_bounds__(256) k_scan_p1(const void *in, uint32_t n, uin
     if (threadIdx.x == 0) { uint32_t tot = 0; for (int i = 0; i < 8; i++) tot += sm[i]; blockSums[blockIdx.x] = tot; }
 }
 
-// the total also goes to host-mapped memory: the host reads it after a stream synchronise, with no device -> host
-// copy that would queue up behind the H2D copies of a pipelined run
-__global__ void __launch_bounds__(1024) k_scan_p2(uint32_t *blockSums, uint32_t nb, uint32_t *total, uint32_t *total_host) {
-    __shared__ uint32_t sm[1024];
-    uint32_t per = (nb + 1023) / 1024;
-    uint32_t lo = min(nb, threadIdx.x * per), hi = min(nb, lo + per);
-    uint32_t s = 0;
-    for (uint32_t x = lo; x < hi; x++) s += blockSums[x];
-    sm[threadIdx.x] = s;
-    __syncthreads();
-    for (int off = 1; off < 1024; off <<= 1) {
-        uint32_t v = threadIdx.x >= off ? sm[threadIdx.x - off] : 0;
-        __syncthreads();
-        sm[threadIdx.x] += v;
-        __syncthreads();
-    }
-    uint32_t run = sm[threadIdx.x] - s;
-    for (uint32_t x = lo; x < hi; x++) { uint32_t v = blockSums[x]; blockSums[x] = run; run += v; }
-    if (threadIdx.x == 1023) { *total = sm[1023]; if (total_host) *total_host = sm[1023]; }
-}
-
 template <int MODE, int S>
-__global__ void __launch_bounds__(256) k_scan_p3(const void *in, uint32_t *out, uint32_t n, const uint32_t *blockSums) {
+__global__ void __launch_bounds__(256) k_scan_p3(const void *in, uint32_t *out, uint32_t n, const uint32_t *blockSums,
+                                                 uint32_t *total, uint32_t *total_host) {
     __shared__ uint32_t sm[8];
+    __shared__ uint32_t sb[8];
+    // the tile's base = sum of the tile sums before it (a few thousand L2-resident values at most: cheaper than a
+    // single-CTA pass over them between the two launches)
+    uint32_t part = 0;
+    for (uint32_t x = threadIdx.x; x < blockIdx.x; x += 256) part += blockSums[x];
+    for (int o = 16; o; o >>= 1) part += __shfl_xor_sync(0xFFFFFFFFu, part, o);
+    if ((threadIdx.x & 31) == 0) sb[threadIdx.x >> 5] = part;
     uint32_t base = blockIdx.x * SCAN_TILE + threadIdx.x * (SCAN_TILE / 256);
     uint32_t v[SCAN_TILE / 256];
     uint32_t s = 0;
@@ -938,15 +925,19 @@ __global__ void __launch_bounds__(256) k_scan_p3(const void *in, uint32_t *out, 
     }
     if ((threadIdx.x & 31) == 31) sm[threadIdx.x >> 5] = incl;
     __syncthreads();
-    uint32_t woff = 0;
+    uint32_t woff = 0, tile_base = 0;
     for (int i = 0; i < (int)(threadIdx.x >> 5); i++) woff += sm[i];
-    uint32_t run = blockSums[blockIdx.x] + woff + incl - s;
+    for (int i = 0; i < 8; i++) tile_base += sb[i];
+    uint32_t run = tile_base + woff + incl - s;
 #pragma unroll
     for (int t = 0; t < SCAN_TILE / 256; t++) {
         uint32_t x = base + t;
         if (x < n) out[(size_t)x * S] = run;
         run += v[t];
     }
+    // the total also goes to host-mapped memory: the host reads it after a stream synchronise, with no device ->
+    // host copy that would queue up behind the H2D copies of a pipelined run
+    if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 255) { *total = run; if (total_host) *total_host = run; }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1624,9 +1615,8 @@ int device_exscan(pfb_ctx *ctx, const void *in, uint32_t *out, uint32_t n, uint3
     if (rc != PFB_OK) return rc;
     uint32_t *bs = (uint32_t *)ctx->scanTmp.p;
     k_scan_p1<MODE, S><<<nb, 256, 0, st>>>(in, n, bs);
-    k_scan_p2<<<1, 1024, 0, st>>>(bs, nb, total_dev, total_host);
-    k_scan_p3<MODE, S><<<nb, 256, 0, st>>>(in, out, n, bs);
-    ctx->launches += 3;
+    k_scan_p3<MODE, S><<<nb, 256, 0, st>>>(in, out, n, bs, total_dev, total_host);
+    ctx->launches += 2;
     return PFB_OK;
 }
 
