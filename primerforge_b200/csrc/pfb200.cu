@@ -1240,6 +1240,7 @@ struct pfb_ctx {
     volatile uint32_t *countsHost = nullptr;    // mapped pinned: [0] nslots, [1] nids, [2] nrec, [3] npick as written by the scans
     uint32_t *countsDev = nullptr;              // the same memory as the device sees it
     uint32_t at_wide = 0xFFFFFFu;               // PFB200_AT_WIDE lowers it so that tests reach the id-list path
+    bool fterm_uploaded = false;
     size_t encoded_upto = 0;                    // pipelined run: genomes [0, encoded_upto) are packed already
     bool tracing = false;
     std::vector<std::pair<std::string, cudaEvent_t>> trace;
@@ -1804,6 +1805,10 @@ static int upload_impl(pfb_ctx *ctx, bool async) {
         ctx->evCopy.push_back(e);
     }
     ctx->fa_launches = 0;
+    if (!ctx->any_fasta) {   // the (small) table copies go first: behind the bases they would wait for a 5 MB chunk
+        if ((rc = build_layout(ctx, nG)) != PFB_OK) return rc;
+        if ((rc = upload_tables(ctx, false)) != PFB_OK) return rc;
+    }
     CK(cudaEventRecord(ctx->ev[0], cs));
     for (size_t g = 0; g < nG; g++) {
         auto &hg = ctx->genomes[g];
@@ -1818,8 +1823,6 @@ static int upload_impl(pfb_ctx *ctx, bool async) {
     CK(cudaEventRecord(ctx->ev[1], cs));
     ctx->pipelined = async;
     if (!ctx->any_fasta) {
-        if ((rc = build_layout(ctx, nG)) != PFB_OK) return rc;
-        if ((rc = upload_tables(ctx, false)) != PFB_OK) return rc;
     } else if (!async) {
         // every file is parsed on the device before the layout is made
         if ((rc = fasta_enqueue(ctx, 0, 0, nG, st)) != PFB_OK) return rc;
@@ -1921,7 +1924,12 @@ static int stage0(pfb_ctx *ctx) {
     k.emitMask = (uint32_t *)ctx->emitMask.p; k.emitOff = (uint32_t *)ctx->emitOff.p;
 
     CK(cudaEventRecord(ctx->ev[2], st));
-    CK(cudaMemcpyAsync(ctx->fterm.p, fterm.data(), FTERM_DOUBLES * 8, cudaMemcpyHostToDevice, st));
+    if (!ctx->fterm_uploaded) {   // the parameters of a context never change: once (a small H2D copy per run would
+                                  // queue up behind the 5 MB chunks of a pipelined run)
+        CK(cudaMemcpyAsync(ctx->fterm.p, fterm.data(), FTERM_DOUBLES * 8, cudaMemcpyHostToDevice, st));
+        CK(cudaStreamSynchronize(st));
+        ctx->fterm_uploaded = true;
+    }
     if ((rc = zero_async(ctx, ctx->misc, 4096, st)) != PFB_OK) return rc;
     if ((rc = zero_async(ctx, ctx->sk, (size_t)NB * 2 * 4, st)) != PFB_OK) return rc;
     const size_t nG = ctx->genomes.size();
