@@ -1863,9 +1863,23 @@ static int fasta_finish(pfb_ctx *ctx) {
     return upload_tables(ctx, true);
 }
 
-int pfb_upload(pfb_ctx *ctx) { return upload_impl(ctx, false); }
+// copies may be in flight when the upload fails half way (e.g. a file without records): the host buffers are
+// borrowed until they are done, error or not
+static int upload_checked(pfb_ctx *ctx, bool async) {
+    int rc = upload_impl(ctx, async);
+    if (rc != PFB_OK && ctx) {
+        cudaStreamSynchronize(ctx->stream);
+        cudaStreamSynchronize(ctx->copyStream);
+        cudaStreamSynchronize(ctx->parseStream);
+        cudaGetLastError();
+        ctx->pipelined = false;
+    }
+    return rc;
+}
 
-int pfb_upload_async(pfb_ctx *ctx) { return upload_impl(ctx, true); }
+int pfb_upload(pfb_ctx *ctx) { return upload_checked(ctx, false); }
+
+int pfb_upload_async(pfb_ctx *ctx) { return upload_checked(ctx, true); }
 
 int pfb_upload_wait(pfb_ctx *ctx) {
     if (!ctx) return PFB_EINVAL;
@@ -2232,7 +2246,7 @@ int pfb_compute(pfb_ctx *ctx) {
 
 int pfb_run(pfb_ctx *ctx) {
     // H2D of genome i+1.. overlaps the key-table build and the scan of the genomes already resident
-    int rc = upload_impl(ctx, true);
+    int rc = upload_checked(ctx, true);
     if (rc != PFB_OK) return rc;
     rc = pfb_compute(ctx);
     int rc2 = pfb_upload_wait(ctx);             // the host buffers are borrowed until here, success or not
