@@ -858,9 +858,16 @@ __global__ void __launch_bounds__(128) k_junction(const __grid_constant__ K p, u
 // ------------------------------------------------------------------------------------------
 // zero fill on the SMs.  cudaMemsetAsync may run on a copy engine, where it queues up behind the 5 MB H2D
 // chunks of a pipelined run (measured: up to 0.1 ms per memset); a kernel does not.
-__global__ void __launch_bounds__(256) k_zero(uint4 *p, size_t n16) {
+struct ZeroArgs {            // up to four buffers per launch
+    uint4 *p[4];
+    unsigned long long n16[4];
+    int cnt;
+};
+
+__global__ void __launch_bounds__(256) k_zero(const ZeroArgs a) {
     const uint4 z = make_uint4(0u, 0u, 0u, 0u);
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (size_t)gridDim.x * blockDim.x) p[i] = z;
+    for (int b = 0; b < a.cnt; b++)
+        for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.n16[b]; i += (size_t)gridDim.x * blockDim.x) a.p[b][i] = z;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1336,13 +1343,30 @@ int ensure_keep(pfb_ctx *ctx, DevBuf &b, size_t bytes, size_t keep) {
     return PFB_OK;
 }
 
-int zero_async(pfb_ctx *ctx, DevBuf &b, size_t bytes, cudaStream_t st) {
+// zero the first `bytes` of up to four DevBufs in one launch (rounded up to 16: every buffer has that much slack,
+// see ensure)
+struct ZeroBatch {
+    ZeroArgs a{};
+    size_t total = 0;
+    int add(pfb_ctx *ctx, DevBuf &b, size_t bytes);
+    int launch(pfb_ctx *ctx, cudaStream_t st);
+};
+
+int ZeroBatch::add(pfb_ctx *ctx, DevBuf &b, size_t bytes) {
     if (!bytes) return PFB_OK;
     const size_t n16 = (bytes + 15) / 16;
-    if (n16 * 16 > b.cap) return fail(ctx, PFB_ECUDA, "zero_async beyond the buffer");
-    const unsigned blocks = (unsigned)std::min<size_t>((n16 + 255) / 256, (size_t)ctx->num_sms * 16);
-    k_zero<<<blocks, 256, 0, st>>>((uint4 *)b.p, n16);
+    if (n16 * 16 > b.cap || a.cnt >= 4) return fail(ctx, PFB_ECUDA, "zero fill beyond the buffer");
+    a.p[a.cnt] = (uint4 *)b.p; a.n16[a.cnt] = n16; a.cnt++;
+    total += n16;
+    return PFB_OK;
+}
+
+int ZeroBatch::launch(pfb_ctx *ctx, cudaStream_t st) {
+    if (!a.cnt) return PFB_OK;
+    const unsigned blocks = (unsigned)std::min<size_t>((total + 255) / 256, (size_t)ctx->num_sms * 16);
+    k_zero<<<blocks, 256, 0, st>>>(a);
     ctx->launches++;
+    a.cnt = 0; total = 0;
     return PFB_OK;
 }
 
@@ -1353,8 +1377,7 @@ void release(DevBuf &b) {
 
 inline unsigned nblk(uint64_t n, unsigned bs) { return (unsigned)((n + bs - 1) / bs); }
 
-// zero the first `bytes` of a DevBuf (rounded up to 16: every buffer has that much slack, see ensure)
-int zero_async(pfb_ctx *ctx, DevBuf &b, size_t bytes, cudaStream_t st);
+
 
 int validate(const pfb_params *p, std::string &why) {
     if (!p) { why = "params is NULL"; return PFB_EINVAL; }
@@ -1944,21 +1967,29 @@ static int stage0(pfb_ctx *ctx) {
         CK(cudaStreamSynchronize(st));
         ctx->fterm_uploaded = true;
     }
-    if ((rc = zero_async(ctx, ctx->misc, 4096, st)) != PFB_OK) return rc;
-    if ((rc = zero_async(ctx, ctx->sk, (size_t)NB * 2 * 4, st)) != PFB_OK) return rc;
+    ZeroBatch zb;
+    if ((rc = zb.add(ctx, ctx->misc, 4096)) != PFB_OK) return rc;
+    if ((rc = zb.add(ctx, ctx->sk, (size_t)NB * 2 * 4)) != PFB_OK) return rc;
+    if ((rc = zb.launch(ctx, st)) != PFB_OK) return rc;
     const size_t nG = ctx->genomes.size();
     const bool piped = ctx->pipelined;
     if (piped) {   // only genome 1 has to be there before the key table can be built
         CK(cudaStreamWaitEvent(st, ctx->evCopy[0], 0));
         if (W1) { k_encode<<<nblk(W1, 256), 256, 0, st>>>(k, 0, W1); ctx->launches++; }
         ctx->encoded_upto = 1;
-    } else if (W) {
-        k_encode<<<nblk(W, 256), 256, 0, st>>>(k, 0, W); ctx->launches++;
+    } else if (W1) {   // genome 1 now; the others are packed while the host waits for the slot count
+        k_encode<<<nblk(W1, 256), 256, 0, st>>>(k, 0, W1); ctx->launches++;
     }
     // pipelined run: pack whatever has landed meanwhile.  Called just before the host waits for a count, so
     // that the GPU has something to do during the round trip.
+    bool rest_packed = false;
     auto encode_landed = [&]() -> int {
-        if (!piped || partial) return PFB_OK;
+        if (!piped) {
+            if (!rest_packed && W > W1) { k_encode<<<nblk(W - W1, 256), 256, 0, st>>>(k, W1, W); ctx->launches++; }
+            rest_packed = true;
+            return PFB_OK;
+        }
+        if (partial) return PFB_OK;
         size_t g2 = ctx->encoded_upto;
         while (g2 < nG && cudaEventQuery(ctx->evCopy[g2]) == cudaSuccess) g2++;
         cudaGetLastError();
@@ -1987,17 +2018,17 @@ static int stage0(pfb_ctx *ctx) {
     if ((rc = ensure(ctx, ctx->rows0, NS * 8)) != PFB_OK) return rc;
     if ((rc = ensure(ctx, ctx->remap, NS * 4)) != PFB_OK) return rc;
     k.rows0 = (unsigned long long *)ctx->rows0.p; k.remap = (uint32_t *)ctx->remap.p;
-    if ((rc = zero_async(ctx, ctx->rows0, NS * 8, st)) != PFB_OK) return rc;
+    if ((rc = zb.add(ctx, ctx->rows0, NS * 8)) != PFB_OK) return rc;
+    if (W1 && (rc = zb.add(ctx, ctx->emitMask, (size_t)W1 * 32 * 4 + 4)) != PFB_OK) return rc;   // filled by k_alive1 after genome 1's pass
     // the filter pays off while it stays sparse (expected fill 1 - exp(-keys_per_k / FILTER_BITS)) and the launch
     // is long enough to amortise the nk filter loads.  Genome 1's own pass meets ALL its candidate keys (a dense
     // filter) in one short launch: measured, the plain L2 probe is faster there at every genome size tried
     // (5 Mbp: 0.14 vs 0.18 ms), so the filter is only used for it when forced (scan mode 2, tests)
     bool use_filter = ctx->scan_mode == 2;
     ctx->used_filter = use_filter;
-    if (use_filter && ctx->nslots) {
-        if ((rc = zero_async(ctx, ctx->filter, (size_t)nk * FILTER_BYTES, st)) != PFB_OK) return rc;
-        k_build_filter<<<nblk(NB, 256), 256, 0, st>>>(k); ctx->launches++;
-    }
+    if (use_filter && ctx->nslots && (rc = zb.add(ctx, ctx->filter, (size_t)nk * FILTER_BYTES)) != PFB_OK) return rc;
+    if ((rc = zb.launch(ctx, st)) != PFB_OK) return rc;
+    if (use_filter && ctx->nslots) { k_build_filter<<<nblk(NB, 256), 256, 0, st>>>(k); ctx->launches++; }
     CK(cudaEventRecord(ctx->ev[4], st));
     trace_mark(ctx, st, "key table built");
     // every genome (the first included): one pass against the key table
@@ -2023,7 +2054,6 @@ static int stage0(pfb_ctx *ctx) {
         scan_range(0, W1, 0, C1, 1);
         k.first_pass = 0;
         trace_mark(ctx, st, "genome 1 scanned");
-        if ((rc = zero_async(ctx, ctx->emitMask, (size_t)N1 * 4 + 4, st)) != PFB_OK) return rc;
         k_alive1<<<nblk(ctx->nslots, 256), 256, 0, st>>>(k); ctx->launches++;
         if ((rc = device_exscan<SV_POPC, 1>(ctx, k.emitMask, k.emitOff, N1, misc + 1, ctx->countsDev + 1)) != PFB_OK) return rc;
         trace_mark(ctx, st, "ids counted (host waits for the count after this)");
@@ -2045,8 +2075,13 @@ static int stage0(pfb_ctx *ctx) {
         k.alive = (uint8_t *)ctx->alive.p; k.recIdx = (uint32_t *)ctx->recIdx.p;
     }
     if (ctx->nids) {
-        if (nG > 1 && (rc = zero_async(ctx, ctx->rows, (size_t)ctx->nids * (nG - 1) * 8, st)) != PFB_OK) return rc;
-        if (nG == 1) { k_assign_ids<<<nblk(ctx->nslots, 256), 256, 0, st>>>(k); ctx->launches++; }   // else: inside k_build_at
+        if (nG > 1 && (rc = zb.add(ctx, ctx->rows, (size_t)ctx->nids * (nG - 1) * 8)) != PFB_OK) return rc;
+        if ((rc = ensure(ctx, ctx->pick, ctx->nids)) != PFB_OK) return rc;          // stage 1's pick bytes
+        if ((rc = zb.add(ctx, ctx->pick, ctx->nids)) != PFB_OK) return rc;
+        if (nG == 1) {   // (with other genomes the ids are assigned inside k_build_at)
+            if ((rc = zb.launch(ctx, st)) != PFB_OK) return rc;
+            k_assign_ids<<<nblk(ctx->nslots, 256), 256, 0, st>>>(k); ctx->launches++;
+        }
         if (nG > 1) {
             // key table of the other genomes (alive keys only, ids inline) and their filter
             k.PW16 = (P.table_size + 15) / 16;
@@ -2062,7 +2097,8 @@ static int stage0(pfb_ctx *ctx) {
             use_filter = ctx->scan_mode == 2 ||
                          (ctx->scan_mode == 0 && (double)ctx->nids / nk < 0.35 * FILTER_BITS && W_alloc >= 4096);
             ctx->used_filter = use_filter;
-            if (use_filter && (rc = zero_async(ctx, ctx->filter, (size_t)nk * FILTER_BYTES, st)) != PFB_OK) return rc;
+            if (use_filter && (rc = zb.add(ctx, ctx->filter, (size_t)nk * FILTER_BYTES)) != PFB_OK) return rc;
+            if ((rc = zb.launch(ctx, st)) != PFB_OK) return rc;
             k_build_at<<<nblk(NA, 256), 256, 0, st>>>(k, use_filter ? 1 : 0); ctx->launches++;
             trace_mark(ctx, st, "key table of the other genomes built");
         }
@@ -2162,7 +2198,7 @@ static int stage1(pfb_ctx *ctx) {
     k.rec = (pfb_record *)ctx->rec.p; k.pos = (uint32_t *)ctx->pos.p; k.posContig = (uint32_t *)ctx->posContig.p;
     k.multiContig = multi ? 1 : 0;
     k.pick = (uint8_t *)ctx->pick.p; k.pickOff = (uint32_t *)ctx->pickOff.p;
-    if ((rc = zero_async(ctx, ctx->pick, NI, st)) != PFB_OK) return rc;
+    // (the pick bytes were zeroed in stage 0 together with the rows)
     if (ctx->nids) {
         // ids are in dict order already: the record index is the rank among the ids that survived every genome
         if ((rc = device_exscan<SV_U8, 1>(ctx, k.alive, k.recIdx, (uint32_t)ctx->nids, misc + 2, ctx->countsDev + 2)) != PFB_OK) return rc;
