@@ -383,16 +383,18 @@ __global__ void __launch_bounds__(CAND_POS + 32) k_cand1(const __grid_constant__
     __shared__ uint32_t s_nn[16];
     __shared__ uint32_t s_P[CAND_POS + 32];
     __shared__ uint32_t s_wsum[(CAND_POS + 32) / 32];
-    __shared__ uint64_t s_km2[32], s_gcok[32], s_run[32];
-    __shared__ uint32_t s_km1[32];
+    __shared__ uint64_t s_km2[32];
+    __shared__ uint32_t s_gclo[32], s_gcspan[32];     // GC counts inside [minGc, maxGc] form an interval per k
     __shared__ uint16_t s_item[(CAND_POS + 32) / 32][32 * 32];
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid < 16) s_nn[tid] = c_nn[tid];
     const int R = p.max_repeat;
     if (tid >= 32 && tid < 32 + (uint32_t)p.nk) {
         const int ki = tid - 32, k = p.kmin + ki;
-        s_km2[ki] = kmask2(k); s_km1[ki] = (uint32_t)kmask1(k); s_gcok[ki] = p.gc_ok[k];
-        s_run[ki] = (R >= 2 && k >= R) ? kmask2(k - R + 1) : 0ull;
+        s_km2[ki] = kmask2(k);
+        const uint64_t ok = p.gc_ok[k];
+        s_gclo[ki] = ok ? (uint32_t)(__ffsll((long long)ok) - 1) : 64u;
+        s_gcspan[ki] = ok ? (uint32_t)(63 - __clzll((long long)ok)) - s_gclo[ki] : 0u;
     }
     __syncthreads();
     // thread t <-> end position b = first position of the CTA - 32 + t (warp 0 is the halo)
@@ -414,36 +416,40 @@ __global__ void __launch_bounds__(CAND_POS + 32) k_cand1(const __grid_constant__
     s_P[tid] = incl + woff;
     __syncthreads();
     if (warp == 0) return;                      // the halo only contributes its pair values
-    // 2. everything that does not depend on k once (G/C bits, "a homopolymer run of max_repeat starts at age i"
-    // bits: pair-equality bits AND-ed max_repeat - 1 times), then the cheap tests per k, branch-free
-    const uint64_t gcbits = hf & 0xAAAAAAAAAAAAAAAAull;
-    uint64_t runs = 0;
-    if (R >= 2) {
-        uint64_t e = hf ^ (hf >> 2);
-        uint64_t z = ~(e | (e >> 1)) & 0x5555555555555555ull;
-        runs = z;
-        for (int t = 1; t < R - 1; t++) runs &= z >> (2 * t);
+    // 2. the cheap tests.  Three of them only bound k from above and fold into ONE limit: the contig start (k <= n,
+    // :40-43), the newest non-ACGT base (age d: k <= d) and, with prefilter, the newest homopolymer run of
+    // max_repeat bases (starting at age i: k <= i + R - 1, :309-320).  What is left per k is one bit of the word
+    // -- is the FIRST base of the window G/C? -- which serves both isOneEndGc (:29-33) and a running GC count
+    // that is compared with the per-k interval (:301-303).  Survivors are compacted per warp right away.
+    const bool pre = p.prefilter != 0;
+    int khi = have ? min(p.kmax, s.n) : 0;
+    const uint32_t nm32 = (uint32_t)s.nmw;                           // bit t = the base of age t is not A C G T
+    if (nm32) khi = min(khi, __ffs((int)nm32) - 1);
+    if (pre) {
+        if (R <= 1) {
+            khi = 0;
+        } else {
+            const uint64_t e = hf ^ (hf >> 2);
+            const uint64_t z = ~(e | (e >> 1)) & 0x5555555555555555ull;     // bit 2i: ages i and i + 1 hold the same base
+            uint64_t runs = z;
+            for (int t = 1; t < R - 1; t++) runs &= z >> (2 * t);           // bit 2i: a run of R bases starts at age i
+            if (runs) khi = min(khi, ((__ffsll((long long)runs) - 1) >> 1) + R - 1);
+        }
     }
     const uint32_t last_gc = (uint32_t)(hf >> 1) & 1u;
-    const int khi = have ? min(p.kmax, s.n) : 0;
-    const bool pre = p.prefilter != 0;
-    uint32_t cm = 0;
-    for (int ki = 0; ki < p.nk; ki++) {
-        const int k = p.kmin + ki;
-        uint32_t ok = (k <= khi) & ((s.nmw & s_km1[ki]) == 0)                                         // :40-43
-                      & (last_gc | ((uint32_t)(hf >> (2 * k - 1)) & 1u));                              // isOneEndGc (:29-33)
-        if (pre)
-            ok &= (uint32_t)(s_gcok[ki] >> __popcll(gcbits & s_km2[ki])) & 1u                         // :301-303
-                  & (R > 1) & ((runs & s_run[ki]) == 0);                                               // :309-320
-        cm |= ok << ki;
-    }
-    // 3. compaction of the surviving (lane, k) pairs of the warp
+    const uint64_t ends = hf >> (2 * p.kmin - 1);                           // bit 2 ki: first base of window kmin + ki is G/C
+    uint32_t gc = p.kmin > 1 ? (uint32_t)__popcll(hf & 0xAAAAAAAAAAAAAAAAull & kmask2(p.kmin - 1)) : 0u;
     uint16_t *items = s_item[warp];
     const uint32_t lt_mask = (1u << lane) - 1u;
     uint32_t n_items = 0;
     for (int ki = 0; ki < p.nk; ki++) {
-        const uint32_t m = __ballot_sync(0xFFFFFFFFu, (cm >> ki) & 1u);
-        if ((cm >> ki) & 1u) items[n_items + __popc(m & lt_mask)] = (uint16_t)(lane | (ki << 5));
+        const int k = p.kmin + ki;
+        const uint32_t b = (uint32_t)(ends >> (2 * ki)) & 1u;
+        gc += b;
+        bool ok = (k <= khi) & ((last_gc | b) != 0u);
+        if (pre) ok &= (gc - s_gclo[ki]) <= s_gcspan[ki];
+        const uint32_t m = __ballot_sync(0xFFFFFFFFu, ok);
+        if (ok) items[n_items + __popc(m & lt_mask)] = (uint16_t)(lane | (ki << 5));
         n_items += __popc(m);
     }
     __syncwarp();
