@@ -96,53 +96,106 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
-def cpu_sample_run(cfg_index: int, threads: int = 0, length: int = 1_000_000):
-    """the CPU restatement on a bounded sample: 3 genomes x `length` bp of the same generator / parameters"""
+def host_threads() -> int:
+    """every host thread the process may use, whatever OMP_NUM_THREADS says (torchrun sets it to 1 per rank)"""
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def cpu_sample_run(cfg_index: int, threads: int = 0, n_genomes: int = 3, length: int | None = None):
+    """the CPU restatement (oracle/pf_oracle.c, OpenMP) on a bounded sample of the workload: the FIRST `n_genomes`
+    genomes of the config's generator at the config's FULL genome length (so the sketch load -- the share of unique
+    k-mers khmer's table drops -- is the workload's own), same k range and filters.  Returns (cpu_baseline dict,
+    seconds, oracle result, genomes): bench.py's parity block compares the GPU with this very result."""
     from oracle import pf_oracle as po
     from primerforge_b200 import synth
     cfg = synth.CONFIGS[cfg_index]
-    n_g = 3
-    if not threads:
-        # every host thread the process may use, whatever OMP_NUM_THREADS says (torchrun sets it to 1 per rank)
-        try:
-            threads = len(os.sched_getaffinity(0))
-        except AttributeError:
-            threads = os.cpu_count() or 1
-    gens = synth.make_genomes(n_g, length, seed=synth.BASE_SEED + cfg_index, n_contigs=cfg["n_contigs"])
+    length = length or cfg["length"]
+    threads = threads or host_threads()
+    gens = synth.make_genomes(n_genomes, length, seed=synth.BASE_SEED + cfg_index, n_contigs=cfg["n_contigs"])
     par = po.default_params(k_min=cfg["k_min"], k_max=cfg["k_max"], max_repeat=cfg["max_repeats"], n_threads=threads)
     t0 = time.perf_counter()
     o = po.run(gens, par)
     dt = time.perf_counter() - t0
-    cores = threads or po.max_threads()
-    return dict(value=n_g * length / 1e6 / dt, unit=UNIT, cores=cores, kind="port",
-                sample=f"{n_g} x {length} bp genomes of the config-{cfg_index} generator, k {cfg['k_min']}-{cfg['k_max']}, "
-                       f"oracle/pf_oracle.c (OpenMP), {dt:.2f} s, {o.n_shared} shared k-mers"), dt
+    nk = cfg["k_max"] - cfg["k_min"] + 1
+    return dict(value=n_genomes * length / 1e6 / dt, unit=UNIT, cores=threads, kind="port",
+                sample=f"the first {n_genomes} of the config-{cfg_index} genomes at {length} bp each ({n_genomes * length / 1e6:g} Mbp), "
+                       f"k {cfg['k_min']}-{cfg['k_max']}, oracle/pf_oracle.c (C restatement of the reference, OpenMP over "
+                       f"{n_genomes * nk} (genome, k) tasks on {threads} threads), {dt:.2f} s, {o.n_shared} shared k-mers"), dt, o, gens
+
+
+def parity_vs_oracle(gens, o, cfg, device: int) -> dict:
+    """the correctness gate: the CUDA path on the very genomes the CPU sample ran on, compared
+    bit for bit with the oracle's result -- the shared k-mers in dict order, flags and picks, Tm, and
+    (contig, start, strand) in every genome -- in both output modes (all shared k-mers / prefiltered, the timed one)"""
+    from primerforge_b200.engine import Engine
+    out = {"against": "oracle/pf_oracle.c on the cpu_baseline sample", "ok": True, "checked": []}
+    for prefilter in (0, 1):
+        with Engine(device=device, k_min=cfg["k_min"], k_max=cfg["k_max"], max_repeat=cfg["max_repeats"], prefilter=prefilter) as eng:
+            for g in gens:
+                eng.add_genome(g.contigs)
+            eng.run()
+            res = eng.result()
+        rec = res.records
+        keep = ((o.flags & 7) == 7) if prefilter else np.ones(o.n_shared, dtype=bool)
+        checks = {"n_records": int(rec.size), "n_oracle": int(keep.sum())}
+        same = rec.size == int(keep.sum())
+        if same:
+            checks["words_and_order"] = bool(np.array_equal(rec["word"], o.word[keep]) and np.array_equal(rec["k"], o.k[keep]))
+            checks["flags_and_picks"] = bool(np.array_equal(rec["flags"] & 15, o.flags[keep]))
+            checks["tm_max_abs_diff"] = float(np.max(np.abs(rec["tm"] - o.tm[keep]), initial=0.0))
+            checks["gc"] = bool(np.array_equal(rec["gc_count"].astype(np.int32), o.gc_count[keep]))
+            checks["positions"] = all(
+                np.array_equal(res.positions[gi]["contig"].astype(np.int32), o.contig[gi][keep]) and
+                np.array_equal(res.positions[gi]["start"].astype(np.int64), o.start[gi][keep]) and
+                np.array_equal(res.positions[gi]["strand"].astype(np.uint8), o.strand[gi][keep]) for gi in range(len(gens)))
+            same = checks["words_and_order"] and checks["flags_and_picks"] and checks["gc"] and checks["positions"] and \
+                checks["tm_max_abs_diff"] <= 0.01
+        checks["prefilter"] = prefilter
+        checks["ok"] = bool(same)
+        out["checked"].append(checks)
+        out["ok"] = bool(out["ok"] and same)
+    return out
 
 
 def run_reference_arm(args, emit):
+    """the reference's CPU implementation of the path on the host cores.  The reference itself is pure Python whose
+    four compiled dependencies cannot be installed in this image, so this times the C
+    restatement (`kind: port`) with every host thread, each step one bounded sample of the arm's workload."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    from primerforge_b200 import synth
+    cfg = synth.CONFIGS[args.config]
     vals, last = [], None
-    # every step is a bounded sample; the sample shrinks when K + W steps of it would take more than ~3 minutes
-    length = 1_000_000
-    _cb, dt0 = cpu_sample_run(args.config, length=length)
+    # every step is a bounded sample (the first n genomes at full length); it shrinks when K + W steps of it would
+    # take more than ~3 minutes: first to 2 genomes, then in length
+    n_g, length = 3, (getattr(args, "length", None) or cfg["length"])
+    _cb, dt0, _o, _g = cpu_sample_run(args.config, n_genomes=n_g, length=length)
     budget = 170.0
     total = max(1, args.warmup + args.steps)
     if dt0 * total > budget:
+        n_g = 2
+        dt0 *= 2.0 / 3.0
+    if dt0 * total > budget:
         length = int(max(100_000, length * budget / (dt0 * total)))
     for i in range(args.warmup + args.steps):
-        cb, dt = cpu_sample_run(args.config, length=length)
+        cb, dt, _o, _g = cpu_sample_run(args.config, n_genomes=n_g, length=length)
         if i >= args.warmup:
             vals.append((cb["value"], dt))
         last = cb
     value = float(np.mean([v for v, _ in vals]))
     ms = float(np.mean([d for _, d in vals]) * 1e3)
     last["value"] = value
-    cfg = workload_config(args.config, 1)
+    # the arm's config, plus what one step of THIS line actually ran (a sample, not the whole workload)
+    conf = workload_config(args.config, 1)
+    conf["reference_step"] = last["sample"]
+    conf["same_workload_as_gpu_arm"] = False
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64",
-            "data": "synthetic", "impl": "reference", "config": cfg, "cpu_baseline": last,
+            "data": "synthetic", "impl": "reference", "config": conf, "cpu_baseline": last,
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
     emit(line)
 
@@ -454,8 +507,8 @@ def main():
         line["exchange"] = {"what": "MIN all-reduce of the per-key alive bytes + MAX all-reduce of the pick bytes (NCCL, on the library's stream)",
                             "bytes_reduced_per_rank": int(xchg["bytes"]), "ms_per_step": ms_x,
                             "wire_GBs_per_direction": wire / (ms_x / 1e3) / 1e9 if ms_x > 0 else None,
-                            "nvlink_peak_GBs_per_direction": 900.0,
-                            "frac_of_nvlink": wire / (ms_x / 1e3) / 1e9 / 900.0 if ms_x > 0 else None,
+                            "nvlink_peak_GBs_per_direction": 770.0,
+                            "frac_of_nvlink": wire / (ms_x / 1e3) / 1e9 / 770.0 if ms_x > 0 else None,
                             "note": "latency-bound: ~2 MB per step; no k-mer crosses NVLink (DESIGN.md section 5)"}
     if fasta_leg is not None:
         line["e2e_fasta"] = fasta_leg
@@ -481,7 +534,9 @@ def main():
                               "what": "_getAllCandidateKmers(params, False) from FASTA files on disk to dict[str, dict[str, list[Primer]]], "
                                       "hairpin / homodimer screening off; the time is building the Python Primer objects"}
     if world == 1 and not args.no_cpu_baseline:
-        line["cpu_baseline"], _ = cpu_sample_run(args.config)
+        # the CPU restatement on a bounded sample; the GPU must reproduce that result bit for bit (the gate)
+        line["cpu_baseline"], _dt, o_cpu, gens_cpu = cpu_sample_run(args.config, length=args.length)
+        line["parity"] = parity_vs_oracle(gens_cpu, o_cpu, cfg, local)
     emit(line)
     if world > 1:
         dist.destroy_process_group()

@@ -228,7 +228,7 @@ static double oligo_tm(uint64_t w, int k, const pfo_params *p, int *gc_out) {
     if (sym) tm = delta_h / (delta_s + 1.987 * log(p->dna / 1000000000.0)) - 273.15;
     else     tm = delta_h / (delta_s + 1.987 * log(p->dna / 4000000000.0)) - 273.15;
     tm -= p->dmso * p->dmso_fact;
-    tm += (0.453 * ((double)gc / k) - 2.88) * p->formamide;
+    tm += (0.453 * gc / k - 2.88) * p->formamide;   /* oligotm.c: 0.453 * GC_count / len, left to right */
     if (gc_out) *gc_out = gc;
     return tm;
 }

@@ -13,10 +13,10 @@ def _parse_fasta(handle):
         if line.startswith(">"):
             if title is not None:
                 yield _fasta_record(title, chunks)
-            title = line[1:].rstrip("\r\n")
+            title = line[1:].rstrip()
             chunks = []
         elif title is not None:
-            chunks.append(line.strip())
+            chunks.append(line.rstrip())        # SimpleFastaParser: trailing white space only
     if title is not None:
         yield _fasta_record(title, chunks)
 
@@ -24,7 +24,7 @@ def _parse_fasta(handle):
 def _fasta_record(title, chunks):
     parts = title.split(None, 1)
     rid = parts[0] if parts else ""
-    return SeqRecord(Seq("".join(chunks).replace(" ", "")), id=rid, name=rid, description=title)
+    return SeqRecord(Seq("".join(chunks).replace(" ", "").replace("\r", "")), id=rid, name=rid, description=title)
 
 
 def _parse_genbank(handle):

@@ -79,7 +79,7 @@ def calc_tm(seq: str, mv_conc: float = 50.0, dv_conc: float = 1.5, dntp_conc: fl
         tm = delta_h / (delta_s + 1.987 * math.log(dna_conc / 4000000000.0)) - 273.15
     gc = sum(1 for ch in s if ch in "GC")
     tm -= dmso_conc * dmso_fact
-    tm += (0.453 * (gc / n) - 2.88) * formamide_conc
+    tm += (0.453 * gc / n - 2.88) * formamide_conc      # oligotm.c evaluates 0.453 * GC_count / len left to right
     return tm
 
 

@@ -55,8 +55,10 @@ assert RECORD_DTYPE.itemsize == 24 and POS_DTYPE.itemsize == 12
 
 def build(force: bool = False, verbose: bool = False) -> str:
     """nvcc -gencode arch=compute_100a,code=sm_100a ... -> primerforge_b200/libpfb200.so (in tree)"""
-    stale = (not os.path.exists(LIB_PATH)) or os.path.getmtime(SRC_PATH) > os.path.getmtime(LIB_PATH) or \
-        os.path.getmtime(os.path.join(INCLUDE_DIR, "pfb200.h")) > os.path.getmtime(LIB_PATH)
+    # every file the library is compiled from: the sources under csrc/ (pfb200.cu includes the .cuh files) and the header
+    srcs = [os.path.join(os.path.dirname(SRC_PATH), f) for f in sorted(os.listdir(os.path.dirname(SRC_PATH)))]
+    srcs.append(os.path.join(INCLUDE_DIR, "pfb200.h"))
+    stale = (not os.path.exists(LIB_PATH)) or any(os.path.getmtime(f) > os.path.getmtime(LIB_PATH) for f in srcs)
     if force or stale:
         cmd = ["nvcc"] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH, SRC_PATH]
         subprocess.check_call(cmd)

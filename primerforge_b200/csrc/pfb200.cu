@@ -1415,7 +1415,7 @@ void fill_filter_constants(const pfb_params &P, K &k, std::vector<double> &fterm
         for (int gc = 0; gc <= kk; gc++) {
             double per = (double)gc / kk * 100;                                   // Primer.py:100
             if (per >= P.min_gc && per <= P.max_gc) ok |= 1ull << gc;              // getCandidateKmers.py:303
-            fterm[kk * 33 + gc] = (0.453 * ((double)gc / kk) - 2.88) * P.formamide_conc;
+            fterm[kk * 33 + gc] = (0.453 * gc / kk - 2.88) * P.formamide_conc;   // oligotm.c: 0.453 * GC_count / len, left to right
             // Tm >= t  <=>  dh >= 0.001 T ds - T A / 100 with T = t + 273.15 + dmso - fterm, A = salt and DNA terms
             const double A = 0.368 * (kk - 1) * k.ln_salt + 1.987 * k.ln_dna4;
             const double c = 273.15 + k.dmso_term - fterm[kk * 33 + gc];

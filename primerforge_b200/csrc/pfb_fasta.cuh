@@ -3,7 +3,9 @@
 // Replaces Bio.SeqIO.parse(fn, "fasta") at /root/reference/bin/getCandidateKmers.py:93,212 (biopython's
 // SimpleFastaParser): text before the first line that starts with '>' is skipped; a line that starts with
 // '>' opens a record (its id is the title up to the first whitespace -- extracted by the host from the
-// header offset reported here); every other line contributes its bytes minus '\n', '\r' and ' '.  Case is
+// header offset reported here); every other line is rstrip()ped -- trailing white space of any kind goes -- and
+// contributes what is left minus ' ' and '\r' (SimpleFastaParser: lines.append(line.rstrip()), then
+// "".join(lines).replace(" ", "").replace("\r", "")); a tab INSIDE a line stays a byte of the sequence.  Case is
 // preserved (only upper-case A C G T are nucleotides for the stage, like on the pfb_add_genome path).
 //
 // The files of a batch sit in one staging buffer (each 256-byte aligned).  A TILE of 4096 bytes is walked
@@ -70,6 +72,7 @@ struct Step {
     uint32_t valid, nl, drop, ls, hs;   // hs: lines that open a record ('>' / LOCUS)
     uint32_t origin, off;               // GenBank: ORIGIN lines; "//" and LOCUS lines (sequence off)
     uint32_t alpha;                     // GenBank: letters
+    uint32_t tws;                       // FASTA: white space other than ' ' '\r' '\n' (dropped only at the end of a line)
 };
 
 __device__ __forceinline__ bool starts_with(const uint8_t *f, uint64_t off, uint64_t len, const char *word, int n) {
@@ -87,9 +90,11 @@ __device__ __forceinline__ Step classify(const uint8_t *f, uint64_t off, uint64_
     s.nl = __ballot_sync(0xFFFFFFFFu, in_file && c == '\n');
     s.ls = ((s.nl << 1) | prev_nl) & s.valid;      // a line starts after every newline (and at offset 0 of the file)
     prev_nl = s.nl >> 31;
-    s.origin = s.off = s.alpha = 0;
+    s.origin = s.off = s.alpha = s.tws = 0;
     if (FORMAT == FMT_FASTA) {
         s.drop = __ballot_sync(0xFFFFFFFFu, in_file && (c == '\r' || c == ' '));
+        // str.isspace() bytes besides those: \t \v \f and the four separators 0x1c..0x1f
+        s.tws = __ballot_sync(0xFFFFFFFFu, in_file && (c == '\t' || c == 0x0b || c == 0x0c || (uint8_t)(c - 0x1c) < 4));
         s.hs = s.ls & __ballot_sync(0xFFFFFFFFu, in_file && c == '>');
     } else {
         s.drop = 0;
@@ -104,6 +109,32 @@ __device__ __forceinline__ Step classify(const uint8_t *f, uint64_t off, uint64_
         s.alpha = __ballot_sync(0xFFFFFFFFu, in_file && (uint8_t)((c | 0x20) - 'a') < 26);
     }
     return s;
+}
+
+// FASTA: the white-space bytes of a step that line.rstrip() removes: those followed by nothing but white space up
+// to the end of their line (or of the file).  Steps without such bytes -- all of them in a regular file -- cost
+// one test; a run that reaches the end of the step is resolved by reading ahead (every lane reads the same bytes).
+__device__ __forceinline__ uint32_t trailing_ws(const uint8_t *f, uint64_t len, uint64_t sb, const Step &s) {
+    if (!s.tws) return 0u;
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t W = s.tws | s.drop;                      // white space that is not a newline
+    const uint32_t solid = s.valid & ~W & ~s.nl;            // bytes that end a run of white space without ending the line
+    const uint32_t above = lane == 31 ? 0u : (0xFFFFFFFEu << lane);
+    const uint32_t stop = (solid | s.nl | ~s.valid) & above;   // first byte after this lane that is not white space (or is off the file)
+    const bool mine = (s.tws >> lane) & 1u;
+    bool trail = false;
+    if (mine && stop) trail = !((solid >> (__ffs(stop) - 1)) & 1u);
+    if (__ballot_sync(0xFFFFFFFFu, mine && !stop)) {         // a run touches the end of the step: look ahead
+        uint64_t x = sb + 32;
+        bool ends_line = true;
+        for (; x < len; x++) {
+            const uint8_t c = f[x];
+            if (c == '\n') break;
+            if (!(c == ' ' || c == '\r' || c == '\t' || c == 0x0b || c == 0x0c || (uint8_t)(c - 0x1c) < 4)) { ends_line = false; break; }
+        }
+        if (mine && !stop) trail = ends_line;
+    }
+    return __ballot_sync(0xFFFFFFFFu, trail);
 }
 
 // is the byte before `off` a newline (or off the start of the file)?
@@ -239,7 +270,8 @@ __global__ void __launch_bounds__(WARPS * 32) k_fa_sweep(const Args a) {
         uint32_t junk = 0;
         if (F == NO_HDR || sb + 32 <= F) junk = 0xFFFFFFFFu;
         else if (sb < F) junk = 0xFFFFFFFFu >> (32 - (uint32_t)(F - sb));
-        const uint32_t keep = FORMAT == FMT_FASTA ? (s.valid & ~on & ~s.nl & ~s.drop & ~junk) : (s.valid & on & s.alpha & ~junk);
+        uint32_t keep = FORMAT == FMT_FASTA ? (s.valid & ~on & ~s.nl & ~s.drop & ~junk) : (s.valid & on & s.alpha & ~junk);
+        if (FORMAT == FMT_FASTA) keep &= ~trailing_ws(f, len, sb, s);
         if (GATHER) {
             const uint32_t pos = run + __popc(keep & lt_mask);
             if ((keep >> lane) & 1u) out[pos] = FORMAT == FMT_FASTA ? c : (uint8_t)(c & 0xDF);   // GenBank sequences are upper-cased

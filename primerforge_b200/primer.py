@@ -67,7 +67,7 @@ def oligo_tm(seq: str, mv=50.0, dv=1.5, dntp=0.6, dna=50.0, dmso=0.0, dmso_fact=
     tm = dh * -100.0 / (delta_s + 1.987 * math.log(dna / (1000000000.0 if sym else 4000000000.0))) - 273.15
     tm -= dmso * dmso_fact
     gc = sum(c in "GC" for c in s)
-    return tm + (0.453 * (gc / n) - 2.88) * formamide
+    return tm + (0.453 * gc / n - 2.88) * formamide      # oligotm.c: 0.453 * GC_count / len, left to right
 
 
 def _calc_tm(seq: str) -> float:

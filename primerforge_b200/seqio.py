@@ -33,6 +33,15 @@ def read_fasta(path: str):
         ids.append(parts[0] if parts else "")
         body = data[min(hdr_end + 1, end):end]
         keep = (body != _NL) & (body != _CR) & (body != _SP)
+        # line.rstrip(): other white space goes only where nothing but white space follows on its line
+        tws = (body == 9) | (body == 11) | (body == 12) | ((body >= 0x1c) & (body <= 0x1f))
+        if tws.any():
+            solid = np.flatnonzero(keep & ~tws)                      # bytes that are neither white space nor newlines
+            nls = np.flatnonzero(body == _NL)
+            at = np.flatnonzero(tws)
+            nxt_solid = np.append(solid, body.size + 1)[np.searchsorted(solid, at)]
+            nxt_nl = np.append(nls, body.size)[np.searchsorted(nls, at)]
+            keep[at[nxt_nl < nxt_solid]] = False
         contigs.append(np.ascontiguousarray(body[keep]))
     return ids, contigs
 

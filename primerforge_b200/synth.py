@@ -41,8 +41,11 @@ def revcomp_ascii(a: np.ndarray) -> np.ndarray:
 
 def make_genomes(n_genomes: int, length: int, seed: int = BASE_SEED, snp_rate: float = 0.01,
                  n_inversions: int = 4, inv_frac: float = 0.05, n_contigs: int = 1,
-                 n_frac: float = 0.0, prefix: str = "ingroup") -> list:
-    """returns ``n_genomes`` Genome objects (in memory)"""
+                 n_frac: float = 0.0, prefix: str = "ingroup", only=None) -> list:
+    """returns ``n_genomes`` Genome objects (in memory).  ``only``: an iterable of genome indices -- the others are
+    returned as ``None`` (their random draws are still made, so genome g is the same sequence whatever else is
+    generated; this is what lets a rank of a sharded run build just its own genomes)"""
+    only = None if only is None else set(int(i) for i in only)
     rng = np.random.Generator(np.random.PCG64(seed))
     anc = rng.integers(0, 4, size=length, dtype=np.uint8)
     sites = np.flatnonzero(rng.random(length) < snp_rate)
@@ -50,33 +53,40 @@ def make_genomes(n_genomes: int, length: int, seed: int = BASE_SEED, snp_rate: f
     out = []
     seg = int(inv_frac * length)
     for g in range(n_genomes):
-        codes = anc.copy()
+        want = only is None or g in only
         take = rng.random(sites.size) < 0.5
-        codes[sites[take]] = alt[take]
-        seq = _ASCII[codes]
+        seq = None
+        if want:
+            codes = anc.copy()
+            codes[sites[take]] = alt[take]
+            seq = _ASCII[codes]
         if n_frac > 0.0:
             nmask = rng.random(length) < n_frac
-            seq = seq.copy()
-            seq[nmask] = ord("N")
+            if want:
+                seq = seq.copy()
+                seq[nmask] = ord("N")
         if g >= 1 and n_inversions > 0 and seg > 0:
             q = length // n_inversions
             for i in range(n_inversions):
                 if q - seg <= 0:
                     break
                 st = i * q + int(rng.integers(0, q - seg))
-                seq[st:st + seg] = revcomp_ascii(seq[st:st + seg].copy())
+                if want:
+                    seq[st:st + seg] = revcomp_ascii(seq[st:st + seg].copy())
         name = f"{prefix}_{g:03d}.fasta"
         if n_contigs <= 1:
             ids = [f"g{g:03d}_c000"]
-            contigs = [np.ascontiguousarray(seq)]
+            contigs = [np.ascontiguousarray(seq)] if want else None
         else:
             cuts = np.sort(rng.choice(np.arange(1, length), size=n_contigs - 1, replace=False))
-            pieces = np.split(seq, cuts)
-            pieces = [revcomp_ascii(p) if (i & 1) else p for i, p in enumerate(pieces)]
             order = rng.permutation(n_contigs)
-            contigs = [np.ascontiguousarray(pieces[i]) for i in order]
+            contigs = None
+            if want:
+                pieces = np.split(seq, cuts)
+                pieces = [revcomp_ascii(p) if (i & 1) else p for i, p in enumerate(pieces)]
+                contigs = [np.ascontiguousarray(pieces[i]) for i in order]
             ids = [f"g{g:03d}_c{c:03d}" for c in range(n_contigs)]
-        out.append(Genome(name=name, contig_ids=ids, contigs=contigs))
+        out.append(Genome(name=name, contig_ids=ids, contigs=contigs) if want else None)
     return out
 
 

@@ -22,6 +22,24 @@ def test_workload_config_weak_and_strong():
 
 def test_cpu_sample_uses_all_threads_whatever_omp_says(monkeypatch):
     monkeypatch.setenv("OMP_NUM_THREADS", "1")          # what torchrun does to every rank
-    cb, dt = bench.cpu_sample_run(2, length=60_000)
+    cb, dt, o, gens = bench.cpu_sample_run(2, length=60_000)
     assert cb["kind"] == "port" and cb["cores"] == len(os.sched_getaffinity(0)) and cb["value"] > 0 and dt > 0
-    assert "3 x 60000 bp" in cb["sample"]
+    assert "first 3 of the config-2 genomes at 60000 bp" in cb["sample"]
+    assert len(gens) == 3 and gens[0].n_bases == 60_000 and o.n_shared > 0
+
+
+def test_cpu_sample_defaults_to_the_full_genome_length():
+    """the sample keeps the workload's sketch load: same genome length, fewer genomes"""
+    import inspect
+    src = inspect.getsource(bench.cpu_sample_run)
+    assert 'length = length or cfg["length"]' in src
+
+
+def test_reference_arm_line_says_what_it_ran(capsys):
+    from types import SimpleNamespace
+    lines = []
+    bench.run_reference_arm(SimpleNamespace(config=2, warmup=0, steps=1, gpus=1, length=40_000), lines.append)
+    d = lines[0]
+    assert d["impl"] == "reference" and d["cpu_baseline"]["kind"] == "port" and d["gpu_launches"] == 0
+    assert d["config"]["same_workload_as_gpu_arm"] is False and "40000 bp" in d["config"]["reference_step"]
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["value"] == d["value"]

@@ -31,9 +31,13 @@ def test_bench_line_has_the_contract_keys():
     assert set(("value", "unit", "cores", "kind", "sample")) <= set(d["cpu_baseline"])
     assert d["e2e_fasta"]["n_picked"] == d["counts"]["n_picked"]          # the device FASTA ingest sees the same genomes
     assert "workload" in d["config"]
+    # the correctness gate ran inside the harness: GPU == oracle on the cpu_baseline sample, both output modes
+    assert d["parity"]["ok"] is True and len(d["parity"]["checked"]) == 2
+    assert all(c["words_and_order"] and c["positions"] and c["flags_and_picks"] for c in d["parity"]["checked"])
 
 
 def test_reference_arm_line():
     d = _run("--impl", "reference")
     assert d["impl"] == "reference" and d["value"] > 0 and d["gpu_launches"] == 0
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["cpu_baseline"]["kind"] == "port"
+    assert d["config"]["same_workload_as_gpu_arm"] is False and "300000 bp" in d["config"]["reference_step"]

@@ -1,13 +1,29 @@
-"""Device FASTA ingest (pfb_add_fasta): the records the GPU parser finds and the stage results computed from
-them must equal what the host reader (primerforge_b200.seqio.read_fasta, Bio.SeqIO's FASTA rules) gives
-through pfb_add_genome -- for well-formed files and for every irregularity the rules cover."""
+"""Device FASTA / GenBank ingest (pfb_add_fasta, pfb_add_genbank): the records the GPU parser finds and the stage
+results computed from them must equal what the ORACLE side's reader gives -- `SeqIO.parse` of oracle/standins/Bio,
+the module the reference's unmodified getCandidateKmers.py:93,212 runs against when the golden fixtures are made --
+through pfb_add_genome, for well-formed files and for every irregularity the rules cover.  The product's own host
+reader (primerforge_b200.seqio) is held to the same stand-in in tests/test_seqio.py."""
+import os
+import sys
+
 import numpy as np
 import pytest
 
 pytestmark = pytest.mark.gpu
 
+_STANDINS = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "standins")
 
-def _fasta_bytes(contigs, ids, width, rng=None, crlf=False, junk=b"", trailing_newline=True, spaces=False):
+
+def _oracle_read(fn, fmt):
+    """(ids, contigs) as the reference sees them: SeqRecord.id and str(rec.seq) of every record"""
+    if _STANDINS not in sys.path:
+        sys.path.insert(0, _STANDINS)
+    from Bio import SeqIO
+    recs = list(SeqIO.parse(fn, fmt))
+    return [r.id for r in recs], [np.frombuffer(str(r.seq).encode("latin-1"), dtype=np.uint8).copy() for r in recs]
+
+
+def _fasta_bytes(contigs, ids, width, rng=None, crlf=False, junk=b"", trailing_newline=True, spaces=False, tabs=False):
     out = bytearray(junk)
     nl = b"\r\n" if crlf else b"\n"
     for cid, arr in zip(ids, contigs):
@@ -19,6 +35,20 @@ def _fasta_bytes(contigs, ids, width, rng=None, crlf=False, junk=b"", trailing_n
             line = seq[i:i + w]
             if spaces and len(line) > 4:
                 line = line[:3] + b" " + line[3:]
+            if tabs and len(line) > 4:
+                # white space that line.rstrip() removes (runs of any length, also across a 32-byte step of the
+                # parser) and a tab INSIDE a line, which stays a byte of the sequence
+                r = (i // max(w, 1)) % 7
+                if r == 0:
+                    line = line + b"\t"
+                elif r == 1:
+                    line = line + b" \t \x0b\x0c" * 9
+                elif r == 2:
+                    line = line[:2] + b"\t" + line[2:]
+                elif r == 3:
+                    line = line[:2] + b"\t" + line[2:] + b"\t\t"
+                elif r == 4:
+                    line = b"\t" + line + b"\x1c\x1f "
             out += line + nl
             i += w
         if rng is not None and rng.random() < 0.3:
@@ -46,14 +76,13 @@ def _run(add, mode):
 
 def _compare(images, mode):
     from primerforge_b200 import seqio
-    import os
     import tempfile
     host = []
     with tempfile.TemporaryDirectory() as d:
         for i, img in enumerate(images):
             fn = os.path.join(d, f"g{i}.fasta")
             img.tofile(fn)
-            host.append(seqio.read_fasta(fn))
+            host.append(_oracle_read(fn, "fasta"))
     res_f, tables, info = _run(lambda e: [e.add_fasta(img) for img in images], mode)
     res_h, _, _ = _run(lambda e: [e.add_genome(c) for _ids, c in host], mode)
     for g, (ids, contigs) in enumerate(host):
@@ -78,7 +107,8 @@ def test_regular_fasta(mode):
 
 
 @pytest.mark.parametrize("mode", ["sync", "pipelined"])
-@pytest.mark.parametrize("variant", ["crlf", "junk", "unwrapped", "ragged", "no_final_newline", "spaces", "long_title", "tiny_records"])
+@pytest.mark.parametrize("variant", ["crlf", "junk", "unwrapped", "ragged", "no_final_newline", "spaces", "long_title", "tiny_records",
+                                     "tabs", "tabs_crlf", "tabs_no_final_newline"])
 def test_irregular_fasta(variant, mode):
     from primerforge_b200 import synth
     import zlib
@@ -102,6 +132,10 @@ def test_irregular_fasta(variant, mode):
             kw["trailing_newline"] = False
         elif variant == "spaces":
             kw["spaces"] = True
+        elif variant.startswith("tabs"):
+            kw["tabs"] = True
+            kw["crlf"] = variant == "tabs_crlf"
+            kw["trailing_newline"] = variant != "tabs_no_final_newline"
         elif variant == "long_title":
             ids = [cid + "_" + "x" * 9000 for cid in ids]  # a title line longer than two tiles
         elif variant == "tiny_records":
@@ -175,14 +209,13 @@ def _genbank_bytes(contigs, ids, version=True, crlf=False, junk=b"", upper=False
 
 def _compare_genbank(images, mode):
     from primerforge_b200 import seqio
-    import os
     import tempfile
     host = []
     with tempfile.TemporaryDirectory() as d:
         for i, img in enumerate(images):
             fn = os.path.join(d, f"g{i}.gbk")
             img.tofile(fn)
-            host.append(seqio.read_genbank(fn))
+            host.append(_oracle_read(fn, "genbank"))
     res_f, tables, info = _run(lambda e: [e.add_genbank(img) for img in images], mode)
     res_h, _, _ = _run(lambda e: [e.add_genome(c) for _ids, c in host], mode)
     for g, (ids, contigs) in enumerate(host):
@@ -228,7 +261,6 @@ def test_genbank_device_parser(variant, mode):
 def test_drop_in_entry_point_genbank(tmp_path, capsys):
     """_getAllCandidateKmers with params.format = 'genbank' (the reference's default): device ingest and host
     reader give the same candidates"""
-    import os
     from types import SimpleNamespace
     from primerforge_b200 import synth
     from primerforge_b200.candidates import _getAllCandidateKmers

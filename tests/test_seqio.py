@@ -48,3 +48,51 @@ def test_ids_from_header_offsets():
     offs = [0, gb.index(b"LOCUS       NOVERSION")]
     assert seqio.genbank_ids(arr, offs) == ["AB000001.2", "NOVERSION"]
     assert seqio.file_ids(arr, offs, "genbank") == ["AB000001.2", "NOVERSION"]
+
+
+import pytest  # noqa: E402
+
+
+@pytest.mark.parametrize("variant", ["crlf", "junk", "ragged", "no_final_newline", "spaces", "tabs", "tabs_crlf", "tabs_no_final_newline"])
+def test_host_reader_equals_the_oracle_side_reader_on_irregular_files(variant, tmp_path):
+    """primerforge_b200.seqio.read_fasta against oracle/standins/Bio (the reader the reference runs on when the golden
+    fixtures are made): ids and bytes of every record, for every irregularity the device parser is tested on"""
+    from tests.test_gpu_fasta import _fasta_bytes, _oracle_read
+    gens = synth.make_genomes(2, 20_000, seed=91, n_contigs=3)
+    kw = {}
+    if variant == "crlf":
+        kw["crlf"] = True
+    elif variant == "junk":
+        kw["junk"] = b"; a comment\n\nsome text before the first record\n"
+    elif variant == "ragged":
+        kw["rng"] = np.random.default_rng(1)
+    elif variant == "no_final_newline":
+        kw["trailing_newline"] = False
+    elif variant == "spaces":
+        kw["spaces"] = True
+    else:
+        kw.update(tabs=True, crlf=variant == "tabs_crlf", trailing_newline=variant != "tabs_no_final_newline")
+    for g in gens:
+        fn = str(tmp_path / f"{g.name}")
+        _fasta_bytes(g.contigs, g.contig_ids, 70, **kw).tofile(fn)
+        ids_o, contigs_o = _oracle_read(fn, "fasta")
+        ids_h, contigs_h = seqio.read_fasta(fn)
+        assert ids_o == ids_h == g.contig_ids
+        assert all(np.array_equal(a, b) for a, b in zip(contigs_o, contigs_h))
+        if variant.startswith("tabs"):
+            assert any((c == 9).any() for c in contigs_h)      # a tab inside a line is a byte of the sequence
+        else:
+            assert all(np.array_equal(a, b) for a, b in zip(contigs_h, g.contigs))
+
+
+def test_genbank_reader_equals_the_oracle_side_reader(tmp_path):
+    from tests.test_gpu_fasta import _genbank_bytes, _oracle_read
+    gens = synth.make_genomes(2, 20_000, seed=92, n_contigs=3)
+    for kw in ({}, {"version": False}, {"crlf": True}, {"upper": True}, {"long_feature": True}):
+        for g in gens:
+            fn = str(tmp_path / "x.gbk")
+            _genbank_bytes(g.contigs, g.contig_ids, **kw).tofile(fn)
+            ids_o, contigs_o = _oracle_read(fn, "genbank")
+            ids_h, contigs_h = seqio.read_genbank(fn)
+            assert ids_o == ids_h
+            assert all(np.array_equal(a, b) for a, b in zip(contigs_o, contigs_h))

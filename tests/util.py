@@ -51,3 +51,23 @@ def candidate_set_from_arrays(kmers, k, picked, contig, start, strand) -> set:
         else:
             out.add((kmers[r], int(contig[r]), s + kk - 1, s, 1))
     return out
+
+
+def assert_equals_oracle(res, o, prefilter: bool, n_genomes: int):
+    """bit-for-bit comparison of a StageResult with an OracleResult of the same inputs: words, order, lengths,
+    flags (GC / Tm / repeat / pick), GC counts, Tm (identical doubles; the contract is 0.01), and contig / leftmost
+    start / strand in every genome.  With prefilter the GPU reports only the k-mers that pass the three filters."""
+    rec = res.records
+    keep = ((o.flags & 7) == 7) if prefilter else np.ones(o.n_shared, dtype=bool)
+    assert rec.size == int(keep.sum()), f"{rec.size} records, oracle has {int(keep.sum())}"
+    assert np.array_equal(rec["word"], o.word[keep]), "k-mer set / dict order differs"
+    assert np.array_equal(rec["k"], o.k[keep])
+    assert np.array_equal(rec["flags"] & 15, o.flags[keep]), "filter flags / picks differ"
+    assert np.array_equal(rec["gc_count"].astype(np.int32), o.gc_count[keep])
+    assert np.max(np.abs(rec["tm"] - o.tm[keep]), initial=0.0) <= 0.01
+    assert np.array_equal(rec["tm"], o.tm[keep]), "Tm doubles differ"
+    for gi in range(n_genomes):
+        pos = res.positions[gi]
+        assert np.array_equal(pos["contig"].astype(np.int32), o.contig[gi][keep]), f"contig differs in genome {gi}"
+        assert np.array_equal(pos["start"].astype(np.int64), o.start[gi][keep]), f"start differs in genome {gi}"
+        assert np.array_equal(pos["strand"].astype(np.uint8), o.strand[gi][keep]), f"strand differs in genome {gi}"
