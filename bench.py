@@ -220,6 +220,38 @@ def workload_config(index: int, n_gpus: int, strong: bool = False) -> dict:
             "parallelism": f"genome-sharded x{n_gpus}, key table replicated" if n_gpus > 1 else "single GPU"}
 
 
+def pin_genomes(gens):
+    """(pinned uint8 tensor, contig offsets) per genome: the host side of the e2e leg"""
+    import torch
+    pinned = []
+    for g in gens:
+        cat = np.concatenate(g.contigs) if len(g.contigs) > 1 else g.contigs[0]
+        t = torch.empty(cat.size, dtype=torch.uint8).pin_memory()
+        t.numpy()[:] = cat
+        off = np.zeros(len(g.contigs) + 1, dtype=np.uint64)
+        off[1:] = np.cumsum([c.size for c in g.contigs])
+        pinned.append((t, off))
+    return pinned
+
+
+def view_digests(view, with_records: bool) -> dict:
+    """digests of one context's per-id result columns: which ids are picked, the picked ids' records, and their place
+    in every genome of the context (local order)"""
+    import hashlib
+    sel = np.flatnonzero(view.pick)
+    out = {"n_ids": int(view.n_ids), "n_picked": int(sel.size),
+           "pick": hashlib.blake2b(np.ascontiguousarray(view.pick).tobytes(), digest_size=16).hexdigest(),
+           "alive": hashlib.blake2b(np.ascontiguousarray(view.alive).tobytes(), digest_size=16).hexdigest(),
+           "pos": [hashlib.blake2b(np.ascontiguousarray(view.pos[g][sel]).tobytes(), digest_size=16).hexdigest()
+                   for g in range(view.pos.shape[0])]}
+    if with_records and view.word is not None:
+        h = hashlib.blake2b(digest_size=16)
+        for col in (view.word, view.tm, view.info):
+            h.update(np.ascontiguousarray(col[sel]).tobytes())
+        out["records"] = h.hexdigest()
+    return out
+
+
 def main():
     # exactly ONE line may reach stdout (the driver parses it): libraries that print banners during
     # initialisation (NCCL's version line) are diverted to stderr
@@ -240,10 +272,9 @@ def main():
     ap.add_argument("--length", type=int, default=None, help="override genome length (debug)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-fasta-leg", action="store_true")
+    ap.add_argument("--no-strong-c4", action="store_true", help="skip the strong-scaling block (BASELINE config 4: 200 genomes over the GPUs)")
+    ap.add_argument("--no-dropin-leg", action="store_true", help="skip the timing of the drop-in entry point from FASTA files on disk")
     ap.add_argument("--scan-mode", type=int, default=0, help="0 auto, 1 plain L2 probe, 2 shared-memory filter (debug)")
-    ap.add_argument("--dropin-leg", action="store_true",
-                    help="also time the drop-in entry point _getAllCandidateKmers(params, False) from FASTA files on disk "
-                         "to the dict of Primer objects (SURVEY 8d T_e2e; dominated by building G x |S| Python objects)")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="weak (default): the config's genome count PER GPU; strong: the config's genome count in total, "
                          "genome 0 on every rank and the others dealt round-robin")
@@ -256,8 +287,8 @@ def main():
 
     import torch
     import torch.distributed as dist
-    from primerforge_b200 import _lib, synth
-    from primerforge_b200.dist import allreduce_stage_buffers, run_sharded
+    from primerforge_b200 import synth
+    from primerforge_b200.dist import attach_comm, shard_genomes
     from primerforge_b200.engine import Engine
 
     rank = int(os.environ.get("RANK", "0"))
@@ -288,35 +319,26 @@ def main():
     if args.length:
         cfg["length"] = args.length
     strong = args.scaling == "strong" and world > 1
+    seed = synth.BASE_SEED + args.config
     if strong:
-        from primerforge_b200.dist import shard_genomes
         n_distinct = cfg["n_genomes"]
         idx = shard_genomes(n_distinct, world, rank)
         per_rank = len(shard_genomes(n_distinct, world, 0))          # the largest shard
-        gens = synth.make_genomes(max(idx) + 1, cfg["length"], seed=synth.BASE_SEED + args.config, n_contigs=cfg["n_contigs"])
-        mine = [gens[i] for i in idx]
     else:
         per_rank = cfg["n_genomes"]
         n_distinct = per_rank if world == 1 else 1 + (per_rank - 1) * world
-        # the generator is sequential in the genome index: every rank generates the prefix it needs
-        last_needed = per_rank if world == 1 else 1 + (per_rank - 1) * (rank + 1)
-        gens = synth.make_genomes(last_needed, cfg["length"], seed=synth.BASE_SEED + args.config, n_contigs=cfg["n_contigs"])
-        mine = gens[:per_rank] if world == 1 else [gens[0]] + gens[1 + (per_rank - 1) * rank: 1 + (per_rank - 1) * (rank + 1)]
+        idx = list(range(per_rank)) if world == 1 else [0] + list(range(1 + (per_rank - 1) * rank, 1 + (per_rank - 1) * (rank + 1)))
+    # (the generator draws every genome's random numbers whatever is asked for: genome g is the same sequence on every rank)
+    gens = synth.make_genomes(max(idx) + 1, cfg["length"], seed=seed, n_contigs=cfg["n_contigs"], only=idx)
+    mine = [gens[i] for i in idx]
     del gens
     distinct_bases = n_distinct * cfg["length"]
-
-    # pinned host buffers (the e2e leg copies from these every step)
-    pinned = []
-    for g in mine:
-        cat = np.concatenate(g.contigs) if len(g.contigs) > 1 else g.contigs[0]
-        t = torch.empty(cat.size, dtype=torch.uint8).pin_memory()
-        t.numpy()[:] = cat
-        off = np.zeros(len(g.contigs) + 1, dtype=np.uint64)
-        off[1:] = np.cumsum([c.size for c in g.contigs])
-        pinned.append((t, off))
+    pinned = pin_genomes(mine)          # the e2e leg copies from these every step
     del mine
 
-    eng = Engine(device=local, k_min=cfg["k_min"], k_max=cfg["k_max"], max_repeat=cfg["max_repeats"], prefilter=1)
+    ekw = dict(k_min=cfg["k_min"], k_max=cfg["k_max"], max_repeat=cfg["max_repeats"], prefilter=1)
+    eng = Engine(device=local, **ekw)
+    attach_comm(eng)                    # N > 1: the exchanges between the ranks happen inside the library from here on
     eng.set_scan_mode(args.scan_mode)
     for t, off in pinned:
         eng.add_genome_ptr(t.data_ptr(), t.numel(), off)
@@ -328,83 +350,86 @@ def main():
             dist.barrier()
             torch.cuda.synchronize()
 
-    xchg = {"ms": [], "bytes": 0}
-    if world > 1:
-        ext = torch.cuda.ExternalStream(eng.stream_handle(), device=torch.device("cuda", local))
-        xev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
-
-    def compute_once():
-        if world == 1:
-            eng.compute()
-        else:
-            # the two reductions are enqueued on the library's stream between the stages (no host waits);
-            # CUDA events on that stream time them
-            eng.compute_stage(0)
-            xev[0].record(ext)
-            allreduce_stage_buffers(eng, _lib.PFB_BUF_ALIVE, "min")
-            xev[1].record(ext)
-            eng.compute_stage(1)
-            xev[2].record(ext)
-            allreduce_stage_buffers(eng, _lib.PFB_BUF_PICK, "max")
-            xev[3].record(ext)
-            eng.compute_stage(2)
-            xchg["ms"].append(xev[0].elapsed_time(xev[1]) + xev[2].elapsed_time(xev[3]))
-            xchg["bytes"] = eng.device_buffer(_lib.PFB_BUF_ALIVE)[1] + eng.device_buffer(_lib.PFB_BUF_PICK)[1]
-
-    def fetch_results():
-        rec, ss, ct = eng.result_picked()     # pinned host buffers, plain D2H copies
-        return rec, [ss] + ([ct] if ct is not None else [])
-
     # ---- device-resident leg
     eng.upload()
     for _ in range(args.warmup):
         flush.zero_()
         barrier()
-        compute_once()
+        eng.compute()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
         time.sleep(0.35)        # nvidia-smi needs a moment to start printing; the loop below keeps the GPU busy
-    dev_ms, launches, scan_ms, scan_main_ms, enc_ms, first_ms, fin_ms = [], 0, [], [], [], [], []
+    dev_ms, launches, scan_ms, scan_main_ms, enc_ms, first_ms, fin_ms, x_ms = [], 0, [], [], [], [], [], []
     dev_counts = {}
     barrier()
     wall0 = time.perf_counter()
     for _ in range(args.steps):
         flush.zero_()
         barrier()
-        compute_once()
+        eng.compute()
         tm = eng.timing()
         dev_ms.append(tm["ms_total"])
         scan_ms.append(tm["ms_scan"])
         scan_main_ms.append(tm["ms_scan_main"])
         enc_ms.append(tm["ms_encode"]); first_ms.append(tm["ms_first"]); fin_ms.append(tm["ms_finalize"])
-        dev_counts = {k: int(tm[k]) for k in ("n_bases", "n_windows", "n_slots", "n_records", "n_picked")}
+        x_ms.append(tm["ms_exchange"])
+        dev_counts = {k: int(tm[k]) for k in ("n_bases", "n_windows", "n_slots", "n_ids", "n_records", "n_picked")}
         launches += tm["n_launches"]
     barrier()
     wall = time.perf_counter() - wall0
     tm = eng.timing()
+    reruns_resident = int(tm["n_reruns"])
 
-    # ---- end-to-end leg (host buffers -> host results through the C ABI)
+    # ---- end-to-end leg (host buffers -> host results through the C ABI): pfb_run queues the H2D copies of the
+    # bases, computes behind them and copies the per-id result columns into pinned host memory WHILE it computes;
+    # the step ends when the last result byte is on the host
     e2e_s, e2e_parts = [], []
     h2d = sum(t.numel() for t, _ in pinned)
     d2h = 0
+    view = None
     for i in range(max(1, args.warmup // 2) + args.steps):
         flush.zero_()
         barrier()
         t0 = time.perf_counter()
-        if world == 1:
-            eng.run()                 # pfb_run: H2D copies overlapped with the key-table build and the scan
-        else:
-            run_sharded(eng, upload=True)
+        eng.run()                 # collective at N > 1
         t1 = time.perf_counter()
-        rec, pos = fetch_results()
+        view = eng.result_by_id()
         eng.sync()
         dt = time.perf_counter() - t0
         if i >= max(1, args.warmup // 2):
             e2e_s.append(dt)
             e2e_parts.append((t1 - t0, dt - (t1 - t0), eng.timing()["ms_total"]))
-            d2h = rec.nbytes + sum(p.nbytes for p in pos)
+            d2h = view.pitch * ((18 if view.word is not None else 0) + 4 * view.pos.shape[0] + 2)
     clocks = sampler.stop() if rank == 0 else None
+    my_digest = view_digests(view, with_records=rank == 0)
+    reruns_total = int(eng.timing()["n_reruns"])
+
+    # ---- the gate at N > 1: the job's result (every rank's picked ids, records, places of its genomes) against ONE
+    # GPU running all the job's genomes -- the only way a multi-GPU line can vouch for the sharded path
+    parity = None
+    if world > 1:
+        gathered = [None] * world
+        dist.all_gather_object(gathered, (idx, my_digest))
+        if rank == 0:
+            all_g = synth.make_genomes(n_distinct, cfg["length"], seed=seed, n_contigs=cfg["n_contigs"])
+            with Engine(device=local, **ekw) as one:
+                for g in all_g:
+                    one.add_genome(g.contigs)
+                del all_g
+                one.upload()
+                one.compute()
+                ref = view_digests(one.result_by_id(), with_records=True)
+            ok = True
+            for gi_list, dg in gathered:
+                ok &= dg["pick"] == ref["pick"] and dg["alive"] == ref["alive"] and dg["n_ids"] == ref["n_ids"]
+                ok &= all(dg["pos"][j] == ref["pos"][gi] for j, gi in enumerate(gi_list))
+                if "records" in dg:
+                    ok &= dg["records"] == ref["records"]
+            parity = {"against": f"the {n_distinct} genomes of the job on ONE GPU (rank 0, outside the timed region)",
+                      "ok": bool(ok), "n_ids": ref["n_ids"], "n_picked": ref["n_picked"],
+                      "checked": "alive and pick bytes of every rank, records on rank 0, places of every genome on the rank that holds it"}
+        barrier()
 
     # ---- end-to-end from the FASTA FILE IMAGES (80-column, pinned host memory): the records are found and
     # compacted on the device (pfb_add_fasta), everything else as above.  Single GPU only.
@@ -430,25 +455,93 @@ def main():
             pt = torch.empty(img.size, dtype=torch.uint8).pin_memory()
             pt.numpy()[:] = img
             images.append(pt)
-        eng_f = Engine(device=local, k_min=cfg["k_min"], k_max=cfg["k_max"], max_repeat=cfg["max_repeats"], prefilter=1)
+        eng_f = Engine(device=local, **ekw)
         for pt in images:
             eng_f.add_fasta(ptr=pt.data_ptr(), n_bytes=pt.numel())
         fa_s = []
+        vf = None
         for i in range(2 + min(args.steps, 50)):
             flush.zero_()
             barrier()
             t0 = time.perf_counter()
             eng_f.run()
-            rec_f, ss_f, ct_f = eng_f.result_picked()
+            vf = eng_f.result_by_id()
             eng_f.sync()
             if i >= 2:
                 fa_s.append(time.perf_counter() - t0)
         fa_ms = float(np.mean(fa_s) * 1e3)
         fasta_leg = {"value": distinct_bases / 1e6 / (fa_ms / 1e3), "unit": UNIT, "ms_per_step": fa_ms,
                      "h2d_bytes_per_step": int(sum(pt.numel() for pt in images)),
-                     "d2h_bytes_per_step": int(rec_f.nbytes + ss_f.nbytes + (ct_f.nbytes if ct_f is not None else 0)),
-                     "n_picked": int(rec_f.size), "input": "80-column FASTA file images in pinned host memory, parsed on the device"}
+                     "d2h_bytes_per_step": int(vf.pitch * (18 + 4 * vf.pos.shape[0] + 2)),
+                     "n_picked": int(np.count_nonzero(vf.pick)), "input": "80-column FASTA file images in pinned host memory, parsed on the device"}
         eng_f.close()
+        del images
+
+    # ---- strong scaling of BASELINE config 4 (200 x 5 Mbp over the GPUs of the job; north_star's target is >= 6x at 8):
+    # device-resident steps, max over ranks; rank 0 also times the whole of config 4 on its one GPU so that the
+    # line carries its own speed-up
+    strong_c4 = None
+    if not args.no_strong_c4 and not args.genomes and not args.length:
+        c4 = synth.CONFIGS[4]
+        idx4 = shard_genomes(c4["n_genomes"], world, rank)
+        k4 = dict(k_min=c4["k_min"], k_max=c4["k_max"], max_repeat=c4["max_repeats"], prefilter=1)
+        steps4 = max(3, min(args.steps, 10))
+
+        def time_c4(genome_idx, with_comm):
+            g4 = synth.make_genomes(max(genome_idx) + 1, c4["length"], seed=synth.BASE_SEED + 4, n_contigs=c4["n_contigs"], only=genome_idx)
+            e4 = Engine(device=local, **k4)
+            if with_comm:
+                attach_comm(e4)
+            keep = []
+            for gi in genome_idx:
+                arr = g4[gi].contigs[0]
+                g4[gi] = None
+                keep.append(arr)
+                e4.add_genome(bases=arr, offsets=np.array([0, arr.size], dtype=np.uint64))
+            e4.upload()
+            ms, xs = [], []
+            for i in range(3 + steps4):
+                flush.zero_()
+                if with_comm:
+                    barrier()
+                else:
+                    torch.cuda.synchronize()
+                e4.compute()
+                if i >= 3:
+                    ms.append(e4.timing()["ms_total"]); xs.append(e4.timing()["ms_exchange"])
+            t4 = e4.timing()
+            e4.close()
+            return float(np.mean(ms)), float(np.mean(xs)), t4
+
+        ms4, x4, t4 = time_c4(idx4, world > 1)
+        if world > 1:
+            red = torch.tensor([ms4], dtype=torch.float64, device="cuda")
+            dist.all_reduce(red, op=dist.ReduceOp.MAX)
+            ms4 = float(red.item())
+        bases4 = c4["n_genomes"] * c4["length"]
+        strong_c4 = {"workload": f"BASELINE config 4: {c4['n_genomes']} x {c4['length'] / 1e6:g} Mbp ingroup genomes in total, "
+                                 f"genome 0 on every GPU + {len(idx4) - 1} others on rank 0's, primer_len {c4['k_min']},{c4['k_max']}",
+                     "n_gpus": world, "steps": steps4, "ms_per_step": ms4, "value": bases4 / 1e6 / (ms4 / 1e3), "unit": UNIT,
+                     "ms_exchange_rank0": x4, "sharded_first_genome": int(t4["sharded_first_genome"]),
+                     "n_ids": int(t4["n_ids"]), "n_slots": int(t4["n_slots"])}
+        if world > 1:
+            # bytes a rank sends per direction (ring / tree all-reduce ~ 2 (N-1)/N of the buffer; all-gather (N-1)/N)
+            # against the measured NVLink peer bandwidth
+            nid, nsl = int(t4["n_ids"]), int(t4["n_slots"])
+            f = (world - 1) / world
+            wire = 2 * f * (nid + nid) + 2 * f * 4 * nsl + f * 4 * 0.1 * 25e6        # alive + pick, packed rows, candidate lists (~10 % of genome 1's windows)
+            strong_c4["exchange"] = {"what": "all-gather of genome 1's candidate lists, SUM all-reduce of its packed rows (4 B per key), "
+                                             "MIN all-reduce of the alive bytes, MAX all-reduce of the pick bytes (NCCL inside the library)",
+                                     "wire_bytes_per_rank_per_direction": int(wire), "ms": x4,
+                                     "nvlink_peak_GBs_per_direction": 770.0,
+                                     "frac_of_nvlink": wire / (x4 / 1e3) / 1e9 / 770.0 if x4 > 0 else None}
+            if rank == 0:
+                ms1, _x, _t = time_c4(list(range(c4["n_genomes"])), False)
+                strong_c4["ms_per_step_one_gpu"] = ms1
+                strong_c4["speedup_vs_one_gpu"] = ms1 / ms4
+            barrier()
+        else:
+            strong_c4["speedup_vs_one_gpu"] = 1.0
 
     step_ms = float(np.mean(dev_ms))
     e2e_ms = float(np.mean(e2e_s) * 1e3)
@@ -456,6 +549,9 @@ def main():
         red = torch.tensor([step_ms, e2e_ms], dtype=torch.float64, device="cuda")
         dist.all_reduce(red, op=dist.ReduceOp.MAX)
         step_ms, e2e_ms = red.tolist()
+        tot = torch.tensor([float(h2d), float(d2h)], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+        h2d, d2h = (int(x) for x in tot.tolist())
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -475,48 +571,62 @@ def main():
     windows = scan_bases * nk
     traffic, traffic_src = None, None
     try:
-        with open(os.path.join(ROOT, "profiles", "r01_scan_traffic.json")) as fh:
+        with open(next(p for p in (os.path.join(ROOT, "profiles", n) for n in ("r02_scan_traffic.json", "r01_scan_traffic.json")) if os.path.exists(p))) as fh:
             tj = json.load(fh)
         if args.config == 2 and world == 1 and not args.genomes and not args.length:
-            traffic, traffic_src = tj["dram_bytes_total"], tj["source"]
+            traffic, traffic_src = tj["dram_bytes_total"], tj["source"] + " -- a STORED figure of that capture, not measured in this run"
     except Exception:
         pass
+    stage_bytes = bpb * distinct_bases
     roofline = {"bound": "hbm", "kernel": "k_scan_filtered (genomes 2..G, one launch)", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_kind": peak_kind,
                 "algorithmic_bytes_per_launch": alg_bytes, "bytes_per_base": bpb,
                 "bytes_per_base_source": "SURVEY.md 8(d) stage model (count-everything design); see DESIGN.md section 4",
                 "ms_per_launch": ms_scan, "share_of_step": ms_scan / step_ms if step_ms else None,
-                "actual_limiter": {"kind": "INT32 ALU pipe issue (hash + filter + queue append per window); DRAM traffic is ~6% of the modelled bytes",
+                "stage_level": {"what": "the same byte model over the WHOLE step (all launches, per GPU)",
+                                "achieved": stage_bytes / world / (step_ms / 1e3) / 1e9, "frac": stage_bytes / world / (step_ms / 1e3) / 1e9 / peak},
+                "actual_limiter": {"kind": "instruction issue / INT32 ALU pipe (hash + filter + queue append per window); the kernel's DRAM traffic is "
+                                           "~10 % of the modelled bytes, i.e. ~10 % of HBM peak: HBM is not the binding roof",
                                    "windows_per_s_G": windows / (ms_scan / 1e3) / 1e9 if ms_scan > 0 else 0.0,
-                                   "evidence": "profiles/r01_scan_ablation.md, profiles/r01_v14_ncu_summary.json"}}
+                                   "evidence": "profiles/ (ncu summary, SASS opcode histogram, ablations)"}}
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": step_ms, "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": "u64",
             "data": "synthetic", "config": workload_config(args.config, world, strong) | ({"genomes_per_gpu": per_rank, "genome_bp": cfg["length"]}),
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_ms,
-                    "ms_run_call": float(np.mean([a for a, _, _ in e2e_parts]) * 1e3), "ms_fetch_results": float(np.mean([b for _, b, _ in e2e_parts]) * 1e3),
-                    "ms_device_span_in_run": float(np.mean([c for _, _, c in e2e_parts]))},
+                    "ms_run_call": float(np.mean([a for a, _, _ in e2e_parts]) * 1e3), "ms_after_run_call": float(np.mean([b for _, b, _ in e2e_parts]) * 1e3),
+                    "ms_device_span_in_run": float(np.mean([c for _, _, c in e2e_parts])),
+                    "what": "pfb_run from pinned host bases to the per-id result columns (word, Tm, info, place in every genome, alive, pick) "
+                            "in pinned host memory; copies in both directions overlap the kernels; bytes are summed over the ranks"},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "host_cpus_bound": affinity,
             "phases_ms": {"ms_encode": float(np.mean(enc_ms)), "ms_first": float(np.mean(first_ms)), "ms_scan": float(np.mean(scan_ms)),
                           "ms_finalize": float(np.mean(fin_ms)), "ms_total": step_ms},
-            "counts": dev_counts,
+            "counts": dev_counts, "reruns": {"resident_leg": reruns_resident, "all_legs": reruns_total,
+                                             "what": "runs repeated because a buffer capacity proved too small (the first run of a context sizes them)"},
             "wall_s_timed_loop": wall}
-    if world > 1 and xchg["ms"]:
+    if world > 1:
         # ring all-reduce: every rank sends and receives 2 (N - 1) / N of the buffer per direction
-        ms_x = float(np.mean(xchg["ms"][-args.steps:]))
-        wire = 2.0 * (world - 1) / world * xchg["bytes"]
-        line["exchange"] = {"what": "MIN all-reduce of the per-key alive bytes + MAX all-reduce of the pick bytes (NCCL, on the library's stream)",
-                            "bytes_reduced_per_rank": int(xchg["bytes"]), "ms_per_step": ms_x,
+        ms_x = float(np.mean(x_ms)) if x_ms else 0.0
+        f = (world - 1) / world
+        nid, nsl = dev_counts.get("n_ids", 0), dev_counts.get("n_slots", 0)
+        wire = 2 * f * 2 * nid + 2 * f * 4 * nsl + f * 4 * 0.1 * cfg["length"] * nk
+        line["exchange"] = {"what": "inside the library (NCCL on the context's stream): all-gather of genome 1's candidate lists, SUM all-reduce of "
+                                    "its packed rows, MIN all-reduce of the alive bytes, MAX all-reduce of the pick bytes",
+                            "wire_bytes_per_rank_per_direction": int(wire), "ms_per_step": ms_x,
                             "wire_GBs_per_direction": wire / (ms_x / 1e3) / 1e9 if ms_x > 0 else None,
                             "nvlink_peak_GBs_per_direction": 770.0,
                             "frac_of_nvlink": wire / (ms_x / 1e3) / 1e9 / 770.0 if ms_x > 0 else None,
-                            "note": "latency-bound: ~2 MB per step; no k-mer crosses NVLink (DESIGN.md section 5)"}
+                            "note": "latency-bound: a few MB per step; no k-mer of genomes 2..G crosses NVLink (DESIGN.md section 5)"}
+    if parity is not None:
+        line["parity"] = parity
+    if strong_c4 is not None:
+        line["strong_c4"] = strong_c4
     if fasta_leg is not None:
         line["e2e_fasta"] = fasta_leg
-    if args.dropin_leg and world == 1:
+    if not args.no_dropin_leg and world == 1:
         import tempfile
         from types import SimpleNamespace
         from primerforge_b200.candidates import _getAllCandidateKmers
-        gens2 = synth.make_genomes(per_rank, cfg["length"], seed=synth.BASE_SEED + args.config, n_contigs=cfg["n_contigs"])
+        gens2 = synth.make_genomes(per_rank, cfg["length"], seed=seed, n_contigs=cfg["n_contigs"])
         with tempfile.TemporaryDirectory() as tmpd:
             paths = synth.write_fasta(gens2, tmpd)
             del gens2
@@ -525,14 +635,14 @@ def main():
                                   minTm=55.0, maxTm=68.0, maxRepeatLen=cfg["max_repeats"], tempTolerance=5.0, numThreads=1,
                                   p3_mvConc=50.0, p3_dvConc=1.5, p3_dntpConc=0.6, p3_dnaConc=50.0, p3_tempC=37.0, p3_maxLoop=30,
                                   log=log, pickles={1: "sharedKmers.p", 2: "candidates.p"}, dumpObj=lambda *a, **k: None,
-                                  loadObj=lambda *a: None)
+                                  loadObj=lambda *a: None, debug=False)
             t0 = time.perf_counter()
             out = _getAllCandidateKmers(prm, False, thal="off", device=local)
             dt = time.perf_counter() - t0
-        n_obj = sum(len(v) for per in out.values() for v in per.values())
-        line["e2e_dropin"] = {"value": distinct_bases / 1e6 / dt, "unit": UNIT, "seconds": dt, "primer_objects": int(n_obj),
-                              "what": "_getAllCandidateKmers(params, False) from FASTA files on disk to dict[str, dict[str, list[Primer]]], "
-                                      "hairpin / homodimer screening off; the time is building the Python Primer objects"}
+            n_obj = sum(len(v) for per in out.values() for v in per.values())
+        line["e2e_dropin"] = {"value": distinct_bases / 1e6 / dt, "unit": UNIT, "seconds": dt, "primers": int(n_obj),
+                              "what": "_getAllCandidateKmers(params, False) from FASTA files on disk to dict[str, dict[str, list[Primer]]] "
+                                      "(hairpin / homodimer screening off): the call the reference's main.py:86 makes"}
     if world == 1 and not args.no_cpu_baseline:
         # the CPU restatement on a bounded sample; the GPU must reproduce that result bit for bit (the gate)
         line["cpu_baseline"], _dt, o_cpu, gens_cpu = cpu_sample_run(args.config, length=args.length)

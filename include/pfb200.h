@@ -8,8 +8,10 @@
  * binds (see INTEGRATION.md and primerforge_b200/_lib.py); each one cites the reference code it
  * replaces.  Plain pointers and sizes only; the library owns all device memory, the caller owns
  * all host buffers.  Every function returns 0 on success or a negative PFB_E* code and never
- * throws; pfb_last_error() gives the message.  A context is not thread-safe; use one per
- * process / per GPU.
+ * throws; pfb_last_error() gives the message.  A context is not thread-safe; it lives on one GPU.
+ * More than one GPU: either one process per GPU (pfb_comm_*: every rank joins a communicator and calls
+ * pfb_run / pfb_compute like a single GPU would; the exchanges happen inside) or one process for all
+ * GPUs (pfb_multi_*: one host thread drives N contexts).
  */
 #ifndef PFB200_H
 #define PFB200_H
@@ -90,8 +92,30 @@ typedef struct pfb_timing {
     uint64_t used_filter;      /* 1: the scan probed through the shared-memory filter (k_scan_filtered) */
     uint64_t scan_main_bases;  /* bases covered by the one scan launch over genomes 2..G (pfb_compute only) */
     float    ms_scan_main;     /* CUDA-event duration of that launch: the roofline kernel of bench.py */
-    float    reserved;
+    float    ms_exchange;      /* CUDA-event time of this run's collectives on this context's stream (0 on one GPU) */
+    uint64_t n_ids;            /* genome-1 k-mers that are unique in genome 1 (= length of the per-id result columns) */
+    uint64_t sharded_first_genome; /* 1: the ranks shared genome 1's own pipeline (candidates + its scan) by position */
+    uint64_t n_reruns;         /* runs of this context that were repeated because a buffer capacity proved too small */
 } pfb_timing;
+
+/* The results as the device keeps them: one entry per id.  ids are the genome-1 k-mers that are unique in
+ * genome 1, numbered in the reference's dict insertion order; alive[id] = shared by every ingroup genome (a key
+ * of sharedKmers, getCandidateKmers.py:190-219), pick[id] = PFB_F_PICK.  Host pointers into pinned buffers owned
+ * by the context, valid until its next run.  info = (k - 1) | gc_count << 5 | flags << 11 (PFB_F_GC_OK,
+ * PFB_F_TM_OK, PFB_F_REP_OK, PFB_F_PALIN); pos[g * pitch + id] = genome-local padded coordinate of the leftmost
+ * base | strand << 31 in the g-th genome of this context (only where alive[id]) -- the contigs of a genome are
+ * laid out in the order added, each starting at a multiple of 32, so for a single-contig genome this IS the
+ * start; pfb_result_positions / pfb_result_picked decode it to (contig, start). */
+typedef struct pfb_idview {
+    uint64_t n_ids, pitch, n_genomes;
+    uint64_t records_valid;     /* 0: word / tm / info were left on the device (PFB_OPT_FETCH_RECORDS = 0) */
+    const uint64_t *word;
+    const double   *tm;
+    const uint16_t *info;
+    const uint32_t *pos;
+    const uint8_t  *alive;
+    const uint8_t  *pick;
+} pfb_idview;
 
 /* lifecycle ------------------------------------------------------------------------------ */
 int  pfb_create(pfb_ctx **out, int device, const pfb_params *params);
@@ -135,32 +159,58 @@ int  pfb_run(pfb_ctx *ctx);
 int  pfb_upload_async(pfb_ctx *ctx);
 int  pfb_upload_wait(pfb_ctx *ctx);
 
-/* multi-GPU (one context per rank; genome 0 is added on every rank, the other genomes are
- * sharded): pfb_compute == stage 0,1,2.  Between stage 0 and 1 the caller min-reduces the
- * PFB_BUF_ALIVE buffer over ranks, between stage 1 and 2 it max-reduces PFB_BUF_PICK. */
-int  pfb_compute_stage(pfb_ctx *ctx, int stage);
-#define PFB_BUF_ALIVE 0   /* uint8 [n_slots]: 1 while the slot's k-mer is unique in every genome seen */
-#define PFB_BUF_PICK  1   /* uint8, 0 / 1 per record; the buffer is padded with zeros (its length is the number of keys
-                             that survived genome 1, >= n_records) so that no stage has to wait for a count */
-int  pfb_device_buffer(pfb_ctx *ctx, int which, void **dev_ptr, uint64_t *n_bytes);
+/* multi-GPU, one process per GPU (replaces the reference's multiprocessing.Pool at getCandidateKmers.py:115-118,
+ * 433-436).  Genome 0 is added on every rank -- it defines the key table and the ids, identically everywhere --
+ * the other genomes are dealt out; genome 0's own pipeline (candidate windows, its scan) is shared out by
+ * position.  Rank 0 makes the id, hands it to the others by any means (128 bytes), every rank joins; from then
+ * on pfb_run / pfb_compute are collective calls: inside, the ranks all-gather genome 1's candidate lists,
+ * SUM-reduce its packed rows, MIN-reduce one byte per id ("shared by every genome this rank holds") and
+ * MAX-reduce one byte per id ("picked in some genome") with NCCL on the context's stream. */
+int  pfb_comm_unique_id(uint8_t *id128);
+int  pfb_comm_init_rank(pfb_ctx *ctx, int n_ranks, int rank, const uint8_t *id128);
 int  pfb_sync(pfb_ctx *ctx);
-/* the CUDA stream (cudaStream_t) every kernel of this context is launched on: a caller that enqueues its
- * reductions on this stream (NCCL, or torch.cuda.ExternalStream) needs no host synchronisation between the
- * stages */
+/* the CUDA stream (cudaStream_t) every kernel of this context is launched on (timing with the caller's events) */
 int  pfb_stream(pfb_ctx *ctx, void **stream_out);
+#define PFB_OPT_SCAN_MODE      0   /* see pfb_set_scan_mode */
+#define PFB_OPT_FETCH_RECORDS  1   /* 0: pfb_run leaves the per-id word / Tm / info columns on the device (they are the
+                                      same on every rank of a job: ranks > 0 need not move them) */
+#define PFB_OPT_SHARD_FIRST    2   /* 0: every rank runs all of genome 0's pipeline itself (default 1) */
+#define PFB_OPT_EMULATE_RANKS  3   /* n > 1 (tests): one context plays n ranks of genome 0's shared-out pipeline in turn --
+                                      candidate lists, table update, packed rows, polluter pass: everything but NCCL */
+int  pfb_set_option(pfb_ctx *ctx, int option, int value);
+
+/* multi-GPU, one process for all GPUs: the same run driven by one host thread over N contexts.  Genomes are
+ * added once, in params.ingroupFns order (the first to every GPU, the others round-robin); pfb_multi_locate says
+ * where a genome went, pfb_multi_context gives the context whose result calls then apply (genome indices there
+ * are the context's own). */
+typedef struct pfb_multi pfb_multi;
+int  pfb_multi_create(pfb_multi **out, const int *device_ids, int n_devices, const pfb_params *params);
+void pfb_multi_destroy(pfb_multi *m);
+const char *pfb_multi_last_error(const pfb_multi *m);
+int  pfb_multi_add_genome(pfb_multi *m, const uint8_t *bases, uint64_t n_bases, const uint64_t *contig_off, uint32_t n_contigs);
+int  pfb_multi_add_fasta(pfb_multi *m, const uint8_t *file_bytes, uint64_t n_bytes);
+int  pfb_multi_add_genbank(pfb_multi *m, const uint8_t *file_bytes, uint64_t n_bytes);
+int  pfb_multi_run(pfb_multi *m);
+int  pfb_multi_size(const pfb_multi *m);
+int  pfb_multi_context(pfb_multi *m, int index, pfb_ctx **out);
+int  pfb_multi_locate(const pfb_multi *m, uint32_t genome_idx, int *context_index, uint32_t *local_idx);
 
 /* output ---------------------------------------------------------------------------------- */
 int  pfb_result_counts(pfb_ctx *ctx, uint64_t *n_records, uint64_t *n_picked);
+/* the hot output path: the per-id columns in pinned host memory.  pfb_run / pfb_multi_run copy them out WHILE the
+ * run goes on (the records as soon as the ids exist, every genome's places as soon as it has been scanned), so
+ * that after the run only two bytes per id are still on their way; after pfb_compute the first result call
+ * fetches them.  What __buildOutput (getCandidateKmers.py:442-489) needs is word / k / Tm / GC of the picked ids
+ * and their place in every genome: columns, no per-record structs. */
+int  pfb_result_by_id(pfb_ctx *ctx, pfb_idview *out);
 int  pfb_result_records(pfb_ctx *ctx, pfb_record *out, uint64_t cap);
 /* positions of every record (picked_only = 0) or of the picked records only, in record order, in
  * the genome that was added as number `genome_idx` on this context */
 int  pfb_result_positions(pfb_ctx *ctx, uint32_t genome_idx, int picked_only, pfb_pos *out, uint64_t cap);
-/* the hot output path -- what __buildOutput (getCandidateKmers.py:442-489) needs: the picked records
- * (PFB_F_PICK) and, for every genome g of this context, start_strand_out[g * cap + i] = leftmost start
- * | strand << 31 and contig_out[g * cap + i] = contig index of picked record i (contig_out may be NULL
- * when every genome is a single contig).  cap >= n_picked is the row pitch of the two arrays.  Plain
- * device -> host copies into the caller's buffers: allocate them with pfb_host_alloc (pinned) to get
- * full PCIe bandwidth. */
+/* the picked records (PFB_F_PICK) compacted, and, for every genome g of this context, start_strand_out[g * cap
+ * + i] = leftmost start within the contig | strand << 31 and contig_out[g * cap + i] = contig index of picked
+ * record i (contig_out may be NULL).  cap >= n_picked is the row pitch of the two arrays.  Compacted on the host
+ * from the per-id columns. */
 int  pfb_result_picked(pfb_ctx *ctx, pfb_record *rec_out, uint32_t *start_strand_out, uint32_t *contig_out, uint64_t cap);
 int  pfb_host_alloc(void **out, uint64_t n_bytes);    /* cudaHostAlloc */
 int  pfb_host_free(void *ptr);

@@ -18,17 +18,21 @@ SRC_PATH = os.path.join(_HERE, "csrc", "pfb200.cu")
 INCLUDE_DIR = os.path.join(os.path.dirname(_HERE), "include")
 
 PFB_OK, PFB_EINVAL, PFB_ECUDA, PFB_ESTATE, PFB_ENOSHARED, PFB_ETOOLARGE = 0, -1, -2, -3, -4, -5
-PFB_BUF_ALIVE, PFB_BUF_PICK = 0, 1
+OPT_SCAN_MODE, OPT_FETCH_RECORDS, OPT_SHARD_FIRST, OPT_EMULATE_RANKS = 0, 1, 2, 3
 F_GC_OK, F_TM_OK, F_REP_OK, F_PICK, F_PALIN = 1, 2, 4, 8, 16
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
+NVCC_LIBS = ["-ldl"]      # NCCL is bound at run time (dlopen), only when more than one GPU takes part
 
 # every symbol include/pfb200.h declares
 EXPORTS = ["pfb_create", "pfb_destroy", "pfb_last_error", "pfb_default_params", "pfb_add_genome",
            "pfb_add_fasta", "pfb_add_genbank", "pfb_genome_info", "pfb_contig_table",
-           "pfb_clear_genomes", "pfb_upload", "pfb_upload_async", "pfb_upload_wait", "pfb_compute", "pfb_run", "pfb_compute_stage",
-           "pfb_device_buffer", "pfb_sync", "pfb_stream", "pfb_result_counts", "pfb_result_records",
+           "pfb_clear_genomes", "pfb_upload", "pfb_upload_async", "pfb_upload_wait", "pfb_compute", "pfb_run",
+           "pfb_comm_unique_id", "pfb_comm_init_rank", "pfb_set_option",
+           "pfb_multi_create", "pfb_multi_destroy", "pfb_multi_last_error", "pfb_multi_add_genome", "pfb_multi_add_fasta",
+           "pfb_multi_add_genbank", "pfb_multi_run", "pfb_multi_size", "pfb_multi_context", "pfb_multi_locate",
+           "pfb_sync", "pfb_stream", "pfb_result_counts", "pfb_result_by_id", "pfb_result_records",
            "pfb_result_positions", "pfb_result_picked", "pfb_host_alloc", "pfb_host_free", "pfb_timings", "pfb_set_scan_mode", "pfb_oligo_tm"]
 
 
@@ -45,7 +49,14 @@ class PfbTiming(C.Structure):
                 ("ms_finalize", C.c_float), ("ms_total", C.c_float), ("n_bases", C.c_uint64), ("n_windows", C.c_uint64),
                 ("n_slots", C.c_uint64), ("n_records", C.c_uint64), ("n_picked", C.c_uint64), ("n_launches", C.c_uint64),
                 ("used_filter", C.c_uint64), ("scan_main_bases", C.c_uint64), ("ms_scan_main", C.c_float),
-                ("reserved", C.c_float)]
+                ("ms_exchange", C.c_float), ("n_ids", C.c_uint64), ("sharded_first_genome", C.c_uint64),
+                ("n_reruns", C.c_uint64)]
+
+
+class PfbIdView(C.Structure):
+    _fields_ = [("n_ids", C.c_uint64), ("pitch", C.c_uint64), ("n_genomes", C.c_uint64), ("records_valid", C.c_uint64),
+                ("word", C.c_void_p), ("tm", C.c_void_p), ("info", C.c_void_p), ("pos", C.c_void_p),
+                ("alive", C.c_void_p), ("pick", C.c_void_p)]
 
 
 RECORD_DTYPE = np.dtype([("word", "<u8"), ("tm", "<f8"), ("slot", "<u4"), ("gc_count", "<u2"), ("k", "u1"), ("flags", "u1")])
@@ -60,7 +71,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     srcs.append(os.path.join(INCLUDE_DIR, "pfb200.h"))
     stale = (not os.path.exists(LIB_PATH)) or any(os.path.getmtime(f) > os.path.getmtime(LIB_PATH) for f in srcs)
     if force or stale:
-        cmd = ["nvcc"] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH, SRC_PATH]
+        cmd = ["nvcc"] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH, SRC_PATH] + NVCC_LIBS
         subprocess.check_call(cmd)
     return LIB_PATH
 
@@ -92,8 +103,22 @@ def load():
     lib.pfb_clear_genomes.argtypes = [vp]
     for fn in ("pfb_upload", "pfb_upload_async", "pfb_upload_wait", "pfb_compute", "pfb_run", "pfb_sync"):
         getattr(lib, fn).argtypes = [vp]
-    lib.pfb_compute_stage.argtypes = [vp, i32]
-    lib.pfb_device_buffer.argtypes = [vp, i32, C.POINTER(vp), C.POINTER(u64)]
+    lib.pfb_comm_unique_id.argtypes = [vp]
+    lib.pfb_comm_init_rank.argtypes = [vp, i32, i32, vp]
+    lib.pfb_set_option.argtypes = [vp, i32, i32]
+    lib.pfb_multi_create.argtypes = [C.POINTER(vp), C.POINTER(C.c_int), i32, C.POINTER(PfbParams)]
+    lib.pfb_multi_destroy.argtypes = [vp]
+    lib.pfb_multi_destroy.restype = None
+    lib.pfb_multi_last_error.argtypes = [vp]
+    lib.pfb_multi_last_error.restype = C.c_char_p
+    lib.pfb_multi_add_genome.argtypes = [vp, vp, u64, vp, u32]
+    lib.pfb_multi_add_fasta.argtypes = [vp, vp, u64]
+    lib.pfb_multi_add_genbank.argtypes = [vp, vp, u64]
+    lib.pfb_multi_run.argtypes = [vp]
+    lib.pfb_multi_size.argtypes = [vp]
+    lib.pfb_multi_context.argtypes = [vp, i32, C.POINTER(vp)]
+    lib.pfb_multi_locate.argtypes = [vp, u32, C.POINTER(C.c_int), C.POINTER(u32)]
+    lib.pfb_result_by_id.argtypes = [vp, C.POINTER(PfbIdView)]
     lib.pfb_stream.argtypes = [vp, C.POINTER(vp)]
     lib.pfb_result_counts.argtypes = [vp, C.POINTER(u64), C.POINTER(u64)]
     lib.pfb_result_records.argtypes = [vp, vp, u64]
@@ -105,7 +130,7 @@ def load():
     lib.pfb_set_scan_mode.argtypes = [vp, i32]
     lib.pfb_oligo_tm.argtypes = [vp, C.c_char_p, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     for name in EXPORTS:
-        if name not in ("pfb_destroy", "pfb_last_error"):
+        if name not in ("pfb_destroy", "pfb_last_error", "pfb_multi_destroy", "pfb_multi_last_error"):
             getattr(lib, name).restype = C.c_int
     _lib = lib
     return lib

@@ -38,6 +38,7 @@
 #include "pfb_fasta.cuh"
 
 #include <cuda_runtime.h>
+#include <dlfcn.h>
 
 #include <algorithm>
 #include <cmath>
@@ -57,7 +58,6 @@ namespace {
 constexpr uint64_t ROW_POS_MASK = 0x03FFFFFFull;   // leftmost start, genome-local padded coordinate
 constexpr uint64_t ROW_ONE = 1ull << 32;           // occupancy count lives in bits 32..59
 constexpr uint64_t ROW_CNT_MASK = 0x0FFFFFFFull;
-constexpr uint64_t ROW_MINUS = 1ull << 61;         // set by k_alive: the single occupant reads as the key's reverse complement
 constexpr uint64_t ROW_JF = 1ull << 62;            // forward-string-only polluter ('~' or non-ACGT window)
 constexpr uint64_t ROW_JR = 1ull << 63;            // reverse-string-only polluter
 constexpr uint32_t MAX_GENOME_WORDS = 1u << 21; // 2^26 padded bases
@@ -108,23 +108,29 @@ struct K {  // kernel arguments (by value, __grid_constant__)
     uint32_t *ovfCount;
     uint32_t PW16, ovfCap;
     uint32_t atWide;           // ids from here on do not fit the inline format (AT_SLOW; lowered by tests)
-    int first_pass;            // 1 while genome 1 itself is scanned (hits go to rows0[slot])
-    uint64_t nslots, nids;
-    uint64_t *key1;            // [nids] the k-mer as it reads on genome 1's (+) strand
-    uint32_t *idMeta;          // [nids] genome-1 start | (k - kmin) << 26
-    uint8_t *alive;            // [nids] 1 while unique in every genome checked so far
-    uint32_t *recIdx;          // [nids] exclusive prefix of alive = record index
-    // output
-    pfb_record *rec;
-    uint32_t *pos;            // [nGenomes][nids] (first nrec used) start within contig | strand << 31
-    uint32_t *posContig;      // [nGenomes][nids] contig index (only when some genome has > 1 contig)
-    int multiContig;
-    uint8_t *pick;            // [nrec] 0 / 1, then (stage 2) its exclusive prefix in pickOff
-    uint32_t *pickOff;
-    pfb_record *outRec;       // picked records, compacted
-    uint32_t *outPos;         // [nGenomes][nids] (rows are nids apart: the host learns nrec / npick only at the end)
-    uint32_t *outContig;      // [nGenomes][nids]
+    int first_pass;            // 1 while genome 1 itself is scanned (hits go to rows0[slot]); 2: the same for one rank's
+                               // share of genome 1 (its polluter windows are handled by k_scan_plain<true> on every rank)
+    // The host never waits for a count in the middle of a run: buffers have CAPACITIES the host knows (capSlots,
+    // capIds = the pitch of every per-id row) and the kernels read the actual counts from device memory (cnt).  A
+    // count that exceeds its capacity raises a flag in cnt[C_FLAGS]; the host sees it at the end, grows and reruns.
+    uint32_t *cnt;             // device counters, C_* below (mirrored in host-mapped memory by the kernels that total them)
+    uint32_t capSlots, capIds;
+    uint64_t *key1;            // [capIds] the k-mer as it reads on genome 1's (+) strand
+    uint32_t *idMeta;          // [capIds] genome-1 start | (k - kmin) << 26
+    uint8_t *alive;            // [capIds] 1 while unique in every genome checked so far
+    // output, indexed by id (= the reference's dict order)
+    double *idTm;              // [capIds]
+    uint16_t *idInfo;          // [capIds] (k - 1) | gc_count << 5 | flags << 11
+    uint32_t *pos32;           // [nGenomes][capIds] genome-local padded coordinate of the leftmost base | strand << 31
+    uint8_t *pick;             // [capIds] 0 / 1
+    // multi-GPU: genome 1's own pipeline is shared out by position
+    uint32_t *candList;        // [nRanks][capCand + 4]: segment r = {count, 0, 0, 0, (bin | ki << 27) ...} of rank r
+    uint32_t capCand, nRanks, rank;
+    uint32_t *rows0p;          // [capSlots] rows0 packed to 32 bits for the SUM all-reduce
 };
+
+enum { C_NSLOTS = 0, C_NIDS = 1, C_NALIVE = 2, C_NPICK = 3, C_OVF = 4, C_FLAGS = 5, C_MAXCAND = 6 };
+enum { OVF_SLOTS = 1u, OVF_IDS = 2u, OVF_LISTS = 4u, OVF_CAND = 8u };
 
 // SantaLucia (1998) nearest-neighbour table in oligotm's integer units; index = 4*first + second
 // with A0 T1 C2 G3; packed (S << 16) | H
@@ -313,10 +319,12 @@ __device__ __forceinline__ uint32_t id_of(const K &p, uint2 e, uint32_t b16) {
 __device__ __forceinline__ unsigned long long *row_of_bin(const K &p, int ki, uint32_t g, uint32_t bin) {
     if (p.first_pass) {
         const uint2 e = probe(p, ki, bin);
-        return probe_hit(e, bin) ? &p.rows0[slot_of(e, bin)] : nullptr;
+        if (!probe_hit(e, bin)) return nullptr;
+        const uint32_t slot = slot_of(e, bin);
+        return slot < p.capSlots ? &p.rows0[slot] : nullptr;      // (beyond the capacity: flagged by k_alive1, the run is repeated)
     }
     const uint32_t id = id_of(p, probe2(p, ki, bin), bin & 15u);
-    return id == ID_NONE ? nullptr : &p.rows[(size_t)(g - 1) * p.nids + id];
+    return id == ID_NONE ? nullptr : &p.rows[(size_t)(g - 1) * p.capIds + id];
 }
 
 __device__ __forceinline__ void pollute(const K &p, int ki, uint32_t g, uint64_t canon, bool rev_table) {
@@ -379,7 +387,18 @@ __device__ __forceinline__ bool load_pos(const K &p, uint32_t b, PosState &s) {
 //      canonical hash and the table update run with full warps instead of a few live lanes per k.
 constexpr int CAND_POS = 256;
 
-__global__ void __launch_bounds__(CAND_POS + 32) k_cand1(const __grid_constant__ K p, uint32_t nbases) {
+// Multi-GPU (LIST): a rank works on its share of genome 1's CTAs and, instead of updating the table, appends
+// (bin | ki << 27) to its segment of candList; the segments are all-gathered and every rank applies all of them
+// (k_apply_cands), so the tables end up identical everywhere -- the order of the updates does not matter.
+__device__ __forceinline__ void cand_table_update(const K &p, int ki, uint32_t bin) {
+    uint32_t *cell = &p.sk[(size_t)ki * 2 * p.PW + (bin >> 4)];
+    const uint32_t bbit = bin & 15u;
+    const uint32_t old = atomicOr(cell, 1u << bbit);
+    if ((old >> bbit) & 1u) atomicOr(cell, 1u << (16 + bbit));
+}
+
+template <bool LIST>
+__global__ void __launch_bounds__(CAND_POS + 32) k_cand1(const __grid_constant__ K p, uint32_t nbases, uint32_t cta0) {
     __shared__ uint32_t s_nn[16];
     __shared__ uint32_t s_P[CAND_POS + 32];
     __shared__ uint32_t s_wsum[(CAND_POS + 32) / 32];
@@ -398,7 +417,7 @@ __global__ void __launch_bounds__(CAND_POS + 32) k_cand1(const __grid_constant__
     }
     __syncthreads();
     // thread t <-> end position b = first position of the CTA - 32 + t (warp 0 is the halo)
-    const long long bb = (long long)blockIdx.x * CAND_POS - 32 + tid;
+    const long long bb = (long long)(blockIdx.x + cta0) * CAND_POS - 32 + tid;
     PosState s;
     s.hf = 0; s.hr = 0; s.nmw = ~0ull; s.n = 0; s.g = 0; s.gpos = 0;
     const bool have = bb >= 0 && bb < (long long)nbases && load_pos(p, (uint32_t)bb, s);
@@ -454,25 +473,50 @@ __global__ void __launch_bounds__(CAND_POS + 32) k_cand1(const __grid_constant__
     }
     __syncwarp();
     const uint32_t hf_lo = (uint32_t)hf, hf_hi = (uint32_t)(hf >> 32);
+    uint32_t *seg = LIST ? p.candList + (size_t)p.rank * (p.capCand + 4u) : nullptr;
     for (uint32_t base = 0; base < n_items; base += 32) {
         const bool live = base + lane < n_items;
         const uint32_t it = live ? items[base + lane] : 0u;
         const uint32_t src = it & 31u;
         const int ki = (int)(it >> 5), k = p.kmin + ki;
         const uint64_t w = ((uint64_t)__shfl_sync(0xFFFFFFFFu, hf_hi, src) << 32) | __shfl_sync(0xFFFFFFFFu, hf_lo, src);
-        if (!live) continue;
-        const uint64_t h = w & s_km2[ki];
-        const uint64_t r = rc64(h) >> (64 - 2 * k);
-        if (pre) {
-            const uint32_t pi = warp * 32 + src;
-            const uint32_t acc = s_P[pi] - s_P[pi - (uint32_t)(k - 1)];
-            if (!tm_in_range(acc, h, k, __popcll(h & 0xAAAAAAAAAAAAAAAAull), p, r == h)) continue;
+        bool ok = live;
+        uint32_t bin = 0;
+        if (ok) {
+            const uint64_t h = w & s_km2[ki];
+            const uint64_t r = rc64(h) >> (64 - 2 * k);
+            if (pre) {
+                const uint32_t pi = warp * 32 + src;
+                const uint32_t acc = s_P[pi] - s_P[pi - (uint32_t)(k - 1)];
+                ok = tm_in_range(acc, h, k, __popcll(h & 0xAAAAAAAAAAAAAAAAull), p, r == h);
+            }
+            if (ok) bin = mod_p(h < r ? h : r, p);
         }
-        const uint32_t bin = mod_p(h < r ? h : r, p);
-        uint32_t *cell = &p.sk[(size_t)ki * 2 * p.PW + (bin >> 4)];
-        const uint32_t bbit = bin & 15u;
-        const uint32_t old = atomicOr(cell, 1u << bbit);
-        if ((old >> bbit) & 1u) atomicOr(cell, 1u << (16 + bbit));
+        if (LIST) {
+            const uint32_t m = __ballot_sync(0xFFFFFFFFu, ok);
+            if (m) {
+                uint32_t at = 0;
+                if (lane == 0) at = atomicAdd(seg, (uint32_t)__popc(m));
+                at = __shfl_sync(0xFFFFFFFFu, at, 0) + __popc(m & lt_mask);
+                if (ok && at < p.capCand) seg[4u + at] = bin | ((uint32_t)ki << 27);   // (a full segment: flagged by k_apply_cands)
+            }
+        } else if (ok) {
+            cand_table_update(p, ki, bin);
+        }
+    }
+}
+
+// every rank's candidates -> this rank's table
+__global__ void __launch_bounds__(256) k_apply_cands(const __grid_constant__ K p) {
+    const uint32_t stride = gridDim.x * blockDim.x, t0 = blockIdx.x * blockDim.x + threadIdx.x;
+    for (uint32_t r = 0; r < p.nRanks; r++) {
+        const uint32_t *seg = p.candList + (size_t)r * (p.capCand + 4u);
+        uint32_t n = seg[0];
+        if (n > p.capCand) { if (t0 == 0) { atomicOr(&p.cnt[C_FLAGS], OVF_CAND); atomicMax(&p.cnt[C_MAXCAND], n); } n = p.capCand; }
+        for (uint32_t i = t0; i < n; i += stride) {
+            const uint32_t e = seg[4u + i];
+            cand_table_update(p, (int)(e >> 27), e & 0x07FFFFFFu);
+        }
     }
 }
 
@@ -482,14 +526,18 @@ __global__ void __launch_bounds__(CAND_POS + 32) k_cand1(const __grid_constant__
 // One thread per 32-base word = 32 end positions x nk lengths with rolling words.
 // Implements sketch membership (:54-55), the strand algebra (:58-63), the per-k intersection
 // (:127-142) and the relocation (:160-187) in one probe.
+// POLLUTERS: only the windows with a non-ACGT byte (the strand-specific polluters) -- run by every rank over all
+// of genome 1 after a shared-out first pass (first_pass == 2), whose own scans leave them alone.
+template <bool POLLUTERS>
 __global__ void __launch_bounds__(256) k_scan_plain(const __grid_constant__ K p, uint32_t w0, uint32_t w1) {
     uint32_t w = w0 + blockIdx.x * blockDim.x + threadIdx.x;
     if (w >= w1) return;
     uint32_t c = p.wordContig[w];
     uint32_t cws = p.cWordStart[c], clen = p.cLen[c], g = p.cGenome[c];
     uint32_t i = w - cws;
-    uint64_t cur = p.seq2[w], prev = i ? p.seq2[w - 1] : 0ull;
     uint64_t nm = ((uint64_t)(i ? p.nmask[w - 1] : 0u) << 32) | p.nmask[w];
+    if (POLLUTERS && nm == 0) return;
+    uint64_t cur = p.seq2[w], prev = i ? p.seq2[w - 1] : 0ull;
     uint64_t hf = prev, hr = rc64(prev);
     uint32_t qbase = 32u * i;
     int nj = (int)min(32u, clen - qbase);
@@ -506,7 +554,8 @@ __global__ void __launch_bounds__(256) k_scan_plain(const __grid_constant__ K p,
             int ki = k - p.kmin;
             uint64_t h = hf & kmask2(k), r = hr >> (64 - 2 * k);
             uint32_t wn = (uint32_t)(nmw & kmask1(k));
-            if (wn) { pollute_invalid_window(p, ki, k, g, h, r, wn); continue; }
+            if (wn) { if (POLLUTERS || p.first_pass != 2) pollute_invalid_window(p, ki, k, g, h, r, wn); continue; }
+            if (POLLUTERS) continue;
             uint64_t canon = h < r ? h : r;
             uint32_t bin = mod_p(canon, p);
             unsigned long long *row = row_of_bin(p, ki, g, bin);
@@ -561,10 +610,11 @@ __device__ __forceinline__ void drain_consume(const K &p, const Pending &pd) {
     const uint32_t b = pd.meta >> 26;          // bin & 31: all the two tables need of the bin besides the probe word
     const unsigned long long add = ROW_ONE | (pd.meta & (uint32_t)ROW_POS_MASK);
     if (p.first_pass) {
-        if ((pd.e.x >> b) & 1u) atomicAdd(&p.rows0[pd.e.y + __popc(pd.e.x & ((1u << b) - 1u))], add);
+        const uint32_t slot = pd.e.y + __popc(pd.e.x & ((1u << b) - 1u));
+        if (((pd.e.x >> b) & 1u) && slot < p.capSlots) atomicAdd(&p.rows0[slot], add);
     } else {
         const uint32_t id = id_of(p, pd.e, b & 15u);
-        if (id != ID_NONE) atomicAdd(&p.rows[(size_t)(pd.g - 1) * p.nids + id], add);
+        if (id != ID_NONE) atomicAdd(&p.rows[(size_t)(pd.g - 1) * p.capIds + id], add);
     }
 }
 
@@ -637,7 +687,8 @@ __device__ __forceinline__ void scan_word(const K &p, int ki, int k, ScanWarp &s
                 valid = (vmask >> j) & 1u;
                 uint32_t wn = (uint32_t)((nm >> (31 - j)) & km1);
                 if (valid && wn) {
-                    pollute_invalid_window(p, ki, k, g, (((uint64_t)h_hi) << 32) | h_lo, (((uint64_t)r_hi) << 32) | r_lo, wn);
+                    if (p.first_pass != 2)
+                        pollute_invalid_window(p, ki, k, g, (((uint64_t)h_hi) << 32) | h_lo, (((uint64_t)r_hi) << 32) | r_lo, wn);
                     valid = 0;
                 }
             }
@@ -769,10 +820,19 @@ __device__ __forceinline__ uint32_t assign_id(const K &p, uint32_t slot, int ki)
     const uint32_t end = start + (uint32_t)k - 1u;
     const uint32_t m = p.emitMask[end];
     const uint32_t id = p.emitOff[end] + __popc(ki < 31 ? (m >> (ki + 1)) : 0u);
+    if (id >= p.capIds) {            // more ids than the buffers hold: the host grows them and repeats the run
+        atomicOr(&p.cnt[C_FLAGS], OVF_IDS);
+        p.remap[slot] = ID_NONE;
+        return ID_NONE;
+    }
+    const uint64_t key = window_at(p, 0, start, k);
     p.remap[slot] = id;
-    p.key1[id] = window_at(p, 0, start, k);
+    p.key1[id] = key;
     p.idMeta[id] = start | ((uint32_t)ki << 26);
     p.alive[id] = 1;
+    // genome 1: every key sits on its (+) strand; a palindrome matches both scans and the later '-' match
+    // overwrites (getCandidateKmers.py:181-187)
+    p.pos32[id] = start | (((rc64(key) >> (64 - 2 * k)) == key) ? 0x80000000u : 0u);
     return id;
 }
 
@@ -791,8 +851,9 @@ __global__ void __launch_bounds__(256) k_build_at(const __grid_constant__ K p, i
             uint32_t bm = 0, n = 0, id0 = 0, id1 = 0;
             bool wide = false;
             for (uint32_t m = half; m; m &= m - 1, slot++) {
-                if (p.remap[slot] == ID_NONE) continue;         // k_alive1: not unique in genome 1
+                if (slot >= p.capSlots || p.remap[slot] == ID_NONE) continue;         // k_alive1: not unique in genome 1
                 const uint32_t id = assign_id(p, slot, (int)ki);
+                if (id == ID_NONE) continue;
                 bm |= 1u << (__ffs(m) - 1);
                 if (n == 0) id0 = id; else if (n == 1) id1 = id;
                 wide |= id >= p.atWide;
@@ -802,7 +863,11 @@ __global__ void __launch_bounds__(256) k_build_at(const __grid_constant__ K p, i
                 const uint32_t idx = atomicAdd(p.ovfCount, 1u);
                 if (idx < p.ovfCap) {
                     slot = e.y + ((wi & 1u) ? __popc(e.x & 0xFFFFu) : 0u);
-                    for (uint32_t m = half; m; m &= m - 1, slot++) p.ovf[(size_t)idx * 16u + (__ffs(m) - 1)] = p.remap[slot];
+                    for (uint32_t m = half; m; m &= m - 1, slot++)
+                        p.ovf[(size_t)idx * 16u + (__ffs(m) - 1)] = slot < p.capSlots ? p.remap[slot] : ID_NONE;
+                } else {
+                    atomicOr(&p.cnt[C_FLAGS], OVF_LISTS);
+                    bm = 0; n = 0;
                 }
                 id0 = AT_SLOW; id1 = idx;
             }
@@ -874,6 +939,16 @@ __global__ void __launch_bounds__(256) k_zero(const ZeroArgs a) {
     const uint4 z = make_uint4(0u, 0u, 0u, 0u);
     for (int b = 0; b < a.cnt; b++)
         for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.n16[b]; i += (size_t)gridDim.x * blockDim.x) a.p[b][i] = z;
+}
+
+// the first n entries (n = min(*n_dev, cap): a count only the device knows) of each of `nrows` rows of `pitch`
+// 8-byte words: the per-genome rows are allocated by capacity and zeroed by need
+__global__ void __launch_bounds__(256) k_zero_rows(unsigned long long *base, uint32_t pitch, uint32_t nrows, const uint32_t *n_dev, uint32_t cap) {
+    const uint32_t n = min(*n_dev, cap);
+    const uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) * 2u;     // pitch is a multiple of 256: rows stay 16-byte aligned
+    if (i >= n) return;
+    const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+    for (uint32_t r = blockIdx.y; r < nrows; r += gridDim.y) *(uint4 *)(base + (size_t)r * pitch + i) = z;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1005,8 +1080,10 @@ __global__ void __launch_bounds__(256) k_alive1(const __grid_constant__ K p) {
     __shared__ uint32_t s_base[32];
     if (threadIdx.x < (unsigned)p.nk) s_base[threadIdx.x] = p.br[(size_t)threadIdx.x * p.PW].y;
     __syncthreads();
+    const uint32_t nslots = p.cnt[C_NSLOTS];
+    if (nslots > p.capSlots && blockIdx.x == 0 && threadIdx.x == 0) atomicOr(&p.cnt[C_FLAGS], OVF_SLOTS);
     uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= p.nslots) return;
+    if (idx >= min(nslots, p.capSlots)) return;
     const int ki = slot_ki(s_base, p.nk, (uint32_t)idx);
     const int k = p.kmin + ki;
     unsigned long long v0 = p.rows0[idx];
@@ -1029,180 +1106,169 @@ __global__ void __launch_bounds__(256) k_assign_ids(const __grid_constant__ K p)
     if (threadIdx.x < (unsigned)p.nk) s_base[threadIdx.x] = p.br[(size_t)threadIdx.x * p.PW].y;
     __syncthreads();
     uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= p.nslots || p.remap[idx] == ID_NONE) return;
+    if (idx >= min(p.cnt[C_NSLOTS], p.capSlots) || p.remap[idx] == ID_NONE) return;
     assign_id(p, (uint32_t)idx, slot_ki(s_base, p.nk, (uint32_t)idx));
 }
 
-// k_aliveN: the rules for one (id, genome >= 2) per thread; ids follow genome 1's coordinates, so the rows
-// stream and -- for genomes that are largely collinear with genome 1 -- so do the read-backs
+// multi-GPU, genome 1's own pass shared out by position: every rank's rows0 holds the windows of ITS share.  What
+// the rules need of a row is "exactly one window in the bin, and where": count saturated at 3 and the start of a
+// lone window fit 32 bits whose plain SUM over the ranks keeps both (count in bits 26.., a carry out of the start
+// field can only occur when two ranks contributed, i.e. when the count says >= 2 anyway).  Half the bytes of the
+// 64-bit rows on the wire; the polluter flags are not exchanged: every rank re-derives them (k_scan_plain<true>,
+// k_junction), they are few.
+__global__ void __launch_bounds__(256) k_rows0_pack(const __grid_constant__ K p) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= p.capSlots) return;
+    const unsigned long long v = p.rows0[i];
+    const uint32_t c = (uint32_t)min((unsigned long long)3, (v >> 32) & ROW_CNT_MASK);
+    p.rows0p[i] = (c << 26) | (c == 1 ? (uint32_t)(v & ROW_POS_MASK) : 0u);
+}
+
+__global__ void __launch_bounds__(256) k_rows0_unpack(const __grid_constant__ K p) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= p.capSlots) return;
+    const uint32_t v = p.rows0p[i];
+    const uint32_t c = v >> 26;
+    p.rows0[i] = ((unsigned long long)min(c, 2u) << 32) | (c == 1 ? (v & (uint32_t)ROW_POS_MASK) : 0u);
+}
+
+// k_aliveN: the rules for one (id, genome >= 2) per thread, for the genomes [ga, gb) of this context; ids follow
+// genome 1's coordinates, so the rows stream and -- for genomes that are largely collinear with genome 1 -- so do
+// the read-backs.  The verdict goes to alive[], the place and strand to pos32 (what the output and k_pick read:
+// half the bytes of the rows, which are not touched again).
 constexpr uint32_t ALIVE_GPT = 2;   // genomes per thread: two independent row -> genome-word load chains in flight
 
-__global__ void __launch_bounds__(256) k_aliveN(const __grid_constant__ K p) {
+__global__ void __launch_bounds__(256) k_aliveN(const __grid_constant__ K p, uint32_t ga, uint32_t gb) {
     const uint64_t id = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (id >= p.nids) return;
-    const uint32_t g0 = 1u + blockIdx.y * ALIVE_GPT;
+    if (id >= min(p.cnt[C_NIDS], p.capIds)) return;
+    const uint32_t g0 = ga + blockIdx.y * ALIVE_GPT;
     const int k = p.kmin + (int)(p.idMeta[id] >> 26);
     const uint64_t key = p.key1[id];
     const uint64_t rc = rc64(key) >> (64 - 2 * k);
     unsigned long long v[ALIVE_GPT];
     uint64_t h[ALIVE_GPT];
 #pragma unroll
-    for (uint32_t i = 0; i < ALIVE_GPT; i++) v[i] = g0 + i < p.nGenomes ? p.rows[(size_t)(g0 + i - 1) * p.nids + id] : 0ull;
+    for (uint32_t i = 0; i < ALIVE_GPT; i++) v[i] = g0 + i < gb ? p.rows[(size_t)(g0 + i - 1) * p.capIds + id] : 0ull;
 #pragma unroll
     for (uint32_t i = 0; i < ALIVE_GPT; i++)
         h[i] = ((v[i] >> 32) & ROW_CNT_MASK) == 1 ? window_at(p, g0 + i, (uint32_t)(v[i] & ROW_POS_MASK), k) : 0ull;
 #pragma unroll
     for (uint32_t i = 0; i < ALIVE_GPT; i++) {
-        if (g0 + i >= p.nGenomes) break;
+        if (g0 + i >= gb) break;
         const int st = row_state_h(v[i], h[i], key, rc, key == rc, false);
         if (st == 0) p.alive[id] = 0;
-        else if (st == 2) p.rows[(size_t)(g0 + i - 1) * p.nids + id] = v[i] | ROW_MINUS;     // k_positions reads the strand from here
+        p.pos32[(size_t)(g0 + i) * p.capIds + id] = st ? ((uint32_t)(v[i] & ROW_POS_MASK) | (st == 2 ? 0x80000000u : 0u)) : 0u;
     }
 }
 
-// k_emit_write: the record of every id that is unique in every genome, at its rank among those
-__global__ void __launch_bounds__(256) k_emit_write(const __grid_constant__ K p) {
+// k_id_records: Tm, GC count, length and filter flags of every id (functions of the key alone: computed as soon
+// as the ids exist, so that they can travel to the host while the other genomes are still being scanned)
+__global__ void __launch_bounds__(256) k_id_records(const __grid_constant__ K p) {
     __shared__ uint32_t s_nn[16];
     if (threadIdx.x < 16) s_nn[threadIdx.x] = c_nn[threadIdx.x];
     __syncthreads();
     const uint64_t id = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (id >= p.nids || !p.alive[id]) return;
+    if (id >= min(p.cnt[C_NIDS], p.capIds)) return;
     const int k = p.kmin + (int)(p.idMeta[id] >> 26);
     const uint64_t h = p.key1[id];
-    pfb_record rec;
     double tm;
     uint32_t f = filter_flags(h, k, p, s_nn, &tm);
     if ((rc64(h) >> (64 - 2 * k)) == h) f |= PFB_F_PALIN;
-    rec.word = h; rec.tm = tm; rec.slot = (uint32_t)id; rec.gc_count = (uint16_t)gc_count(h);
-    rec.k = (uint8_t)k; rec.flags = (uint8_t)f;
-    p.rec[p.recIdx[id]] = rec;
+    p.idTm[id] = tm;
+    p.idInfo[id] = (uint16_t)((uint32_t)(k - 1) | ((uint32_t)gc_count(h) << 5) | (f << 11));
 }
 
-// k_positions: (contig, leftmost start, strand) of every record in every genome
-// (getCandidateKmers.py:173-187) and the per-position pick (:222-247, 376-388): a record is picked when,
-// in at least one genome, no earlier record that passes the filters sits at the same (contig, start).
+// k_pick: the per-position pick (getCandidateKmers.py:222-247, 376-388): a k-mer is picked when, in at least one
+// genome, no earlier k-mer that passes the filters sits at the same (contig, start).
 // Group mates need no sort and no per-position array: two shared k-mers that start at the same place of
 // some genome read the same sequence there, so one is a prefix of the other ('+' strand) or a suffix of it
 // ('-' strand), and as both are unique in genome 1 they share their START (resp. their END) in genome 1.
 // The only possible earlier mates of record (start1, k) are therefore the records (same end1, k' > k) and
 // (same start1, k' < k), which the emit bitmap locates directly; whether such a record really is a mate
-// in genome g is decided by comparing the two starts in g.  One thread per id, loop over genomes: every
-// access of the loop is coalesced (rows, mates' rows and coordinates are all in id order).
+// in genome g is decided by comparing the two places in g.  One thread per id, loop over genomes: every
+// access of the loop is coalesced (places are in id order).
 struct Mates {
     static constexpr int CAP = 8;
     uint32_t id[CAP];
-    uint32_t same_start;    // bit i: mate i shares the START in genome 1 (so it is a mate there)
     int n;                  // > CAP: overflow, re-enumerate per genome
 };
 
-__device__ __forceinline__ bool mate_passes(const K &p, uint32_t mid) {
-    return p.alive[mid] && (p.rec[p.recIdx[mid]].flags & 7u) == 7u;
+__device__ __forceinline__ bool id_passes(const K &p, uint32_t id) {
+    return p.alive[id] && ((p.idInfo[id] >> 11) & 7u) == 7u;
 }
 
-// visits the earlier potential mates of (start1, ki); f(mate id, shares start) returns true to stop
+// visits the earlier potential mates of (start1, ki); f(mate id) returns true to stop
 template <typename F>
 __device__ __forceinline__ bool for_each_mate(const K &p, uint32_t start1, int ki, F f) {
     const uint32_t end1 = start1 + (uint32_t)(p.kmin + ki) - 1u;
     const uint32_t m = p.emitMask[end1], off = p.emitOff[end1];
     for (uint32_t hi = ki < 31 ? (m >> (ki + 1)) : 0u, kj = ki + 1; hi; hi >>= 1, kj++)        // same end, longer
-        if ((hi & 1u) && f(off + __popc(kj < 31 ? (m >> (kj + 1)) : 0u), false)) return true;
+        if ((hi & 1u) && f(off + __popc(kj < 31 ? (m >> (kj + 1)) : 0u))) return true;
     for (int kj = 0; kj < ki; kj++) {                                                            // same start, shorter
         const uint32_t e2 = start1 + (uint32_t)(p.kmin + kj) - 1u;
         const uint32_t m2 = p.emitMask[e2];
-        if (((m2 >> kj) & 1u) && f(p.emitOff[e2] + __popc(m2 >> (kj + 1)), true)) return true;
+        if (((m2 >> kj) & 1u) && f(p.emitOff[e2] + __popc(m2 >> (kj + 1)))) return true;
     }
     return false;
 }
 
-__global__ void __launch_bounds__(256) k_positions(const __grid_constant__ K p) {
+__global__ void __launch_bounds__(256) k_pick(const __grid_constant__ K p) {
     const uint64_t id = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (id >= p.nids || !p.alive[id]) return;
-    const uint32_t r = p.recIdx[id];
-    const uint32_t flags = p.rec[r].flags;
-    const bool pass = (flags & 7u) == 7u;
+    if (id >= min(p.cnt[C_NIDS], p.capIds) || !id_passes(p, (uint32_t)id)) return;
     const uint32_t meta = p.idMeta[id];
     const uint32_t start1 = meta & (uint32_t)ROW_POS_MASK;
     const int ki = (int)(meta >> 26);
     Mates mt;
-    mt.n = 0; mt.same_start = 0;
-    if (pass)
-        for_each_mate(p, start1, ki, [&](uint32_t mid, bool same_start) {
-            if (mate_passes(p, mid)) {
-                if (mt.n < Mates::CAP) { mt.id[mt.n] = mid; if (same_start) mt.same_start |= 1u << mt.n; }
-                mt.n++;
-            }
-            return false;
-        });
+    mt.n = 0;
+    for_each_mate(p, start1, ki, [&](uint32_t mid) {
+        if (mid < p.capIds && id_passes(p, mid)) {
+            if (mt.n < Mates::CAP) mt.id[mt.n] = mid;
+            mt.n++;
+        }
+        return false;
+    });
+    bool picked = mt.n == 0;
     const bool overflow = mt.n > Mates::CAP;
-    bool picked = false;
-    auto one_genome = [&](uint32_t g, unsigned long long v) {
-        uint32_t lp, minus;
-        if (g == 0) {
-            lp = start1;
-            minus = (flags & PFB_F_PALIN) ? 1u : 0u;    // a palindrome matches both scans, the later '-' match overwrites (:181-187)
-        } else {
-            lp = (uint32_t)(v & ROW_POS_MASK);
-            minus = (uint32_t)(v >> 61) & 1u;           // left there by k_aliveN
-        }
-        uint32_t start = lp;                            // single-contig genomes: the padded coordinate is the start
-        if (p.multiContig) {
-            const uint32_t c = p.wordContig[p.gWordStart[g] + (lp >> 5)];
-            start = lp - 32u * (p.cWordStart[c] - p.gWordStart[g]);
-            p.posContig[(size_t)g * p.nids + r] = c - p.gFirstContig[g];
-        }
-        p.pos[(size_t)g * p.nids + r] = start | (minus << 31);
-        if (pass && !picked) {
+    // the places of four genomes are requested before the first is used: four times the bytes in flight per thread
+    for (uint32_t g0 = 0; g0 < p.nGenomes && !picked; g0 += 4) {
+        uint32_t lp[4];
+#pragma unroll
+        for (uint32_t i = 0; i < 4; i++) lp[i] = g0 + i < p.nGenomes ? p.pos32[(size_t)(g0 + i) * p.capIds + id] & 0x7FFFFFFFu : 0u;
+#pragma unroll
+        for (uint32_t i = 0; i < 4; i++) {
+            if (g0 + i >= p.nGenomes || picked) continue;
+            const uint32_t *row = p.pos32 + (size_t)(g0 + i) * p.capIds;
             bool first = true;
             if (overflow) {
-                first = !for_each_mate(p, start1, ki, [&](uint32_t mid, bool same_start) {
-                    if (!mate_passes(p, mid)) return false;
-                    return g == 0 ? same_start : (uint32_t)(p.rows[(size_t)(g - 1) * p.nids + mid] & ROW_POS_MASK) == lp;
+                first = !for_each_mate(p, start1, ki, [&](uint32_t mid) {
+                    return mid < p.capIds && id_passes(p, mid) && (row[mid] & 0x7FFFFFFFu) == lp[i];
                 });
-            } else if (g == 0) {
-                first = mt.same_start == 0;
             } else {
-                for (int i = 0; i < mt.n; i++)
-                    if ((uint32_t)(p.rows[(size_t)(g - 1) * p.nids + mt.id[i]] & ROW_POS_MASK) == lp) first = false;
+                for (int j = 0; j < mt.n; j++)
+                    if ((row[mt.id[j]] & 0x7FFFFFFFu) == lp[i]) first = false;
             }
             picked = first;
         }
-    };
-    one_genome(0, 0ull);
-    // the rows of four genomes are requested before the first is used: four times the bytes in flight per thread
-    for (uint32_t g0 = 1; g0 < p.nGenomes; g0 += 4) {
-        unsigned long long v[4];
-#pragma unroll
-        for (uint32_t i = 0; i < 4; i++) v[i] = g0 + i < p.nGenomes ? p.rows[(size_t)(g0 + i - 1) * p.nids + id] : 0ull;
-#pragma unroll
-        for (uint32_t i = 0; i < 4; i++)
-            if (g0 + i < p.nGenomes) one_genome(g0 + i, v[i]);
     }
-    if (picked) p.pick[r] = 1;
+    if (picked) p.pick[id] = 1;
 }
 
-// k_compact: picked records and their coordinates in every genome, densely packed for the D2H copy
-__global__ void __launch_bounds__(256) k_compact(const __grid_constant__ K p) {
-    uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= p.nids) return;                    // pick is 0 beyond the last record
-    if (!p.pick[r]) return;
-    p.rec[r].flags |= PFB_F_PICK;
-    uint32_t o = p.pickOff[r];
-    pfb_record rec = p.rec[r];
-    p.outRec[o] = rec;
-    for (uint32_t g0 = 0; g0 < p.nGenomes; g0 += 4) {     // four loads in flight before the first store
-        uint32_t a[4], c[4];
-#pragma unroll
-        for (uint32_t i = 0; i < 4; i++) {
-            a[i] = g0 + i < p.nGenomes ? p.pos[(size_t)(g0 + i) * p.nids + r] : 0u;
-            c[i] = (p.multiContig && g0 + i < p.nGenomes) ? p.posContig[(size_t)(g0 + i) * p.nids + r] : 0u;
-        }
-#pragma unroll
-        for (uint32_t i = 0; i < 4; i++) {
-            if (g0 + i >= p.nGenomes) break;
-            p.outPos[(size_t)(g0 + i) * p.nids + o] = a[i];
-            if (p.multiContig) p.outContig[(size_t)(g0 + i) * p.nids + o] = c[i];
-        }
+// k_count: shared k-mers and picked ones (the two numbers the host reports; the arrays stay indexed by id)
+__global__ void __launch_bounds__(256) k_count(const __grid_constant__ K p) {
+    const uint32_t n = min(p.cnt[C_NIDS], p.capIds);
+    uint32_t a = 0, b = 0;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) { a += p.alive[i]; b += p.pick[i]; }
+    for (int o = 16; o; o >>= 1) { a += __shfl_xor_sync(0xFFFFFFFFu, a, o); b += __shfl_xor_sync(0xFFFFFFFFu, b, o); }
+    if ((threadIdx.x & 31) == 0) {
+        if (a) atomicAdd(&p.cnt[C_NALIVE], a);
+        if (b) atomicAdd(&p.cnt[C_NPICK], b);
     }
+}
+
+// the counters -> host-mapped memory (read by the host after the stream synchronise that ends a run: no
+// device -> host copy that would queue up behind the result copies)
+__global__ void k_publish(const uint32_t *cnt, uint32_t *host_counts) {
+    if (threadIdx.x < 8) host_counts[threadIdx.x] = cnt[threadIdx.x];
 }
 
 __global__ void k_oligo(const __grid_constant__ K p, uint64_t h, int k, double *out) {
@@ -1239,6 +1305,30 @@ struct FaBatch {
 
 }  // namespace
 
+// ------------------------------------------------------------------------------------------
+// NCCL, bound at run time (dlopen): a single-GPU user needs no NCCL at all, a torch process gets the copy
+// torch has already loaded (same soname), anything else the system library.
+namespace nccl {
+struct Comm;
+struct UniqueId { char internal[128]; };
+enum { SUM = 0, MAX = 2, MIN = 3 };
+enum { U8 = 1, U32 = 3 };
+struct Api {
+    void *handle = nullptr;
+    int (*GetUniqueId)(UniqueId *) = nullptr;
+    int (*CommInitRank)(Comm **, int, UniqueId, int) = nullptr;
+    int (*CommInitAll)(Comm **, int, const int *) = nullptr;
+    int (*CommDestroy)(Comm *) = nullptr;
+    int (*AllReduce)(const void *, void *, size_t, int, int, Comm *, cudaStream_t) = nullptr;
+    int (*AllGather)(const void *, void *, size_t, int, Comm *, cudaStream_t) = nullptr;
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
+    const char *(*GetErrorString)(int) = nullptr;
+};
+}  // namespace nccl
+
+struct pfb_multi;
+
 struct pfb_ctx {
     int device = 0;
     int num_sms = 148;
@@ -1247,14 +1337,15 @@ struct pfb_ctx {
     std::string err;
     cudaStream_t stream = nullptr;
     cudaStream_t copyStream = nullptr;          // H2D copies of pfb_run run here, overlapped with compute
+    cudaStream_t d2hStream = nullptr;           // result copies of pfb_run run here, overlapped with compute
     std::vector<cudaEvent_t> evCopy;            // one per genome: its bases have arrived
+    std::vector<cudaEvent_t> evOut;             // result pieces ready for their device -> host copy
     bool pipelined = false;
     // PFB200_TRACE=1: timestamps (ms after the first H2D copy was queued) of the pipeline's milestones on stderr
-    volatile uint32_t *countsHost = nullptr;    // mapped pinned: [0] nslots, [1] nids, [2] nrec, [3] npick as written by the scans
+    volatile uint32_t *countsHost = nullptr;    // mapped pinned: the C_* counters as published by the last run
     uint32_t *countsDev = nullptr;              // the same memory as the device sees it
     uint32_t at_wide = 0xFFFFFFu;               // PFB200_AT_WIDE lowers it so that tests reach the id-list path
     bool fterm_uploaded = false;
-    size_t encoded_upto = 0;                    // pipelined run: genomes [0, encoded_upto) are packed already
     bool tracing = false;
     std::vector<std::pair<std::string, cudaEvent_t>> trace;
     // FASTA ingest: file images are staged in `fa`, parsed on parseStream, record tables land in mapped host memory
@@ -1270,7 +1361,9 @@ struct pfb_ctx {
     std::vector<uint32_t> t32host, t32hostb;    // contig / genome tables (kept alive for the async copy)
     std::vector<uint64_t> t64host, t64hostb;
     uint64_t totalFa = 0, fa_launches = 0;
-    cudaEvent_t ev[10]{};
+    cudaEvent_t ev[12]{};
+    cudaEvent_t evX[4][2]{};                    // around each collective of a run
+    bool xUsed[4] = {false, false, false, false};
     std::vector<HostGenome> genomes;
     // layout (host)
     std::vector<uint32_t> cWordStart, cLen, cGenome, cVirt, gWordStart, gFirstContig, gNumContigs, gVirtLen;
@@ -1278,15 +1371,51 @@ struct pfb_ctx {
     uint64_t totalRaw = 0;
     uint32_t totalWords = 0;
     bool uploaded = false, computed = false;
-    int stage_done = -1;
+    // capacities (see K): `cap*` is what the kernels of the next run are given, `alloc*` what the buffers hold;
+    // `last*` the counts of the last completed run (0: none yet)
+    uint32_t capSlots = 0, capIds = 0, capCand = 0, capCandMin = 0;
+    uint64_t lastSlots = 0, lastIds = 0;
+    double cap_share = 0.0;                     // PFB200_CAP_SHARE (tests): a-priori share of genome 1's windows the buffers are sized for
+    int reruns = 0;                             // runs repeated because a capacity was too small (all runs of the context)
+    int caps_for_prefilter = -1;
+    uint64_t caps_for_windows = 0;
+    // multi-GPU
+    nccl::Comm *comm = nullptr;
+    bool comm_owned = false;
+    int nRanks = 1, rank = 0;
+    int shard_g1 = 1;                           // share genome 1's own pipeline out over the ranks (PFB200_SHARD_G1=0 disables)
+    bool sharded_now = false;                   // ... and whether the current run does
+    int fetch_records = 1;                      // 0: the per-id records stay on the device (ranks > 0 of a job: identical everywhere)
+    int emulate_ranks = 0;                      // > 1 (tests): ONE context plays that many ranks of the shared-out genome-1
+                                                // pipeline one after the other (lists, table update, packed rows: all but NCCL)
+    int eff_ranks() const { return emulate_ranks > 1 ? emulate_ranks : nRanks; }
+    pfb_multi *owner = nullptr;
+    // results on the host (pinned, indexed by id, rows `hostPitch` apart)
+    bool stream_out = false;                    // the run copies results out as they become final
+    bool host_valid = false;
+    uint64_t hostPitch = 0;
+    DevBuf hWord, hTm, hInfo, hPos, hAlive, hPick;   // (p = pinned host memory)
     // device
     DevBuf raw, fa, faWork[2], tabs32b, tabs64b, seq2, nmask, wordContig, tabs32, tabs64, sk, br, filter, fterm, scanTmp, misc, emitMask, emitOff,
-        rows0, rows, remap, at, ovf, key1, idMeta, alive, recIdx, rec, pos, posContig, pick, pickOff, outRec, outPos, outContig;
+        rows0, rows0p, rows, remap, at, ovf, key1, idMeta, alive, idTm, idInfo, pos32, pick, candList;
     K k{};
     uint64_t nslots = 0, nids = 0, nrec = 0, npick = 0;
     uint64_t launches = 0;
     bool used_filter = false;
     pfb_timing tm{};
+    // scratch of one run (shared by the phases)
+    struct Run {
+        bool piped = false, partial = false, use_filter1 = false;
+        uint32_t W = 0, W1 = 0, N1 = 0, NB = 0;
+        uint64_t W_alloc = 0, windows1 = 0;
+        int n_out = 0;
+    } run;
+};
+
+struct pfb_multi {
+    std::vector<pfb_ctx *> ctx;
+    std::vector<std::pair<int, uint32_t>> where;   // global genome index -> (context, local index); genome 0: (0, 0) and everywhere
+    std::string err;
 };
 
 static std::string g_create_err;
@@ -1650,6 +1779,36 @@ int device_exscan(pfb_ctx *ctx, const void *in, uint32_t *out, uint32_t n, uint3
     return PFB_OK;
 }
 
+// NCCL entry points, bound once
+nccl::Api *nccl_api(std::string &why) {
+    static nccl::Api api;
+    static bool tried = false;
+    static std::string err;
+    if (!tried) {
+        tried = true;
+        const char *names[] = {"libnccl.so.2", "libnccl.so"};
+        for (const char *n : names) { api.handle = dlopen(n, RTLD_NOW | RTLD_GLOBAL); if (api.handle) break; }
+        if (!api.handle) {
+            err = std::string("NCCL is needed for more than one GPU and could not be loaded: ") + dlerror();
+        } else {
+            bool ok = true;
+            auto sym = [&](const char *name) { void *f = dlsym(api.handle, name); if (!f) { ok = false; err = std::string("NCCL lacks ") + name; } return f; };
+            api.GetUniqueId = (int (*)(nccl::UniqueId *))sym("ncclGetUniqueId");
+            api.CommInitRank = (int (*)(nccl::Comm **, int, nccl::UniqueId, int))sym("ncclCommInitRank");
+            api.CommInitAll = (int (*)(nccl::Comm **, int, const int *))sym("ncclCommInitAll");
+            api.CommDestroy = (int (*)(nccl::Comm *))sym("ncclCommDestroy");
+            api.AllReduce = (int (*)(const void *, void *, size_t, int, int, nccl::Comm *, cudaStream_t))sym("ncclAllReduce");
+            api.AllGather = (int (*)(const void *, void *, size_t, int, nccl::Comm *, cudaStream_t))sym("ncclAllGather");
+            api.GroupStart = (int (*)())sym("ncclGroupStart");
+            api.GroupEnd = (int (*)())sym("ncclGroupEnd");
+            api.GetErrorString = (const char *(*)(int))sym("ncclGetErrorString");
+            if (!ok) { dlclose(api.handle); api.handle = nullptr; }
+        }
+    }
+    if (!api.handle) { why = err; return nullptr; }
+    return &api;
+}
+
 }  // namespace
 
 // ==========================================================================================
@@ -1690,6 +1849,9 @@ int pfb_create(pfb_ctx **out, int device, const pfb_params *params) {
     e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->copyStream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->parseStream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->d2hStream, cudaStreamNonBlocking);
+    { const char *sg = getenv("PFB200_SHARD_G1"); if (sg && sg[0] == '0') ctx->shard_g1 = 0; }
+    { const char *cs = getenv("PFB200_CAP_SHARE"); if (cs && atof(cs) > 0) ctx->cap_share = atof(cs); }
     if (e == cudaSuccess)
         e = cudaFuncSetAttribute(k_scan_filtered, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SCANF_SMEM);
     if (e != cudaSuccess) { std::string m = cudaGetErrorString(e); delete ctx; return fail(nullptr, PFB_ECUDA, m); }
@@ -1710,14 +1872,20 @@ void pfb_destroy(pfb_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    if (ctx->d2hStream) cudaStreamSynchronize(ctx->d2hStream);
+    if (ctx->comm && ctx->comm_owned) { std::string why; if (nccl::Api *a = nccl_api(why)) a->CommDestroy(ctx->comm); }
+    ctx->comm = nullptr;
     DevBuf *all[] = {&ctx->raw, &ctx->seq2, &ctx->nmask, &ctx->wordContig, &ctx->tabs32, &ctx->tabs64, &ctx->sk, &ctx->br,
                      &ctx->filter, &ctx->fterm, &ctx->scanTmp, &ctx->misc, &ctx->emitMask, &ctx->emitOff,
-                     &ctx->rows0, &ctx->rows, &ctx->remap, &ctx->at, &ctx->ovf, &ctx->key1, &ctx->idMeta, &ctx->alive, &ctx->recIdx,
-                     &ctx->rec, &ctx->pos, &ctx->posContig, &ctx->pick,
-                     &ctx->pickOff, &ctx->outRec, &ctx->outPos, &ctx->outContig};
+                     &ctx->rows0, &ctx->rows0p, &ctx->rows, &ctx->remap, &ctx->at, &ctx->ovf, &ctx->key1, &ctx->idMeta, &ctx->alive,
+                     &ctx->idTm, &ctx->idInfo, &ctx->pos32, &ctx->pick, &ctx->candList};
     for (auto *b : all) release(*b);
+    DevBuf *hosts[] = {&ctx->hWord, &ctx->hTm, &ctx->hInfo, &ctx->hPos, &ctx->hAlive, &ctx->hPick};
+    for (auto *b : hosts) { if (b->p) cudaFreeHost(b->p); b->p = nullptr; b->cap = 0; }
     for (auto &ev : ctx->ev) if (ev) cudaEventDestroy(ev);
     for (auto &ev : ctx->evCopy) if (ev) cudaEventDestroy(ev);
+    for (auto &ev : ctx->evOut) if (ev) cudaEventDestroy(ev);
+    if (ctx->d2hStream) cudaStreamDestroy(ctx->d2hStream);
     if (ctx->countsHost) cudaFreeHost((void *)ctx->countsHost);
     if (ctx->copyStream) { cudaStreamSynchronize(ctx->copyStream); cudaStreamDestroy(ctx->copyStream); }
     if (ctx->parseStream) { cudaStreamSynchronize(ctx->parseStream); cudaStreamDestroy(ctx->parseStream); }
@@ -1741,7 +1909,7 @@ int pfb_add_genome(pfb_ctx *ctx, const uint8_t *bases, uint64_t n_bases, const u
     g.bases = bases; g.n_bases = n_bases;
     g.off.assign(contig_off, contig_off + n_contigs + 1);
     ctx->genomes.push_back(std::move(g));
-    ctx->uploaded = false; ctx->computed = false; ctx->stage_done = -1;
+    ctx->uploaded = false; ctx->computed = false; ctx->host_valid = false;
     return PFB_OK;
 }
 
@@ -1752,7 +1920,7 @@ static int add_file(pfb_ctx *ctx, const uint8_t *file_bytes, uint64_t n_bytes, i
     HostGenome g;
     g.bases = file_bytes; g.n_bases = 0; g.fasta = format; g.file_bytes = n_bytes;
     ctx->genomes.push_back(std::move(g));
-    ctx->uploaded = false; ctx->computed = false; ctx->stage_done = -1;
+    ctx->uploaded = false; ctx->computed = false; ctx->host_valid = false;
     return PFB_OK;
 }
 
@@ -1787,7 +1955,7 @@ int pfb_contig_table(pfb_ctx *ctx, uint32_t genome_idx, uint64_t *header_off, ui
 int pfb_clear_genomes(pfb_ctx *ctx) {
     if (!ctx) return PFB_EINVAL;
     ctx->genomes.clear();
-    ctx->uploaded = false; ctx->computed = false; ctx->stage_done = -1;
+    ctx->uploaded = false; ctx->computed = false; ctx->host_valid = false;
     return PFB_OK;
 }
 
@@ -1795,6 +1963,7 @@ int pfb_sync(pfb_ctx *ctx) {
     if (!ctx) return PFB_EINVAL;
     CK(cudaSetDevice(ctx->device));
     CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaStreamSynchronize(ctx->d2hStream));
     return PFB_OK;
 }
 
@@ -1878,7 +2047,7 @@ static int upload_impl(pfb_ctx *ctx, bool async) {
         cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]);
         ctx->tm.ms_upload = ms;
     }
-    ctx->uploaded = true; ctx->computed = false; ctx->stage_done = -1;
+    ctx->uploaded = true; ctx->computed = false; ctx->host_valid = false;
     return PFB_OK;
 }
 
@@ -1922,7 +2091,97 @@ int pfb_upload_wait(pfb_ctx *ctx) {
     return PFB_OK;
 }
 
-static int stage0(pfb_ctx *ctx) {
+// ------------------------------------------------------------------------------------------
+// One run = five phases of kernels separated by (at most) four collectives.  No phase waits for the device: the
+// buffers are sized by capacities (pick_capacities), the kernels read the actual counts from device memory, and
+// a count that did not fit raises a flag that the host finds at the very end -- it then grows the capacities and
+// repeats the run.  With one context the collectives are no-ops; with several contexts in one process
+// (pfb_multi) one host thread walks all of them through each phase and issues the collectives as one NCCL group;
+// with one process per GPU every rank does the same on its own context.
+//
+//   A  zero fills, genome 1 packed, genome 1's candidate windows (its share of them when the ranks share the work)
+//      -- all-gather of the candidate lists --
+//   B  candidates -> table, key bitmap + ranks, genome 1's own pass (its share)
+//      -- SUM all-reduce of genome 1's packed rows --
+//   C  genome 1's verdicts, ids in dict order, key table of the other genomes, the per-id records; then the
+//      other genomes in batches: pack, scan, uniqueness rules, places (results leave for the host as they are made)
+//      -- MIN all-reduce of the alive bytes --
+//   D  per-position pick
+//      -- MAX all-reduce of the pick bytes --
+//   E  counts, last result copies
+
+static void pick_capacities(pfb_ctx *ctx, uint64_t windows1) {
+    const pfb_params &P = ctx->prm;
+    const int nk = P.k_max - P.k_min + 1;
+    auto round256 = [](uint64_t x) { return (uint32_t)std::min<uint64_t>((x + 255) & ~255ull, 0xFFFFFF00ull); };
+    if (ctx->caps_for_prefilter != P.prefilter || ctx->caps_for_windows != windows1) {
+        // nothing known yet about these inputs: a generous share of genome 1's windows (every key is a candidate
+        // window of genome 1; with the prefilter ~9 % of the windows of a random 50 % GC genome are candidates)
+        const double share = ctx->cap_share > 0 ? ctx->cap_share : (P.prefilter ? 0.14 : 0.80);
+        const uint64_t est = std::min<uint64_t>((uint64_t)(share * (double)windows1) + (ctx->cap_share > 0 ? 256 : 65536), (uint64_t)nk * P.table_size);
+        ctx->capSlots = round256(est);
+        ctx->capIds = ctx->capSlots;
+        ctx->caps_for_prefilter = P.prefilter;
+        ctx->caps_for_windows = windows1;
+        ctx->lastSlots = ctx->lastIds = 0;
+    } else if (ctx->lastSlots) {
+        // same shape of input as the last completed run: its counts + 6 % (a bench loop, a service that sees similar
+        // genomes); a run that needs more finds out and repeats itself
+        ctx->capSlots = round256(ctx->lastSlots + ctx->lastSlots / 16 + 1024);
+        ctx->capIds = round256(ctx->lastIds + ctx->lastIds / 16 + 1024);
+    }
+    const double share = ctx->cap_share > 0 ? ctx->cap_share : (P.prefilter ? 0.14 : 0.80);
+    ctx->capCand = std::max(ctx->capCandMin, round256((uint64_t)(share * (double)windows1 / std::max(1, ctx->eff_ranks())) + (ctx->cap_share > 0 ? 0 : 4096)));
+}
+
+static int ensure_host(pfb_ctx *ctx, DevBuf &b, size_t bytes) {
+    if (bytes <= b.cap && b.p) return PFB_OK;
+    CK(cudaStreamSynchronize(ctx->d2hStream));
+    if (b.p) CK(cudaFreeHost(b.p));
+    b.p = nullptr; b.cap = 0;
+    const size_t want = bytes + bytes / 8 + 4096;
+    CK(cudaHostAlloc(&b.p, want, cudaHostAllocDefault));
+    b.cap = want;
+    return PFB_OK;
+}
+
+static cudaEvent_t out_event(pfb_ctx *ctx) {
+    if ((size_t)ctx->run.n_out >= ctx->evOut.size()) {
+        cudaEvent_t e = nullptr;
+        cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+        ctx->evOut.push_back(e);
+    }
+    return ctx->evOut[ctx->run.n_out++];
+}
+
+// device -> host copy of a result piece behind everything queued on the compute stream so far
+static int copy_out(pfb_ctx *ctx, void *dst, const void *src, size_t bytes, const char *what = "") {
+    if (!bytes) return PFB_OK;
+    cudaEvent_t e = out_event(ctx);
+    if (!e) return fail(ctx, PFB_ECUDA, "cudaEventCreate failed");
+    CK(cudaEventRecord(e, ctx->stream));
+    CK(cudaStreamWaitEvent(ctx->d2hStream, e, 0));
+    if (ctx->tracing) trace_mark(ctx, ctx->d2hStream, std::string("result copy starts: ") + what);
+    CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->d2hStream));
+    if (ctx->tracing) trace_mark(ctx, ctx->d2hStream, std::string("result copy landed: ") + what + " (" + std::to_string(bytes >> 10) + " KiB)");
+    return PFB_OK;
+}
+
+static int host_buffers(pfb_ctx *ctx) {
+    const size_t nG = ctx->genomes.size(), CI = ctx->capIds;
+    int rc;
+    if ((rc = ensure_host(ctx, ctx->hWord, CI * 8)) != PFB_OK) return rc;
+    if ((rc = ensure_host(ctx, ctx->hTm, CI * 8)) != PFB_OK) return rc;
+    if ((rc = ensure_host(ctx, ctx->hInfo, CI * 2)) != PFB_OK) return rc;
+    if ((rc = ensure_host(ctx, ctx->hPos, CI * nG * 4)) != PFB_OK) return rc;
+    if ((rc = ensure_host(ctx, ctx->hAlive, CI)) != PFB_OK) return rc;
+    if ((rc = ensure_host(ctx, ctx->hPick, CI)) != PFB_OK) return rc;
+    ctx->hostPitch = CI;
+    return PFB_OK;
+}
+
+static int phaseA(pfb_ctx *ctx, bool piped) {
+    CK(cudaSetDevice(ctx->device));
     const pfb_params &P = ctx->prm;
     cudaStream_t st = ctx->stream;
     K &k = ctx->k;
@@ -1930,6 +2189,7 @@ static int stage0(pfb_ctx *ctx) {
     const int nk = P.k_max - P.k_min + 1;
     k.kmin = P.k_min; k.kmax = P.k_max; k.nk = nk;
     k.P = P.table_size; k.PW = (P.table_size + 31) / 32;
+    k.PW16 = (P.table_size + 15) / 16;
     k.barrett = (uint64_t)((((unsigned __int128)1) << 64) / P.table_size);
     k.fscale = (uint64_t)FILTER_WORDS >= P.table_size
                    ? 0xFFFFFFFFu
@@ -1937,34 +2197,81 @@ static int stage0(pfb_ctx *ctx) {
     k.max_repeat = P.max_repeat; k.prefilter = P.prefilter;
     std::vector<double> fterm;
     fill_filter_constants(P, k, fterm);
-    uint32_t W = ctx->totalWords;
-    const uint32_t W1 = ctx->laid_out > 1 ? ctx->gWordStart[1] : W;         // genome 1 = words [0, W1)
-    const uint32_t NB = (uint32_t)nk * k.PW;                                // words of the concatenated bitmaps
+    pfb_ctx::Run &R = ctx->run;
+    R = pfb_ctx::Run();
+    R.piped = piped;
+    R.W = ctx->totalWords;
+    R.W1 = ctx->laid_out > 1 ? ctx->gWordStart[1] : R.W;                       // genome 1 = words [0, W1)
+    R.N1 = R.W1 * 32u;                                                         // padded end positions of genome 1
+    R.NB = (uint32_t)nk * k.PW;                                                // words of the concatenated bitmaps
     ctx->launches = 0;
     // FASTA genomes still being parsed (pipelined run): the layout covers genome 1 only, the word arrays are
     // sized by an estimate of the rest (re-checked in fasta_finish)
-    const bool partial = ctx->laid_out < ctx->genomes.size();
-    uint64_t W_alloc = W;
-    if (partial)
+    R.partial = ctx->laid_out < ctx->genomes.size();
+    R.W_alloc = R.W;
+    if (R.partial)
         for (size_t g = ctx->laid_out; g < ctx->genomes.size(); g++)
-            W_alloc += ctx->genomes[g].file_bytes / 32 + ctx->genomes[g].file_bytes / 1024 + 4096;
+            R.W_alloc += ctx->genomes[g].file_bytes / 32 + ctx->genomes[g].file_bytes / 1024 + 4096;
+    uint64_t windows1 = 0;
+    for (uint32_t c = 0; c < ctx->gNumContigs[0]; c++)
+        for (int kk = P.k_min; kk <= P.k_max; kk++)
+            if (ctx->cLen[c] >= (uint32_t)kk) windows1 += ctx->cLen[c] - kk + 1;
+    pick_capacities(ctx, windows1);
+    R.windows1 = windows1;
+    const size_t nG = ctx->genomes.size();
+    const size_t CS = ctx->capSlots, CI = ctx->capIds;
+    const size_t NA = (size_t)nk * k.PW16;
+    const size_t ovfCap = std::min<size_t>(CI / 3 + (CI > ctx->at_wide ? CI - ctx->at_wide : 0), NA) + 16;
+    if (ovfCap >= (1u << 24)) return fail(ctx, PFB_ETOOLARGE, "too many keys share 16-bin words for the inline id table");
+    // genome 1's own pipeline is shared out when there are ranks to share it with and the candidate lists are short
+    const int nR = ctx->eff_ranks();
+    ctx->sharded_now = ((ctx->comm && ctx->nRanks > 1) || ctx->emulate_ranks > 1) && ctx->shard_g1 && P.prefilter &&
+                       P.table_size <= (1u << 27) && nk <= 32 && ctx->scan_mode != 2;
     // buffers
-    if ((rc = ensure(ctx, ctx->seq2, (size_t)(W_alloc + 2) * 8)) != PFB_OK) return rc;
-    if ((rc = ensure(ctx, ctx->nmask, (size_t)(W_alloc + 1) * 4)) != PFB_OK) return rc;
-    if ((rc = ensure(ctx, ctx->wordContig, (size_t)(W_alloc + 1) * 4)) != PFB_OK) return rc;
-    if ((rc = ensure(ctx, ctx->sk, (size_t)NB * 2 * 4)) != PFB_OK) return rc;
-    if ((rc = ensure(ctx, ctx->br, (size_t)NB * 8)) != PFB_OK) return rc;
+    if ((rc = ensure(ctx, ctx->seq2, (size_t)(R.W_alloc + 2) * 8)) != PFB_OK) return rc;
+    if ((rc = ensure(ctx, ctx->nmask, (size_t)(R.W_alloc + 1) * 4)) != PFB_OK) return rc;
+    if ((rc = ensure(ctx, ctx->wordContig, (size_t)(R.W_alloc + 1) * 4)) != PFB_OK) return rc;
+    if ((rc = ensure(ctx, ctx->sk, (size_t)R.NB * 2 * 4)) != PFB_OK) return rc;
+    if ((rc = ensure(ctx, ctx->br, (size_t)R.NB * 8)) != PFB_OK) return rc;
     if ((rc = ensure(ctx, ctx->filter, (size_t)nk * FILTER_BYTES)) != PFB_OK) return rc;
     if ((rc = ensure(ctx, ctx->fterm, FTERM_DOUBLES * 8)) != PFB_OK) return rc;
     if ((rc = ensure(ctx, ctx->misc, 4096)) != PFB_OK) return rc;
-    if ((rc = ensure(ctx, ctx->emitMask, (size_t)W1 * 32 * 4 + 4)) != PFB_OK) return rc;
-    if ((rc = ensure(ctx, ctx->emitOff, (size_t)W1 * 32 * 4 + 4)) != PFB_OK) return rc;
+    if ((rc = ensure(ctx, ctx->emitMask, (size_t)R.W1 * 32 * 4 + 4)) != PFB_OK) return rc;
+    if ((rc = ensure(ctx, ctx->emitOff, (size_t)R.W1 * 32 * 4 + 4)) != PFB_OK) return rc;
+    if ((rc = ensure(ctx, ctx->rows0, CS * 8)) != PFB_OK) return rc;
+    if ((rc = ensure(ctx, ctx->remap, CS * 4)) != PFB_OK) return rc;
+    if ((rc = ensure(ctx, ctx->rows, CI * (nG > 1 ? nG - 1 : 1) * 8)) != PFB_OK) return rc;
+    if ((rc = ensure(ctx, ctx->key1, CI * 8)) != PFB_OK) return rc;
+    if ((rc = ensure(ctx, ctx->idMeta, CI * 4)) != PFB_OK) return rc;
+    if ((rc = ensure(ctx, ctx->alive, CI)) != PFB_OK) return rc;
+    if ((rc = ensure(ctx, ctx->pick, CI)) != PFB_OK) return rc;
+    if ((rc = ensure(ctx, ctx->idTm, CI * 8)) != PFB_OK) return rc;
+    if ((rc = ensure(ctx, ctx->idInfo, CI * 2)) != PFB_OK) return rc;
+    if ((rc = ensure(ctx, ctx->pos32, CI * nG * 4)) != PFB_OK) return rc;
+    if (nG > 1) {
+        if ((rc = ensure(ctx, ctx->at, NA * 8)) != PFB_OK) return rc;
+        if ((rc = ensure(ctx, ctx->ovf, ovfCap * 64)) != PFB_OK) return rc;
+    }
+    if (ctx->sharded_now) {
+        if ((rc = ensure(ctx, ctx->candList, (size_t)nR * (ctx->capCand + 4) * 4)) != PFB_OK) return rc;
+        if ((rc = ensure(ctx, ctx->rows0p, CS * 4)) != PFB_OK) return rc;
+    }
+    if (ctx->stream_out && (rc = host_buffers(ctx)) != PFB_OK) return rc;
     k.seq2 = (uint64_t *)ctx->seq2.p; k.nmask = (uint32_t *)ctx->nmask.p; k.wordContig = (uint32_t *)ctx->wordContig.p;
     k.sk = (uint32_t *)ctx->sk.p; k.br = (uint2 *)ctx->br.p;
     k.filter = (uint32_t *)ctx->filter.p; k.fterm = (const double *)ctx->fterm.p;
     k.tmb = (const float4 *)((const double *)ctx->fterm.p + TMB_OFF);
-    uint32_t *misc = (uint32_t *)ctx->misc.p;   // [0] nslots, [1] nids, [2] nrec, [3] npick, [4] id lists of k_build_at
+    k.cnt = (uint32_t *)ctx->misc.p;
     k.emitMask = (uint32_t *)ctx->emitMask.p; k.emitOff = (uint32_t *)ctx->emitOff.p;
+    k.rows0 = (unsigned long long *)ctx->rows0.p; k.remap = (uint32_t *)ctx->remap.p; k.rows0p = (uint32_t *)ctx->rows0p.p;
+    k.rows = (unsigned long long *)ctx->rows.p; k.key1 = (uint64_t *)ctx->key1.p; k.idMeta = (uint32_t *)ctx->idMeta.p;
+    k.alive = (uint8_t *)ctx->alive.p; k.pick = (uint8_t *)ctx->pick.p;
+    k.idTm = (double *)ctx->idTm.p; k.idInfo = (uint16_t *)ctx->idInfo.p; k.pos32 = (uint32_t *)ctx->pos32.p;
+    k.at = (uint2 *)ctx->at.p; k.ovf = (uint32_t *)ctx->ovf.p; k.ovfCount = k.cnt + C_OVF; k.ovfCap = (uint32_t)ovfCap;
+    k.atWide = ctx->at_wide;
+    k.capSlots = (uint32_t)CS; k.capIds = (uint32_t)CI;
+    k.candList = (uint32_t *)ctx->candList.p; k.capCand = ctx->capCand; k.nRanks = (uint32_t)nR; k.rank = (uint32_t)ctx->rank;
+    k.first_pass = 0;
 
     CK(cudaEventRecord(ctx->ev[2], st));
     if (!ctx->fterm_uploaded) {   // the parameters of a context never change: once (a small H2D copy per run would
@@ -1975,270 +2282,335 @@ static int stage0(pfb_ctx *ctx) {
     }
     ZeroBatch zb;
     if ((rc = zb.add(ctx, ctx->misc, 4096)) != PFB_OK) return rc;
-    if ((rc = zb.add(ctx, ctx->sk, (size_t)NB * 2 * 4)) != PFB_OK) return rc;
+    if ((rc = zb.add(ctx, ctx->sk, (size_t)R.NB * 2 * 4)) != PFB_OK) return rc;
+    if ((rc = zb.add(ctx, ctx->alive, CI)) != PFB_OK) return rc;
+    if ((rc = zb.add(ctx, ctx->pick, CI)) != PFB_OK) return rc;
     if ((rc = zb.launch(ctx, st)) != PFB_OK) return rc;
-    const size_t nG = ctx->genomes.size();
-    const bool piped = ctx->pipelined;
-    if (piped) {   // only genome 1 has to be there before the key table can be built
-        CK(cudaStreamWaitEvent(st, ctx->evCopy[0], 0));
-        if (W1) { k_encode<<<nblk(W1, 256), 256, 0, st>>>(k, 0, W1); ctx->launches++; }
-        ctx->encoded_upto = 1;
-    } else if (W1) {   // genome 1 now; the others are packed while the host waits for the slot count
-        k_encode<<<nblk(W1, 256), 256, 0, st>>>(k, 0, W1); ctx->launches++;
+    if (ctx->sharded_now) {      // every segment starts with its count
+        for (int r = 0; r < nR; r++)
+            CK(cudaMemsetAsync((uint32_t *)ctx->candList.p + (size_t)r * (ctx->capCand + 4), 0, 16, st));
     }
-    // pipelined run: pack whatever has landed meanwhile.  Called just before the host waits for a count, so
-    // that the GPU has something to do during the round trip.
-    bool rest_packed = false;
-    auto encode_landed = [&]() -> int {
-        if (!piped) {
-            if (!rest_packed && W > W1) { k_encode<<<nblk(W - W1, 256), 256, 0, st>>>(k, W1, W); ctx->launches++; }
-            rest_packed = true;
-            return PFB_OK;
-        }
-        if (partial) return PFB_OK;
-        size_t g2 = ctx->encoded_upto;
-        while (g2 < nG && cudaEventQuery(ctx->evCopy[g2]) == cudaSuccess) g2++;
-        cudaGetLastError();
-        if (g2 > ctx->encoded_upto) {
-            const uint32_t wa = ctx->gWordStart[ctx->encoded_upto], wb = g2 < nG ? ctx->gWordStart[g2] : ctx->totalWords;
-            if (wb > wa) { k_encode<<<nblk(wb - wa, 256), 256, 0, st>>>(k, wa, wb); ctx->launches++; }
-            ctx->encoded_upto = g2;
-        }
-        return PFB_OK;
-    };
+    if (piped) CK(cudaStreamWaitEvent(st, ctx->evCopy[0], 0));      // only genome 1 has to be there before the key table can be built
+    if (R.W1) { k_encode<<<nblk(R.W1, 256), 256, 0, st>>>(k, 0, R.W1); ctx->launches++; }
     CK(cudaEventRecord(ctx->ev[3], st));
     trace_mark(ctx, st, "genome 1 encoded");
     // genome 1: candidates -> key table
-    const uint32_t N1 = W1 * 32u;                                           // padded end positions of genome 1
-    if (W1) { k_cand1<<<nblk(N1, CAND_POS), CAND_POS + 32, 0, st>>>(k, N1); ctx->launches++; }
-    k_candbits<<<nblk(NB, 256), 256, 0, st>>>(k); ctx->launches++;
-    if ((rc = device_exscan<SV_POPC, 2>(ctx, k.br, (uint32_t *)k.br + 1, NB, misc, ctx->countsDev)) != PFB_OK) return rc;
-    trace_mark(ctx, st, "slots counted (host waits for the count after this)");
-    if ((rc = encode_landed()) != PFB_OK) return rc;
-    CK(cudaStreamSynchronize(st));   // fterm (host vector) is also consumed by now
-    trace_mark(ctx, st, "host has the slot count");
-    ctx->nslots = ctx->countsHost[0];
-    k.nslots = ctx->nslots;
-    ctx->nids = 0; k.nids = 0;
-    const size_t NS = ctx->nslots ? ctx->nslots : 1;
-    if ((rc = ensure(ctx, ctx->rows0, NS * 8)) != PFB_OK) return rc;
-    if ((rc = ensure(ctx, ctx->remap, NS * 4)) != PFB_OK) return rc;
-    k.rows0 = (unsigned long long *)ctx->rows0.p; k.remap = (uint32_t *)ctx->remap.p;
-    if ((rc = zb.add(ctx, ctx->rows0, NS * 8)) != PFB_OK) return rc;
-    if (W1 && (rc = zb.add(ctx, ctx->emitMask, (size_t)W1 * 32 * 4 + 4)) != PFB_OK) return rc;   // filled by k_alive1 after genome 1's pass
+    if (R.W1) {
+        const uint32_t nCta = nblk(R.N1, CAND_POS);
+        if (ctx->sharded_now) {
+            const uint32_t per = (nCta + nR - 1) / nR;
+            for (int r = 0; r < nR; r++) {        // this context's rank -- or, emulating, every rank in turn
+                if (ctx->emulate_ranks <= 1 && r != ctx->rank) continue;
+                const uint32_t c0 = std::min(nCta, per * (uint32_t)r), c1 = std::min(nCta, c0 + per);
+                k.rank = (uint32_t)r;
+                if (c1 > c0) { k_cand1<true><<<c1 - c0, CAND_POS + 32, 0, st>>>(k, R.N1, c0); ctx->launches++; }
+            }
+            k.rank = (uint32_t)ctx->rank;
+        } else {
+            k_cand1<false><<<nCta, CAND_POS + 32, 0, st>>>(k, R.N1, 0); ctx->launches++;
+        }
+    }
+    CK(cudaGetLastError());
+    return PFB_OK;
+}
+
+static int phaseB(pfb_ctx *ctx) {
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    K &k = ctx->k;
+    pfb_ctx::Run &R = ctx->run;
+    const pfb_params &P = ctx->prm;
+    const int nk = k.nk;
+    int rc;
+    if (ctx->sharded_now) { k_apply_cands<<<ctx->num_sms * 8, 256, 0, st>>>(k); ctx->launches++; }
+    k_candbits<<<nblk(R.NB, 256), 256, 0, st>>>(k); ctx->launches++;
+    if ((rc = device_exscan<SV_POPC, 2>(ctx, k.br, (uint32_t *)k.br + 1, R.NB, k.cnt + C_NSLOTS, nullptr)) != PFB_OK) return rc;
+    ZeroBatch zb;
+    if ((rc = zb.add(ctx, ctx->rows0, (size_t)ctx->capSlots * 8)) != PFB_OK) return rc;
+    if (R.W1 && (rc = zb.add(ctx, ctx->emitMask, (size_t)R.W1 * 32 * 4 + 4)) != PFB_OK) return rc;   // filled by k_alive1 after genome 1's pass
     // the filter pays off while it stays sparse (expected fill 1 - exp(-keys_per_k / FILTER_BITS)) and the launch
     // is long enough to amortise the nk filter loads.  Genome 1's own pass meets ALL its candidate keys (a dense
     // filter) in one short launch: measured, the plain L2 probe is faster there at every genome size tried
     // (5 Mbp: 0.14 vs 0.18 ms), so the filter is only used for it when forced (scan mode 2, tests)
-    bool use_filter = ctx->scan_mode == 2;
-    ctx->used_filter = use_filter;
-    if (use_filter && ctx->nslots && (rc = zb.add(ctx, ctx->filter, (size_t)nk * FILTER_BYTES)) != PFB_OK) return rc;
+    R.use_filter1 = ctx->scan_mode == 2;
+    ctx->used_filter = R.use_filter1;
+    if (R.use_filter1 && (rc = zb.add(ctx, ctx->filter, (size_t)nk * FILTER_BYTES)) != PFB_OK) return rc;
     if ((rc = zb.launch(ctx, st)) != PFB_OK) return rc;
-    if (use_filter && ctx->nslots) { k_build_filter<<<nblk(NB, 256), 256, 0, st>>>(k); ctx->launches++; }
+    if (R.use_filter1) { k_build_filter<<<nblk(R.NB, 256), 256, 0, st>>>(k); ctx->launches++; }
     CK(cudaEventRecord(ctx->ev[4], st));
     trace_mark(ctx, st, "key table built");
-    // every genome (the first included): one pass against the key table
-    auto scan_range = [&](uint32_t wa, uint32_t wb, uint32_t ca, uint32_t cb, uint32_t n_gen) {
-        if (wb > wa) {
-            if (use_filter) k_scan_filtered<<<ctx->num_sms, 1024, SCANF_SMEM, st>>>(k, wa, wb);
-            else k_scan_plain<<<nblk(wb - wa, 256), 256, 0, st>>>(k, wa, wb);
-            ctx->launches++;
-        }
-        if (cb - ca > n_gen) {   // some genome of the range has more than one contig
-            uint64_t nthr = (uint64_t)(cb - ca) * nk * 2 * (2 * P.k_max - 1);
-            k_junction<<<nblk(nthr, 128), 128, 0, st>>>(k, ca, cb);
-            ctx->launches++;
-        }
-    };
-    if (W && ctx->nslots) {
+    if (R.W1) {
         // genome 1 first: its rows are indexed by slot.  The keys that collide inside genome 1 itself
         // (~1 - exp(-L / P) of them) are dead already; the survivors get an id in the reference's dict order,
         // the rows of every other genome are indexed by id, and a filter rebuilt without the dead keys sends
         // fewer windows of the other genomes to L2
+        k.first_pass = ctx->sharded_now ? 2 : 1;
+        const int nR = ctx->sharded_now ? ctx->eff_ranks() : 1;
+        for (int r = 0; r < nR; r++) {            // this context's share -- or, emulating, every share in turn
+            if (ctx->sharded_now && ctx->emulate_ranks <= 1 && r != ctx->rank) continue;
+            const uint32_t wa = (uint32_t)((uint64_t)R.W1 * r / nR), wb = (uint32_t)((uint64_t)R.W1 * (r + 1) / nR);
+            if (wb > wa) {
+                if (R.use_filter1) k_scan_filtered<<<ctx->num_sms, 1024, SCANF_SMEM, st>>>(k, wa, wb);
+                else k_scan_plain<false><<<nblk(wb - wa, 256), 256, 0, st>>>(k, wa, wb);
+                ctx->launches++;
+            }
+        }
+        if (ctx->sharded_now) { k_rows0_pack<<<nblk(ctx->capSlots, 256), 256, 0, st>>>(k); ctx->launches++; }
+    }
+    (void)P;
+    CK(cudaGetLastError());
+    return PFB_OK;
+}
+
+// one batch of the other genomes: [ga, gb) are packed (unless they are already), scanned against the key table,
+// judged, and their places leave for the host
+static int scan_batch(pfb_ctx *ctx, size_t ga, size_t gb, bool encode, bool use_filter) {
+    cudaStream_t st = ctx->stream;
+    K &k = ctx->k;
+    pfb_ctx::Run &R = ctx->run;
+    const pfb_params &P = ctx->prm;
+    const size_t nG = ctx->genomes.size();
+    const uint32_t wa = ctx->gWordStart[ga], wb = gb < nG ? ctx->gWordStart[gb] : R.W;
+    const uint32_t ca = ctx->gFirstContig[ga], cb = gb < nG ? ctx->gFirstContig[gb] : (uint32_t)ctx->cLen.size();
+    if (encode && wb > wa) { k_encode<<<nblk(wb - wa, 256), 256, 0, st>>>(k, wa, wb); ctx->launches++; }
+    trace_mark(ctx, st, "scan starts: genomes " + std::to_string(ga) + ".." + std::to_string(gb - 1));
+    if (wb > wa) {
+        if (use_filter) k_scan_filtered<<<ctx->num_sms, 1024, SCANF_SMEM, st>>>(k, wa, wb);
+        else k_scan_plain<false><<<nblk(wb - wa, 256), 256, 0, st>>>(k, wa, wb);
+        ctx->launches++;
+    }
+    if (cb - ca > gb - ga) {   // some genome of the range has more than one contig
+        uint64_t nthr = (uint64_t)(cb - ca) * k.nk * 2 * (2 * P.k_max - 1);
+        k_junction<<<nblk(nthr, 128), 128, 0, st>>>(k, ca, cb);
+        ctx->launches++;
+    }
+    trace_mark(ctx, st, "scan done:   genomes " + std::to_string(ga) + ".." + std::to_string(gb - 1));
+    return PFB_OK;
+}
+
+static int judge_batch(pfb_ctx *ctx, size_t ga, size_t gb) {
+    cudaStream_t st = ctx->stream;
+    K &k = ctx->k;
+    if (gb - ga > 65535u * ALIVE_GPT) return fail(ctx, PFB_ETOOLARGE, "more than 131070 genomes on one context");
+    k_aliveN<<<dim3(nblk(ctx->capIds, 256), nblk(gb - ga, ALIVE_GPT)), 256, 0, st>>>(k, (uint32_t)ga, (uint32_t)gb); ctx->launches++;
+    if (ctx->stream_out)
+        return copy_out(ctx, (uint32_t *)ctx->hPos.p + ga * ctx->hostPitch, k.pos32 + ga * (size_t)ctx->capIds, (gb - ga) * (size_t)ctx->capIds * 4,
+                        "places of a batch of genomes");
+    return PFB_OK;
+}
+
+static int phaseC(pfb_ctx *ctx) {
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    K &k = ctx->k;
+    pfb_ctx::Run &R = ctx->run;
+    const pfb_params &P = ctx->prm;
+    const int nk = k.nk;
+    const size_t nG = ctx->genomes.size();
+    int rc;
+    if (R.W1) {
+        if (ctx->sharded_now) {
+            // the ranks' shares of genome 1's pass have been summed: back to the row format, then the (few)
+            // strand-specific polluters of all of genome 1 on every rank
+            k_rows0_unpack<<<nblk(ctx->capSlots, 256), 256, 0, st>>>(k); ctx->launches++;
+            k.first_pass = 1;
+            k_scan_plain<true><<<nblk(R.W1, 256), 256, 0, st>>>(k, 0, R.W1); ctx->launches++;
+        }
         const uint32_t C1 = ctx->gFirstContig[0] + ctx->gNumContigs[0];
-        k.first_pass = 1;
-        scan_range(0, W1, 0, C1, 1);
+        if (C1 > 1) {
+            uint64_t nthr = (uint64_t)C1 * nk * 2 * (2 * P.k_max - 1);
+            k_junction<<<nblk(nthr, 128), 128, 0, st>>>(k, 0, C1);
+            ctx->launches++;
+        }
         k.first_pass = 0;
         trace_mark(ctx, st, "genome 1 scanned");
-        k_alive1<<<nblk(ctx->nslots, 256), 256, 0, st>>>(k); ctx->launches++;
-        if ((rc = device_exscan<SV_POPC, 1>(ctx, k.emitMask, k.emitOff, N1, misc + 1, ctx->countsDev + 1)) != PFB_OK) return rc;
-        trace_mark(ctx, st, "ids counted (host waits for the count after this)");
-        if ((rc = encode_landed()) != PFB_OK) return rc;
-        CK(cudaStreamSynchronize(st));
-        trace_mark(ctx, st, "host has the id count");
-        const uint32_t ni = ctx->countsHost[1];
-        ctx->nids = ni; k.nids = ni;
+        k_alive1<<<nblk(ctx->capSlots, 256), 256, 0, st>>>(k); ctx->launches++;
+        if ((rc = device_exscan<SV_POPC, 1>(ctx, k.emitMask, k.emitOff, R.N1, k.cnt + C_NIDS, nullptr)) != PFB_OK) return rc;
+        trace_mark(ctx, st, "ids counted");
     }
+    bool use_filter = false;
     {
-        const size_t NI = ctx->nids ? ctx->nids : 1;
-        const size_t nOther = nG > 1 ? nG - 1 : 1;
-        if ((rc = ensure(ctx, ctx->rows, NI * nOther * 8)) != PFB_OK) return rc;
-        if ((rc = ensure(ctx, ctx->key1, NI * 8)) != PFB_OK) return rc;
-        if ((rc = ensure(ctx, ctx->idMeta, NI * 4)) != PFB_OK) return rc;
-        if ((rc = ensure(ctx, ctx->alive, NI)) != PFB_OK) return rc;
-        if ((rc = ensure(ctx, ctx->recIdx, NI * 4)) != PFB_OK) return rc;
-        k.rows = (unsigned long long *)ctx->rows.p; k.key1 = (uint64_t *)ctx->key1.p; k.idMeta = (uint32_t *)ctx->idMeta.p;
-        k.alive = (uint8_t *)ctx->alive.p; k.recIdx = (uint32_t *)ctx->recIdx.p;
-    }
-    if (ctx->nids) {
-        if (nG > 1 && (rc = zb.add(ctx, ctx->rows, (size_t)ctx->nids * (nG - 1) * 8)) != PFB_OK) return rc;
-        if ((rc = ensure(ctx, ctx->pick, ctx->nids)) != PFB_OK) return rc;          // stage 1's pick bytes
-        if ((rc = zb.add(ctx, ctx->pick, ctx->nids)) != PFB_OK) return rc;
-        if (nG == 1) {   // (with other genomes the ids are assigned inside k_build_at)
-            if ((rc = zb.launch(ctx, st)) != PFB_OK) return rc;
-            k_assign_ids<<<nblk(ctx->nslots, 256), 256, 0, st>>>(k); ctx->launches++;
-        }
+        ZeroBatch zb;
         if (nG > 1) {
-            // key table of the other genomes (alive keys only, ids inline) and their filter
-            k.PW16 = (P.table_size + 15) / 16;
-            const size_t NA = (size_t)nk * k.PW16;
-            const size_t cap = ctx->nids / 3 + (ctx->nids > ctx->at_wide ? ctx->nids - ctx->at_wide : 0) + 16;
-            k.atWide = ctx->at_wide;
-            if (cap >= (1u << 24)) return fail(ctx, PFB_ETOOLARGE, "too many keys share 16-bin words for the inline id table");
-            if ((rc = ensure(ctx, ctx->at, NA * 8)) != PFB_OK) return rc;
-            if ((rc = ensure(ctx, ctx->ovf, cap * 64)) != PFB_OK) return rc;
-            k.at = (uint2 *)ctx->at.p; k.ovf = (uint32_t *)ctx->ovf.p; k.ovfCount = misc + 4; k.ovfCap = (uint32_t)cap;
+            // the per-genome rows: allocated by capacity, zeroed by need (the count is on the device)
+            const unsigned ry = (unsigned)std::min<size_t>(nG - 1, 65535);
+            k_zero_rows<<<dim3(nblk((ctx->capIds + 1) / 2, 256), ry), 256, 0, st>>>(k.rows, k.capIds, (uint32_t)(nG - 1), k.cnt + C_NIDS, k.capIds);
+            ctx->launches++;
             // the other genomes only meet the keys that survived genome 1: decide again whether their filter
-            // stays sparse enough (long genomes lose most keys to collisions inside genome 1)
-            use_filter = ctx->scan_mode == 2 ||
-                         (ctx->scan_mode == 0 && (double)ctx->nids / nk < 0.35 * FILTER_BITS && W_alloc >= 4096);
+            // stays sparse enough (long genomes lose most keys to collisions inside genome 1).  The decision must
+            // not wait for the id count: it is made from the last run's count, or from an estimate
+            // (expected: the typical share of candidate windows, times the share exp(-L / P) of them that are alone
+            // in their bin after genome 1's own pass)
+            const double ids = ctx->lastIds ? (double)ctx->lastIds
+                                            : (P.prefilter ? 0.09 : 0.75) * (double)R.windows1 *
+                                                  std::exp(-(double)ctx->genomes[0].n_bases / (double)P.table_size);
+            use_filter = ctx->scan_mode == 2 || (ctx->scan_mode == 0 && ids / nk < 0.35 * FILTER_BITS && R.W_alloc >= 4096);
             ctx->used_filter = use_filter;
             if (use_filter && (rc = zb.add(ctx, ctx->filter, (size_t)nk * FILTER_BYTES)) != PFB_OK) return rc;
             if ((rc = zb.launch(ctx, st)) != PFB_OK) return rc;
+            const size_t NA = (size_t)nk * k.PW16;
             k_build_at<<<nblk(NA, 256), 256, 0, st>>>(k, use_filter ? 1 : 0); ctx->launches++;
             trace_mark(ctx, st, "key table of the other genomes built");
+        } else if (R.W1) {
+            k_assign_ids<<<nblk(ctx->capSlots, 256), 256, 0, st>>>(k); ctx->launches++;
         }
     }
-    if (partial) {
+    // what is known per id once the ids exist: length, GC, Tm, filter flags (and genome 1's places)
+    k_id_records<<<nblk(ctx->capIds, 256), 256, 0, st>>>(k); ctx->launches++;
+    if (ctx->stream_out) {
+        if (ctx->fetch_records) {
+            if ((rc = copy_out(ctx, ctx->hWord.p, k.key1, (size_t)ctx->capIds * 8, "words")) != PFB_OK) return rc;
+            CK(cudaMemcpyAsync(ctx->hTm.p, k.idTm, (size_t)ctx->capIds * 8, cudaMemcpyDeviceToHost, ctx->d2hStream));
+            CK(cudaMemcpyAsync(ctx->hInfo.p, k.idInfo, (size_t)ctx->capIds * 2, cudaMemcpyDeviceToHost, ctx->d2hStream));
+            CK(cudaMemcpyAsync(ctx->hPos.p, k.pos32, (size_t)ctx->capIds * 4, cudaMemcpyDeviceToHost, ctx->d2hStream));
+            if (ctx->tracing) trace_mark(ctx, ctx->d2hStream, "result copy landed: Tm, info, places in genome 1");
+        } else if ((rc = copy_out(ctx, ctx->hPos.p, k.pos32, (size_t)ctx->capIds * 4)) != PFB_OK) return rc;
+    }
+    if (R.partial) {
         // the other FASTA files have been parsed behind their copies: complete the layout
         if ((rc = fasta_finish(ctx)) != PFB_OK) return rc;
-        W = ctx->totalWords;
-        if ((rc = ensure_keep(ctx, ctx->seq2, (size_t)(W + 2) * 8, (size_t)(W1 + 2) * 8)) != PFB_OK) return rc;
-        if ((rc = ensure_keep(ctx, ctx->nmask, (size_t)(W + 1) * 4, (size_t)(W1 + 1) * 4)) != PFB_OK) return rc;
-        if ((rc = ensure_keep(ctx, ctx->wordContig, (size_t)(W + 1) * 4, (size_t)(W1 + 1) * 4)) != PFB_OK) return rc;
+        R.W = ctx->totalWords;
+        if ((rc = ensure_keep(ctx, ctx->seq2, (size_t)(R.W + 2) * 8, (size_t)(R.W1 + 2) * 8)) != PFB_OK) return rc;
+        if ((rc = ensure_keep(ctx, ctx->nmask, (size_t)(R.W + 1) * 4, (size_t)(R.W1 + 1) * 4)) != PFB_OK) return rc;
+        if ((rc = ensure_keep(ctx, ctx->wordContig, (size_t)(R.W + 1) * 4, (size_t)(R.W1 + 1) * 4)) != PFB_OK) return rc;
         k.seq2 = (uint64_t *)ctx->seq2.p; k.nmask = (uint32_t *)ctx->nmask.p; k.wordContig = (uint32_t *)ctx->wordContig.p;
     }
-    if (ctx->nids && nG > 1) {
-        if (!piped) {
+    if (nG > 1) {
+        if (!R.piped) {
+            if (R.W > R.W1) { k_encode<<<nblk(R.W - R.W1, 256), 256, 0, st>>>(k, R.W1, R.W); ctx->launches++; }
             CK(cudaEventRecord(ctx->ev[7], st));
-            scan_range(W1, W, ctx->gFirstContig[0] + ctx->gNumContigs[0], (uint32_t)ctx->cLen.size(), (uint32_t)nG - 1);
+            if ((rc = scan_batch(ctx, 1, nG, false, use_filter)) != PFB_OK) return rc;
             CK(cudaEventRecord(ctx->ev[8], st));
+            CK(cudaEventRecord(ctx->ev[5], st));
+            if ((rc = judge_batch(ctx, 1, nG)) != PFB_OK) return rc;
         } else {
-            // the other genomes are encoded and scanned in batches as their H2D copies land (the copies run on
-            // their own stream, see upload_impl): a batch = every genome that has arrived by the time the host
-            // gets here (at least 4 MB of them unless they are the last), so the batches adapt to how far the
-            // copies are ahead of the kernels
+            // the other genomes are packed and scanned in batches behind their H2D copies (which run on their own
+            // stream, see upload_impl): the stream waits for a batch's last copy, the host does not.  Batches halve:
+            // the first is large (the copies had the whole key-table build to get ahead), the last ones are small,
+            // so that little is left to do once the last copy has landed; the places of a batch leave for the host
+            // while the next one is scanned
             size_t g = 1;
-            bool first_batch = true;
-            uint64_t prev_bytes = 0;
+            const size_t min_batch = std::max<size_t>(1, (nG - 1) / 12);
             while (g < nG) {
-                // decide the next batch when the GPU STARTS the previous one: the host stays one batch ahead and
-                // never idles the GPU.  Copies land about as fast as genomes are scanned, so the batch waits for
-                // as many bytes as will land while the previous batch runs (60 % of its size; at least 4 MB):
-                // few large launches instead of a tail of one-genome launches
-                if (!first_batch) CK(cudaEventSynchronize(ctx->ev[9]));
-                uint64_t want = first_batch ? (4u << 20) : std::max<uint64_t>(4u << 20, prev_bytes * 6 / 10);
-                {   // when what is still in flight is small next to what is ready, one launch over everything beats
-                    // a second short launch: wait for the stragglers
-                    uint64_t ready = 0, flying = 0;
-                    size_t gq = g;
-                    while (gq < nG && (gq < ctx->encoded_upto || cudaEventQuery(ctx->evCopy[gq]) == cudaSuccess)) ready += ctx->genomes[gq++].n_bases;
-                    for (; gq < nG; gq++) flying += ctx->genomes[gq].n_bases;
-                    cudaGetLastError();
-                    if (flying * 10 <= ready * 3) want = ~0ull;
-                }
-                first_batch = false;
-                size_t g2 = g;
-                uint64_t bytes = 0;
-                while (g2 < nG) {
-                    if (g2 >= ctx->encoded_upto) {       // (packed genomes have landed: no need to ask)
-                        if (bytes >= want && cudaEventQuery(ctx->evCopy[g2]) != cudaSuccess) break;
-                        CK(cudaEventSynchronize(ctx->evCopy[g2]));
-                    }
-                    bytes += ctx->genomes[g2++].n_bases;
-                }
-                cudaGetLastError();   // cudaErrorNotReady of the query is not an error
-                prev_bytes = bytes;
-                const size_t ge = std::max(g, std::min(ctx->encoded_upto, g2));      // [g, ge) is packed already
-                uint32_t wa = ctx->gWordStart[g], wb = g2 < nG ? ctx->gWordStart[g2] : W;
-                uint32_t we = ge < nG ? ctx->gWordStart[ge] : W;
-                uint32_t ca = ctx->gFirstContig[g], cb = g2 < nG ? ctx->gFirstContig[g2] : (uint32_t)ctx->cLen.size();
-                if (wb > we) { k_encode<<<nblk(wb - we, 256), 256, 0, st>>>(k, we, wb); ctx->launches++; }
-                ctx->encoded_upto = std::max(ctx->encoded_upto, g2);
-                CK(cudaEventRecord(ctx->ev[9], st));
-                trace_mark(ctx, st, "scan starts: genomes " + std::to_string(g) + ".." + std::to_string(g2 - 1));
-                scan_range(wa, wb, ca, cb, (uint32_t)(g2 - g));
-                trace_mark(ctx, st, "scan done:   genomes " + std::to_string(g) + ".." + std::to_string(g2 - 1));
+                size_t n = std::max(min_batch, (nG - g + 1) / 2);
+                if (nG - g - n < min_batch) n = nG - g;
+                const size_t g2 = g + n;
+                CK(cudaStreamWaitEvent(st, ctx->evCopy[g2 - 1], 0));
+                if ((rc = scan_batch(ctx, g, g2, true, use_filter)) != PFB_OK) return rc;
+                if ((rc = judge_batch(ctx, g, g2)) != PFB_OK) return rc;
                 g = g2;
             }
+            CK(cudaEventRecord(ctx->ev[5], st));
         }
-    } else if (piped) {
-        CK(cudaStreamWaitEvent(st, ctx->evCopy[nG - 1], 0));
+    } else {
+        if (R.piped) CK(cudaStreamWaitEvent(st, ctx->evCopy[nG - 1], 0));
+        CK(cudaEventRecord(ctx->ev[5], st));
     }
-    CK(cudaEventRecord(ctx->ev[5], st));
-    trace_mark(ctx, st, "ids assigned / all scans queued behind");
-    if (nG - 1 > 65535u * ALIVE_GPT) return fail(ctx, PFB_ETOOLARGE, "more than 131070 genomes on one context");
-    if (ctx->nids && nG > 1) {
-        k_aliveN<<<dim3(nblk(ctx->nids, 256), nblk(nG - 1, ALIVE_GPT)), 256, 0, st>>>(k); ctx->launches++;
-    }
+    trace_mark(ctx, st, "all genomes scanned and judged");
     CK(cudaGetLastError());
     return PFB_OK;
 }
 
-// stages 1 and 2 never wait for the device: every buffer is sized by the number of ids (>= records >= picked
-// records), rows are nids apart, and the counts are read back once at the very end
-static int stage1(pfb_ctx *ctx) {
-    cudaStream_t st = ctx->stream;
-    K &k = ctx->k;
-    int rc;
-    const size_t nG = ctx->genomes.size();
-    uint32_t *misc = (uint32_t *)ctx->misc.p;
-    ctx->nrec = 0; ctx->npick = 0;
-    const size_t NI = ctx->nids ? ctx->nids : 1;
-    if ((rc = ensure(ctx, ctx->rec, NI * sizeof(pfb_record))) != PFB_OK) return rc;
-    const bool multi = ctx->cLen.size() > nG;
-    if ((rc = ensure(ctx, ctx->pos, NI * nG * 4)) != PFB_OK) return rc;
-    if ((rc = ensure(ctx, ctx->posContig, multi ? NI * nG * 4 : 4)) != PFB_OK) return rc;
-    if ((rc = ensure(ctx, ctx->pick, NI)) != PFB_OK) return rc;
-    if ((rc = ensure(ctx, ctx->pickOff, NI * 4)) != PFB_OK) return rc;
-    k.rec = (pfb_record *)ctx->rec.p; k.pos = (uint32_t *)ctx->pos.p; k.posContig = (uint32_t *)ctx->posContig.p;
-    k.multiContig = multi ? 1 : 0;
-    k.pick = (uint8_t *)ctx->pick.p; k.pickOff = (uint32_t *)ctx->pickOff.p;
-    // (the pick bytes were zeroed in stage 0 together with the rows)
-    if (ctx->nids) {
-        // ids are in dict order already: the record index is the rank among the ids that survived every genome
-        if ((rc = device_exscan<SV_U8, 1>(ctx, k.alive, k.recIdx, (uint32_t)ctx->nids, misc + 2, ctx->countsDev + 2)) != PFB_OK) return rc;
-        k_emit_write<<<nblk(ctx->nids, 256), 256, 0, st>>>(k); ctx->launches++;
-        k_positions<<<nblk(ctx->nids, 256), 256, 0, st>>>(k); ctx->launches++;
-    }
+static int phaseD(pfb_ctx *ctx) {
+    CK(cudaSetDevice(ctx->device));
+    k_pick<<<nblk(ctx->capIds, 256), 256, 0, ctx->stream>>>(ctx->k); ctx->launches++;
     CK(cudaGetLastError());
     return PFB_OK;
 }
 
-static int stage2(pfb_ctx *ctx) {
+static int phaseE(pfb_ctx *ctx) {
+    CK(cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
-    K &k = ctx->k;
     int rc;
-    uint32_t *misc = (uint32_t *)ctx->misc.p;
-    const size_t nG = ctx->genomes.size();
-    const size_t NI = ctx->nids ? ctx->nids : 1;
-    if ((rc = ensure(ctx, ctx->outRec, NI * sizeof(pfb_record))) != PFB_OK) return rc;
-    if ((rc = ensure(ctx, ctx->outPos, NI * nG * 4)) != PFB_OK) return rc;
-    if ((rc = ensure(ctx, ctx->outContig, k.multiContig ? NI * nG * 4 : 4)) != PFB_OK) return rc;
-    k.outRec = (pfb_record *)ctx->outRec.p; k.outPos = (uint32_t *)ctx->outPos.p; k.outContig = (uint32_t *)ctx->outContig.p;
-    if (ctx->nids) {
-        if ((rc = device_exscan<SV_U8, 1>(ctx, k.pick, k.pickOff, (uint32_t)ctx->nids, misc + 3, ctx->countsDev + 3)) != PFB_OK) return rc;
-        k_compact<<<nblk(ctx->nids, 256), 256, 0, st>>>(k); ctx->launches++;
-    }
+    k_count<<<ctx->num_sms * 2, 256, 0, st>>>(ctx->k); ctx->launches++;
+    k_publish<<<1, 32, 0, st>>>(ctx->k.cnt, ctx->countsDev); ctx->launches++;
     CK(cudaEventRecord(ctx->ev[6], st));
-    CK(cudaStreamSynchronize(st));
-    CK(cudaGetLastError());
-    ctx->nrec = ctx->nids ? ctx->countsHost[2] : 0; ctx->npick = ctx->nids ? ctx->countsHost[3] : 0;
-    if (ctx->tracing) {
-        trace_mark(ctx, st, "results compacted (end of the stage)");
-        CK(cudaStreamSynchronize(st));
-        trace_dump(ctx);
+    if (ctx->stream_out) {
+        if ((rc = copy_out(ctx, ctx->hAlive.p, ctx->k.alive, ctx->capIds, "alive")) != PFB_OK) return rc;
+        CK(cudaMemcpyAsync(ctx->hPick.p, ctx->k.pick, ctx->capIds, cudaMemcpyDeviceToHost, ctx->d2hStream));
+        if (ctx->tracing) trace_mark(ctx, ctx->d2hStream, "result copy landed: pick (the last byte)");
     }
+    trace_mark(ctx, st, "results final (end of the stage)");
+    CK(cudaGetLastError());
+    return PFB_OK;
+}
+
+// the collectives between the phases; C = the contexts this host thread drives
+enum { COLL_CANDS = 0, COLL_ROWS0 = 1, COLL_ALIVE = 2, COLL_PICK = 3 };
+
+static int collective(std::vector<pfb_ctx *> &C, int which) {
+    bool any = false;
+    for (pfb_ctx *c : C) any |= c->comm && c->nRanks > 1;
+    if (!any) return PFB_OK;
+    std::string why;
+    nccl::Api *a = nccl_api(why);
+    if (!a) return fail(C[0], PFB_ECUDA, why);
+    for (pfb_ctx *c : C) {
+        if (cudaSetDevice(c->device) != cudaSuccess) return fail(c, PFB_ECUDA, "cudaSetDevice failed");
+        cudaEventRecord(c->evX[which][0], c->stream);      // the two events bracket this collective on the context's stream
+        c->xUsed[which] = true;
+    }
+    int rc = 0;
+    if (C.size() > 1) a->GroupStart();
+    for (pfb_ctx *c : C) {
+        if (!(c->comm && c->nRanks > 1)) continue;
+        cudaSetDevice(c->device);
+        K &k = c->k;
+        switch (which) {
+        case COLL_CANDS:
+            if (c->sharded_now)
+                rc = a->AllGather(k.candList + (size_t)c->rank * (c->capCand + 4), k.candList, c->capCand + 4, nccl::U32, c->comm, c->stream);
+            break;
+        case COLL_ROWS0:
+            if (c->sharded_now && c->run.W1) rc = a->AllReduce(k.rows0p, k.rows0p, c->capSlots, nccl::U32, nccl::SUM, c->comm, c->stream);
+            break;
+        case COLL_ALIVE:
+            rc = a->AllReduce(k.alive, k.alive, c->capIds, nccl::U8, nccl::MIN, c->comm, c->stream);
+            break;
+        case COLL_PICK:
+            rc = a->AllReduce(k.pick, k.pick, c->capIds, nccl::U8, nccl::MAX, c->comm, c->stream);
+            break;
+        }
+        if (rc) break;
+    }
+    if (C.size() > 1) { int rc2 = a->GroupEnd(); if (!rc) rc = rc2; }
+    if (rc) return fail(C[0], PFB_ECUDA, std::string("NCCL: ") + a->GetErrorString(rc));
+    for (pfb_ctx *c : C) {
+        cudaSetDevice(c->device);
+        cudaEventRecord(c->evX[which][1], c->stream);
+    }
+    return PFB_OK;
+}
+
+// end of a run on one context: wait, read the counters, decide whether the capacities were enough
+static int finish(pfb_ctx *ctx, bool &again) {
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaGetLastError());
+    const uint32_t nslots = ctx->countsHost[C_NSLOTS], nids = ctx->countsHost[C_NIDS], flags = ctx->countsHost[C_FLAGS];
+    ctx->nslots = nslots; ctx->nids = nids;
+    ctx->nrec = ctx->countsHost[C_NALIVE]; ctx->npick = ctx->countsHost[C_NPICK];
+    auto round256 = [](uint64_t x) { return (uint32_t)std::min<uint64_t>((x + 255) & ~255ull, 0xFFFFFF00ull); };
+    if (flags) {
+        // a count did not fit: grow what overflowed and repeat (the slot count is exact whatever happened; the id
+        // count only when every slot had its row)
+        if ((flags & OVF_SLOTS) || nslots > ctx->capSlots) {
+            ctx->capSlots = round256((uint64_t)nslots + nslots / 16 + 1024);
+            ctx->capIds = std::max(ctx->capIds, ctx->capSlots);
+        } else if (flags & OVF_IDS) {
+            ctx->capIds = round256((uint64_t)nids + nids / 16 + 1024);
+        }
+        if (flags & OVF_LISTS) ctx->at_wide = std::min(ctx->at_wide, 0xFFFFFFu);   // (the list capacity follows capIds)
+        if (flags & OVF_CAND) {            // a rank's candidate list was longer than planned (every rank sees every list's length)
+            const uint32_t need = ctx->countsHost[C_MAXCAND];
+            ctx->capCandMin = round256((uint64_t)need + need / 16 + 1024);
+        }
+        ctx->lastSlots = ctx->lastIds = 0;
+        ctx->reruns++;
+        again = true;
+        return PFB_OK;
+    }
+    ctx->lastSlots = nslots; ctx->lastIds = nids;
     pfb_timing &t = ctx->tm;
     cudaEventElapsedTime(&t.ms_encode, ctx->ev[2], ctx->ev[3]);
     cudaEventElapsedTime(&t.ms_first, ctx->ev[3], ctx->ev[4]);
@@ -2246,13 +2618,20 @@ static int stage2(pfb_ctx *ctx) {
     cudaEventElapsedTime(&t.ms_finalize, ctx->ev[5], ctx->ev[6]);
     t.ms_scan_main = 0.f;
     t.scan_main_bases = 0;
-    if (!ctx->pipelined && ctx->nids && ctx->genomes.size() > 1 && cudaEventElapsedTime(&t.ms_scan_main, ctx->ev[7], ctx->ev[8]) == cudaSuccess) {
+    if (!ctx->run.piped && ctx->genomes.size() > 1 && cudaEventElapsedTime(&t.ms_scan_main, ctx->ev[7], ctx->ev[8]) == cudaSuccess) {
         for (size_t g = 1; g < ctx->genomes.size(); g++) t.scan_main_bases += ctx->genomes[g].n_bases;
     } else {
         t.ms_scan_main = 0.f;
         cudaGetLastError();
     }
     cudaEventElapsedTime(&t.ms_total, ctx->ev[2], ctx->ev[6]);
+    t.ms_exchange = 0.f;
+    for (int x = 0; x < 4; x++) {
+        float ms = 0.f;
+        if (ctx->xUsed[x] && cudaEventElapsedTime(&ms, ctx->evX[x][0], ctx->evX[x][1]) == cudaSuccess) t.ms_exchange += ms;
+        ctx->xUsed[x] = false;
+    }
+    cudaGetLastError();
     uint64_t nb = 0, nw = 0;
     for (auto &g : ctx->genomes) {
         nb += g.n_bases;
@@ -2262,50 +2641,250 @@ static int stage2(pfb_ctx *ctx) {
         }
     }
     t.n_bases = nb; t.n_windows = nw; t.n_slots = ctx->nslots; t.n_records = ctx->nrec; t.n_picked = ctx->npick;
+    t.n_ids = ctx->nids;
     t.n_launches = ctx->launches + ctx->fa_launches;
     t.used_filter = ctx->used_filter ? 1 : 0;
+    t.sharded_first_genome = ctx->sharded_now ? 1 : 0;
+    t.n_reruns = (uint64_t)ctx->reruns;
     ctx->computed = true;
+    ctx->host_valid = ctx->stream_out;
     return PFB_OK;
 }
 
-int pfb_compute_stage(pfb_ctx *ctx, int stage) {
-    if (!ctx) return PFB_EINVAL;
-    if (!ctx->uploaded) return fail(ctx, PFB_ESTATE, "pfb_upload has not run");
-    if (stage < 0 || stage > 2) return fail(ctx, PFB_EINVAL, "stage must be 0, 1 or 2");
-    if (stage > 0 && ctx->stage_done < stage - 1) return fail(ctx, PFB_ESTATE, "stages must run in order");
-    CK(cudaSetDevice(ctx->device));
-    int rc = stage == 0 ? stage0(ctx) : stage == 1 ? stage1(ctx) : stage2(ctx);
-    if (rc == PFB_OK) ctx->stage_done = stage;
-    return rc;
+// all contexts driven by this host thread through one run (see the phase list above)
+static int run_group(std::vector<pfb_ctx *> &C, bool piped) {
+    int rc;
+    for (int attempt = 0; attempt < 6; attempt++) {
+        for (pfb_ctx *c : C) if ((rc = phaseA(c, piped)) != PFB_OK) return rc;
+        if ((rc = collective(C, COLL_CANDS)) != PFB_OK) return rc;
+        for (pfb_ctx *c : C) if ((rc = phaseB(c)) != PFB_OK) return rc;
+        if ((rc = collective(C, COLL_ROWS0)) != PFB_OK) return rc;
+        for (pfb_ctx *c : C) if ((rc = phaseC(c)) != PFB_OK) return rc;
+        if ((rc = collective(C, COLL_ALIVE)) != PFB_OK) return rc;
+        for (pfb_ctx *c : C) if ((rc = phaseD(c)) != PFB_OK) return rc;
+        if ((rc = collective(C, COLL_PICK)) != PFB_OK) return rc;
+        for (pfb_ctx *c : C) if ((rc = phaseE(c)) != PFB_OK) return rc;
+        bool again = false;
+        for (pfb_ctx *c : C) if ((rc = finish(c, again)) != PFB_OK) return rc;
+        if (!again) return PFB_OK;
+        // every rank of a job sees the same counts (genome 1 is everywhere, the candidate lists are gathered), so
+        // all of them come here together.  The inputs are resident by now: the repeat does not wait for copies
+        if (piped) {
+            for (pfb_ctx *c : C) {
+                cudaSetDevice(c->device);
+                cudaStreamSynchronize(c->copyStream);
+                cudaStreamSynchronize(c->parseStream);
+                if (c->laid_out < c->genomes.size()) return fail(c, PFB_ESTATE, "layout incomplete after a pipelined run");
+            }
+            piped = false;
+        }
+        for (pfb_ctx *c : C) { cudaSetDevice(c->device); cudaStreamSynchronize(c->d2hStream); }
+    }
+    return fail(C[0], PFB_ECUDA, "the buffer capacities did not settle");
 }
 
 int pfb_compute(pfb_ctx *ctx) {
-    int rc;
-    for (int s = 0; s < 3; s++)
-        if ((rc = pfb_compute_stage(ctx, s)) != PFB_OK) return rc;
-    return PFB_OK;
+    if (!ctx) return PFB_EINVAL;
+    if (!ctx->uploaded) return fail(ctx, PFB_ESTATE, "pfb_upload has not run");
+    ctx->stream_out = false;
+    ctx->host_valid = false;
+    std::vector<pfb_ctx *> C{ctx};
+    return run_group(C, ctx->pipelined);
 }
 
 int pfb_run(pfb_ctx *ctx) {
-    // H2D of genome i+1.. overlaps the key-table build and the scan of the genomes already resident
+    // H2D of genome i+1.. overlaps the key-table build and the scan of the genomes already resident, and the
+    // results travel back while later genomes are still scanned
     int rc = upload_checked(ctx, true);
     if (rc != PFB_OK) return rc;
-    rc = pfb_compute(ctx);
+    ctx->stream_out = true;
+    ctx->host_valid = false;
+    std::vector<pfb_ctx *> C{ctx};
+    rc = run_group(C, true);
     int rc2 = pfb_upload_wait(ctx);             // the host buffers are borrowed until here, success or not
+    if (rc == PFB_OK && rc2 == PFB_OK) { if (cudaStreamSynchronize(ctx->d2hStream) != cudaSuccess) rc = fail(ctx, PFB_ECUDA, "result copies failed"); }
+    if (ctx->tracing) trace_dump(ctx);
     return rc != PFB_OK ? rc : rc2;
 }
 
-int pfb_device_buffer(pfb_ctx *ctx, int which, void **dev_ptr, uint64_t *n_bytes) {
-    if (!ctx || !dev_ptr || !n_bytes) return PFB_EINVAL;
-    if (which == PFB_BUF_ALIVE) {
-        if (ctx->stage_done < 0) return fail(ctx, PFB_ESTATE, "stage 0 has not run");
-        *dev_ptr = ctx->alive.p; *n_bytes = ctx->nids;
-    } else if (which == PFB_BUF_PICK) {
-        if (ctx->stage_done < 1) return fail(ctx, PFB_ESTATE, "stage 1 has not run");
-        *dev_ptr = ctx->pick.p; *n_bytes = ctx->nids;     // zero beyond the last record
-    } else {
-        return fail(ctx, PFB_EINVAL, "unknown buffer");
+// ---- multi-GPU, one process per GPU: every rank creates its context, rank 0 makes the id, all ranks join
+int pfb_comm_unique_id(uint8_t *id128) {
+    if (!id128) return PFB_EINVAL;
+    std::string why;
+    nccl::Api *a = nccl_api(why);
+    if (!a) return fail(nullptr, PFB_ECUDA, why);
+    nccl::UniqueId id;
+    int rc = a->GetUniqueId(&id);
+    if (rc) return fail(nullptr, PFB_ECUDA, std::string("ncclGetUniqueId: ") + a->GetErrorString(rc));
+    memcpy(id128, id.internal, 128);
+    return PFB_OK;
+}
+
+int pfb_comm_init_rank(pfb_ctx *ctx, int n_ranks, int rank, const uint8_t *id128) {
+    if (!ctx || !id128) return PFB_EINVAL;
+    if (n_ranks < 1 || rank < 0 || rank >= n_ranks) return fail(ctx, PFB_EINVAL, "need 0 <= rank < n_ranks");
+    if (ctx->comm) return fail(ctx, PFB_ESTATE, "the context already has a communicator");
+    std::string why;
+    nccl::Api *a = nccl_api(why);
+    if (!a) return fail(ctx, PFB_ECUDA, why);
+    CK(cudaSetDevice(ctx->device));
+    nccl::UniqueId id;
+    memcpy(id.internal, id128, 128);
+    int rc = a->CommInitRank(&ctx->comm, n_ranks, id, rank);
+    if (rc) { ctx->comm = nullptr; return fail(ctx, PFB_ECUDA, std::string("ncclCommInitRank: ") + a->GetErrorString(rc)); }
+    ctx->comm_owned = true;
+    ctx->nRanks = n_ranks; ctx->rank = rank;
+    return PFB_OK;
+}
+
+int pfb_set_option(pfb_ctx *ctx, int option, int value) {
+    if (!ctx) return PFB_EINVAL;
+    switch (option) {
+    case PFB_OPT_SCAN_MODE: return pfb_set_scan_mode(ctx, value);
+    case PFB_OPT_FETCH_RECORDS: ctx->fetch_records = value ? 1 : 0; return PFB_OK;
+    case PFB_OPT_SHARD_FIRST: ctx->shard_g1 = value ? 1 : 0; return PFB_OK;
+    case PFB_OPT_EMULATE_RANKS: ctx->emulate_ranks = value > 1 ? value : 0; ctx->caps_for_prefilter = -1; return PFB_OK;
+    default: return fail(ctx, PFB_EINVAL, "unknown option");
     }
+}
+
+// ---- multi-GPU, one process: N contexts, one communicator per context, one host thread
+int pfb_multi_create(pfb_multi **out, const int *device_ids, int n_dev, const pfb_params *params) {
+    if (!out) return fail(nullptr, PFB_EINVAL, "out is NULL");
+    *out = nullptr;
+    if (!device_ids || n_dev < 1) return fail(nullptr, PFB_EINVAL, "need at least one device");
+    for (int i = 0; i < n_dev; i++)
+        for (int j = 0; j < i; j++)
+            if (device_ids[i] == device_ids[j]) return fail(nullptr, PFB_EINVAL, "a device is listed twice");
+    pfb_multi *m = new pfb_multi();
+    for (int i = 0; i < n_dev; i++) {
+        pfb_ctx *c = nullptr;
+        int rc = pfb_create(&c, device_ids[i], params);
+        if (rc != PFB_OK) { pfb_multi_destroy(m); return rc; }
+        c->owner = m;
+        m->ctx.push_back(c);
+    }
+    if (n_dev > 1) {
+        std::string why;
+        nccl::Api *a = nccl_api(why);
+        if (!a) { pfb_multi_destroy(m); return fail(nullptr, PFB_ECUDA, why); }
+        std::vector<nccl::Comm *> comms(n_dev, nullptr);
+        int rc = a->CommInitAll(comms.data(), n_dev, device_ids);
+        if (rc) { pfb_multi_destroy(m); return fail(nullptr, PFB_ECUDA, std::string("ncclCommInitAll: ") + a->GetErrorString(rc)); }
+        for (int i = 0; i < n_dev; i++) {
+            m->ctx[i]->comm = comms[i]; m->ctx[i]->comm_owned = true;
+            m->ctx[i]->nRanks = n_dev; m->ctx[i]->rank = i;
+            m->ctx[i]->fetch_records = i == 0;      // the per-id records are the same on every GPU
+        }
+    }
+    *out = m;
+    return PFB_OK;
+}
+
+void pfb_multi_destroy(pfb_multi *m) {
+    if (!m) return;
+    for (pfb_ctx *c : m->ctx) pfb_destroy(c);
+    delete m;
+}
+
+const char *pfb_multi_last_error(const pfb_multi *m) {
+    if (!m) return g_create_err.c_str();
+    for (pfb_ctx *c : m->ctx) if (!c->err.empty()) return c->err.c_str();
+    return m->err.c_str();
+}
+
+// genome 0 goes to every context (it defines the key table and the ids), the others round-robin
+static int multi_add(pfb_multi *m, int (*add)(pfb_ctx *, const uint8_t *, uint64_t, const uint64_t *, uint32_t), const uint8_t *data,
+                     uint64_t n, const uint64_t *off, uint32_t nc) {
+    if (!m) return PFB_EINVAL;
+    const size_t g = m->where.size();
+    int rc;
+    if (g == 0) {
+        for (pfb_ctx *c : m->ctx) if ((rc = add(c, data, n, off, nc)) != PFB_OK) return rc;
+        m->where.emplace_back(0, 0u);
+    } else {
+        const int ci = (int)((g - 1) % m->ctx.size());
+        pfb_ctx *c = m->ctx[ci];
+        if ((rc = add(c, data, n, off, nc)) != PFB_OK) return rc;
+        m->where.emplace_back(ci, (uint32_t)c->genomes.size() - 1);
+    }
+    return PFB_OK;
+}
+
+static int add_fasta4(pfb_ctx *c, const uint8_t *d, uint64_t n, const uint64_t *, uint32_t) { return pfb_add_fasta(c, d, n); }
+static int add_genbank4(pfb_ctx *c, const uint8_t *d, uint64_t n, const uint64_t *, uint32_t) { return pfb_add_genbank(c, d, n); }
+
+int pfb_multi_add_genome(pfb_multi *m, const uint8_t *bases, uint64_t n_bases, const uint64_t *contig_off, uint32_t n_contigs) {
+    return multi_add(m, pfb_add_genome, bases, n_bases, contig_off, n_contigs);
+}
+int pfb_multi_add_fasta(pfb_multi *m, const uint8_t *file_bytes, uint64_t n_bytes) { return multi_add(m, add_fasta4, file_bytes, n_bytes, nullptr, 0); }
+int pfb_multi_add_genbank(pfb_multi *m, const uint8_t *file_bytes, uint64_t n_bytes) { return multi_add(m, add_genbank4, file_bytes, n_bytes, nullptr, 0); }
+
+int pfb_multi_run(pfb_multi *m) {
+    if (!m || m->ctx.empty()) return PFB_EINVAL;
+    if (m->where.empty()) return fail(m->ctx[0], PFB_ESTATE, "no genome added");
+    int rc = PFB_OK;
+    for (pfb_ctx *c : m->ctx) {
+        c->err.clear();
+        if ((rc = upload_checked(c, true)) != PFB_OK) break;
+        c->stream_out = true; c->host_valid = false;
+    }
+    if (rc == PFB_OK) rc = run_group(m->ctx, true);
+    for (pfb_ctx *c : m->ctx) {
+        int rc2 = pfb_upload_wait(c);
+        if (rc == PFB_OK) rc = rc2;
+        if (rc == PFB_OK && (cudaSetDevice(c->device) != cudaSuccess || cudaStreamSynchronize(c->d2hStream) != cudaSuccess))
+            rc = fail(c, PFB_ECUDA, "result copies failed");
+    }
+    return rc;
+}
+
+int pfb_multi_size(const pfb_multi *m) { return m ? (int)m->ctx.size() : 0; }
+
+int pfb_multi_context(pfb_multi *m, int index, pfb_ctx **out) {
+    if (!m || !out || index < 0 || index >= (int)m->ctx.size()) return PFB_EINVAL;
+    *out = m->ctx[index];
+    return PFB_OK;
+}
+
+int pfb_multi_locate(const pfb_multi *m, uint32_t genome_idx, int *context_index, uint32_t *local_idx) {
+    if (!m || genome_idx >= m->where.size()) return PFB_EINVAL;
+    if (context_index) *context_index = m->where[genome_idx].first;
+    if (local_idx) *local_idx = m->where[genome_idx].second;
+    return PFB_OK;
+}
+
+// ---- results.  The device keeps everything indexed by id (the reference's dict order); the host gets the per-id
+// columns once per run -- during the run (pfb_run, pfb_multi_run) or on the first result call (pfb_compute) -- and
+// the record-oriented calls below compact them on the host.
+static int fetch_host(pfb_ctx *ctx) {
+    if (!ctx->computed) return fail(ctx, PFB_ESTATE, "no completed run");
+    if (ctx->host_valid) return PFB_OK;
+    CK(cudaSetDevice(ctx->device));
+    int rc;
+    if ((rc = host_buffers(ctx)) != PFB_OK) return rc;
+    const size_t CI = ctx->capIds, nG = ctx->genomes.size();
+    cudaStream_t st = ctx->stream;
+    CK(cudaMemcpyAsync(ctx->hWord.p, ctx->k.key1, CI * 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(ctx->hTm.p, ctx->k.idTm, CI * 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(ctx->hInfo.p, ctx->k.idInfo, CI * 2, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(ctx->hPos.p, ctx->k.pos32, CI * nG * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(ctx->hAlive.p, ctx->k.alive, CI, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(ctx->hPick.p, ctx->k.pick, CI, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    ctx->host_valid = true;
+    return PFB_OK;
+}
+
+// records stayed on the device (fetch_records = 0) and are asked for after all: get them now
+static int fetch_records_now(pfb_ctx *ctx) {
+    if (ctx->fetch_records || !ctx->stream_out) return PFB_OK;
+    CK(cudaSetDevice(ctx->device));
+    const size_t CI = ctx->capIds;
+    CK(cudaMemcpyAsync(ctx->hWord.p, ctx->k.key1, CI * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->hTm.p, ctx->k.idTm, CI * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->hInfo.p, ctx->k.idInfo, CI * 2, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
     return PFB_OK;
 }
 
@@ -2317,61 +2896,101 @@ int pfb_result_counts(pfb_ctx *ctx, uint64_t *n_records, uint64_t *n_picked) {
     return ctx->nrec ? PFB_OK : PFB_ENOSHARED;
 }
 
+int pfb_result_by_id(pfb_ctx *ctx, pfb_idview *out) {
+    if (!ctx || !out) return PFB_EINVAL;
+    int rc = fetch_host(ctx);
+    if (rc != PFB_OK) return rc;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->d2hStream));
+    out->n_ids = ctx->nids; out->pitch = ctx->hostPitch; out->n_genomes = ctx->genomes.size();
+    out->records_valid = (ctx->fetch_records || !ctx->stream_out) ? 1 : 0;
+    out->word = (const uint64_t *)ctx->hWord.p; out->tm = (const double *)ctx->hTm.p; out->info = (const uint16_t *)ctx->hInfo.p;
+    out->pos = (const uint32_t *)ctx->hPos.p; out->alive = (const uint8_t *)ctx->hAlive.p; out->pick = (const uint8_t *)ctx->hPick.p;
+    return PFB_OK;
+}
+
+static inline pfb_record make_record(const pfb_ctx *ctx, uint64_t id) {
+    const uint16_t info = ((const uint16_t *)ctx->hInfo.p)[id];
+    pfb_record r;
+    r.word = ((const uint64_t *)ctx->hWord.p)[id];
+    r.tm = ((const double *)ctx->hTm.p)[id];
+    r.slot = (uint32_t)id;
+    r.gc_count = (uint16_t)((info >> 5) & 63u);
+    r.k = (uint8_t)((info & 31u) + 1u);
+    r.flags = (uint8_t)((info >> 11) | (((const uint8_t *)ctx->hPick.p)[id] ? PFB_F_PICK : 0u));
+    return r;
+}
+
+// genome-local padded coordinate -> (contig index within the genome, start within the contig)
+static inline void decode_place(const pfb_ctx *ctx, uint32_t g, uint32_t lp, uint32_t &contig, uint32_t &start) {
+    const uint32_t c0 = ctx->gFirstContig[g], nc = ctx->gNumContigs[g];
+    if (nc == 1) { contig = 0; start = lp; return; }
+    const uint32_t w = ctx->gWordStart[g] + (lp >> 5);
+    uint32_t lo = c0, hi = c0 + nc;
+    while (hi - lo > 1) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (ctx->cWordStart[mid] <= w) lo = mid; else hi = mid;
+    }
+    while (lo + 1 < c0 + nc && ctx->cWordStart[lo + 1] <= w) lo++;          // (empty contigs share their first word)
+    contig = lo - c0;
+    start = lp - 32u * (ctx->cWordStart[lo] - ctx->gWordStart[g]);
+}
+
 int pfb_result_records(pfb_ctx *ctx, pfb_record *out, uint64_t cap) {
     if (!ctx || (!out && cap)) return PFB_EINVAL;
-    if (!ctx->computed) return fail(ctx, PFB_ESTATE, "no completed run");
+    int rc = fetch_host(ctx);
+    if (rc != PFB_OK) return rc;
+    if ((rc = fetch_records_now(ctx)) != PFB_OK) return rc;
     if (cap < ctx->nrec) return fail(ctx, PFB_EINVAL, "record buffer too small");
-    CK(cudaSetDevice(ctx->device));
-    if (ctx->nrec) {
-        CK(cudaMemcpyAsync(out, ctx->rec.p, ctx->nrec * sizeof(pfb_record), cudaMemcpyDeviceToHost, ctx->stream));
-        CK(cudaStreamSynchronize(ctx->stream));
-    }
+    const uint8_t *alive = (const uint8_t *)ctx->hAlive.p;
+    uint64_t n = 0;
+    for (uint64_t id = 0; id < ctx->nids; id++)
+        if (alive[id]) out[n++] = make_record(ctx, id);
     return PFB_OK;
 }
 
 int pfb_result_positions(pfb_ctx *ctx, uint32_t genome_idx, int picked_only, pfb_pos *out, uint64_t cap) {
     if (!ctx || (!out && cap)) return PFB_EINVAL;
-    if (!ctx->computed) return fail(ctx, PFB_ESTATE, "no completed run");
+    int rc = fetch_host(ctx);
+    if (rc != PFB_OK) return rc;
     if (genome_idx >= ctx->genomes.size()) return fail(ctx, PFB_EINVAL, "genome index out of range");
-    CK(cudaSetDevice(ctx->device));
-    const uint64_t n = picked_only ? ctx->npick : ctx->nrec;
-    if (cap < n) return fail(ctx, PFB_EINVAL, "position buffer too small");
-    if (!n) return PFB_OK;
-    const uint32_t *ps = (picked_only ? (const uint32_t *)ctx->outPos.p : (const uint32_t *)ctx->pos.p) + (size_t)genome_idx * ctx->nids;
-    const uint32_t *cs = (picked_only ? (const uint32_t *)ctx->outContig.p : (const uint32_t *)ctx->posContig.p) + (size_t)genome_idx * ctx->nids;
-    std::vector<uint32_t> hp(n), hc;
-    CK(cudaMemcpyAsync(hp.data(), ps, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
-    if (ctx->k.multiContig) {
-        hc.resize(n);
-        CK(cudaMemcpyAsync(hc.data(), cs, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
-    }
-    CK(cudaStreamSynchronize(ctx->stream));
-    for (uint64_t r = 0; r < n; r++) {
-        out[r].contig = ctx->k.multiContig ? hc[r] : 0u;
-        out[r].start = hp[r] & 0x7FFFFFFFu;
-        out[r].strand = hp[r] >> 31;
+    const uint64_t want = picked_only ? ctx->npick : ctx->nrec;
+    if (cap < want) return fail(ctx, PFB_EINVAL, "position buffer too small");
+    const uint8_t *sel = (const uint8_t *)(picked_only ? ctx->hPick.p : ctx->hAlive.p);
+    const uint32_t *row = (const uint32_t *)ctx->hPos.p + (size_t)genome_idx * ctx->hostPitch;
+    uint64_t n = 0;
+    for (uint64_t id = 0; id < ctx->nids; id++) {
+        if (!sel[id]) continue;
+        decode_place(ctx, genome_idx, row[id] & 0x7FFFFFFFu, out[n].contig, out[n].start);
+        out[n].strand = row[id] >> 31;
+        n++;
     }
     return PFB_OK;
 }
 
 int pfb_result_picked(pfb_ctx *ctx, pfb_record *rec_out, uint32_t *start_strand_out, uint32_t *contig_out, uint64_t cap) {
     if (!ctx) return PFB_EINVAL;
-    if (!ctx->computed) return fail(ctx, PFB_ESTATE, "no completed run");
+    int rc = fetch_host(ctx);
+    if (rc != PFB_OK) return rc;
+    if ((rc = fetch_records_now(ctx)) != PFB_OK) return rc;
     if (cap < ctx->npick) return fail(ctx, PFB_EINVAL, "output buffers too small");
     if (!ctx->npick) return PFB_OK;
     if (!rec_out || !start_strand_out) return fail(ctx, PFB_EINVAL, "NULL output buffer");
-    CK(cudaSetDevice(ctx->device));
-    const size_t nG = ctx->genomes.size(), np = ctx->npick;
-    CK(cudaMemcpyAsync(rec_out, ctx->outRec.p, np * sizeof(pfb_record), cudaMemcpyDeviceToHost, ctx->stream));
-    // the caller's rows are `cap` apart, the device rows `nids` apart
-    CK(cudaMemcpy2DAsync(start_strand_out, cap * 4, ctx->outPos.p, ctx->nids * 4, np * 4, nG, cudaMemcpyDeviceToHost, ctx->stream));
-    if (contig_out) {
-        if (ctx->k.multiContig)
-            CK(cudaMemcpy2DAsync(contig_out, cap * 4, ctx->outContig.p, ctx->nids * 4, np * 4, nG, cudaMemcpyDeviceToHost, ctx->stream));
-        else
-            for (size_t g = 0; g < nG; g++) memset(contig_out + g * cap, 0, np * 4);
+    const size_t nG = ctx->genomes.size();
+    const uint8_t *pick = (const uint8_t *)ctx->hPick.p;
+    uint64_t n = 0;
+    for (uint64_t id = 0; id < ctx->nids; id++) {
+        if (!pick[id]) continue;
+        rec_out[n] = make_record(ctx, id);
+        for (size_t g = 0; g < nG; g++) {
+            const uint32_t v = ((const uint32_t *)ctx->hPos.p)[g * ctx->hostPitch + id];
+            uint32_t contig, start;
+            decode_place(ctx, (uint32_t)g, v & 0x7FFFFFFFu, contig, start);
+            start_strand_out[g * cap + n] = start | (v & 0x80000000u);
+            if (contig_out) contig_out[g * cap + n] = contig;
+        }
+        n++;
     }
-    CK(cudaStreamSynchronize(ctx->stream));
     return PFB_OK;
 }
 

@@ -1,15 +1,14 @@
-"""Multi-GPU plumbing (one process per GPU, torch.distributed).
+"""Multi-GPU plumbing, one process per GPU (torchrun / torch.distributed for the rendezvous only).
 
-The stage shards by GENOME: every rank holds genome 0 -- it alone defines the key table, so the
-table is identical on every rank without any exchange -- plus its own share of the other genomes.
-What has to be agreed between ranks is tiny: one byte per key ("still unique in every genome this
-rank scanned", MIN all-reduce) and one byte per record ("picked in some genome", MAX all-reduce).
-No k-mer ever crosses NVLink.  See DESIGN.md for why the all-to-all of north_star's sketch
-is not needed once the key table is replicated.
+The stage shards by GENOME: every rank holds genome 0 -- it alone defines the key table and the ids, so both are
+identical on every rank -- plus its own share of the other genomes; genome 0's own pipeline (candidate windows,
+its scan) is shared out by position.  The exchanges (an all-gather of genome 0's candidate lists, a SUM
+all-reduce of its packed rows, a MIN all-reduce of one byte per id and a MAX all-reduce of one byte per id) are
+NCCL calls INSIDE libpfb200.so on each context's own stream; torch.distributed only carries the 128-byte NCCL
+id from rank 0 to the others.  See DESIGN.md for why the all-to-all of north_star's sketch is not needed once
+the key table is replicated.  One process for all GPUs: primerforge_b200.engine.MultiEngine.
 """
 from __future__ import annotations
-
-import numpy as np
 
 
 def shard_genomes(n_genomes: int, world: int, rank: int) -> list:
@@ -20,50 +19,28 @@ def shard_genomes(n_genomes: int, world: int, rank: int) -> list:
     return [0] + rest[rank::world]
 
 
-class _DeviceBytes:
-    """exposes a raw device pointer through __cuda_array_interface__ (zero copy into torch)"""
-
-    def __init__(self, ptr: int, n: int):
-        self.__cuda_array_interface__ = {"shape": (n,), "typestr": "|u1", "data": (ptr, False), "version": 2}
-
-
-def reduce_bytes(t, op: str):
-    """in-place all-reduce of a uint8 tensor over the default process group (any backend)"""
+def broadcast_unique_id(make_id) -> bytes:
+    """rank 0 calls make_id() (-> 128 bytes); every rank returns those bytes (any torch.distributed backend)"""
     import torch.distributed as dist
-    if not dist.is_initialized() or dist.get_world_size() == 1:
-        return t
-    dist.all_reduce(t, op=dist.ReduceOp.MIN if op == "min" else dist.ReduceOp.MAX)
-    return t
+    rank = dist.get_rank()
+    box = [make_id() if rank == 0 else None]
+    dist.broadcast_object_list(box, src=0)
+    uid = bytes(box[0])
+    if len(uid) != 128:
+        raise ValueError("an NCCL unique id is 128 bytes")
+    return uid
 
 
-def allreduce_stage_buffers(eng, which: int, op: str):
-    """all-reduce one of the engine's per-key / per-record byte vectors in place (NCCL on device memory).
-    The reduction is enqueued behind the stage's kernels on the engine's own stream (ExternalStream), so
-    the host never waits between the stages."""
-    import torch
-    ptr, n = eng.device_buffer(which)
-    if n == 0:
-        return
-    dev = torch.device("cuda", torch.cuda.current_device())
-    ext = getattr(eng, "_torch_stream", None)
-    if ext is None:
-        ext = torch.cuda.ExternalStream(eng.stream_handle(), device=dev)
-        eng._torch_stream = ext
-    t = torch.as_tensor(_DeviceBytes(ptr, n), device=dev)
-    with torch.cuda.stream(ext):
-        reduce_bytes(t, op)
-
-
-def run_sharded(eng, upload: bool = False):
-    """the three compute stages with the two reductions in between; with upload=True the H2D copies of
-    the rank's genomes are queued first and overlap stage 0"""
+def attach_comm(eng) -> bool:
+    """joins `eng` (this rank's Engine) to a communicator spanning the default process group; afterwards eng.run()
+    and eng.compute() are collective calls.  Ranks > 0 leave the per-id record columns on their device (they are
+    identical on every rank).  Returns False when there is nothing to attach (one rank)."""
+    import torch.distributed as dist
     from . import _lib
-    if upload:
-        eng.upload_async()
-    eng.compute_stage(0)
-    allreduce_stage_buffers(eng, _lib.PFB_BUF_ALIVE, "min")
-    eng.compute_stage(1)
-    allreduce_stage_buffers(eng, _lib.PFB_BUF_PICK, "max")
-    eng.compute_stage(2)
-    if upload:
-        eng.upload_wait()
+    if not dist.is_initialized() or dist.get_world_size() == 1:
+        return False
+    world, rank = dist.get_world_size(), dist.get_rank()
+    uid = broadcast_unique_id(type(eng).unique_id)
+    eng.comm_init(world, rank, uid)
+    eng.set_option(_lib.OPT_FETCH_RECORDS, 1 if rank == 0 else 0)
+    return True

@@ -12,7 +12,7 @@ def main():
     import torch
     import torch.distributed as dist
     from primerforge_b200 import synth
-    from primerforge_b200.dist import run_sharded, shard_genomes
+    from primerforge_b200.dist import attach_comm, shard_genomes
     from primerforge_b200.engine import Engine
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
@@ -23,6 +23,7 @@ def main():
     gens = synth.make_genomes(n_genomes, length, seed=909, snp_rate=0.004, n_inversions=3, n_contigs=n_contigs)
     mine = shard_genomes(n_genomes, world, rank)
     eng = Engine(device=local)
+    attach_comm(eng)          # from here on eng.run() is a collective call: the exchanges happen inside the library
     for gi in mine:
         if as_fasta:
             img = bytearray()
@@ -34,7 +35,8 @@ def main():
             eng.add_fasta(np.frombuffer(bytes(img), dtype=np.uint8).copy())
         else:
             eng.add_genome(gens[gi].contigs)
-    run_sharded(eng, upload=True)
+    eng.run()
+    assert eng.timing()["sharded_first_genome"] == 1      # the ranks shared genome 1's own pipeline
     rec, ss, ct = eng.result_picked()
     rec, ss = rec.copy(), ss.copy()
     ct = None if ct is None else ct.copy()

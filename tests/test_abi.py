@@ -29,7 +29,8 @@ def test_struct_sizes_match_header():
     import ctypes as C
     assert C.sizeof(_lib.PfbParams) == 112
     assert _lib.RECORD_DTYPE.itemsize == 24 and _lib.POS_DTYPE.itemsize == 12
-    assert C.sizeof(_lib.PfbTiming) == 6 * 4 + 8 * 8 + 2 * 4
+    assert C.sizeof(_lib.PfbTiming) == 6 * 4 + 8 * 8 + 2 * 4 + 3 * 8
+    assert C.sizeof(_lib.PfbIdView) == 4 * 8 + 6 * 8
 
 
 def test_defaults_are_the_reference_defaults():
@@ -58,4 +59,6 @@ def test_product_never_imports_the_oracle():
                 assert "libpf_oracle" not in text, fn
             elif text:
                 assert not re.search(r"#include.*oracle", text), fn
-                assert "dlopen" not in text, fn
+                assert "libpf_oracle" not in text, fn
+                # the only library bound at run time is NCCL (more than one GPU)
+                assert all("nccl" in lit for lit in re.findall(r'"([^"]*\.so[^"]*)"', text)), fn

@@ -414,3 +414,55 @@ def test_id_list_path_of_the_key_table(monkeypatch):
         assert np.array_equal(rec_a[f], rec_b[f])
     for a, b in zip(pos_a, pos_b):
         assert np.array_equal(a, b)
+
+
+@pytest.mark.parametrize("n_ranks", [2, 3, 8])
+@pytest.mark.parametrize("n_contigs,n_frac", [(1, 0.0), (6, 0.0005)])
+def test_shared_out_first_genome_pipeline_equals_oracle(n_ranks, n_contigs, n_frac):
+    """the multi-GPU formulation of genome 1's own pipeline -- candidate windows listed per rank and applied by all,
+    its scan in per-rank shares whose rows are packed to 32 bits and summed, polluter windows re-derived by every
+    rank -- played by ONE context for n ranks in turn (PFB_OPT_EMULATE_RANKS: everything but the NCCL calls), so
+    that a single-GPU box checks it against the oracle"""
+    from oracle import pf_oracle as po
+    from primerforge_b200 import _lib, synth
+    from primerforge_b200.engine import Engine
+    from tests.util import assert_equals_oracle
+    gens = synth.make_genomes(4, 150_000, seed=520 + n_ranks, snp_rate=0.003, n_inversions=3, n_contigs=n_contigs, n_frac=n_frac)
+    kw = dict(k_min=16, k_max=20, min_gc=40.0, max_gc=60.0, min_tm=55.0, max_tm=68.0, max_repeat=4,
+              table_size=9999991 if n_contigs == 1 else 250007)       # the small table: collisions + junction pollution
+    o = po.run(gens, po.default_params(**kw))
+    with Engine(device=0, prefilter=1, **kw) as eng:
+        eng.set_option(_lib.OPT_EMULATE_RANKS, n_ranks)
+        for g in gens:
+            eng.add_genome(g.contigs)
+        eng.run()
+        assert eng.timing()["sharded_first_genome"] == 1
+        res = eng.result()
+    assert_equals_oracle(res, o, True, len(gens))
+
+
+def test_capacities_that_prove_too_small_repeat_the_run(monkeypatch):
+    """no step of a run waits for a count: buffers have capacities, and a count that does not fit is found at the end,
+    the capacity grown and the run repeated -- here forced with a tiny a-priori share, single and shared-out"""
+    from oracle import pf_oracle as po
+    from primerforge_b200 import _lib, synth
+    from primerforge_b200.engine import Engine
+    from tests.util import assert_equals_oracle
+    gens = synth.make_genomes(3, 120_000, seed=530, snp_rate=0.003, n_inversions=2, n_contigs=2)
+    kw = dict(k_min=16, k_max=20, min_gc=40.0, max_gc=60.0, min_tm=55.0, max_tm=68.0, max_repeat=4, table_size=9999991)
+    o = po.run(gens, po.default_params(**kw))
+    monkeypatch.setenv("PFB200_CAP_SHARE", "0.0005")
+    for prefilter, emulate in ((0, 0), (1, 0), (1, 4)):
+        with Engine(device=0, prefilter=prefilter, **kw) as eng:
+            if emulate:
+                eng.set_option(_lib.OPT_EMULATE_RANKS, emulate)
+            for g in gens:
+                eng.add_genome(g.contigs)
+            eng.run()
+            assert eng.timing()["n_reruns"] >= 1
+            res = eng.result()
+            assert_equals_oracle(res, o, bool(prefilter), len(gens))
+            eng.upload()
+            eng.compute()                              # the capacities have settled: no repeat the second time
+            assert eng.timing()["n_reruns"] == res.timing["n_reruns"]
+            assert_equals_oracle(eng.result(), o, bool(prefilter), len(gens))

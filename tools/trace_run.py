@@ -23,7 +23,7 @@ for i in range(4):
     t0 = time.perf_counter()
     eng.run()
     t1 = time.perf_counter()
-    eng.result_picked()
+    eng.result_by_id()
     eng.sync()
     t2 = time.perf_counter()
     print(f"host: run {1e3 * (t1 - t0):.3f} ms, fetch {1e3 * (t2 - t1):.3f} ms", file=sys.stderr)
