@@ -103,7 +103,8 @@ typedef struct pfb_timing {
  * of sharedKmers, getCandidateKmers.py:190-219), pick[id] = PFB_F_PICK.  Host pointers into pinned buffers owned
  * by the context, valid until its next run.  info = (k - 1) | gc_count << 5 | flags << 11 (PFB_F_GC_OK,
  * PFB_F_TM_OK, PFB_F_REP_OK, PFB_F_PALIN); pos[g * pitch + id] = genome-local padded coordinate of the leftmost
- * base | strand << 31 in the g-th genome of this context (only where alive[id]) -- the contigs of a genome are
+ * base | strand << 31 in the g-th genome of this context, 0xFFFFFFFF where the k-mer is not unique in that genome
+ * (alive[id] = none of the rows of any rank says so) -- the contigs of a genome are
  * laid out in the order added, each starting at a multiple of 32, so for a single-contig genome this IS the
  * start; pfb_result_positions / pfb_result_picked decode it to (contig, start). */
 typedef struct pfb_idview {

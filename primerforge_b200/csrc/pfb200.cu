@@ -63,11 +63,15 @@ constexpr uint64_t ROW_JR = 1ull << 63;            // reverse-string-only pollut
 constexpr uint32_t MAX_GENOME_WORDS = 1u << 21; // 2^26 padded bases
 constexpr uint32_t ID_NONE = 0xFFFFFFFFu;
 
-constexpr uint32_t FILTER_BYTES = 192u * 1024u; // shared-memory filter of k_scan_filtered
+constexpr uint32_t FILTER_BYTES = 179u * 1024u; // shared-memory filter of the filtered scans
 constexpr uint32_t FILTER_BITS = FILTER_BYTES * 8u;
 constexpr uint32_t FILTER_WORDS = FILTER_BYTES / 4u;
 constexpr uint32_t QCAP = 64;                   // per-warp queue of filter-positive windows (16 B items)
 constexpr uint32_t SCANF_SMEM = FILTER_BYTES + 32u * QCAP * 16u;
+// k_scan_filtered2: per warp a stack of 96 16-byte items (two windows per lane may arrive between two "batch ready" tests)
+constexpr uint32_t Q2_ITEMS = 96;
+constexpr uint32_t SCAN2_SMEM = FILTER_BYTES + 32u * Q2_ITEMS * 16u;
+static_assert(SCAN2_SMEM <= 227u * 1024u, "shared memory of k_scan_filtered2");
 constexpr int SCAN_TILE = 2048;                 // elements per block of the device-wide scans
 
 struct K {  // kernel arguments (by value, __grid_constant__)
@@ -791,6 +795,187 @@ __global__ void __launch_bounds__(1024, 1) k_scan_filtered(const __grid_constant
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// k_scan_filtered2: the hot kernel, second formulation.  Same contract as k_scan_filtered (a per-k filter in
+// shared memory, filter-positive windows queued per warp, probed 32 at a time, fire-and-forget REDs) with the
+// instruction count per window cut down (ncu, config 2: 66 -> see profiles/):
+//   * a thread's 32 windows are two runs of 16 over FIXED registers with COMPILE-TIME shift amounts: the reverse-
+//     complement stream is shifted once per word (by 66 - 2k bits) so that its windows change source registers at
+//     the same place as the forward ones (window o: forward bits [2o, 2o + 2k), reverse bits [62 - 2o, ...)); no
+//     segment bookkeeping, no loop counter, no shift registers; two windows are in flight per thread (the
+//     "is a batch ready" test runs every second window);
+//   * the queue is a plain stack: items (bin, start, genome) are appended at the top and a batch is the TOP 32
+//     -- no ring arithmetic, nothing to move (the REDs commute, so the order of the probes is free);
+//   * the pass over genome 1 itself (another key table) is a separate instantiation: no run-time branch in the
+//     drain.
+struct Scan2 {
+    uint32_t q_addr;         // shared-window address of this warp's queue (uint4 items)
+    uint32_t qn;             // items queued (warp-uniform)
+    bool pend;               // a batch of 32 probes is in flight
+    Pending pd;
+    uint32_t lane, lt_mask;
+};
+
+template <bool FIRST>
+__device__ __forceinline__ void drain2_consume(const K &p, const Pending &pd) {
+    const uint32_t b = pd.meta >> 26;          // bin & 31: all the two tables need of the bin besides the probe word
+    const unsigned long long add = ROW_ONE | (pd.meta & (uint32_t)ROW_POS_MASK);
+    if (FIRST) {
+        const uint32_t slot = pd.e.y + __popc(pd.e.x & ((1u << b) - 1u));
+        if (((pd.e.x >> b) & 1u) && slot < p.capSlots) atomicAdd(&p.rows0[slot], add);
+    } else {
+        const uint32_t id = id_of(p, pd.e, b & 15u);
+        if (id != ID_NONE) atomicAdd(&p.rows[(size_t)(pd.g - 1) * p.capIds + id], add);
+    }
+}
+
+template <bool FIRST>
+__device__ __forceinline__ void drain2(const K &p, int ki, Scan2 &sw) {
+    __syncwarp();                                            // every lane's appends are visible
+    if (sw.pend) drain2_consume<FIRST>(p, sw.pd);
+    const uint32_t taken = min(sw.qn, 32u);                  // a full batch but for the flush at the end of a pass
+    sw.qn -= taken;
+    uint4 it = make_uint4(0u, 0u, 0u, 0u);
+    sw.pd.e = make_uint2(0u, 0u);
+    if (sw.lane < taken) {
+        it = lds128(sw.q_addr + ((sw.qn + sw.lane) << 4));   // x = bin, y = start, z = genome
+        sw.pd.e = FIRST ? probe(p, ki, it.x) : probe2(p, ki, it.x);
+    }
+    sw.pd.meta = (it.y & (uint32_t)ROW_POS_MASK) | ((it.x & 31u) << 26);
+    sw.pd.g = it.z;
+    sw.pend = true;
+    __syncwarp();
+}
+
+template <bool FASTMOD, bool KBIG>
+__device__ __forceinline__ void window2(const K &p, Scan2 &sw, uint32_t f_addr, uint32_t h_lo, uint32_t h_hi, uint32_t r_lo, uint32_t r_hi,
+                                        uint32_t m32, uint32_t a32, uint32_t neg_p, uint32_t start, uint32_t g, bool valid) {
+    const uint32_t bin = canon_bin<FASTMOD, KBIG>(p, h_lo, h_hi, r_lo, r_hi, m32, a32, neg_p);
+    // filter bit = (word umulhi(bin, scale), bit bin & 31); read unconditionally: no branch before the LDS
+    uint32_t hit = lds32(f_addr + __umulhi(bin, p.fscale) * 4u) & __funnelshift_l(0u, 1u, bin);   // word & (1 << (bin & 31))
+    if (!valid) hit = 0u;
+    const uint32_t m = __ballot_sync(0xFFFFFFFFu, hit != 0u);
+    sts128_if(hit, sw.q_addr + ((sw.qn + __popc(m & sw.lt_mask)) << 4), bin, start, g, 0u);
+    sw.qn += __popc(m);
+}
+
+template <bool FASTMOD, bool KBIG, bool FIRST>
+__device__ __forceinline__ void scan2_pass(const K &p, int ki, int k, Scan2 &sw, uint32_t f_addr, uint32_t first, uint32_t w1,
+                                           uint32_t stride, uint32_t warp) {
+    const uint64_t km2 = kmask2(k);
+    const uint64_t km1 = kmask1(k);
+    const uint32_t mlo = (uint32_t)km2, mhi = (uint32_t)(km2 >> 32);
+    const uint32_t m32 = (uint32_t)(0x100000000ull / p.P);            // floor(2^32 / P)
+    const uint32_t a32 = (uint32_t)(0x100000000ull % p.P);            // 2^32 mod P
+    const uint32_t neg_p = 0u - p.P;
+    const int rs = 66 - 2 * k;                                        // the reverse stream's one shift per word (2 .. 64)
+    const int rws = rs >> 5;
+    const uint32_t rbs = (uint32_t)rs & 31u;
+    for (uint32_t wb = first + warp * 32; wb < w1; wb += stride) {
+        const uint32_t w = wb + sw.lane;
+        uint32_t vmask = 0, g = 0, gpos0 = 0;
+        uint64_t cur = 0, prev = 0, nm = 0;
+        if (w < w1) {
+            uint32_t c = p.wordContig[w];
+            uint32_t i = w - p.cWordStart[c];
+            uint32_t qbase = 32u * i;
+            uint32_t nj = min(32u, p.cLen[c] - qbase);
+            uint32_t jlo = qbase + 1 >= (uint32_t)k ? 0u : (uint32_t)k - 1 - qbase;   // first end position with a full window
+            if (jlo < nj) vmask = (nj == 32 ? 0xFFFFFFFFu : ((1u << nj) - 1u)) & ~((1u << jlo) - 1u);
+            g = p.cGenome[c];
+            cur = p.seq2[w];
+            prev = i ? p.seq2[w - 1] : 0ull;
+            nm = ((uint64_t)(i ? p.nmask[w - 1] : 0u) << 32) | p.nmask[w];
+            gpos0 = 32u * (w - p.gWordStart[g]);
+        }
+        const uint32_t start31 = gpos0 + 31u - (uint32_t)k + 1u;     // start of the window ending at base 31 of the word (o = 0)
+        const uint32_t F0 = (uint32_t)cur, F1 = (uint32_t)(cur >> 32), F2 = (uint32_t)prev, F3 = (uint32_t)(prev >> 32);
+        const uint64_t rcc = rc64(cur), rcp = rc64(prev);
+        // the stream rc(cur) : rc(prev) shifted right by 66 - 2k bits: the window of o now starts at bit 62 - 2o
+        const uint32_t S0 = (uint32_t)rcp, S1 = (uint32_t)(rcp >> 32), S2 = (uint32_t)rcc, S3 = (uint32_t)(rcc >> 32);
+        const uint32_t T0 = rws == 0 ? S0 : rws == 1 ? S1 : S2, T1 = rws == 0 ? S1 : rws == 1 ? S2 : S3;
+        const uint32_t T2 = rws == 0 ? S2 : rws == 1 ? S3 : 0u, T3 = rws == 0 ? S3 : 0u;
+        const uint32_t R0 = __funnelshift_r(T0, T1, rbs), R1 = __funnelshift_r(T1, T2, rbs), R2 = __funnelshift_r(T2, T3, rbs),
+                       R3 = __funnelshift_r(T3, 0u, rbs);
+        // every lane's word entirely inside a contig and free of non-ACGT bytes: no validity work at all
+        const bool clean = __all_sync(0xFFFFFFFFu, vmask == 0xFFFFFFFFu && nm == 0);
+#pragma unroll 1
+        for (int seg = 0; seg < 2; seg++) {
+            const uint32_t a0 = seg ? F1 : F0, a1 = seg ? F2 : F1, a2 = seg ? F3 : F2;
+            const uint32_t b0 = seg ? R0 : R1, b1 = seg ? R1 : R2, b2 = seg ? R2 : R3;
+            const uint32_t s0 = start31 - 16u * (uint32_t)seg;
+            if (clean) {
+#pragma unroll
+                for (int oo = 0; oo < 16; oo++) {
+                    uint32_t h_lo = __funnelshift_r(a0, a1, 2 * oo), h_hi = 0, r_lo = __funnelshift_r(b0, b1, 30 - 2 * oo), r_hi = 0;
+                    if (KBIG) { h_hi = __funnelshift_r(a1, a2, 2 * oo) & mhi; r_hi = __funnelshift_r(b1, b2, 30 - 2 * oo) & mhi; }
+                    else { h_lo &= mlo; r_lo &= mlo; }
+                    window2<FASTMOD, KBIG>(p, sw, f_addr, h_lo, h_hi, r_lo, r_hi, m32, a32, neg_p, s0 - (uint32_t)oo, g, true);
+                    if (oo & 1) { while (sw.qn >= 32u) drain2<FIRST>(p, ki, sw); }      // (at most 31 + 2 * 32 items between two tests: the queue holds 96)
+                }
+            } else {
+#pragma unroll 1
+                for (int oo = 0; oo < 16; oo++) {
+                    const int o = seg * 16 + oo, j = 31 - o;
+                    uint32_t h_lo = __funnelshift_r(a0, a1, 2 * oo), h_hi = 0, r_lo = __funnelshift_r(b0, b1, 30 - 2 * oo), r_hi = 0;
+                    if (KBIG) { h_hi = __funnelshift_r(a1, a2, 2 * oo) & mhi; r_hi = __funnelshift_r(b1, b2, 30 - 2 * oo) & mhi; }
+                    else { h_lo &= mlo; r_lo &= mlo; }
+                    bool valid = (vmask >> j) & 1u;
+                    const uint32_t wn = (uint32_t)((nm >> (31 - j)) & km1);
+                    if (valid && wn) {
+                        if (p.first_pass != 2)
+                            pollute_invalid_window(p, ki, k, g, (((uint64_t)h_hi) << 32) | h_lo, (((uint64_t)r_hi) << 32) | r_lo, wn);
+                        valid = false;
+                    }
+                    window2<FASTMOD, KBIG>(p, sw, f_addr, h_lo, h_hi, r_lo, r_hi, m32, a32, neg_p, s0 - (uint32_t)oo, g, valid);
+                    while (sw.qn >= 32u) drain2<FIRST>(p, ki, sw);
+                }
+            }
+        }
+    }
+}
+
+template <bool FIRST>
+__global__ void __launch_bounds__(1024, 1) k_scan_filtered2(const __grid_constant__ K p, uint32_t w0_, uint32_t w1) {
+    extern __shared__ uint32_t s_filter[];
+    Scan2 sw;
+    sw.lane = threadIdx.x & 31;
+    const uint32_t warp = threadIdx.x >> 5;
+    const uint32_t f_addr = (uint32_t)__cvta_generic_to_shared(s_filter);
+    sw.q_addr = f_addr + FILTER_BYTES + warp * (Q2_ITEMS * 16u);
+    sw.lt_mask = (1u << sw.lane) - 1u;
+    const uint32_t stride = gridDim.x * blockDim.x;
+    const uint32_t w0 = w0_ + blockIdx.x * blockDim.x;
+    for (int ki = 0; ki < p.nk; ki++) {
+        const int k = p.kmin + ki;
+        __syncthreads();
+        {   // LDGSTS: every thread has all its 16 B pieces in flight at once, nothing goes through registers
+            const uint8_t *src = (const uint8_t *)(p.filter + (size_t)ki * FILTER_WORDS);
+            for (uint32_t t = threadIdx.x; t < FILTER_WORDS / 4; t += blockDim.x)
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(f_addr + t * 16u), "l"(src + (size_t)t * 16u) : "memory");
+            asm volatile("cp.async.commit_group;" ::: "memory");
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+        }
+        __syncthreads();
+        sw.qn = 0; sw.pend = false;
+        sw.pd.e = make_uint2(0u, 0u); sw.pd.meta = 0; sw.pd.g = 0;
+        const bool fastmod = k <= 20 && p.P < (1u << 24);
+        if (k > 16) {
+            if (fastmod) scan2_pass<true, true, FIRST>(p, ki, k, sw, f_addr, w0, w1, stride, warp);
+            else scan2_pass<false, true, FIRST>(p, ki, k, sw, f_addr, w0, w1, stride, warp);
+        } else {
+            if (p.P < (1u << 24)) scan2_pass<true, false, FIRST>(p, ki, k, sw, f_addr, w0, w1, stride, warp);
+            else scan2_pass<false, false, FIRST>(p, ki, k, sw, f_addr, w0, w1, stride, warp);
+        }
+        // the remainder of the k pass
+        while (sw.qn) drain2<FIRST>(p, ki, sw);
+        __syncwarp();
+        if (sw.pend) drain2_consume<FIRST>(p, sw.pd);
+        sw.pend = false;
+        __syncwarp();
+    }
+}
+
 // filter bit of every key bin (genome 1's pass: all keys)
 __global__ void __launch_bounds__(256) k_build_filter(const __grid_constant__ K p) {
     uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1157,7 +1342,8 @@ __global__ void __launch_bounds__(256) k_aliveN(const __grid_constant__ K p, uin
         if (g0 + i >= gb) break;
         const int st = row_state_h(v[i], h[i], key, rc, key == rc, false);
         if (st == 0) p.alive[id] = 0;
-        p.pos32[(size_t)(g0 + i) * p.capIds + id] = st ? ((uint32_t)(v[i] & ROW_POS_MASK) | (st == 2 ? 0x80000000u : 0u)) : 0u;
+        // (0xFFFFFFFF: not a shared k-mer as far as this genome is concerned)
+        p.pos32[(size_t)(g0 + i) * p.capIds + id] = st ? ((uint32_t)(v[i] & ROW_POS_MASK) | (st == 2 ? 0x80000000u : 0u)) : 0xFFFFFFFFu;
     }
 }
 
@@ -1333,6 +1519,7 @@ struct pfb_ctx {
     int device = 0;
     int num_sms = 148;
     int scan_mode = 0;   // 0 auto, 1 plain L2 probe, 2 shared-memory filter
+    int scan_kernel = 2; // which formulation of the filtered scan: 2 (default) or 1 (PFB200_SCAN_KERNEL=1, the first one; A/B)
     pfb_params prm{};
     std::string err;
     cudaStream_t stream = nullptr;
@@ -1854,6 +2041,11 @@ int pfb_create(pfb_ctx **out, int device, const pfb_params *params) {
     { const char *cs = getenv("PFB200_CAP_SHARE"); if (cs && atof(cs) > 0) ctx->cap_share = atof(cs); }
     if (e == cudaSuccess)
         e = cudaFuncSetAttribute(k_scan_filtered, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SCANF_SMEM);
+    if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(k_scan_filtered2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SCAN2_SMEM);
+    if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(k_scan_filtered2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SCAN2_SMEM);
+    { const char *sk = getenv("PFB200_SCAN_KERNEL"); if (sk && sk[0] == '1') ctx->scan_kernel = 1; }
     if (e != cudaSuccess) { std::string m = cudaGetErrorString(e); delete ctx; return fail(nullptr, PFB_ECUDA, m); }
     for (auto &ev : ctx->ev) cudaEventCreate(&ev);
     {
@@ -2350,7 +2542,8 @@ static int phaseB(pfb_ctx *ctx) {
             if (ctx->sharded_now && ctx->emulate_ranks <= 1 && r != ctx->rank) continue;
             const uint32_t wa = (uint32_t)((uint64_t)R.W1 * r / nR), wb = (uint32_t)((uint64_t)R.W1 * (r + 1) / nR);
             if (wb > wa) {
-                if (R.use_filter1) k_scan_filtered<<<ctx->num_sms, 1024, SCANF_SMEM, st>>>(k, wa, wb);
+                if (R.use_filter1 && ctx->scan_kernel == 1) k_scan_filtered<<<ctx->num_sms, 1024, SCANF_SMEM, st>>>(k, wa, wb);
+                else if (R.use_filter1) k_scan_filtered2<true><<<ctx->num_sms, 1024, SCAN2_SMEM, st>>>(k, wa, wb);
                 else k_scan_plain<false><<<nblk(wb - wa, 256), 256, 0, st>>>(k, wa, wb);
                 ctx->launches++;
             }
@@ -2375,7 +2568,8 @@ static int scan_batch(pfb_ctx *ctx, size_t ga, size_t gb, bool encode, bool use_
     if (encode && wb > wa) { k_encode<<<nblk(wb - wa, 256), 256, 0, st>>>(k, wa, wb); ctx->launches++; }
     trace_mark(ctx, st, "scan starts: genomes " + std::to_string(ga) + ".." + std::to_string(gb - 1));
     if (wb > wa) {
-        if (use_filter) k_scan_filtered<<<ctx->num_sms, 1024, SCANF_SMEM, st>>>(k, wa, wb);
+        if (use_filter && ctx->scan_kernel == 1) k_scan_filtered<<<ctx->num_sms, 1024, SCANF_SMEM, st>>>(k, wa, wb);
+        else if (use_filter) k_scan_filtered2<false><<<ctx->num_sms, 1024, SCAN2_SMEM, st>>>(k, wa, wb);
         else k_scan_plain<false><<<nblk(wb - wa, 256), 256, 0, st>>>(k, wa, wb);
         ctx->launches++;
     }
@@ -2397,6 +2591,47 @@ static int judge_batch(pfb_ctx *ctx, size_t ga, size_t gb) {
         return copy_out(ctx, (uint32_t *)ctx->hPos.p + ga * ctx->hostPitch, k.pos32 + ga * (size_t)ctx->capIds, (gb - ga) * (size_t)ctx->capIds * 4,
                         "places of a batch of genomes");
     return PFB_OK;
+}
+
+// pipelined run: the batches of genomes 2..G that finish earliest under a simple model -- copies land in order at
+// ~45 GB/s from t = 0, genome 1's pipeline takes a fixed part plus a part per window, a batch costs a fixed part
+// plus its windows at the hot kernel's rate and starts when the previous one is done and its own last copy has
+// landed.  Returns the end (exclusive) of every batch.  Only the SPLIT depends on the model, never a result.
+static std::vector<size_t> plan_batches(const pfb_ctx *ctx) {
+    const size_t nG = ctx->genomes.size();
+    const double nk = ctx->k.nk;
+    std::vector<double> land(nG + 1, 0.0), bases(nG + 1, 0.0);
+    double acc = 0;
+    for (size_t g = 0; g < nG; g++) {
+        const HostGenome &hg = ctx->genomes[g];
+        acc += (double)(hg.fasta ? hg.file_bytes : hg.n_bases);
+        land[g] = acc / 45e9;
+        bases[g + 1] = bases[g] + (double)(hg.fasta ? hg.file_bytes : hg.n_bases);
+    }
+    const double n1 = (double)(ctx->genomes[0].fasta ? ctx->genomes[0].file_bytes : ctx->genomes[0].n_bases);
+    const double t0 = land[0] + 250e-6 + n1 * nk * 12e-12;
+    const double fixed = 90e-6, per_window = 1.0 / 330e9;
+    const size_t n = nG - 1;                      // genomes 1..nG-1
+    // coarse grid when there are many genomes (the plan is O(n^2))
+    const size_t step = std::max<size_t>(1, n / 256);
+    std::vector<size_t> pts;                      // candidate cut points (exclusive ends), last = nG
+    for (size_t g = 1 + step; g < nG; g += step) pts.push_back(g);
+    pts.push_back(nG);
+    std::vector<double> best(pts.size(), 0.0);
+    std::vector<int> from(pts.size(), -1);
+    for (size_t i = 0; i < pts.size(); i++) {
+        best[i] = 1e30;
+        for (int j = -1; j < (int)i; j++) {
+            const size_t a = j < 0 ? 1 : pts[j], b = pts[i];
+            const double start = std::max(j < 0 ? t0 : best[j], land[b - 1]);
+            const double t = start + fixed + (bases[b] - bases[a]) * nk * per_window;
+            if (t < best[i]) { best[i] = t; from[i] = j; }
+        }
+    }
+    std::vector<size_t> cuts;
+    for (int i = (int)pts.size() - 1; i >= 0; i = from[i]) cuts.push_back(pts[i]);
+    std::reverse(cuts.begin(), cuts.end());
+    return cuts;
 }
 
 static int phaseC(pfb_ctx *ctx) {
@@ -2485,16 +2720,13 @@ static int phaseC(pfb_ctx *ctx) {
             if ((rc = judge_batch(ctx, 1, nG)) != PFB_OK) return rc;
         } else {
             // the other genomes are packed and scanned in batches behind their H2D copies (which run on their own
-            // stream, see upload_impl): the stream waits for a batch's last copy, the host does not.  Batches halve:
-            // the first is large (the copies had the whole key-table build to get ahead), the last ones are small,
-            // so that little is left to do once the last copy has landed; the places of a batch leave for the host
-            // while the next one is scanned
+            // stream, see upload_impl): the stream waits for a batch's last copy, the host does not.  Where to cut
+            // is planned here, before anything runs, from rough rates (a launch over few genomes is inefficient --
+            // nk filter loads, one word per thread -- so batches must not be small; a batch cannot start before its
+            // last copy has landed; the places of a batch leave for the host while the next one is scanned)
+            std::vector<size_t> cuts = plan_batches(ctx);
             size_t g = 1;
-            const size_t min_batch = std::max<size_t>(1, (nG - 1) / 12);
-            while (g < nG) {
-                size_t n = std::max(min_batch, (nG - g + 1) / 2);
-                if (nG - g - n < min_batch) n = nG - g;
-                const size_t g2 = g + n;
+            for (size_t g2 : cuts) {
                 CK(cudaStreamWaitEvent(st, ctx->evCopy[g2 - 1], 0));
                 if ((rc = scan_batch(ctx, g, g2, true, use_filter)) != PFB_OK) return rc;
                 if ((rc = judge_batch(ctx, g, g2)) != PFB_OK) return rc;

@@ -203,7 +203,7 @@ def test_picked_output_path_matches_full_output():
 
 
 @pytest.mark.parametrize("name,thal", [("basic", "off"), ("collide_multi", "pseudo")])
-def test_drop_in_entry_point(name, thal, tmp_path, capsys):
+def test_drop_in_entry_point(name, thal, tmp_path, capsys, monkeypatch):
     """_getAllCandidateKmers(params, sharedExists) from FASTA files, as bin/main.py:86 calls it"""
     from types import SimpleNamespace
     from primerforge_b200 import synth
@@ -221,15 +221,8 @@ def test_drop_in_entry_point(name, thal, tmp_path, capsys):
                              pickles={1: "sharedKmers.p", 2: "candidates.p"},
                              dumpObj=lambda obj, fn, what, prefix="": dumped.__setitem__(fn, obj), loadObj=dumped.get)
     if gold.table_size != 9999991:
-        # the golden case forces a small table; run the same through run_stage-level knobs instead
-        import primerforge_b200.candidates as cand
-        orig = cand.run_stage
-        cand.run_stage = lambda genomes, **kw: orig(genomes, table_size=gold.table_size, **kw)
-    try:
-        out = _getAllCandidateKmers(params, False, thal=("off" if thal == "off" else _pseudo_thal))
-    finally:
-        if gold.table_size != 9999991:
-            cand.run_stage = orig
+        monkeypatch.setenv("PFB200_TABLE_SIZE", str(gold.table_size))      # the golden case forces a small table
+    out = _getAllCandidateKmers(params, False, thal=("off" if thal == "off" else _pseudo_thal))
     assert "candidate kmers" in capsys.readouterr().out
     assert dumped["candidates.p"] is out and list(out.keys()) == gold.names
     for gi, (nm, gen) in enumerate(zip(gold.names, gold.genomes)):

@@ -8,7 +8,8 @@ import pytest
 
 from oracle import pf_oracle as po
 from primerforge_b200 import _lib
-from primerforge_b200.candidates import build_output, screen_groups
+from primerforge_b200.candidates import _word_starts, screen_groups
+from primerforge_b200.lazy import Columns, build_lazy_output
 from primerforge_b200.engine import words_to_strings
 from tests.util import golden_candidate_set, load_golden
 
@@ -43,8 +44,15 @@ def test_screening_and_output_equal_reference(name):
     thal = _pseudo_thal if gold.thal == "pseudo" else (lambda s, r: (0.0, 0.0, 0.0, 0.0))
     picked, values = screen_groups(rec, pos, kmers, thal, gold.min_tm - gold.temp_tolerance)
     sel = np.flatnonzero(picked)
-    out = build_output(gold.names, [g.contig_ids for g in gold.genomes], rec[sel], [p[sel] for p in pos],
-                       [kmers[i] for i in sel], {i: values[int(r)] for i, r in enumerate(sel)})
+    # the picked records as the columns the drop-in builds from the GPU's per-id view
+    wstarts = [_word_starts([c.size for c in g.contigs]) for g in gold.genomes]
+    enc = []
+    for g in range(len(gold.genomes)):
+        lp = pos[g]["start"][sel].astype(np.int64) + (32 * wstarts[g][pos[g]["contig"][sel]] if wstarts[g] is not None else 0)
+        enc.append(lp.astype(np.uint32) | (pos[g]["strand"][sel].astype(np.uint32) << np.uint32(31)))
+    cols = Columns(gold.names, [g.contig_ids for g in gold.genomes], wstarts, rec["word"][sel], rec["k"][sel], rec["tm"][sel],
+                   rec["gc_count"][sel], enc, thal={i: values[int(r)] for i, r in enumerate(sel)})
+    out = build_lazy_output(cols)
     for gi, (name_g, gen) in enumerate(zip(gold.names, gold.genomes)):
         cidx = {c: i for i, c in enumerate(gen.contig_ids)}
         mine = set()
