@@ -2048,6 +2048,7 @@ int pfb_create(pfb_ctx **out, int device, const pfb_params *params) {
     { const char *sk = getenv("PFB200_SCAN_KERNEL"); if (sk && sk[0] == '1') ctx->scan_kernel = 1; }
     if (e != cudaSuccess) { std::string m = cudaGetErrorString(e); delete ctx; return fail(nullptr, PFB_ECUDA, m); }
     for (auto &ev : ctx->ev) cudaEventCreate(&ev);
+    for (auto &pair : ctx->evX) for (auto &ev : pair) cudaEventCreate(&ev);
     {
         void *h = nullptr, *d = nullptr;
         if (cudaHostAlloc(&h, 64, cudaHostAllocMapped) != cudaSuccess || cudaHostGetDevicePointer(&d, h, 0) != cudaSuccess) {
@@ -2075,6 +2076,7 @@ void pfb_destroy(pfb_ctx *ctx) {
     DevBuf *hosts[] = {&ctx->hWord, &ctx->hTm, &ctx->hInfo, &ctx->hPos, &ctx->hAlive, &ctx->hPick};
     for (auto *b : hosts) { if (b->p) cudaFreeHost(b->p); b->p = nullptr; b->cap = 0; }
     for (auto &ev : ctx->ev) if (ev) cudaEventDestroy(ev);
+    for (auto &pair : ctx->evX) for (auto &ev : pair) if (ev) cudaEventDestroy(ev);
     for (auto &ev : ctx->evCopy) if (ev) cudaEventDestroy(ev);
     for (auto &ev : ctx->evOut) if (ev) cudaEventDestroy(ev);
     if (ctx->d2hStream) cudaStreamDestroy(ctx->d2hStream);
