@@ -96,6 +96,7 @@ typedef struct pfb_timing {
     uint64_t n_ids;            /* genome-1 k-mers that are unique in genome 1 (= length of the per-id result columns) */
     uint64_t sharded_first_genome; /* 1: the ranks shared genome 1's own pipeline (candidates + its scan) by position */
     uint64_t n_reruns;         /* runs of this context that were repeated because a buffer capacity proved too small */
+    uint64_t exchange_mode;    /* 0 one GPU; 1 NCCL collectives; 2 the ranks read each other's exchange arenas over NVLink */
 } pfb_timing;
 
 /* The results as the device keeps them: one entry per id.  ids are the genome-1 k-mers that are unique in

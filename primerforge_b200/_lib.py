@@ -50,7 +50,7 @@ class PfbTiming(C.Structure):
                 ("n_slots", C.c_uint64), ("n_records", C.c_uint64), ("n_picked", C.c_uint64), ("n_launches", C.c_uint64),
                 ("used_filter", C.c_uint64), ("scan_main_bases", C.c_uint64), ("ms_scan_main", C.c_float),
                 ("ms_exchange", C.c_float), ("n_ids", C.c_uint64), ("sharded_first_genome", C.c_uint64),
-                ("n_reruns", C.c_uint64)]
+                ("n_reruns", C.c_uint64), ("exchange_mode", C.c_uint64)]
 
 
 class PfbIdView(C.Structure):

@@ -131,10 +131,20 @@ struct K {  // kernel arguments (by value, __grid_constant__)
     uint32_t *candList;        // [nRanks][capCand + 4]: segment r = {count, 0, 0, 0, (bin | ki << 27) ...} of rank r
     uint32_t capCand, nRanks, rank;
     uint32_t *rows0p;          // [capSlots] rows0 packed to 32 bits for the SUM all-reduce
+    // multi-GPU over peer memory (NVLink): what the ranks exchange -- candidate segment, packed rows, the reduced
+    // slice of the packed rows, alive bytes, pick bytes -- lives in ONE arena per rank that every other rank has
+    // mapped (cudaIpc* between processes, peer access inside one); consumers read the peers' arenas directly, a
+    // flag per (phase, rank) written into every peer's arena says when a producer is done
+    uint8_t *peer[16];         // the arenas, peer[rank] = this rank's own
+    uint32_t xRows0p, xRows0s, xAlive, xPick, xCand;   // byte offsets of the parts within an arena (flags at 0)
+    uint32_t xEpoch;           // number of this run on the communicator: the value the flags must reach
 };
 
+enum { XP_CANDS = 0, XP_ROWS_A = 1, XP_ROWS_B = 2, XP_ALIVE = 3, XP_PICK = 4, XP_DONE = 5, XP_PHASES = 6 };
+constexpr uint32_t X_FLAGS_BYTES = 4096;       // [XP_PHASES][16] uint32 (+ slack) at the start of an arena
+
 enum { C_NSLOTS = 0, C_NIDS = 1, C_NALIVE = 2, C_NPICK = 3, C_OVF = 4, C_FLAGS = 5, C_MAXCAND = 6 };
-enum { OVF_SLOTS = 1u, OVF_IDS = 2u, OVF_LISTS = 4u, OVF_CAND = 8u };
+enum { OVF_SLOTS = 1u, OVF_IDS = 2u, OVF_LISTS = 4u, OVF_CAND = 8u, OVF_PEER_TIMEOUT = 16u };
 
 // SantaLucia (1998) nearest-neighbour table in oligotm's integer units; index = 4*first + second
 // with A0 T1 C2 G3; packed (S << 16) | H
@@ -477,7 +487,7 @@ __global__ void __launch_bounds__(CAND_POS + 32) k_cand1(const __grid_constant__
     }
     __syncwarp();
     const uint32_t hf_lo = (uint32_t)hf, hf_hi = (uint32_t)(hf >> 32);
-    uint32_t *seg = LIST ? p.candList + (size_t)p.rank * (p.capCand + 4u) : nullptr;
+    uint32_t *seg = !LIST ? nullptr : p.xCand ? (uint32_t *)(p.peer[p.rank] + p.xCand) : p.candList + (size_t)p.rank * (p.capCand + 4u);
     for (uint32_t base = 0; base < n_items; base += 32) {
         const bool live = base + lane < n_items;
         const uint32_t it = live ? items[base + lane] : 0u;
@@ -511,17 +521,21 @@ __global__ void __launch_bounds__(CAND_POS + 32) k_cand1(const __grid_constant__
 }
 
 // every rank's candidates -> this rank's table
+template <bool PEER>
 __global__ void __launch_bounds__(256) k_apply_cands(const __grid_constant__ K p) {
-    const uint32_t stride = gridDim.x * blockDim.x, t0 = blockIdx.x * blockDim.x + threadIdx.x;
-    for (uint32_t r = 0; r < p.nRanks; r++) {
-        const uint32_t *seg = p.candList + (size_t)r * (p.capCand + 4u);
-        uint32_t n = seg[0];
-        if (n > p.capCand) { if (t0 == 0) { atomicOr(&p.cnt[C_FLAGS], OVF_CAND); atomicMax(&p.cnt[C_MAXCAND], n); } n = p.capCand; }
-        for (uint32_t i = t0; i < n; i += stride) {
-            const uint32_t e = seg[4u + i];
-            cand_table_update(p, (int)(e >> 27), e & 0x07FFFFFFu);
-        }
-    }
+    // one entry per thread (blockIdx.y = the rank whose segment it is): every table update of the launch is in
+    // flight at once -- the updates return a value, a thread that made several in a row would wait for each
+    const uint32_t r = blockIdx.y, i = blockIdx.x * blockDim.x + threadIdx.x;
+    // PEER: rank r's segment is read where it was written, in r's arena, over NVLink (no all-gather at all)
+    const uint32_t *seg = PEER ? (const uint32_t *)(p.peer[r] + p.xCand) : p.candList + (size_t)r * (p.capCand + 4u);
+    __shared__ uint32_t s_n;
+    if (threadIdx.x == 0) s_n = __ldcg(seg);               // (one read of the count per CTA, not one per thread)
+    __syncthreads();
+    uint32_t n = s_n;
+    if (n > p.capCand) { if (i == 0) { atomicOr(&p.cnt[C_FLAGS], OVF_CAND); atomicMax(&p.cnt[C_MAXCAND], n); } n = p.capCand; }
+    if (i >= n) return;
+    const uint32_t e = __ldcg(seg + 4u + i);
+    cand_table_update(p, (int)(e >> 27), e & 0x07FFFFFFu);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1317,6 +1331,80 @@ __global__ void __launch_bounds__(256) k_rows0_unpack(const __grid_constant__ K 
     p.rows0[i] = ((unsigned long long)min(c, 2u) << 32) | (c == 1 ? (v & (uint32_t)ROW_POS_MASK) : 0u);
 }
 
+// ---- exchanges over peer memory.  A producer signals by writing the run's number into ITS slot of every peer's
+// flag table (after a system-wide fence; the kernel boundary before it has made the data visible); a consumer
+// waits until every slot of its own table has reached that number, then reads the peers' arenas with loads that
+// bypass L1 (peer memory is cached at its home, not here).  The wait is bounded (~9 s): a rank that never signals ends in an error, not in a hang.
+__global__ void k_xsignal(const __grid_constant__ K p, int phase) {
+    if (threadIdx.x < p.nRanks) {
+        __threadfence_system();
+        volatile uint32_t *f = (volatile uint32_t *)(p.peer[threadIdx.x]) + phase * 16 + p.rank;
+        *f = p.xEpoch;
+    }
+}
+
+__global__ void k_xwait(const __grid_constant__ K p, int phase, uint32_t value) {
+    if (threadIdx.x < p.nRanks) {
+        const volatile uint32_t *f = (const volatile uint32_t *)(p.peer[p.rank]) + phase * 16 + threadIdx.x;
+        const long long t0 = clock64();
+        while ((int32_t)(*f - value) < 0) {
+            if (clock64() - t0 > (1ll << 34)) { atomicOr(&p.cnt[C_FLAGS], OVF_PEER_TIMEOUT); break; }
+            __nanosleep(200);
+        }
+        __threadfence_system();
+    }
+}
+
+// packed rows, stage A: this rank sums ITS slice of the slots over all ranks' shares; stage B: every rank
+// collects all slices (each from the rank that summed it) and goes back to the row format
+__device__ __forceinline__ void slice_of(uint32_t n, uint32_t nRanks, uint32_t r, uint32_t &a, uint32_t &b) {
+    const uint32_t per = ((n + nRanks - 1) / nRanks + 3u) & ~3u;
+    a = min(n, per * r); b = min(n, a + per);
+}
+
+__global__ void __launch_bounds__(256) k_rows0_reduce_slice(const __grid_constant__ K p) {
+    uint32_t a, b;
+    slice_of(p.capSlots, p.nRanks, p.rank, a, b);          // (slices start and end at multiples of 4 slots; so does capSlots)
+    const uint32_t i = a + 4u * (blockIdx.x * blockDim.x + threadIdx.x);
+    if (i >= b) return;
+    uint4 s = make_uint4(0u, 0u, 0u, 0u);
+    for (uint32_t r = 0; r < p.nRanks; r++) {
+        const uint4 x = __ldcg((const uint4 *)(p.peer[r] + p.xRows0p + 4ull * i));
+        s.x += x.x; s.y += x.y; s.z += x.z; s.w += x.w;
+    }
+    *(uint4 *)(p.peer[p.rank] + p.xRows0s + 4ull * i) = s;
+}
+
+__device__ __forceinline__ unsigned long long unpack_row(uint32_t v) {
+    const uint32_t c = v >> 26;
+    return ((unsigned long long)min(c, 2u) << 32) | (c == 1 ? (v & (uint32_t)ROW_POS_MASK) : 0u);
+}
+
+__global__ void __launch_bounds__(256) k_rows0_gather_unpack(const __grid_constant__ K p) {
+    const uint32_t i = 4u * (blockIdx.x * blockDim.x + threadIdx.x);
+    if (i >= p.capSlots) return;
+    const uint32_t per = ((p.capSlots + p.nRanks - 1) / p.nRanks + 3u) & ~3u;
+    const uint4 v = __ldcg((const uint4 *)(p.peer[i / per] + p.xRows0s + 4ull * i));
+    ulonglong2 lo, hi;
+    lo.x = unpack_row(v.x); lo.y = unpack_row(v.y); hi.x = unpack_row(v.z); hi.y = unpack_row(v.w);
+    *(ulonglong2 *)(p.rows0 + i) = lo;
+    *(ulonglong2 *)(p.rows0 + i + 2) = hi;
+}
+
+// one byte per id over all ranks: MIN (alive) / MAX (pick), four ids per thread.  In place: a peer that reads this
+// rank's bytes while they are being replaced by the merged ones sees either, and both give it the same result
+template <bool IS_MAX>
+__global__ void __launch_bounds__(256) k_bytes_merge(const __grid_constant__ K p, uint32_t off) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i * 4u >= p.capIds) return;
+    uint32_t v = IS_MAX ? 0u : 0xFFFFFFFFu;
+    for (uint32_t r = 0; r < p.nRanks; r++) {
+        const uint32_t x = __ldcg((const uint32_t *)(p.peer[r] + off) + i);
+        v = IS_MAX ? __vmaxu4(v, x) : __vminu4(v, x);
+    }
+    ((uint32_t *)(p.peer[p.rank] + off))[i] = v;
+}
+
 // k_aliveN: the rules for one (id, genome >= 2) per thread, for the genomes [ga, gb) of this context; ids follow
 // genome 1's coordinates, so the rows stream and -- for genomes that are largely collinear with genome 1 -- so do
 // the read-backs.  The verdict goes to alive[], the place and strand to pos32 (what the output and k_pick read:
@@ -1573,6 +1661,15 @@ struct pfb_ctx {
     int shard_g1 = 1;                           // share genome 1's own pipeline out over the ranks (PFB200_SHARD_G1=0 disables)
     bool sharded_now = false;                   // ... and whether the current run does
     int fetch_records = 1;                      // 0: the per-id records stay on the device (ranks > 0 of a job: identical everywhere)
+    // exchanges over peer memory (see K::peer): 0 = NCCL collectives, 1 = peer arenas
+    int xchg_pref = 1;                          // PFB200_XCHG=nccl -> 0
+    bool peer_now = false;                      // the current run exchanges through the arenas
+    bool x_dirty = false;                       // the arena was (re)allocated: the ranks must map each other's again
+    DevBuf xa, xh;                              // the arena; staging of the IPC handles
+    uint8_t *xPeer[16] = {};                    // mapped arenas of the other ranks (IPC) / their pointers (one process)
+    bool xOpened[16] = {};
+    uint32_t xCaps[3] = {0, 0, 0};              // capCand, capSlots, capIds the arena was laid out for
+    uint32_t epoch = 0;                         // runs (attempts) on this arena
     int emulate_ranks = 0;                      // > 1 (tests): ONE context plays that many ranks of the shared-out genome-1
                                                 // pipeline one after the other (lists, table update, packed rows: all but NCCL)
     int eff_ranks() const { return emulate_ranks > 1 ? emulate_ranks : nRanks; }
@@ -1621,7 +1718,8 @@ void trace_dump(pfb_ctx *ctx) {
     if (!ctx->tracing) return;
     for (auto &t : ctx->trace) {
         float ms = 0;
-        if (cudaEventElapsedTime(&ms, ctx->ev[0], t.second) == cudaSuccess) fprintf(stderr, "[pfb trace] %8.3f ms  %s\n", ms, t.first.c_str());
+        if (cudaEventElapsedTime(&ms, ctx->ev[ctx->run.piped ? 0 : 2], t.second) == cudaSuccess)
+            fprintf(stderr, "[pfb trace r%d] %8.3f ms  %s\n", ctx->rank, ms, t.first.c_str());
         cudaEventDestroy(t.second);
     }
     cudaGetLastError();
@@ -2001,6 +2099,24 @@ nccl::Api *nccl_api(std::string &why) {
 // ==========================================================================================
 extern "C" {
 
+// the peer arena: wait (bounded) until no other rank can still be reading it, unmap the others', free
+static void x_release(pfb_ctx *ctx) {
+    if (!ctx->xa.p) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->peer_now && ctx->epoch && ctx->nRanks > 1) {
+        k_xwait<<<1, 32, 0, ctx->stream>>>(ctx->k, XP_DONE, ctx->epoch);
+        cudaStreamSynchronize(ctx->stream);
+    }
+    for (int r = 0; r < 16; r++) {
+        if (ctx->xOpened[r] && ctx->xPeer[r]) cudaIpcCloseMemHandle(ctx->xPeer[r]);
+        ctx->xOpened[r] = false; ctx->xPeer[r] = nullptr;
+    }
+    release(ctx->xa);
+    cudaGetLastError();
+    ctx->peer_now = false; ctx->epoch = 0;
+    ctx->xCaps[0] = ctx->xCaps[1] = ctx->xCaps[2] = 0;
+}
+
 int pfb_default_params(pfb_params *p) {
     if (!p) return PFB_EINVAL;
     memset(p, 0, sizeof(*p));
@@ -2039,6 +2155,7 @@ int pfb_create(pfb_ctx **out, int device, const pfb_params *params) {
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->d2hStream, cudaStreamNonBlocking);
     { const char *sg = getenv("PFB200_SHARD_G1"); if (sg && sg[0] == '0') ctx->shard_g1 = 0; }
     { const char *cs = getenv("PFB200_CAP_SHARE"); if (cs && atof(cs) > 0) ctx->cap_share = atof(cs); }
+    { const char *xc = getenv("PFB200_XCHG"); if (xc && (xc[0] == 'n' || xc[0] == 'N')) ctx->xchg_pref = 0; }
     if (e == cudaSuccess)
         e = cudaFuncSetAttribute(k_scan_filtered, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SCANF_SMEM);
     if (e == cudaSuccess)
@@ -2066,6 +2183,7 @@ void pfb_destroy(pfb_ctx *ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     if (ctx->d2hStream) cudaStreamSynchronize(ctx->d2hStream);
+    x_release(ctx);
     if (ctx->comm && ctx->comm_owned) { std::string why; if (nccl::Api *a = nccl_api(why)) a->CommDestroy(ctx->comm); }
     ctx->comm = nullptr;
     DevBuf *all[] = {&ctx->raw, &ctx->seq2, &ctx->nmask, &ctx->wordContig, &ctx->tabs32, &ctx->tabs64, &ctx->sk, &ctx->br,
@@ -2374,6 +2492,10 @@ static int host_buffers(pfb_ctx *ctx) {
     return PFB_OK;
 }
 
+static void x_signal(pfb_ctx *ctx, int phase);
+static void x_wait(pfb_ctx *ctx, int phase);
+static void x_done(pfb_ctx *ctx, int phase);
+
 static int phaseA(pfb_ctx *ctx, bool piped) {
     CK(cudaSetDevice(ctx->device));
     const pfb_params &P = ctx->prm;
@@ -2437,8 +2559,36 @@ static int phaseA(pfb_ctx *ctx, bool piped) {
     if ((rc = ensure(ctx, ctx->rows, CI * (nG > 1 ? nG - 1 : 1) * 8)) != PFB_OK) return rc;
     if ((rc = ensure(ctx, ctx->key1, CI * 8)) != PFB_OK) return rc;
     if ((rc = ensure(ctx, ctx->idMeta, CI * 4)) != PFB_OK) return rc;
-    if ((rc = ensure(ctx, ctx->alive, CI)) != PFB_OK) return rc;
-    if ((rc = ensure(ctx, ctx->pick, CI)) != PFB_OK) return rc;
+    // more than one rank: what the ranks exchange lives in one arena that the others map (unless NCCL is asked for)
+    const bool want_peer = ctx->comm && ctx->nRanks > 1 && ctx->nRanks <= 16 && ctx->xchg_pref == 1 && ctx->emulate_ranks <= 1;
+    auto al256 = [](size_t x) { return (x + 255) & ~(size_t)255; };
+    if (want_peer) {
+        k.xCand = X_FLAGS_BYTES;
+        k.xRows0p = (uint32_t)(k.xCand + al256((size_t)(ctx->capCand + 4) * 4));
+        k.xRows0s = (uint32_t)(k.xRows0p + al256(CS * 4));
+        k.xAlive = (uint32_t)(k.xRows0s + al256(CS * 4));
+        k.xPick = (uint32_t)(k.xAlive + al256(CI));
+        const size_t total = (size_t)k.xPick + al256(CI);
+        if (total >= (1ull << 32)) return fail(ctx, PFB_ETOOLARGE, "exchange arena of 4 GiB or more");
+        if (!ctx->xa.p || ctx->xCaps[0] != ctx->capCand || ctx->xCaps[1] != CS || ctx->xCaps[2] != CI) {
+            x_release(ctx);                                    // (waits until no peer can still be reading the old one)
+            if ((rc = ensure(ctx, ctx->xa, total)) != PFB_OK) return rc;
+            CK(cudaMemsetAsync(ctx->xa.p, 0, X_FLAGS_BYTES, st));
+            CK(cudaStreamSynchronize(st));
+            ctx->xCaps[0] = ctx->capCand; ctx->xCaps[1] = (uint32_t)CS; ctx->xCaps[2] = (uint32_t)CI;
+            ctx->x_dirty = true;
+            ctx->epoch = 0;
+        }
+        ctx->peer_now = true;
+        ctx->epoch++;
+    } else {
+        if (ctx->xa.p) x_release(ctx);
+        ctx->peer_now = false;
+        k.xCand = k.xRows0p = k.xRows0s = k.xAlive = k.xPick = 0;
+        if ((rc = ensure(ctx, ctx->alive, CI)) != PFB_OK) return rc;
+        if ((rc = ensure(ctx, ctx->pick, CI)) != PFB_OK) return rc;
+    }
+    k.xEpoch = ctx->epoch;
     if ((rc = ensure(ctx, ctx->idTm, CI * 8)) != PFB_OK) return rc;
     if ((rc = ensure(ctx, ctx->idInfo, CI * 2)) != PFB_OK) return rc;
     if ((rc = ensure(ctx, ctx->pos32, CI * nG * 4)) != PFB_OK) return rc;
@@ -2446,7 +2596,7 @@ static int phaseA(pfb_ctx *ctx, bool piped) {
         if ((rc = ensure(ctx, ctx->at, NA * 8)) != PFB_OK) return rc;
         if ((rc = ensure(ctx, ctx->ovf, ovfCap * 64)) != PFB_OK) return rc;
     }
-    if (ctx->sharded_now) {
+    if (ctx->sharded_now && !ctx->peer_now) {
         if ((rc = ensure(ctx, ctx->candList, (size_t)nR * (ctx->capCand + 4) * 4)) != PFB_OK) return rc;
         if ((rc = ensure(ctx, ctx->rows0p, CS * 4)) != PFB_OK) return rc;
     }
@@ -2460,6 +2610,13 @@ static int phaseA(pfb_ctx *ctx, bool piped) {
     k.rows0 = (unsigned long long *)ctx->rows0.p; k.remap = (uint32_t *)ctx->remap.p; k.rows0p = (uint32_t *)ctx->rows0p.p;
     k.rows = (unsigned long long *)ctx->rows.p; k.key1 = (uint64_t *)ctx->key1.p; k.idMeta = (uint32_t *)ctx->idMeta.p;
     k.alive = (uint8_t *)ctx->alive.p; k.pick = (uint8_t *)ctx->pick.p;
+    DevBuf aliveBuf = ctx->alive, pickBuf = ctx->pick;
+    if (ctx->peer_now) {
+        uint8_t *xa = (uint8_t *)ctx->xa.p;
+        k.peer[ctx->rank] = xa;
+        k.alive = xa + k.xAlive; k.pick = xa + k.xPick; k.rows0p = (uint32_t *)(xa + k.xRows0p);
+        aliveBuf.p = k.alive; aliveBuf.cap = al256(CI); pickBuf.p = k.pick; pickBuf.cap = al256(CI);
+    }
     k.idTm = (double *)ctx->idTm.p; k.idInfo = (uint16_t *)ctx->idInfo.p; k.pos32 = (uint32_t *)ctx->pos32.p;
     k.at = (uint2 *)ctx->at.p; k.ovf = (uint32_t *)ctx->ovf.p; k.ovfCount = k.cnt + C_OVF; k.ovfCap = (uint32_t)ovfCap;
     k.atWide = ctx->at_wide;
@@ -2477,12 +2634,17 @@ static int phaseA(pfb_ctx *ctx, bool piped) {
     ZeroBatch zb;
     if ((rc = zb.add(ctx, ctx->misc, 4096)) != PFB_OK) return rc;
     if ((rc = zb.add(ctx, ctx->sk, (size_t)R.NB * 2 * 4)) != PFB_OK) return rc;
-    if ((rc = zb.add(ctx, ctx->alive, CI)) != PFB_OK) return rc;
-    if ((rc = zb.add(ctx, ctx->pick, CI)) != PFB_OK) return rc;
+    // (peer mode: nothing of the arena is touched before every rank is done with the previous run's -- its final merge
+    // reads the others' pick bytes; in a steady loop that has long happened)
+    if (ctx->peer_now && ctx->epoch > 1) { k_xwait<<<1, 32, 0, st>>>(k, XP_DONE, ctx->epoch - 1); ctx->launches++; }
+    if ((rc = zb.add(ctx, aliveBuf, CI)) != PFB_OK) return rc;
+    if ((rc = zb.add(ctx, pickBuf, CI)) != PFB_OK) return rc;
     if ((rc = zb.launch(ctx, st)) != PFB_OK) return rc;
     if (ctx->sharded_now) {      // every segment starts with its count
-        for (int r = 0; r < nR; r++)
-            CK(cudaMemsetAsync((uint32_t *)ctx->candList.p + (size_t)r * (ctx->capCand + 4), 0, 16, st));
+        if (ctx->peer_now) CK(cudaMemsetAsync((uint8_t *)ctx->xa.p + k.xCand, 0, 16, st));
+        else
+            for (int r = 0; r < nR; r++)
+                CK(cudaMemsetAsync((uint32_t *)ctx->candList.p + (size_t)r * (ctx->capCand + 4), 0, 16, st));
     }
     if (piped) CK(cudaStreamWaitEvent(st, ctx->evCopy[0], 0));      // only genome 1 has to be there before the key table can be built
     if (R.W1) { k_encode<<<nblk(R.W1, 256), 256, 0, st>>>(k, 0, R.W1); ctx->launches++; }
@@ -2508,6 +2670,97 @@ static int phaseA(pfb_ctx *ctx, bool piped) {
     return PFB_OK;
 }
 
+// peer mode: producer side of an exchange (the data is final on this stream) and consumer side (every rank's is)
+static void x_signal(pfb_ctx *ctx, int phase) {
+    cudaEventRecord(ctx->evX[phase < XP_ROWS_B ? phase : phase - 1][0], ctx->stream);
+    ctx->xUsed[phase < XP_ROWS_B ? phase : phase - 1] = true;
+    k_xsignal<<<1, 32, 0, ctx->stream>>>(ctx->k, phase); ctx->launches++;
+}
+static void x_wait(pfb_ctx *ctx, int phase) {
+    trace_mark(ctx, ctx->stream, "exchange " + std::to_string(phase) + ": signalled, waiting for the peers");
+    k_xwait<<<1, 32, 0, ctx->stream>>>(ctx->k, phase, ctx->epoch); ctx->launches++;
+    trace_mark(ctx, ctx->stream, "exchange " + std::to_string(phase) + ": every peer has signalled");
+}
+static void x_done(pfb_ctx *ctx, int phase) {
+    cudaEventRecord(ctx->evX[phase < XP_ROWS_B ? phase : phase - 1][1], ctx->stream);
+    trace_mark(ctx, ctx->stream, "exchange " + std::to_string(phase) + ": merged");
+}
+
+// the ranks map each other's arenas (after any of them has been (re)allocated -- all of them are then, the
+// capacities being the same everywhere).  One process: peer access + the pointers; one process per GPU: the IPC
+// handles travel through an NCCL all-gather.  If the arenas cannot be mapped the ranks agree to use NCCL
+// collectives instead and the attempt is repeated.
+static int x_connect(std::vector<pfb_ctx *> &C, bool &fallback) {
+    fallback = false;
+    bool any = false;
+    for (pfb_ctx *c : C) any |= c->peer_now && c->x_dirty;
+    if (!any) return PFB_OK;
+    bool ok = true;
+    if (C.size() > 1) {
+        for (pfb_ctx *c : C) {
+            cudaSetDevice(c->device);
+            for (pfb_ctx *d : C) {
+                if (d == c) continue;
+                int can = 0;
+                if (cudaDeviceCanAccessPeer(&can, c->device, d->device) != cudaSuccess || !can) { ok = false; continue; }
+                cudaError_t e = cudaDeviceEnablePeerAccess(d->device, 0);
+                if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) ok = false;
+                cudaGetLastError();
+            }
+        }
+        if (ok)
+            for (pfb_ctx *c : C)
+                for (pfb_ctx *d : C) { c->xPeer[d->rank] = (uint8_t *)d->xa.p; c->k.peer[d->rank] = (uint8_t *)d->xa.p; }
+    } else {
+        pfb_ctx *ctx = C[0];
+        std::string why;
+        nccl::Api *a = nccl_api(why);
+        if (!a) return fail(ctx, PFB_ECUDA, why);
+        CK(cudaSetDevice(ctx->device));
+        const int n = ctx->nRanks;
+        int rc;
+        if ((rc = ensure(ctx, ctx->xh, 64 * 16 + 64)) != PFB_OK) return rc;
+        cudaIpcMemHandle_t mine;
+        std::vector<cudaIpcMemHandle_t> all(n);
+        bool mine_ok = cudaIpcGetMemHandle(&mine, ctx->xa.p) == cudaSuccess;
+        if (!mine_ok) { memset(&mine, 0, sizeof mine); cudaGetLastError(); }
+        static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+        CK(cudaMemcpyAsync((uint8_t *)ctx->xh.p + 64 * ctx->rank, &mine, 64, cudaMemcpyHostToDevice, ctx->stream));
+        int nrc = a->AllGather((uint8_t *)ctx->xh.p + 64 * ctx->rank, ctx->xh.p, 64, nccl::U8, ctx->comm, ctx->stream);
+        if (nrc) return fail(ctx, PFB_ECUDA, std::string("NCCL: ") + a->GetErrorString(nrc));
+        CK(cudaMemcpyAsync(all.data(), ctx->xh.p, 64 * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        ok = mine_ok;
+        for (int r = 0; r < n && ok; r++) {
+            if (r == ctx->rank) { ctx->xPeer[r] = (uint8_t *)ctx->xa.p; continue; }
+            void *ptr = nullptr;
+            if (cudaIpcOpenMemHandle(&ptr, all[r], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { ok = false; cudaGetLastError(); break; }
+            ctx->xPeer[r] = (uint8_t *)ptr; ctx->xOpened[r] = true;
+        }
+        // every rank must have mapped every arena, or none uses them
+        uint8_t flag = ok ? 1 : 0;
+        CK(cudaMemcpyAsync(ctx->xh.p, &flag, 1, cudaMemcpyHostToDevice, ctx->stream));
+        nrc = a->AllReduce(ctx->xh.p, ctx->xh.p, 1, nccl::U8, nccl::MIN, ctx->comm, ctx->stream);
+        if (nrc) return fail(ctx, PFB_ECUDA, std::string("NCCL: ") + a->GetErrorString(nrc));
+        CK(cudaMemcpyAsync(&flag, ctx->xh.p, 1, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        ok = flag != 0;
+        if (ok) for (int r = 0; r < n; r++) ctx->k.peer[r] = ctx->xPeer[r];
+    }
+    for (pfb_ctx *c : C) c->x_dirty = false;
+    if (!ok) {
+        for (pfb_ctx *c : C) {
+            cudaSetDevice(c->device);
+            cudaStreamSynchronize(c->stream);
+            c->epoch = 0;                  // (nobody has signalled anything into anybody's arena)
+            x_release(c);
+            c->xchg_pref = 0;
+        }
+        fallback = true;
+    }
+    return PFB_OK;
+}
+
 static int phaseB(pfb_ctx *ctx) {
     CK(cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
@@ -2516,7 +2769,12 @@ static int phaseB(pfb_ctx *ctx) {
     const pfb_params &P = ctx->prm;
     const int nk = k.nk;
     int rc;
-    if (ctx->sharded_now) { k_apply_cands<<<ctx->num_sms * 8, 256, 0, st>>>(k); ctx->launches++; }
+    if (ctx->sharded_now && ctx->peer_now) {
+        x_signal(ctx, XP_CANDS);      // (here, not at the end of phase A: the peers' arenas are mapped between the two)
+        x_wait(ctx, XP_CANDS);
+        k_apply_cands<true><<<dim3(nblk(ctx->capCand, 256), k.nRanks), 256, 0, st>>>(k); ctx->launches++;
+        x_done(ctx, XP_CANDS);
+    } else if (ctx->sharded_now) { k_apply_cands<false><<<dim3(nblk(ctx->capCand, 256), k.nRanks), 256, 0, st>>>(k); ctx->launches++; }
     k_candbits<<<nblk(R.NB, 256), 256, 0, st>>>(k); ctx->launches++;
     if ((rc = device_exscan<SV_POPC, 2>(ctx, k.br, (uint32_t *)k.br + 1, R.NB, k.cnt + C_NSLOTS, nullptr)) != PFB_OK) return rc;
     ZeroBatch zb;
@@ -2551,6 +2809,7 @@ static int phaseB(pfb_ctx *ctx) {
             }
         }
         if (ctx->sharded_now) { k_rows0_pack<<<nblk(ctx->capSlots, 256), 256, 0, st>>>(k); ctx->launches++; }
+        if (ctx->sharded_now && ctx->peer_now) x_signal(ctx, XP_ROWS_A);
     }
     (void)P;
     CK(cudaGetLastError());
@@ -2649,7 +2908,18 @@ static int phaseC(pfb_ctx *ctx) {
         if (ctx->sharded_now) {
             // the ranks' shares of genome 1's pass have been summed: back to the row format, then the (few)
             // strand-specific polluters of all of genome 1 on every rank
-            k_rows0_unpack<<<nblk(ctx->capSlots, 256), 256, 0, st>>>(k); ctx->launches++;
+            if (ctx->peer_now) {
+                // every rank sums its slice of the slots over all shares, then collects all slices
+                x_wait(ctx, XP_ROWS_A);
+                const uint32_t per = ((ctx->capSlots + ctx->nRanks - 1) / ctx->nRanks + 3u) & ~3u;
+                k_rows0_reduce_slice<<<nblk(per / 4, 256), 256, 0, st>>>(k); ctx->launches++;
+                k_xsignal<<<1, 32, 0, st>>>(k, XP_ROWS_B); ctx->launches++;
+                x_wait(ctx, XP_ROWS_B);
+                k_rows0_gather_unpack<<<nblk(ctx->capSlots / 4, 256), 256, 0, st>>>(k); ctx->launches++;
+                x_done(ctx, XP_ROWS_A);
+            } else {
+                k_rows0_unpack<<<nblk(ctx->capSlots, 256), 256, 0, st>>>(k); ctx->launches++;
+            }
             k.first_pass = 1;
             k_scan_plain<true><<<nblk(R.W1, 256), 256, 0, st>>>(k, 0, R.W1); ctx->launches++;
         }
@@ -2740,6 +3010,7 @@ static int phaseC(pfb_ctx *ctx) {
         if (R.piped) CK(cudaStreamWaitEvent(st, ctx->evCopy[nG - 1], 0));
         CK(cudaEventRecord(ctx->ev[5], st));
     }
+    if (ctx->peer_now) x_signal(ctx, XP_ALIVE);
     trace_mark(ctx, st, "all genomes scanned and judged");
     CK(cudaGetLastError());
     return PFB_OK;
@@ -2747,7 +3018,13 @@ static int phaseC(pfb_ctx *ctx) {
 
 static int phaseD(pfb_ctx *ctx) {
     CK(cudaSetDevice(ctx->device));
+    if (ctx->peer_now) {      // alive = MIN over the ranks, read from their arenas
+        x_wait(ctx, XP_ALIVE);
+        k_bytes_merge<false><<<nblk(ctx->capIds / 4, 256), 256, 0, ctx->stream>>>(ctx->k, ctx->k.xAlive); ctx->launches++;
+        x_done(ctx, XP_ALIVE);
+    }
     k_pick<<<nblk(ctx->capIds, 256), 256, 0, ctx->stream>>>(ctx->k); ctx->launches++;
+    if (ctx->peer_now) x_signal(ctx, XP_PICK);
     CK(cudaGetLastError());
     return PFB_OK;
 }
@@ -2756,6 +3033,12 @@ static int phaseE(pfb_ctx *ctx) {
     CK(cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
     int rc;
+    if (ctx->peer_now) {      // pick = MAX over the ranks
+        x_wait(ctx, XP_PICK);
+        k_bytes_merge<true><<<nblk(ctx->capIds / 4, 256), 256, 0, st>>>(ctx->k, ctx->k.xPick); ctx->launches++;
+        x_done(ctx, XP_PICK);
+        k_xsignal<<<1, 32, 0, st>>>(ctx->k, XP_DONE); ctx->launches++;
+    }
     k_count<<<ctx->num_sms * 2, 256, 0, st>>>(ctx->k); ctx->launches++;
     k_publish<<<1, 32, 0, st>>>(ctx->k.cnt, ctx->countsDev); ctx->launches++;
     CK(cudaEventRecord(ctx->ev[6], st));
@@ -2774,7 +3057,7 @@ enum { COLL_CANDS = 0, COLL_ROWS0 = 1, COLL_ALIVE = 2, COLL_PICK = 3 };
 
 static int collective(std::vector<pfb_ctx *> &C, int which) {
     bool any = false;
-    for (pfb_ctx *c : C) any |= c->comm && c->nRanks > 1;
+    for (pfb_ctx *c : C) any |= c->comm && c->nRanks > 1 && !c->peer_now;
     if (!any) return PFB_OK;
     std::string why;
     nccl::Api *a = nccl_api(why);
@@ -2787,7 +3070,7 @@ static int collective(std::vector<pfb_ctx *> &C, int which) {
     int rc = 0;
     if (C.size() > 1) a->GroupStart();
     for (pfb_ctx *c : C) {
-        if (!(c->comm && c->nRanks > 1)) continue;
+        if (!(c->comm && c->nRanks > 1) || c->peer_now) continue;
         cudaSetDevice(c->device);
         K &k = c->k;
         switch (which) {
@@ -2825,6 +3108,7 @@ static int finish(pfb_ctx *ctx, bool &again) {
     ctx->nslots = nslots; ctx->nids = nids;
     ctx->nrec = ctx->countsHost[C_NALIVE]; ctx->npick = ctx->countsHost[C_NPICK];
     auto round256 = [](uint64_t x) { return (uint32_t)std::min<uint64_t>((x + 255) & ~255ull, 0xFFFFFF00ull); };
+    if (flags & OVF_PEER_TIMEOUT) return fail(ctx, PFB_ECUDA, "a rank did not reach an exchange within the time limit (peer arenas)");
     if (flags) {
         // a count did not fit: grow what overflowed and repeat (the slot count is exact whatever happened; the id
         // count only when every slot had its row)
@@ -2880,6 +3164,7 @@ static int finish(pfb_ctx *ctx, bool &again) {
     t.used_filter = ctx->used_filter ? 1 : 0;
     t.sharded_first_genome = ctx->sharded_now ? 1 : 0;
     t.n_reruns = (uint64_t)ctx->reruns;
+    t.exchange_mode = ctx->nRanks > 1 && ctx->comm ? (ctx->peer_now ? 2 : 1) : 0;
     ctx->computed = true;
     ctx->host_valid = ctx->stream_out;
     return PFB_OK;
@@ -2890,6 +3175,9 @@ static int run_group(std::vector<pfb_ctx *> &C, bool piped) {
     int rc;
     for (int attempt = 0; attempt < 6; attempt++) {
         for (pfb_ctx *c : C) if ((rc = phaseA(c, piped)) != PFB_OK) return rc;
+        bool fallback = false;
+        if ((rc = x_connect(C, fallback)) != PFB_OK) return rc;
+        if (fallback) continue;       // the arenas could not be mapped: the same run again with NCCL collectives
         if ((rc = collective(C, COLL_CANDS)) != PFB_OK) return rc;
         for (pfb_ctx *c : C) if ((rc = phaseB(c)) != PFB_OK) return rc;
         if ((rc = collective(C, COLL_ROWS0)) != PFB_OK) return rc;
@@ -2923,7 +3211,9 @@ int pfb_compute(pfb_ctx *ctx) {
     ctx->stream_out = false;
     ctx->host_valid = false;
     std::vector<pfb_ctx *> C{ctx};
-    return run_group(C, ctx->pipelined);
+    int rc = run_group(C, ctx->pipelined);
+    if (ctx->tracing) trace_dump(ctx);
+    return rc;
 }
 
 int pfb_run(pfb_ctx *ctx) {

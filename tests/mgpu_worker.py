@@ -36,7 +36,10 @@ def main():
         else:
             eng.add_genome(gens[gi].contigs)
     eng.run()
-    assert eng.timing()["sharded_first_genome"] == 1      # the ranks shared genome 1's own pipeline
+    tmg = eng.timing()
+    assert tmg["sharded_first_genome"] == 1               # the ranks shared genome 1's own pipeline
+    want_mode = 1 if os.environ.get("PFB200_XCHG", "").lower().startswith("n") else 2
+    assert tmg["exchange_mode"] == want_mode, tmg["exchange_mode"]     # 2: through each other's arenas over NVLink, 1: NCCL
     rec, ss, ct = eng.result_picked()
     rec, ss = rec.copy(), ss.copy()
     ct = None if ct is None else ct.copy()

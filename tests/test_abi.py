@@ -29,7 +29,7 @@ def test_struct_sizes_match_header():
     import ctypes as C
     assert C.sizeof(_lib.PfbParams) == 112
     assert _lib.RECORD_DTYPE.itemsize == 24 and _lib.POS_DTYPE.itemsize == 12
-    assert C.sizeof(_lib.PfbTiming) == 6 * 4 + 8 * 8 + 2 * 4 + 3 * 8
+    assert C.sizeof(_lib.PfbTiming) == 6 * 4 + 8 * 8 + 2 * 4 + 4 * 8
     assert C.sizeof(_lib.PfbIdView) == 4 * 8 + 6 * 8
 
 

@@ -8,8 +8,9 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
+@pytest.mark.parametrize("xchg", ["peer", "nccl"])
 @pytest.mark.parametrize("n_contigs,ingest", [(1, "bases"), (5, "bases"), (3, "fasta")])
-def test_sharded_equals_single_gpu(n_contigs, ingest):
+def test_sharded_equals_single_gpu(n_contigs, ingest, xchg):
     import torch
     n = torch.cuda.device_count()
     if n < 2:
@@ -17,7 +18,7 @@ def test_sharded_equals_single_gpu(n_contigs, ingest):
     world = 2 if n < 4 else 4
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
            "--master-port", "29611", os.path.join(ROOT, "tests", "mgpu_worker.py"), "7", "300000", str(n_contigs), ingest]
-    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=dict(os.environ, PFB200_XCHG=xchg))
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-4000:]
     assert "ok=True" in out.stdout
 
@@ -59,6 +60,7 @@ def test_one_process_for_all_gpus_equals_single_gpu(n_contigs, ingest):
                 me.add_genome(g.contigs)
         me.run()
         assert me.engines[0].timing()["sharded_first_genome"] == 1
+        assert me.engines[0].timing()["exchange_mode"] == 2          # peer access between the contexts of one process
         for gi in range(len(gens)):
             ei, li = me.where(gi)
             rec, ss, ct = me.engines[ei].result_picked()
