@@ -1343,6 +1343,21 @@ __global__ void k_xsignal(const __grid_constant__ K p, int phase) {
     }
 }
 
+// both in one launch (a producer's signal is always followed by its own wait for the others)
+__global__ void k_xsync(const __grid_constant__ K p, int phase) {
+    if (threadIdx.x < p.nRanks) {
+        __threadfence_system();
+        *((volatile uint32_t *)(p.peer[threadIdx.x]) + phase * 16 + p.rank) = p.xEpoch;
+        const volatile uint32_t *f = (const volatile uint32_t *)(p.peer[p.rank]) + phase * 16 + threadIdx.x;
+        const long long t0 = clock64();
+        while ((int32_t)(*f - p.xEpoch) < 0) {
+            if (clock64() - t0 > (1ll << 34)) { atomicOr(&p.cnt[C_FLAGS], OVF_PEER_TIMEOUT); break; }
+            __nanosleep(100);
+        }
+        __threadfence_system();
+    }
+}
+
 __global__ void k_xwait(const __grid_constant__ K p, int phase, uint32_t value) {
     if (threadIdx.x < p.nRanks) {
         const volatile uint32_t *f = (const volatile uint32_t *)(p.peer[p.rank]) + phase * 16 + threadIdx.x;
@@ -1613,6 +1628,9 @@ struct pfb_ctx {
     cudaStream_t stream = nullptr;
     cudaStream_t copyStream = nullptr;          // H2D copies of pfb_run run here, overlapped with compute
     cudaStream_t d2hStream = nullptr;           // result copies of pfb_run run here, overlapped with compute
+    cudaStream_t sideStream = nullptr;          // packing of genomes 2..G runs here, beside genome 1's pipeline of small kernels
+    std::vector<cudaEvent_t> evEnc;             // one per batch: packed
+    cudaEvent_t evSide = nullptr;
     std::vector<cudaEvent_t> evCopy;            // one per genome: its bases have arrived
     std::vector<cudaEvent_t> evOut;             // result pieces ready for their device -> host copy
     bool pipelined = false;
@@ -1693,6 +1711,8 @@ struct pfb_ctx {
         uint32_t W = 0, W1 = 0, N1 = 0, NB = 0;
         uint64_t W_alloc = 0, windows1 = 0;
         int n_out = 0;
+        std::vector<size_t> cuts;               // ends (exclusive) of the batches of genomes 2..G
+        bool packed_aside = false;              // ... and whether they are being packed on the side stream
     } run;
 };
 
@@ -2153,6 +2173,8 @@ int pfb_create(pfb_ctx **out, int device, const pfb_params *params) {
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->copyStream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->parseStream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->d2hStream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->sideStream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->evSide, cudaEventDisableTiming);
     { const char *sg = getenv("PFB200_SHARD_G1"); if (sg && sg[0] == '0') ctx->shard_g1 = 0; }
     { const char *cs = getenv("PFB200_CAP_SHARE"); if (cs && atof(cs) > 0) ctx->cap_share = atof(cs); }
     { const char *xc = getenv("PFB200_XCHG"); if (xc && (xc[0] == 'n' || xc[0] == 'N')) ctx->xchg_pref = 0; }
@@ -2198,6 +2220,9 @@ void pfb_destroy(pfb_ctx *ctx) {
     for (auto &ev : ctx->evCopy) if (ev) cudaEventDestroy(ev);
     for (auto &ev : ctx->evOut) if (ev) cudaEventDestroy(ev);
     if (ctx->d2hStream) cudaStreamDestroy(ctx->d2hStream);
+    if (ctx->sideStream) { cudaStreamSynchronize(ctx->sideStream); cudaStreamDestroy(ctx->sideStream); }
+    if (ctx->evSide) cudaEventDestroy(ctx->evSide);
+    for (auto &ev : ctx->evEnc) if (ev) cudaEventDestroy(ev);
     if (ctx->countsHost) cudaFreeHost((void *)ctx->countsHost);
     if (ctx->copyStream) { cudaStreamSynchronize(ctx->copyStream); cudaStreamDestroy(ctx->copyStream); }
     if (ctx->parseStream) { cudaStreamSynchronize(ctx->parseStream); cudaStreamDestroy(ctx->parseStream); }
@@ -2492,6 +2517,76 @@ static int host_buffers(pfb_ctx *ctx) {
     return PFB_OK;
 }
 
+// pipelined run: the batches of genomes 2..G that finish earliest under a simple model -- copies land in order at
+// ~45 GB/s from t = 0, genome 1's pipeline takes a fixed part plus a part per window, a batch costs a fixed part
+// plus its windows at the hot kernel's rate and starts when the previous one is done and its own last copy has
+// landed.  Returns the end (exclusive) of every batch.  Only the SPLIT depends on the model, never a result.
+static std::vector<size_t> plan_batches(const pfb_ctx *ctx) {
+    const size_t nG = ctx->genomes.size();
+    const double nk = ctx->k.nk;
+    std::vector<double> land(nG + 1, 0.0), bases(nG + 1, 0.0);
+    double acc = 0;
+    for (size_t g = 0; g < nG; g++) {
+        const HostGenome &hg = ctx->genomes[g];
+        acc += (double)(hg.fasta ? hg.file_bytes : hg.n_bases);
+        land[g] = acc / 45e9;
+        bases[g + 1] = bases[g] + (double)(hg.fasta ? hg.file_bytes : hg.n_bases);
+    }
+    const double n1 = (double)(ctx->genomes[0].fasta ? ctx->genomes[0].file_bytes : ctx->genomes[0].n_bases);
+    const double t0 = land[0] + 250e-6 + n1 * nk * 12e-12;
+    const double fixed = 90e-6, per_window = 1.0 / 330e9;
+    const size_t n = nG - 1;                      // genomes 1..nG-1
+    // coarse grid when there are many genomes (the plan is O(n^2))
+    const size_t step = std::max<size_t>(1, n / 256);
+    std::vector<size_t> pts;                      // candidate cut points (exclusive ends), last = nG
+    for (size_t g = 1 + step; g < nG; g += step) pts.push_back(g);
+    pts.push_back(nG);
+    std::vector<double> best(pts.size(), 0.0);
+    std::vector<int> from(pts.size(), -1);
+    for (size_t i = 0; i < pts.size(); i++) {
+        best[i] = 1e30;
+        for (int j = -1; j < (int)i; j++) {
+            const size_t a = j < 0 ? 1 : pts[j], b = pts[i];
+            const double start = std::max(j < 0 ? t0 : best[j], land[b - 1]);
+            const double t = start + fixed + (bases[b] - bases[a]) * nk * per_window;
+            if (t < best[i]) { best[i] = t; from[i] = j; }
+        }
+    }
+    std::vector<size_t> cuts;
+    for (int i = (int)pts.size() - 1; i >= 0; i = from[i]) cuts.push_back(pts[i]);
+    std::reverse(cuts.begin(), cuts.end());
+    return cuts;
+}
+
+// genomes 2..G are packed on the side stream, beside genome 1's pipeline (a string of small kernels that leaves
+// most of the GPU idle): the resident run in one launch, the pipelined run batch by batch behind the H2D copies
+static int pack_aside(pfb_ctx *ctx) {
+    pfb_ctx::Run &R = ctx->run;
+    const size_t nG = ctx->genomes.size();
+    K &k = ctx->k;
+    if (nG < 2 || R.packed_aside) return PFB_OK;
+    R.cuts.clear();
+    if (R.piped) R.cuts = plan_batches(ctx); else R.cuts.push_back(nG);
+    while (ctx->evEnc.size() < R.cuts.size()) {
+        cudaEvent_t e = nullptr;
+        CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        ctx->evEnc.push_back(e);
+    }
+    CK(cudaEventRecord(ctx->evSide, ctx->stream));               // (tables uploaded, previous run's readers done)
+    CK(cudaStreamWaitEvent(ctx->sideStream, ctx->evSide, 0));
+    size_t g = 1;
+    for (size_t b = 0; b < R.cuts.size(); b++) {
+        const size_t g2 = R.cuts[b];
+        const uint32_t wa = ctx->gWordStart[g], wb = g2 < nG ? ctx->gWordStart[g2] : R.W;
+        if (R.piped) CK(cudaStreamWaitEvent(ctx->sideStream, ctx->evCopy[g2 - 1], 0));
+        if (wb > wa) { k_encode<<<nblk(wb - wa, 256), 256, 0, ctx->sideStream>>>(k, wa, wb); ctx->launches++; }
+        CK(cudaEventRecord(ctx->evEnc[b], ctx->sideStream));
+        g = g2;
+    }
+    R.packed_aside = true;
+    return PFB_OK;
+}
+
 static void x_signal(pfb_ctx *ctx, int phase);
 static void x_wait(pfb_ctx *ctx, int phase);
 static void x_done(pfb_ctx *ctx, int phase);
@@ -2648,6 +2743,7 @@ static int phaseA(pfb_ctx *ctx, bool piped) {
     }
     if (piped) CK(cudaStreamWaitEvent(st, ctx->evCopy[0], 0));      // only genome 1 has to be there before the key table can be built
     if (R.W1) { k_encode<<<nblk(R.W1, 256), 256, 0, st>>>(k, 0, R.W1); ctx->launches++; }
+    if (!R.partial && (rc = pack_aside(ctx)) != PFB_OK) return rc;
     CK(cudaEventRecord(ctx->ev[3], st));
     trace_mark(ctx, st, "genome 1 encoded");
     // genome 1: candidates -> key table
@@ -2671,14 +2767,13 @@ static int phaseA(pfb_ctx *ctx, bool piped) {
 }
 
 // peer mode: producer side of an exchange (the data is final on this stream) and consumer side (every rank's is)
-static void x_signal(pfb_ctx *ctx, int phase) {
+static void x_signal(pfb_ctx *ctx, int phase) {      // (the signal itself goes out with the wait: k_xsync)
     cudaEventRecord(ctx->evX[phase < XP_ROWS_B ? phase : phase - 1][0], ctx->stream);
     ctx->xUsed[phase < XP_ROWS_B ? phase : phase - 1] = true;
-    k_xsignal<<<1, 32, 0, ctx->stream>>>(ctx->k, phase); ctx->launches++;
 }
 static void x_wait(pfb_ctx *ctx, int phase) {
-    trace_mark(ctx, ctx->stream, "exchange " + std::to_string(phase) + ": signalled, waiting for the peers");
-    k_xwait<<<1, 32, 0, ctx->stream>>>(ctx->k, phase, ctx->epoch); ctx->launches++;
+    trace_mark(ctx, ctx->stream, "exchange " + std::to_string(phase) + ": data ready, signalling and waiting for the peers");
+    k_xsync<<<1, 32, 0, ctx->stream>>>(ctx->k, phase); ctx->launches++;
     trace_mark(ctx, ctx->stream, "exchange " + std::to_string(phase) + ": every peer has signalled");
 }
 static void x_done(pfb_ctx *ctx, int phase) {
@@ -2854,47 +2949,6 @@ static int judge_batch(pfb_ctx *ctx, size_t ga, size_t gb) {
     return PFB_OK;
 }
 
-// pipelined run: the batches of genomes 2..G that finish earliest under a simple model -- copies land in order at
-// ~45 GB/s from t = 0, genome 1's pipeline takes a fixed part plus a part per window, a batch costs a fixed part
-// plus its windows at the hot kernel's rate and starts when the previous one is done and its own last copy has
-// landed.  Returns the end (exclusive) of every batch.  Only the SPLIT depends on the model, never a result.
-static std::vector<size_t> plan_batches(const pfb_ctx *ctx) {
-    const size_t nG = ctx->genomes.size();
-    const double nk = ctx->k.nk;
-    std::vector<double> land(nG + 1, 0.0), bases(nG + 1, 0.0);
-    double acc = 0;
-    for (size_t g = 0; g < nG; g++) {
-        const HostGenome &hg = ctx->genomes[g];
-        acc += (double)(hg.fasta ? hg.file_bytes : hg.n_bases);
-        land[g] = acc / 45e9;
-        bases[g + 1] = bases[g] + (double)(hg.fasta ? hg.file_bytes : hg.n_bases);
-    }
-    const double n1 = (double)(ctx->genomes[0].fasta ? ctx->genomes[0].file_bytes : ctx->genomes[0].n_bases);
-    const double t0 = land[0] + 250e-6 + n1 * nk * 12e-12;
-    const double fixed = 90e-6, per_window = 1.0 / 330e9;
-    const size_t n = nG - 1;                      // genomes 1..nG-1
-    // coarse grid when there are many genomes (the plan is O(n^2))
-    const size_t step = std::max<size_t>(1, n / 256);
-    std::vector<size_t> pts;                      // candidate cut points (exclusive ends), last = nG
-    for (size_t g = 1 + step; g < nG; g += step) pts.push_back(g);
-    pts.push_back(nG);
-    std::vector<double> best(pts.size(), 0.0);
-    std::vector<int> from(pts.size(), -1);
-    for (size_t i = 0; i < pts.size(); i++) {
-        best[i] = 1e30;
-        for (int j = -1; j < (int)i; j++) {
-            const size_t a = j < 0 ? 1 : pts[j], b = pts[i];
-            const double start = std::max(j < 0 ? t0 : best[j], land[b - 1]);
-            const double t = start + fixed + (bases[b] - bases[a]) * nk * per_window;
-            if (t < best[i]) { best[i] = t; from[i] = j; }
-        }
-    }
-    std::vector<size_t> cuts;
-    for (int i = (int)pts.size() - 1; i >= 0; i = from[i]) cuts.push_back(pts[i]);
-    std::reverse(cuts.begin(), cuts.end());
-    return cuts;
-}
-
 static int phaseC(pfb_ctx *ctx) {
     CK(cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
@@ -2913,7 +2967,6 @@ static int phaseC(pfb_ctx *ctx) {
                 x_wait(ctx, XP_ROWS_A);
                 const uint32_t per = ((ctx->capSlots + ctx->nRanks - 1) / ctx->nRanks + 3u) & ~3u;
                 k_rows0_reduce_slice<<<nblk(per / 4, 256), 256, 0, st>>>(k); ctx->launches++;
-                k_xsignal<<<1, 32, 0, st>>>(k, XP_ROWS_B); ctx->launches++;
                 x_wait(ctx, XP_ROWS_B);
                 k_rows0_gather_unpack<<<nblk(ctx->capSlots / 4, 256), 256, 0, st>>>(k); ctx->launches++;
                 x_done(ctx, XP_ROWS_A);
@@ -2983,8 +3036,9 @@ static int phaseC(pfb_ctx *ctx) {
         k.seq2 = (uint64_t *)ctx->seq2.p; k.nmask = (uint32_t *)ctx->nmask.p; k.wordContig = (uint32_t *)ctx->wordContig.p;
     }
     if (nG > 1) {
+        if ((rc = pack_aside(ctx)) != PFB_OK) return rc;          // (FASTA files parsed late: only now)
         if (!R.piped) {
-            if (R.W > R.W1) { k_encode<<<nblk(R.W - R.W1, 256), 256, 0, st>>>(k, R.W1, R.W); ctx->launches++; }
+            CK(cudaStreamWaitEvent(st, ctx->evEnc[0], 0));
             CK(cudaEventRecord(ctx->ev[7], st));
             if ((rc = scan_batch(ctx, 1, nG, false, use_filter)) != PFB_OK) return rc;
             CK(cudaEventRecord(ctx->ev[8], st));
@@ -2996,11 +3050,11 @@ static int phaseC(pfb_ctx *ctx) {
             // is planned here, before anything runs, from rough rates (a launch over few genomes is inefficient --
             // nk filter loads, one word per thread -- so batches must not be small; a batch cannot start before its
             // last copy has landed; the places of a batch leave for the host while the next one is scanned)
-            std::vector<size_t> cuts = plan_batches(ctx);
             size_t g = 1;
-            for (size_t g2 : cuts) {
-                CK(cudaStreamWaitEvent(st, ctx->evCopy[g2 - 1], 0));
-                if ((rc = scan_batch(ctx, g, g2, true, use_filter)) != PFB_OK) return rc;
+            for (size_t b = 0; b < R.cuts.size(); b++) {
+                const size_t g2 = R.cuts[b];
+                CK(cudaStreamWaitEvent(st, ctx->evEnc[b], 0));
+                if ((rc = scan_batch(ctx, g, g2, false, use_filter)) != PFB_OK) return rc;
                 if ((rc = judge_batch(ctx, g, g2)) != PFB_OK) return rc;
                 g = g2;
             }
