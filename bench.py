@@ -126,6 +126,93 @@ def cpu_sample_run(cfg_index: int, threads: int = 0, n_genomes: int = 3, length:
                        f"{n_genomes * nk} (genome, k) tasks on {threads} threads), {dt:.2f} s, {o.n_shared} shared k-mers"), dt, o, gens
 
 
+def outgroup_block(device: int, flush, with_cpu: bool, n_outgroup: int = 10, length: int = 5_000_000, n_pairs: int = 50_000,
+                   steps: int = 10) -> dict:
+    """SURVEY.md 8(f)-3, the outgroup screen (bin/removeOutgroupPrimers.py:181-313) on BASELINE config 3's outgroup
+    shape: 10 outgroup genomes of 5 Mbp (the first ingroup genome with 5 % substitutions) against the primers of
+    50 000 synthetic pairs.  Device-resident steps (CUDA events inside the library, L2 flushed), the same through the C
+    ABI from pinned host bases to host results, and -- the gate -- the result compared with oracle/pf_oracle_outgroup.c
+    run on the same inputs with every host thread."""
+    import torch
+    from primerforge_b200 import synth
+    from primerforge_b200.engine import words_to_strings
+    from primerforge_b200.outgroup import OutgroupScreen
+    first = synth.make_genomes(1, length, seed=synth.BASE_SEED + 3)[0]
+    outs = synth.make_outgroup(first, n_outgroup)
+    w, k, pf, pr = synth.make_pairs(first, n_pairs)
+    pinned = []
+    for g in outs:
+        cat = np.concatenate(g.contigs)
+        t = torch.empty(cat.size, dtype=torch.uint8).pin_memory()
+        t.numpy()[:] = cat
+        pinned.append((t, np.cumsum([0] + [c.size for c in g.contigs]).astype(np.uint64)))
+    bases = sum(t.numel() for t, _ in pinned)
+    with OutgroupScreen(device=device) as scr:
+        scr.set_keys_and_pairs(w, k, pf, pr, 120, 2400)
+
+        def add_all():
+            scr.clear_genomes()
+            for t, off in pinned:
+                scr._ck(scr._lib.pfb_og_add_genome(scr._h, t.data_ptr(), t.numel(), off.ctypes.data, off.size - 1))
+        add_all()
+        scr.run()
+        ms, parts = [], []
+        for i in range(3 + steps):
+            flush.zero_()
+            torch.cuda.synchronize()
+            scr.compute()
+            if i >= 3:
+                tm = scr.timing()
+                ms.append(tm["ms_total"]); parts.append((tm["ms_encode"], tm["ms_scan"], tm["ms_bucket"], tm["ms_products"]))
+        e2e = []
+        for i in range(2 + steps):
+            flush.zero_()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            add_all()
+            scr.run()                       # H2D of the bases, scan, products, D2H of hits / products / verdicts
+            if i >= 2:
+                e2e.append(time.perf_counter() - t0)
+        res = scr.result()
+        tm = scr.timing()
+    step_ms, e2e_ms = float(np.mean(ms)), float(np.mean(e2e) * 1e3)
+    enc, scan, bucket, prod = (float(x) for x in np.mean(np.array(parts), axis=0))
+    peak, _ = measured_peaks()
+    out = {"what": "outgroup screen (bin/removeOutgroupPrimers.py:181-313): every outgroup contig on both strands against the pairs' primers, "
+                   "product sizes per pair, pairs with a disallowed size deleted",
+           "workload": f"BASELINE config 3's outgroup: {n_outgroup} x {length / 1e6:g} Mbp (first ingroup genome, 5 % substitutions), "
+                       f"{n_pairs} synthetic pairs = {int(w.size)} distinct primers of 16-20 bases, disallowed sizes 120-2400",
+           "value": bases / 1e6 / (step_ms / 1e3), "unit": "outgroup Mbp/s", "ms_per_step": step_ms, "steps": steps,
+           "phases_ms": {"encode": enc, "scan": scan, "bucket": bucket, "products": prod},
+           "e2e": {"value": bases / 1e6 / (e2e_ms / 1e3), "unit": "outgroup Mbp/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": int(bases),
+                   "d2h_bytes_per_step": int(16 * tm["n_hits"] + 16 * tm["n_products"] + 4 * n_pairs)},
+           "gpu_launches_per_step": int(tm["n_launches"]),
+           "counts": {k2: int(tm[k2]) for k2 in ("n_bases", "n_windows", "n_hits", "n_products", "n_probe_occupied", "table_bytes",
+                                                 "filter_in_smem", "filter_bits_per_record")} | {"pairs_kept": int(res.kept.sum())},
+           "roofline": {"kernel": "k_og_scan_smem", "ms_per_launch": scan, "windows_per_s_G": tm["n_windows"] / (scan / 1e3) / 1e9,
+                        "algorithmic_bytes_per_launch": 0.375 * bases, "hbm_frac": 0.375 * bases / (scan / 1e3) / 1e9 / peak,
+                        "bound": "instruction issue + shared-memory filter look-ups (one per window and length); HBM only streams the packed "
+                                 "bases once (0.375 B per base), so the HBM fraction is small by construction"}}
+    if with_cpu:
+        from oracle import pf_oracle as po
+        t0 = time.perf_counter()
+        o = po.run_outgroup(words_to_strings(w, k), pf, pr, 120, 2400, outs)
+        dt = time.perf_counter() - t0
+        h = res.hits
+        mine = np.stack([h["key"], h["genome"], h["contig"], h["start"], h["strand"]], axis=1).astype(np.uint32)
+        theirs = o.hits[np.lexsort((o.hits[:, 3], o.hits[:, 0], o.hits[:, 4], o.hits[:, 2], o.hits[:, 1]))]
+        pp = res.products
+        ok_h = bool(np.array_equal(mine, theirs))
+        ok_r = bool(np.array_equal(res.removed_at, o.removed_at))
+        ok_p = bool(np.array_equal(np.stack([pp["pair"], pp["genome"], pp["contig"], pp["size"].astype(np.uint32)], axis=1).reshape(-1, 4), o.products))
+        out["cpu_baseline"] = {"value": bases / 1e6 / dt, "unit": "outgroup Mbp/s", "cores": host_threads(), "kind": "port",
+                               "sample": f"the same {n_outgroup} genomes and pairs, oracle/pf_oracle_outgroup.c (C restatement of the reference's "
+                                         f"string scan, OpenMP over the contigs), {dt:.2f} s"}
+        out["parity"] = {"against": "oracle/pf_oracle_outgroup.c on the same inputs", "ok": ok_h and ok_r and ok_p, "hits": ok_h,
+                         "deleted_pairs": ok_r, "product_sets": ok_p, "n_hits": int(mine.shape[0])}
+    return out
+
+
 def parity_vs_oracle(gens, o, cfg, device: int) -> dict:
     """the correctness gate: the CUDA path on the very genomes the CPU sample ran on, compared
     bit for bit with the oracle's result -- the shared k-mers in dict order, flags and picks, Tm, and
@@ -274,6 +361,7 @@ def main():
     ap.add_argument("--no-fasta-leg", action="store_true")
     ap.add_argument("--no-strong-c4", action="store_true", help="skip the strong-scaling block (BASELINE config 4: 200 genomes over the GPUs)")
     ap.add_argument("--no-dropin-leg", action="store_true", help="skip the timing of the drop-in entry point from FASTA files on disk")
+    ap.add_argument("--no-outgroup", action="store_true", help="skip the outgroup-screen block (BASELINE config 3's 10 outgroup genomes)")
     ap.add_argument("--scan-mode", type=int, default=0, help="0 auto, 1 plain L2 probe, 2 shared-memory filter (debug)")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="weak (default): the config's genome count PER GPU; strong: the config's genome count in total, "
@@ -643,6 +731,8 @@ def main():
         line["e2e_dropin"] = {"value": distinct_bases / 1e6 / dt, "unit": UNIT, "seconds": dt, "primers": int(n_obj),
                               "what": "_getAllCandidateKmers(params, False) from FASTA files on disk to dict[str, dict[str, list[Primer]]] "
                                       "(hairpin / homodimer screening off): the call the reference's main.py:86 makes"}
+    if world == 1 and not args.no_outgroup and not args.genomes and not args.length:
+        line["outgroup"] = outgroup_block(local, flush, with_cpu=not args.no_cpu_baseline)
     if world == 1 and not args.no_cpu_baseline:
         # the CPU restatement on a bounded sample; the GPU must reproduce that result bit for bit (the gate)
         line["cpu_baseline"], _dt, o_cpu, gens_cpu = cpu_sample_run(args.config, length=args.length)

@@ -225,6 +225,56 @@ int  pfb_set_scan_mode(pfb_ctx *ctx, int mode);
  * README.md:375-377); returns PFB_EINVAL for non-ACGT input */
 int  pfb_oligo_tm(pfb_ctx *ctx, const char *seq, double *tm, double *gc_percent);
 
+/* outgroup screen -------------------------------------------------------------------------
+ * Replaces _removeOutgroupPrimers' scan and product arithmetic (bin/removeOutgroupPrimers.py:181-313): the
+ * Aho-Corasick automaton over the distinct primer strings of the pairs (:14-31), its run over every outgroup
+ * contig on both strands (:34-62, 215-226), the product sizes per pair and contig (:65-122) and the deletion of
+ * pairs with a size in params.disallowedLens (:281-287).  A handle lives on one GPU and is not thread-safe.
+ * Keys are the DISTINCT primer strings as (2-bit word, length) -- A0 T1 C2 G3, first base most significant, like
+ * pfb_record.word; pairs are (key of str(fwd), key of str(rev)) in the order of the pairs dict. */
+typedef struct pfb_og pfb_og;
+typedef struct pfb_og_hit {       /* one entry of __extractKmerData's lists (:34-62) */
+    uint32_t key;                 /* index into the key set */
+    uint32_t genome, contig;      /* outgroup genome in pfb_og_add_genome order, contig index within it */
+    uint32_t start;               /* '+': end - len + 1 (:51); '-': len(seq) - start_in_rc - 1 = the rightmost (+) coordinate (:54-55) */
+    uint32_t strand;              /* 0 '+', 1 '-' */
+} pfb_og_hit;
+typedef struct pfb_og_product {   /* one (contig, pcrLen) of a pair that is NOT disallowed (:289-291); duplicates possible */
+    uint32_t pair, genome, contig;
+    int32_t  size;                /* rStart - fStart + 1 > 0 (:80-85) */
+} pfb_og_product;
+typedef struct pfb_og_timing {
+    float    ms_upload, ms_encode, ms_scan, ms_bucket, ms_products, ms_total;   /* CUDA events; total = encode .. products */
+    uint64_t n_bases, n_windows, n_hits, n_products;
+    uint64_t n_probe_occupied;    /* probes that met an occupied table slot (the others ended on their first load) */
+    uint64_t n_launches, n_reruns, table_bytes;
+    uint64_t filter_in_smem;      /* 1: the scan tested its windows against the filter in shared memory (k_og_scan_smem) */
+    uint64_t filter_bits_per_record;
+} pfb_og_timing;
+int  pfb_og_create(pfb_og **out, int device);
+void pfb_og_destroy(pfb_og *og);
+const char *pfb_og_last_error(const pfb_og *og);   /* og may be NULL: error of the last failed pfb_og_create */
+int  pfb_og_set_keys(pfb_og *og, const uint64_t *word, const uint8_t *k, uint32_t n_keys);     /* __getAutomaton (:14-31) */
+/* disallowed_lo..disallowed_hi inclusive = params.disallowedLens (a range, bin/Parameters.py:678,762,874) */
+int  pfb_og_set_pairs(pfb_og *og, const uint32_t *fwd_key, const uint32_t *rev_key, uint32_t n_pairs,
+                      int32_t disallowed_lo, int32_t disallowed_hi);
+/* one call per outgroup genome (same conventions as pfb_add_genome; an empty contig is allowed); the bytes are
+ * str(contig.seq) (:221): only upper-case A C G T can be part of a match */
+int  pfb_og_add_genome(pfb_og *og, const uint8_t *bases, uint64_t n_bases, const uint64_t *contig_off, uint32_t n_contigs);
+int  pfb_og_clear_genomes(pfb_og *og);
+/* 0 auto (default): the window filter lives in shared memory when the key set allows; 1: always in global memory.
+ * Results are identical; tests run both. */
+int  pfb_og_set_scan_mode(pfb_og *og, int mode);
+int  pfb_og_run(pfb_og *og);        /* upload + scan every genome + products */
+int  pfb_og_compute(pfb_og *og);    /* the same again on the resident genomes (timing) */
+int  pfb_og_counts(pfb_og *og, uint64_t *n_hits, uint64_t *n_products, uint64_t *n_removed);
+int  pfb_og_hits(pfb_og *og, pfb_og_hit *out, uint64_t cap);              /* unordered */
+int  pfb_og_products(pfb_og *og, pfb_og_product *out, uint64_t cap);      /* unordered */
+/* per pair: the first outgroup genome (pfb_og_add_genome order) in which it has a disallowed product size -- the
+ * pass of the loop at :255-291 that deletes it -- or 0xFFFFFFFF when the pair is kept */
+int  pfb_og_removed_at(pfb_og *og, uint32_t *out, uint64_t cap);
+int  pfb_og_timings(pfb_og *og, pfb_og_timing *out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -14,6 +14,7 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _SRC = os.path.join(_HERE, "pf_oracle.c")
+_SRCS = [_SRC, os.path.join(_HERE, "pf_oracle_outgroup.c")]
 _LIB = os.path.join(_HERE, "libpf_oracle.so")
 
 
@@ -34,11 +35,17 @@ class PfoResult(C.Structure):
                 ("n_allowed", C.POINTER(C.c_uint64)), ("err", C.c_char * 256)]
 
 
+class PfoOgResult(C.Structure):
+    _fields_ = [("n_hits", C.c_uint64), ("n_products", C.c_uint64), ("hits", C.POINTER(C.c_uint32)),
+                ("products", C.POINTER(C.c_uint32)), ("removed_at", C.POINTER(C.c_uint32)), ("err", C.c_char * 256)]
+
+
 def build(force: bool = False) -> str:
     """gcc -O2 -fopenmp -shared; rebuilt when the source is newer"""
-    if force or not os.path.exists(_LIB) or (os.path.exists(_SRC) and os.path.getmtime(_SRC) > os.path.getmtime(_LIB)):
+    have = [f for f in _SRCS if os.path.exists(f)]      # (a box without the sources uses the prebuilt library)
+    if force or not os.path.exists(_LIB) or any(os.path.getmtime(f) > os.path.getmtime(_LIB) for f in have):
         subprocess.check_call(["gcc", "-O2", "-fopenmp", "-fno-fast-math", "-ffp-contract=off", "-shared", "-fPIC",
-                               "-o", _LIB, _SRC, "-lm"])
+                               "-o", _LIB] + _SRCS + ["-lm"])
     return _LIB
 
 
@@ -58,6 +65,12 @@ def lib():
         _lib.pfo_calc_tm.restype = C.c_double
         _lib.pfo_calc_tm.argtypes = [C.c_char_p, C.POINTER(PfoParams)]
         _lib.pfo_max_threads.restype = C.c_int
+        _lib.pfo_outgroup.restype = C.POINTER(PfoOgResult)
+        _lib.pfo_outgroup.argtypes = [C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p,
+                                      C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
+                                      C.POINTER(C.c_int32)]
+        _lib.pfo_og_free.argtypes = [C.POINTER(PfoOgResult)]
+        _lib.pfo_og_free.restype = None
     return _lib
 
 
@@ -139,3 +152,52 @@ def run(genomes, params: PfoParams) -> OracleResult:
     finally:
         L.pfo_free(rp)
     return out
+
+
+@dataclass
+class OutgroupOracleResult:
+    hits: np.ndarray        # [n, 5] uint32: key, genome, contig, start, strand -- __extractKmerData's lists in scan order
+    products: np.ndarray    # [n, 4] uint32: pair, genome, contig, size -- distinct, sorted, kept pairs only
+    removed_at: np.ndarray  # [n_pairs] uint32, 0xFFFFFFFF = kept
+
+
+def run_outgroup(keys, pair_fwd, pair_rev, bad_lo: int, bad_hi: int, genomes) -> OutgroupOracleResult:
+    """oracle/pf_oracle_outgroup.c: keys = distinct primer strings, pair_fwd / pair_rev = key indices of str(fwd) /
+    str(rev) per pair (dict order), genomes = objects with ``.contigs`` (outgroup genomes in order)"""
+    L = lib()
+    kb = [str(k).encode("ascii") for k in keys]
+    key_bytes = np.frombuffer(b"".join(kb) + b"\0", dtype=np.uint8).copy()
+    key_len = np.array([len(k) for k in kb], dtype=np.uint8)
+    key_off = np.zeros(len(kb) + 1, dtype=np.uint64)
+    key_off[1:] = np.cumsum([len(k) for k in kb])
+    pf = np.ascontiguousarray(pair_fwd, dtype=np.uint32)
+    pr = np.ascontiguousarray(pair_rev, dtype=np.uint32)
+    G = len(genomes)
+    bases_keep, offs_keep = [], []
+    for gen in genomes:
+        contigs = [np.ascontiguousarray(c, dtype=np.uint8) for c in gen.contigs]
+        cat = np.concatenate(contigs) if contigs else np.zeros(0, np.uint8)
+        off = np.zeros(len(contigs) + 1, dtype=np.int64)
+        off[1:] = np.cumsum([c.size for c in contigs])
+        bases_keep.append(np.ascontiguousarray(np.r_[cat, np.zeros(1, np.uint8)]))
+        offs_keep.append(off)
+    bptr = (C.c_void_p * max(G, 1))(*[b.ctypes.data for b in bases_keep])
+    optr = (C.c_void_p * max(G, 1))(*[o.ctypes.data for o in offs_keep])
+    nct = (C.c_int32 * max(G, 1))(*[len(g.contigs) for g in genomes])
+    rp = L.pfo_outgroup(len(kb), key_bytes.ctypes.data, key_off.ctypes.data, key_len.ctypes.data, pf.size, pf.ctypes.data,
+                        pr.ctypes.data, int(bad_lo), int(bad_hi), G, bptr, optr, nct)
+    try:
+        r = rp.contents
+        if r.err:
+            raise RuntimeError(f"oracle: {r.err.decode()}")
+
+        def arr(ptr, n, w):
+            if n == 0:
+                return np.zeros((0, w) if w > 1 else 0, dtype=np.uint32)
+            a = np.ctypeslib.as_array(ptr, shape=(n * w,)).astype(np.uint32, copy=True)
+            return a.reshape(n, w) if w > 1 else a
+
+        return OutgroupOracleResult(hits=arr(r.hits, int(r.n_hits), 5), products=arr(r.products, int(r.n_products), 4),
+                                    removed_at=arr(r.removed_at, pf.size, 1))
+    finally:
+        L.pfo_og_free(rp)

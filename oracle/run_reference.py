@@ -88,3 +88,44 @@ def run_reference(ingroup_fns, thal_mode="pass", **kw):
     with contextlib.redirect_stdout(io.StringIO()):
         cands = mod._getAllCandidateKmers(params, False)
     return sink["sharedKmers.p"], cands
+
+
+def run_reference_pairs(candidates, ingroup_fns, min_len=16, max_len=20, min_pcr=120, max_pcr=2400, max_tm_diff=5.0,
+                        max_bin_size=64):
+    """the reference's UNMODIFIED ``bin/getPrimerPairs.py::_getPrimerPairs`` on a candidate dict"""
+    _import_reference("pass")
+    gpp = importlib.import_module("bin.getPrimerPairs")
+    prm = SimpleNamespace(ingroupFns=list(ingroup_fns), maxBinSize=max_bin_size, minLen=min_len, maxLen=max_len,
+                          minPcr=min_pcr, maxPcr=max_pcr, maxTmDiff=max_tm_diff, numThreads=1, tempTolerance=5.0,
+                          p3_mvConc=50.0, p3_dvConc=1.5, p3_dntpConc=0.6, p3_dnaConc=50.0, p3_tempC=37.0, p3_maxLoop=30,
+                          log=_NullLog())
+    return gpp._getPrimerPairs(candidates, prm)
+
+
+def run_reference_outgroup(outgroup_fns, pairs, disallowed, fmt="fasta"):
+    """the reference's UNMODIFIED ``bin/removeOutgroupPrimers.py::_removeOutgroupPrimers`` (modifies ``pairs`` in
+    place like the reference does); the outgroup generators are made the way ``bin/main.py:41-60`` makes them.
+    Returns the debug log lines; raises what the reference raises."""
+    _import_reference("pass")
+    rop = importlib.import_module("bin.removeOutgroupPrimers")
+    from Bio import SeqIO  # the stand-in
+    log = _NullLog()
+    prm = SimpleNamespace(disallowedLens=disallowed, log=log)
+    outgroup = {os.path.basename(fn): SeqIO.parse(fn, fmt) for fn in outgroup_fns}
+    import contextlib
+    import io
+    with contextlib.redirect_stdout(io.StringIO()):
+        rop._removeOutgroupPrimers(outgroup, pairs, prm)
+    return log.debug_lines
+
+
+def reference_extract_kmer_data(seq: str, strand: str, kmers):
+    """``bin/removeOutgroupPrimers.py::__extractKmerData`` (:34-62) on one string; kmers = list of primer strings"""
+    _import_reference("pass")
+    rop = importlib.import_module("bin.removeOutgroupPrimers")
+    from ahocorasick import Automaton  # the stand-in
+    aut = Automaton()
+    for k in kmers:
+        aut.add_word(k, k)
+    aut.make_automaton()
+    return getattr(rop, "__extractKmerData")(seq, strand, aut)

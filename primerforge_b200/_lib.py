@@ -15,6 +15,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("PFB200_LIB") or os.path.join(_HERE, "libpfb200.so")   # PFB200_LIB: A/B builds
 SRC_PATH = os.path.join(_HERE, "csrc", "pfb200.cu")
+SRC_PATHS = [SRC_PATH, os.path.join(_HERE, "csrc", "pfb_outgroup.cu")]      # one translation unit per stage
 INCLUDE_DIR = os.path.join(os.path.dirname(_HERE), "include")
 
 PFB_OK, PFB_EINVAL, PFB_ECUDA, PFB_ESTATE, PFB_ENOSHARED, PFB_ETOOLARGE = 0, -1, -2, -3, -4, -5
@@ -33,7 +34,10 @@ EXPORTS = ["pfb_create", "pfb_destroy", "pfb_last_error", "pfb_default_params", 
            "pfb_multi_create", "pfb_multi_destroy", "pfb_multi_last_error", "pfb_multi_add_genome", "pfb_multi_add_fasta",
            "pfb_multi_add_genbank", "pfb_multi_run", "pfb_multi_size", "pfb_multi_context", "pfb_multi_locate",
            "pfb_sync", "pfb_stream", "pfb_result_counts", "pfb_result_by_id", "pfb_result_records",
-           "pfb_result_positions", "pfb_result_picked", "pfb_host_alloc", "pfb_host_free", "pfb_timings", "pfb_set_scan_mode", "pfb_oligo_tm"]
+           "pfb_result_positions", "pfb_result_picked", "pfb_host_alloc", "pfb_host_free", "pfb_timings", "pfb_set_scan_mode", "pfb_oligo_tm",
+           "pfb_og_create", "pfb_og_destroy", "pfb_og_last_error", "pfb_og_set_keys", "pfb_og_set_pairs", "pfb_og_add_genome",
+           "pfb_og_clear_genomes", "pfb_og_set_scan_mode", "pfb_og_run", "pfb_og_compute", "pfb_og_counts", "pfb_og_hits", "pfb_og_products",
+           "pfb_og_removed_at", "pfb_og_timings"]
 
 
 class PfbParams(C.Structure):
@@ -59,6 +63,16 @@ class PfbIdView(C.Structure):
                 ("alive", C.c_void_p), ("pick", C.c_void_p)]
 
 
+class PfbOgTiming(C.Structure):
+    _fields_ = [("ms_upload", C.c_float), ("ms_encode", C.c_float), ("ms_scan", C.c_float), ("ms_bucket", C.c_float),
+                ("ms_products", C.c_float), ("ms_total", C.c_float), ("n_bases", C.c_uint64), ("n_windows", C.c_uint64),
+                ("n_hits", C.c_uint64), ("n_products", C.c_uint64), ("n_probe_occupied", C.c_uint64),
+                ("n_launches", C.c_uint64), ("n_reruns", C.c_uint64), ("table_bytes", C.c_uint64),
+                ("filter_in_smem", C.c_uint64), ("filter_bits_per_record", C.c_uint64)]
+
+
+OG_HIT_DTYPE = np.dtype([("key", "<u4"), ("genome", "<u4"), ("contig", "<u4"), ("start", "<u4"), ("strand", "<u4")])
+OG_PRODUCT_DTYPE = np.dtype([("pair", "<u4"), ("genome", "<u4"), ("contig", "<u4"), ("size", "<i4")])
 RECORD_DTYPE = np.dtype([("word", "<u8"), ("tm", "<f8"), ("slot", "<u4"), ("gc_count", "<u2"), ("k", "u1"), ("flags", "u1")])
 POS_DTYPE = np.dtype([("contig", "<u4"), ("start", "<u4"), ("strand", "<u4")])
 assert RECORD_DTYPE.itemsize == 24 and POS_DTYPE.itemsize == 12
@@ -71,7 +85,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     srcs.append(os.path.join(INCLUDE_DIR, "pfb200.h"))
     stale = (not os.path.exists(LIB_PATH)) or any(os.path.getmtime(f) > os.path.getmtime(LIB_PATH) for f in srcs)
     if force or stale:
-        cmd = ["nvcc"] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH, SRC_PATH] + NVCC_LIBS
+        cmd = ["nvcc"] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH] + SRC_PATHS + NVCC_LIBS
         subprocess.check_call(cmd)
     return LIB_PATH
 
@@ -129,8 +143,25 @@ def load():
     lib.pfb_timings.argtypes = [vp, C.POINTER(PfbTiming)]
     lib.pfb_set_scan_mode.argtypes = [vp, i32]
     lib.pfb_oligo_tm.argtypes = [vp, C.c_char_p, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    lib.pfb_og_create.argtypes = [C.POINTER(vp), i32]
+    lib.pfb_og_destroy.argtypes = [vp]
+    lib.pfb_og_destroy.restype = None
+    lib.pfb_og_last_error.argtypes = [vp]
+    lib.pfb_og_last_error.restype = C.c_char_p
+    lib.pfb_og_set_keys.argtypes = [vp, vp, vp, u32]
+    lib.pfb_og_set_pairs.argtypes = [vp, vp, vp, u32, C.c_int32, C.c_int32]
+    lib.pfb_og_add_genome.argtypes = [vp, vp, u64, vp, u32]
+    for fn in ("pfb_og_clear_genomes", "pfb_og_set_scan_mode", "pfb_og_run", "pfb_og_compute"):
+        getattr(lib, fn).argtypes = [vp]
+    lib.pfb_og_set_scan_mode.argtypes = [vp, i32]
+    lib.pfb_og_counts.argtypes = [vp, C.POINTER(u64), C.POINTER(u64), C.POINTER(u64)]
+    lib.pfb_og_hits.argtypes = [vp, vp, u64]
+    lib.pfb_og_products.argtypes = [vp, vp, u64]
+    lib.pfb_og_removed_at.argtypes = [vp, vp, u64]
+    lib.pfb_og_timings.argtypes = [vp, C.POINTER(PfbOgTiming)]
     for name in EXPORTS:
-        if name not in ("pfb_destroy", "pfb_last_error", "pfb_multi_destroy", "pfb_multi_last_error"):
+        if name not in ("pfb_destroy", "pfb_last_error", "pfb_multi_destroy", "pfb_multi_last_error", "pfb_og_destroy",
+                        "pfb_og_last_error"):
             getattr(lib, name).restype = C.c_int
     _lib = lib
     return lib

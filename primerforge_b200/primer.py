@@ -142,6 +142,30 @@ class Primer:
 _LocalPrimer = Primer
 
 
+class Product:
+    """mirror of /root/reference/bin/Product.py:4-44 (PCR product of a primer pair in one genome); used only when
+    bin.Product is not importable"""
+
+    def __init__(self, contig, size, fbin, rbin, dimerTm, fStart, fEnd, fStrand, rStart, rEnd, rStrand):
+        self.contig = contig
+        self.size = size
+        self.dimerTm = dimerTm
+        self.fbin = fbin
+        self.rbin = rbin
+        self.fStart = fStart
+        self.fEnd = fEnd
+        self.fStrand = fStrand
+        self.rStart = rStart
+        self.rEnd = rEnd
+        self.rStrand = rStrand
+
+    def __str__(self):
+        return f"{self.contig}: {self.size} bp"
+
+    def __repr__(self):
+        return str(self)
+
+
 def primer_class():
     """bin.Primer.Primer when primerForge is importable, else the local mirror"""
     try:

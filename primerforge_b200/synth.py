@@ -132,3 +132,54 @@ def make_config(index: int, n_genomes: int | None = None, length: int | None = N
         cfg["length"] = length
     gens = make_genomes(cfg["n_genomes"], cfg["length"], seed=BASE_SEED + index, n_contigs=cfg["n_contigs"])
     return gens, cfg
+
+
+def make_outgroup(first_genome: Genome, n_genomes: int = 10, rate: float = 0.05, seed: int = BASE_SEED + 1000) -> list:
+    """BASELINE config 3's outgroup genomes: the ingroup's first genome with ``rate`` iid substitutions
+    each, same contig structure"""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    out = []
+    for g in range(n_genomes):
+        contigs = []
+        for c in first_genome.contigs:
+            seq = c.copy()
+            sites = np.flatnonzero(rng.random(seq.size) < rate)
+            cur = ((seq[sites] >> 1) & 3).astype(np.uint8)          # A0 C1 T2 G3
+            new = (cur + rng.integers(1, 4, size=sites.size, dtype=np.uint8)) & 3
+            seq[sites] = np.frombuffer(b"ACTG", dtype=np.uint8)[new]
+            contigs.append(seq)
+        out.append(Genome(name=f"outgroup_{g:03d}.fasta", contig_ids=[f"o{g:03d}_c{i:03d}" for i in range(len(contigs))],
+                          contigs=contigs))
+    return out
+
+
+def make_pairs(first_genome: Genome, n_pairs: int, k_min: int = 16, k_max: int = 20, min_pcr: int = 120, max_pcr: int = 2400,
+               seed: int = BASE_SEED + 2000) -> tuple:
+    """synthetic primer pairs on the first ingroup genome: the forward primer is a window of its (+) strand, the reverse
+    primer the reverse complement of a window min_pcr..max_pcr downstream -- what bin/getPrimerPairs.py hands to
+    the outgroup screen (str(fwd), str(rev)).  Returns (key words uint64, key lengths uint8, pair_fwd, pair_rev):
+    distinct keys, pairs as key indices."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    seq = first_genome.contigs[0]
+    n = seq.size
+    code = np.zeros(256, dtype=np.uint64)
+    for i, ch in enumerate(b"ATCG"):
+        code[ch] = i
+    c = code[seq]
+    kf = rng.integers(k_min, k_max + 1, size=n_pairs)
+    kr = rng.integers(k_min, k_max + 1, size=n_pairs)
+    size = rng.integers(min_pcr, max_pcr + 1, size=n_pairs)
+    a = rng.integers(0, n - max_pcr - 1, size=n_pairs)
+    b = a + size - kr                                    # the reverse primer's window starts here, ends at a + size - 1
+    words = np.zeros(2 * n_pairs, dtype=np.uint64)
+    ks = np.concatenate([kf, kr]).astype(np.uint8)
+    for j in range(int(k_max)):
+        live = j < kf
+        words[:n_pairs][live] = (words[:n_pairs][live] << np.uint64(2)) | c[a[live] + j]
+        live = j < kr                                    # reverse complement: last base first, complemented (code ^ 1)
+        words[n_pairs:][live] = (words[n_pairs:][live] << np.uint64(2)) | (c[b[live] + kr[live] - 1 - j] ^ np.uint64(1))
+    both = np.stack([words, ks.astype(np.uint64)], axis=1)
+    uniq, inverse = np.unique(both, axis=0, return_inverse=True)
+    inverse = inverse.reshape(-1)
+    return (np.ascontiguousarray(uniq[:, 0]), uniq[:, 1].astype(np.uint8), inverse[:n_pairs].astype(np.uint32),
+            inverse[n_pairs:].astype(np.uint32))

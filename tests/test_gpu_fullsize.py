@@ -82,3 +82,29 @@ def test_config5_shape_full_length_equals_oracle():
     assert gens[0].n_bases == 10_000_000 and len(gens[0].contigs) == 50
     assert int(o.k.min()) >= 12 and int(o.k.max()) <= 30
     assert np.any(o.strand[1] == 1) and np.any(o.contig[1] > 0)
+
+
+def test_config3_outgroup_screen_full_size_equals_oracle():
+    """BASELINE config 3's 10 outgroup genomes (5 Mbp each, the ingroup's first genome with 5 % substitutions), 200 000
+    synthetic primer pairs on that genome: hits, deleted pairs and product sets equal oracle/pf_oracle_outgroup.c"""
+    from oracle import pf_oracle as po
+    from primerforge_b200 import synth
+    from primerforge_b200.engine import words_to_strings
+    from primerforge_b200.outgroup import OutgroupScreen
+    first = synth.make_genomes(1, 5_000_000, seed=synth.BASE_SEED + 3)[0]
+    outs = synth.make_outgroup(first, 10)
+    w, k, pf, pr = synth.make_pairs(first, 200_000)
+    o = po.run_outgroup(words_to_strings(w, k), pf, pr, 120, 2400, outs)
+    with OutgroupScreen(device=0) as scr:
+        scr.set_keys_and_pairs(w, k, pf, pr, 120, 2400)
+        for g in outs:
+            scr.add_genome(g.contigs)
+        scr.run()
+        res = scr.result()
+    h = res.hits
+    mine = np.stack([h["key"], h["genome"], h["contig"], h["start"], h["strand"]], axis=1).astype(np.uint32)
+    theirs = o.hits[np.lexsort((o.hits[:, 3], o.hits[:, 0], o.hits[:, 4], o.hits[:, 2], o.hits[:, 1]))]
+    assert mine.shape[0] > 100_000 and np.array_equal(mine, theirs)
+    assert np.array_equal(res.removed_at, o.removed_at) and 0 < int(res.kept.sum()) < res.kept.size
+    p = res.products
+    assert np.array_equal(np.stack([p["pair"], p["genome"], p["contig"], p["size"].astype(np.uint32)], axis=1), o.products)

@@ -12,7 +12,35 @@ GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 
 def golden_cases() -> list:
-    return sorted(os.path.splitext(os.path.basename(p))[0] for p in glob.glob(os.path.join(GOLDEN, "*.npz")))
+    """fixtures of the candidate-k-mer stage (og_* = outgroup screen, pp_* = pair search)"""
+    names = sorted(os.path.splitext(os.path.basename(p))[0] for p in glob.glob(os.path.join(GOLDEN, "*.npz")))
+    return [n for n in names if not n.startswith(("og_", "pp_"))]
+
+
+def og_cases() -> list:
+    return sorted(os.path.splitext(os.path.basename(p))[0] for p in glob.glob(os.path.join(GOLDEN, "og_*.npz")))
+
+
+def load_og(name: str) -> SimpleNamespace:
+    """an outgroup-screen fixture (oracle/make_golden_outgroup.py): the pairs, the outgroup genomes and what the
+    reference's unmodified bin/removeOutgroupPrimers.py did with them"""
+    z = np.load(os.path.join(GOLDEN, f"{name}.npz"))
+    from primerforge_b200.synth import Genome
+    names = [str(x) for x in z["outgroup_names"]]
+    gens = []
+    for gi, nm in enumerate(names):
+        bases, off = z[f"o{gi}_bases"], z[f"o{gi}_offsets"]
+        gens.append(Genome(name=nm, contig_ids=[str(x) for x in z[f"o{gi}_contig_ids"]],
+                           contigs=[np.ascontiguousarray(bases[off[i]:off[i + 1]]) for i in range(off.size - 1)]))
+    keys = [s.decode() for s in z["keys"]]
+    index = {k: i for i, k in enumerate(keys)}
+    fwd = [s.decode() for s in z["fwd"]]
+    rev = [s.decode() for s in z["rev"]]
+    return SimpleNamespace(z=z, genomes=gens, names=names, keys=keys, fwd=fwd, rev=rev,
+                           pair_fwd=np.array([index[s] for s in fwd], dtype=np.uint32),
+                           pair_rev=np.array([index[s] for s in rev], dtype=np.uint32),
+                           bad_lo=int(z["disallowed"][0]), bad_hi=int(z["disallowed"][1]), kept=z["kept"].astype(bool),
+                           products=z["products"], hits=z["hits"], error=str(z["error"]), debug=[str(x) for x in z["debug"]])
 
 
 def load_golden(name: str) -> SimpleNamespace:
