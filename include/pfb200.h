@@ -275,6 +275,52 @@ int  pfb_og_products(pfb_og *og, pfb_og_product *out, uint64_t cap);      /* uno
 int  pfb_og_removed_at(pfb_og *og, uint32_t *out, uint64_t cap);
 int  pfb_og_timings(pfb_og *og, pfb_og_timing *out);
 
+/* pair search --------------------------------------------------------------------------------
+ * Replaces the arithmetic of _getPrimerPairs (bin/getPrimerPairs.py:490-564): binning of every genome's candidates
+ * (__binCandidateKmers :39-98), the substring reduction of the first genome's bins (__reduceBinSize :10-36), the
+ * bin pairs (__getBinPairs :101-143), the first suitable primer pair of every bin pair (the generator of
+ * __getCandidatePrimerPairs :283-341), the look-up of every pair in every other genome (__getAllSharedPrimerPairs
+ * :367-464) and its bin numbers there (__updateBinsForUnprocessedGenomes :467-502).  primer3's heterodimer check
+ * (:146-178, 330-341) stays the caller's: it filters the proposed pairs, each of which is independent of the others.
+ * Candidates are columns: the S candidate k-mers (the same set in every genome, getCandidateKmers.py:442-489) as
+ * 2-bit words reading like the first genome's (+) strand, lengths and Tm; per genome the candidates in the order of
+ * its dict of lists (contigs in dict order, each list in list order). */
+typedef struct pfb_pp pfb_pp;
+typedef struct pfb_pp_params {
+    int32_t max_bin;          /* params.maxBinSize (:533) */
+    int32_t min_primer_len;   /* params.minLen (:536) */
+    int32_t min_pcr, max_pcr; /* params.minPcr / maxPcr */
+    double  max_tm_diff;      /* params.maxTmDiff (:227) */
+} pfb_pp_params;
+typedef struct pfb_pp_pair {  /* one pair the generator yields (:297-341), in its order; first-genome values */
+    uint32_t fwd, rev;        /* candidate indices: p1 = fwd, p2 = reverse complement of rev (:333) */
+    uint32_t contig, fbin, rbin, pcr_len;
+} pfb_pp_pair;
+typedef struct pfb_pp_product {   /* a pair in one genome (:463, :501-502); genome 0 = the first genome */
+    uint32_t valid;           /* 0: no Product in this genome (other contig / other strand / size out of range) */
+    uint32_t length, fbin, rbin;
+} pfb_pp_product;
+typedef struct pfb_pp_timing {
+    float    ms_bin, ms_pairs, ms_shared, ms_total;    /* CUDA events: binning of all genomes; reduction + bin pairs + primer pairs; cross-genome look-up */
+    uint64_t n_candidates, n_genomes, n_bins, n_pairs, n_kept, n_launches;
+} pfb_pp_timing;
+int  pfb_pp_create(pfb_pp **out, int device);
+void pfb_pp_destroy(pfb_pp *pp);
+const char *pfb_pp_last_error(const pfb_pp *pp);   /* pp may be NULL: error of the last failed pfb_pp_create */
+int  pfb_pp_set_candidates(pfb_pp *pp, const uint64_t *word, const uint8_t *k, const double *tm, uint64_t n);
+/* one call per genome, the first genome first: n = the number of candidates; per list position the candidate index,
+ * the contig number (dense, in dict order: non-decreasing), min(Primer.start, Primer.end) and the strand (0 '+', 1 '-') */
+int  pfb_pp_add_genome(pfb_pp *pp, const uint32_t *id, const uint32_t *contig, const uint32_t *left, const uint8_t *strand, uint64_t n);
+int  pfb_pp_clear_genomes(pfb_pp *pp);
+int  pfb_pp_run(pfb_pp *pp, const pfb_pp_params *params);
+int  pfb_pp_counts(pfb_pp *pp, uint64_t *n_pairs, uint64_t *n_kept, uint64_t *n_bins);   /* kept = valid in every genome (:459-462) */
+int  pfb_pp_pairs(pfb_pp *pp, pfb_pp_pair *out, uint64_t cap);
+int  pfb_pp_shared(pfb_pp *pp, pfb_pp_product *out, uint64_t cap);      /* [n_pairs][n_genomes] */
+/* bin number of every candidate within its contig in one genome; reduced (first genome only, may be NULL): 1 = dropped
+ * from its bin by __reduceBinSize */
+int  pfb_pp_bins(pfb_pp *pp, uint32_t genome, uint32_t *bin_of, uint8_t *reduced, uint64_t cap);
+int  pfb_pp_timings(pfb_pp *pp, pfb_pp_timing *out);
+
 #ifdef __cplusplus
 }
 #endif

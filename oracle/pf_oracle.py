@@ -14,7 +14,7 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _SRC = os.path.join(_HERE, "pf_oracle.c")
-_SRCS = [_SRC, os.path.join(_HERE, "pf_oracle_outgroup.c")]
+_SRCS = [_SRC, os.path.join(_HERE, "pf_oracle_outgroup.c"), os.path.join(_HERE, "pf_oracle_pairs.c")]
 _LIB = os.path.join(_HERE, "libpf_oracle.so")
 
 
@@ -38,6 +38,16 @@ class PfoResult(C.Structure):
 class PfoOgResult(C.Structure):
     _fields_ = [("n_hits", C.c_uint64), ("n_products", C.c_uint64), ("hits", C.POINTER(C.c_uint32)),
                 ("products", C.POINTER(C.c_uint32)), ("removed_at", C.POINTER(C.c_uint32)), ("err", C.c_char * 256)]
+
+
+class PfoPpParams(C.Structure):
+    _fields_ = [("max_bin", C.c_int32), ("min_primer_len", C.c_int32), ("min_pcr", C.c_int32), ("max_pcr", C.c_int32),
+                ("max_tm_diff", C.c_double)]
+
+
+class PfoPpResult(C.Structure):
+    _fields_ = [("n_pairs", C.c_uint64), ("pairs", C.POINTER(C.c_uint32)), ("shared", C.POINTER(C.c_uint32)),
+                ("bin_of", C.POINTER(C.c_uint32)), ("reduced", C.POINTER(C.c_uint8)), ("err", C.c_char * 256)]
 
 
 def build(force: bool = False) -> str:
@@ -71,6 +81,11 @@ def lib():
                                       C.POINTER(C.c_int32)]
         _lib.pfo_og_free.argtypes = [C.POINTER(PfoOgResult)]
         _lib.pfo_og_free.restype = None
+        _lib.pfo_pairs.restype = C.POINTER(PfoPpResult)
+        _lib.pfo_pairs.argtypes = [C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.POINTER(C.c_void_p),
+                                   C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(PfoPpParams)]
+        _lib.pfo_pp_free.argtypes = [C.POINTER(PfoPpResult)]
+        _lib.pfo_pp_free.restype = None
     return _lib
 
 
@@ -201,3 +216,43 @@ def run_outgroup(keys, pair_fwd, pair_rev, bad_lo: int, bad_hi: int, genomes) ->
                                     removed_at=arr(r.removed_at, pf.size, 1))
     finally:
         L.pfo_og_free(rp)
+
+
+@dataclass
+class PairOracleResult:
+    pairs: np.ndarray       # [n, 6] uint32: fwd candidate, rev candidate, contig, fbin, rbin, pcrLen -- the generator's order
+    shared: np.ndarray      # [n, G, 4] uint32: valid, length, fbin, rbin per genome (genome 0 = the first genome)
+    bin_of: np.ndarray      # [G, S] uint32
+    reduced: np.ndarray     # [S] uint8
+
+    @property
+    def kept(self) -> np.ndarray:
+        """pairs with a product in every genome (getPrimerPairs.py:459-462)"""
+        return self.shared[:, :, 0].all(axis=1) if self.pairs.shape[0] else np.zeros(0, dtype=bool)
+
+
+def run_pairs(word, k, tm, genomes, max_bin=64, min_primer_len=16, min_pcr=120, max_pcr=2400, max_tm_diff=5.0) -> PairOracleResult:
+    """oracle/pf_oracle_pairs.c.  word / k / tm: the S candidates; genomes: per genome a tuple (id, contig, left, strand)
+    of arrays of length S in the genome's list order (first genome first)"""
+    L = lib()
+    word = np.ascontiguousarray(word, dtype=np.uint64)
+    k = np.ascontiguousarray(k, dtype=np.uint8)
+    tm = np.ascontiguousarray(tm, dtype=np.float64)
+    S, G = word.size, len(genomes)
+    keep = [[np.ascontiguousarray(g[0], dtype=np.uint32), np.ascontiguousarray(g[1], dtype=np.uint32),
+             np.ascontiguousarray(g[2], dtype=np.uint32), np.ascontiguousarray(g[3], dtype=np.uint8)] for g in genomes]
+    ptrs = [(C.c_void_p * G)(*[kk[j].ctypes.data for kk in keep]) for j in range(4)]
+    prm = PfoPpParams(max_bin=max_bin, min_primer_len=min_primer_len, min_pcr=min_pcr, max_pcr=max_pcr, max_tm_diff=max_tm_diff)
+    rp = L.pfo_pairs(S, word.ctypes.data, k.ctypes.data, tm.ctypes.data, G, ptrs[0], ptrs[1], ptrs[2], ptrs[3], C.byref(prm))
+    try:
+        r = rp.contents
+        if r.err:
+            raise RuntimeError(f"oracle: {r.err.decode()}")
+        n = int(r.n_pairs)
+        pairs = np.ctypeslib.as_array(r.pairs, shape=(max(n, 1) * 6,))[:n * 6].astype(np.uint32).reshape(n, 6)
+        shared = np.ctypeslib.as_array(r.shared, shape=(max(n * G, 1) * 4,))[:n * G * 4].astype(np.uint32).reshape(n, G, 4)
+        bin_of = np.ctypeslib.as_array(r.bin_of, shape=(max(G * S, 1),))[:G * S].astype(np.uint32).reshape(G, S)
+        reduced = np.ctypeslib.as_array(r.reduced, shape=(max(S, 1),))[:S].astype(np.uint8)
+        return PairOracleResult(pairs=pairs, shared=shared, bin_of=bin_of, reduced=reduced)
+    finally:
+        L.pfo_pp_free(rp)

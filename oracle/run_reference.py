@@ -56,7 +56,7 @@ def _import_reference(thal_mode: str):
 
 
 def make_params(ingroup_fns, fmt="fasta", min_len=16, max_len=20, min_gc=40.0, max_gc=60.0,
-                min_tm=55.0, max_tm=68.0, max_repeats=4, temp_tolerance=5.0, num_threads=1, sink=None):
+                min_tm=55.0, max_tm=68.0, max_repeats=4, temp_tolerance=5.0, num_threads=1, sink=None, **_unused):
     """a stand-in for ``bin.Parameters.Parameters`` carrying the fields the stage reads
     (SURVEY.md section 8b); ``sink`` receives what the stage pickles"""
     sink = sink if sink is not None else {}

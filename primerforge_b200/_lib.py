@@ -15,7 +15,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("PFB200_LIB") or os.path.join(_HERE, "libpfb200.so")   # PFB200_LIB: A/B builds
 SRC_PATH = os.path.join(_HERE, "csrc", "pfb200.cu")
-SRC_PATHS = [SRC_PATH, os.path.join(_HERE, "csrc", "pfb_outgroup.cu")]      # one translation unit per stage
+SRC_PATHS = [SRC_PATH, os.path.join(_HERE, "csrc", "pfb_outgroup.cu"), os.path.join(_HERE, "csrc", "pfb_pairs.cu")]      # one translation unit per stage
 INCLUDE_DIR = os.path.join(os.path.dirname(_HERE), "include")
 
 PFB_OK, PFB_EINVAL, PFB_ECUDA, PFB_ESTATE, PFB_ENOSHARED, PFB_ETOOLARGE = 0, -1, -2, -3, -4, -5
@@ -37,7 +37,9 @@ EXPORTS = ["pfb_create", "pfb_destroy", "pfb_last_error", "pfb_default_params", 
            "pfb_result_positions", "pfb_result_picked", "pfb_host_alloc", "pfb_host_free", "pfb_timings", "pfb_set_scan_mode", "pfb_oligo_tm",
            "pfb_og_create", "pfb_og_destroy", "pfb_og_last_error", "pfb_og_set_keys", "pfb_og_set_pairs", "pfb_og_add_genome",
            "pfb_og_clear_genomes", "pfb_og_set_scan_mode", "pfb_og_run", "pfb_og_compute", "pfb_og_counts", "pfb_og_hits", "pfb_og_products",
-           "pfb_og_removed_at", "pfb_og_timings"]
+           "pfb_og_removed_at", "pfb_og_timings",
+           "pfb_pp_create", "pfb_pp_destroy", "pfb_pp_last_error", "pfb_pp_set_candidates", "pfb_pp_add_genome",
+           "pfb_pp_clear_genomes", "pfb_pp_run", "pfb_pp_counts", "pfb_pp_pairs", "pfb_pp_shared", "pfb_pp_bins", "pfb_pp_timings"]
 
 
 class PfbParams(C.Structure):
@@ -71,6 +73,19 @@ class PfbOgTiming(C.Structure):
                 ("filter_in_smem", C.c_uint64), ("filter_bits_per_record", C.c_uint64)]
 
 
+class PfbPpParams(C.Structure):
+    _fields_ = [("max_bin", C.c_int32), ("min_primer_len", C.c_int32), ("min_pcr", C.c_int32), ("max_pcr", C.c_int32),
+                ("max_tm_diff", C.c_double)]
+
+
+class PfbPpTiming(C.Structure):
+    _fields_ = [("ms_bin", C.c_float), ("ms_pairs", C.c_float), ("ms_shared", C.c_float), ("ms_total", C.c_float),
+                ("n_candidates", C.c_uint64), ("n_genomes", C.c_uint64), ("n_bins", C.c_uint64), ("n_pairs", C.c_uint64),
+                ("n_kept", C.c_uint64), ("n_launches", C.c_uint64)]
+
+
+PP_PAIR_DTYPE = np.dtype([("fwd", "<u4"), ("rev", "<u4"), ("contig", "<u4"), ("fbin", "<u4"), ("rbin", "<u4"), ("pcr_len", "<u4")])
+PP_PRODUCT_DTYPE = np.dtype([("valid", "<u4"), ("length", "<u4"), ("fbin", "<u4"), ("rbin", "<u4")])
 OG_HIT_DTYPE = np.dtype([("key", "<u4"), ("genome", "<u4"), ("contig", "<u4"), ("start", "<u4"), ("strand", "<u4")])
 OG_PRODUCT_DTYPE = np.dtype([("pair", "<u4"), ("genome", "<u4"), ("contig", "<u4"), ("size", "<i4")])
 RECORD_DTYPE = np.dtype([("word", "<u8"), ("tm", "<f8"), ("slot", "<u4"), ("gc_count", "<u2"), ("k", "u1"), ("flags", "u1")])
@@ -159,9 +174,23 @@ def load():
     lib.pfb_og_products.argtypes = [vp, vp, u64]
     lib.pfb_og_removed_at.argtypes = [vp, vp, u64]
     lib.pfb_og_timings.argtypes = [vp, C.POINTER(PfbOgTiming)]
+    lib.pfb_pp_create.argtypes = [C.POINTER(vp), i32]
+    lib.pfb_pp_destroy.argtypes = [vp]
+    lib.pfb_pp_destroy.restype = None
+    lib.pfb_pp_last_error.argtypes = [vp]
+    lib.pfb_pp_last_error.restype = C.c_char_p
+    lib.pfb_pp_set_candidates.argtypes = [vp, vp, vp, vp, u64]
+    lib.pfb_pp_add_genome.argtypes = [vp, vp, vp, vp, vp, u64]
+    lib.pfb_pp_clear_genomes.argtypes = [vp]
+    lib.pfb_pp_run.argtypes = [vp, C.POINTER(PfbPpParams)]
+    lib.pfb_pp_counts.argtypes = [vp, C.POINTER(u64), C.POINTER(u64), C.POINTER(u64)]
+    lib.pfb_pp_pairs.argtypes = [vp, vp, u64]
+    lib.pfb_pp_shared.argtypes = [vp, vp, u64]
+    lib.pfb_pp_bins.argtypes = [vp, u32, vp, vp, u64]
+    lib.pfb_pp_timings.argtypes = [vp, C.POINTER(PfbPpTiming)]
     for name in EXPORTS:
         if name not in ("pfb_destroy", "pfb_last_error", "pfb_multi_destroy", "pfb_multi_last_error", "pfb_og_destroy",
-                        "pfb_og_last_error"):
+                        "pfb_og_last_error", "pfb_pp_destroy", "pfb_pp_last_error"):
             getattr(lib, name).restype = C.c_int
     _lib = lib
     return lib

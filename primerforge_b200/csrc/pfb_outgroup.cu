@@ -19,6 +19,7 @@
 // is only read when the tag matches.
 
 #include "../../include/pfb200.h"
+#include "pfb_devscan.cuh"
 
 #include <cuda_runtime.h>
 
@@ -347,65 +348,6 @@ __global__ void __launch_bounds__(1024, 1) k_og_scan_smem(const __grid_constant_
     if (occupied) atomicAdd(&p.cnt[2], occupied);
 }
 
-// exclusive prefix sum of bucketCount, three launches (tile sums, scan of the tile sums, tile scans)
-constexpr int OG_TILE = 1024;
-__global__ void __launch_bounds__(256) k_og_tile_sums(const uint32_t *in, uint32_t n, uint32_t *tileSums) {
-    __shared__ uint32_t ws[8];
-    const uint32_t base = blockIdx.x * OG_TILE;
-    uint32_t s = 0;
-    for (uint32_t j = threadIdx.x; j < OG_TILE; j += 256) s += (base + j < n) ? in[base + j] : 0u;
-    for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(~0u, s, o);
-    if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = s;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        uint32_t t = 0;
-        for (int j = 0; j < 8; j++) t += ws[j];
-        tileSums[blockIdx.x] = t;
-    }
-}
-__global__ void __launch_bounds__(1024) k_og_scan_tiles(uint32_t *tileSums, uint32_t nTiles, uint32_t *total) {
-    __shared__ uint32_t ws[32];
-    __shared__ uint32_t carry;
-    if (threadIdx.x == 0) carry = 0;
-    __syncthreads();
-    for (uint32_t b = 0; b < nTiles; b += 1024) {
-        const uint32_t j = b + threadIdx.x;
-        const uint32_t v = j < nTiles ? tileSums[j] : 0u;
-        uint32_t x = v;
-        for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(~0u, x, o); if ((threadIdx.x & 31) >= o) x += y; }
-        if ((threadIdx.x & 31) == 31) ws[threadIdx.x >> 5] = x;
-        __syncthreads();
-        if (threadIdx.x < 32) {
-            uint32_t z = ws[threadIdx.x];
-            for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(~0u, z, o); if (threadIdx.x >= o) z += y; }
-            ws[threadIdx.x] = z;
-        }
-        __syncthreads();
-        const uint32_t before = carry + (threadIdx.x >= 32 ? ws[(threadIdx.x >> 5) - 1] : 0u) + x - v;
-        if (j < nTiles) tileSums[j] = before;
-        __syncthreads();
-        if (threadIdx.x == 1023) carry = before + v;
-        __syncthreads();
-    }
-    if (threadIdx.x == 0) *total = carry;
-}
-__global__ void __launch_bounds__(256) k_og_tile_scan(const uint32_t *in, uint32_t n, const uint32_t *tileSums, uint32_t *out) {
-    __shared__ uint32_t ws[8];
-    const uint32_t base = blockIdx.x * OG_TILE + threadIdx.x * 4;
-    uint32_t v[4], s = 0;
-#pragma unroll
-    for (int j = 0; j < 4; j++) { v[j] = (base + j < n) ? in[base + j] : 0u; s += v[j]; }
-    uint32_t x = s;
-    for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(~0u, x, o); if ((threadIdx.x & 31) >= o) x += y; }
-    if ((threadIdx.x & 31) == 31) ws[threadIdx.x >> 5] = x;
-    __syncthreads();
-    uint32_t before = tileSums[blockIdx.x] + x - s;
-    for (int j = 0; j < (int)(threadIdx.x >> 5); j++) before += ws[j];
-#pragma unroll
-    for (int j = 0; j < 4; j++) { if (base + j < n) out[base + j] = before; before += v[j]; }
-    if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 255) out[n] = before;
-}
-
 // hits -> buckets of (key, strand) (the per-contig dicts of :215-226 turned inside out: contig is a column)
 __global__ void __launch_bounds__(256) k_og_bucket(const __grid_constant__ Args p, uint32_t nHits) {
     const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
@@ -613,7 +555,7 @@ int upload_keys(pfb_og *o) {
     if ((rc = ensure(o, o->bCount, (2 * n + 2) * 4)) != PFB_OK) return rc;
     if ((rc = ensure(o, o->bOff, (2 * n + 2) * 4)) != PFB_OK) return rc;
     if ((rc = ensure(o, o->bCursor, (2 * n + 2) * 4)) != PFB_OK) return rc;
-    if ((rc = ensure(o, o->tiles, ((2 * n + 2) / OG_TILE + 2) * 4)) != PFB_OK) return rc;
+    if ((rc = ensure(o, o->tiles, ((2 * n + 2) / devscan::TILE + 4) * 4)) != PFB_OK) return rc;
     a.tab = (const uint2 *)o->tab.p; a.recs = (const uint4 *)o->recs.p;
     a.kmin = kmin; a.nk = o->nk; a.nKeys = (uint32_t)n;
     a.bucketCount = (uint32_t *)o->bCount.p; a.bucketOff = (uint32_t *)o->bOff.p; a.bucketCursor = (uint32_t *)o->bCursor.p;
@@ -738,10 +680,7 @@ int compute(pfb_og *o) {
         if (cnt[0] > o->hitCap) { o->hitCap = (size_t)cnt[0] + cnt[0] / 4; o->nReruns++; continue; }
         o->nHits = cnt[0]; o->nProbeOccupied = cnt[2];
         // bucket the hits by (key, strand), then one thread per pair
-        const uint32_t nTiles = (nB + OG_TILE) / OG_TILE;    // covers nB + 1 entries
-        k_og_tile_sums<<<nTiles, 256, 0, o->stream>>>(a.bucketCount, nB, (uint32_t *)o->tiles.p);
-        k_og_scan_tiles<<<1, 1024, 0, o->stream>>>((uint32_t *)o->tiles.p, nTiles, a.cnt + 3);
-        k_og_tile_scan<<<nTiles, 256, 0, o->stream>>>(a.bucketCount, nB, (const uint32_t *)o->tiles.p, a.bucketOff);
+        devscan::exscan(a.bucketCount, nB, a.bucketOff, (uint32_t *)o->tiles.p, a.cnt + 3, o->stream);
         o->nLaunches += 3;
         if (cnt[0]) { k_og_bucket<<<(cnt[0] + 255) / 256, 256, 0, o->stream>>>(a, cnt[0]); o->nLaunches++; }
         OGCK(cudaEventRecord(o->ev[5], o->stream));

@@ -83,6 +83,7 @@ class LazyPrimerList(list):
     def __init__(self, cols: Columns, contig_name: str, idx, left, right, minus):
         super().__init__()
         self._lazy = (cols, contig_name, idx, left, right, minus)
+        self._view = (cols, idx, left, minus)      # the columns behind the list while nobody has edited it (pairs.py)
         self._n = int(len(idx))
 
     @_no_gc
@@ -176,6 +177,8 @@ class LazyPrimerList(list):
 def _filling(name):
     def method(self, *a, **kw):
         self._fill()
+        if name not in ("index", "count", "copy", "__mul__", "__rmul__", "__lt__", "__le__", "__gt__", "__ge__"):
+            self._view = None                      # edited: the columns no longer describe the list
         return getattr(list, name)(self, *a, **kw)
     method.__name__ = name
     return method

@@ -99,3 +99,58 @@ def assert_equals_oracle(res, o, prefilter: bool, n_genomes: int):
         assert np.array_equal(pos["contig"].astype(np.int32), o.contig[gi][keep]), f"contig differs in genome {gi}"
         assert np.array_equal(pos["start"].astype(np.int64), o.start[gi][keep]), f"start differs in genome {gi}"
         assert np.array_equal(pos["strand"].astype(np.uint8), o.strand[gi][keep]), f"strand differs in genome {gi}"
+
+
+def pp_cases() -> list:
+    return sorted(os.path.splitext(os.path.basename(p))[0] for p in glob.glob(os.path.join(GOLDEN, "pp_*.npz")))
+
+
+_CODE = {65: 0, 84: 1, 67: 2, 71: 3}
+
+
+def str_to_word(s) -> int:
+    w = 0
+    for b in (s if isinstance(s, bytes) else s.encode()):
+        w = (w << 2) | _CODE[b]
+    return w
+
+
+def load_pp(name: str) -> SimpleNamespace:
+    """a pair-search fixture (oracle/make_golden_pairs.py): the candidate dict as columns, the parameters, and the
+    pairs + Products the reference's unmodified bin/getPrimerPairs.py made of them"""
+    z = np.load(os.path.join(GOLDEN, f"{name}.npz"))
+    cand = [s.decode() for s in z["cand"]]
+    G = len(z["genome_names"])
+    genomes = [(z[f"g{g}_id"], z[f"g{g}_contig"], z[f"g{g}_left"], z[f"g{g}_strand"]) for g in range(G)]
+    index = {s: i for i, s in enumerate(cand)}
+    rc = str.maketrans("ACGT", "TGCA")
+    fwd = np.array([index[s.decode()] for s in z["pair_fwd"]], dtype=np.uint32)
+    rev = np.array([index[s.decode()[::-1].translate(rc)] for s in z["pair_rev"]], dtype=np.uint32)   # p2 = rev.reverseComplement()
+    max_bin, min_len, min_pcr, max_pcr = (int(x) for x in z["params"])
+    return SimpleNamespace(z=z, cand=cand, word=np.array([str_to_word(s) for s in cand], dtype=np.uint64),
+                           k=np.array([len(s) for s in cand], dtype=np.uint8), tm=z["cand_tm"], genomes=genomes,
+                           names=[str(x) for x in z["genome_names"]],
+                           contig_names=[[str(x) for x in z[f"g{g}_contig_names"]] for g in range(G)],
+                           max_bin=max_bin, min_len=min_len, min_pcr=min_pcr, max_pcr=max_pcr, max_tm_diff=float(z["max_tm_diff"]),
+                           pair_fwd=fwd, pair_rev=rev, products=z["products"])
+
+
+def expected_products(fix, pairs, shared, kept):
+    """the Product fields (getPrimerPairs.py:336, 463, 501-502) of the kept pairs, derived from a pair-search result
+    (pairs [n, 6], shared [n, G, 4]) and the fixture's candidate columns: [n_kept, G, 10] like the fixture's array"""
+    G = len(fix.genomes)
+    S = fix.word.size
+    out = np.zeros((int(kept.sum()), G, 10), dtype=np.int64)
+    for g in range(G):
+        gid, gct, glf, gst = fix.genomes[g]
+        ct = np.zeros(S, np.int64); lf = np.zeros(S, np.int64); st = np.zeros(S, np.int64)
+        ct[gid] = gct; lf[gid] = glf; st[gid] = gst
+        for row, q in enumerate(np.flatnonzero(kept)):
+            a, b = int(pairs[q, 0]), int(pairs[q, 1])
+            ka, kb = int(fix.k[a]), int(fix.k[b])
+            # k1 as it is, k2 reverse complemented (:458): Primer.start is the leftmost base on (+), the rightmost on (-)
+            f_start, f_end = (lf[a], lf[a] + ka - 1) if st[a] == 0 else (lf[a] + ka - 1, lf[a])
+            r_strand = 1 - st[b]
+            r_start, r_end = (lf[b], lf[b] + kb - 1) if r_strand == 0 else (lf[b] + kb - 1, lf[b])
+            out[row, g] = (ct[a], shared[q, g, 1], shared[q, g, 2], shared[q, g, 3], f_start, f_end, st[a], r_start, r_end, r_strand)
+    return out
