@@ -213,6 +213,60 @@ def outgroup_block(device: int, flush, with_cpu: bool, n_outgroup: int = 10, len
     return out
 
 
+def pairs_block(candidates, first_name: str, device: int, flush, with_cpu: bool, steps: int = 10) -> dict:
+    """SURVEY.md 8(f)-4, the pair search (bin/getPrimerPairs.py:505-564) on the candidates the drop-in leg has just
+    produced (lazy containers: their columns go to the GPU as they are): binning of every genome, the substring
+    reduction, bin pairs, the first suitable primer pair of each, the look-up in every other genome.  The heterodimer
+    check is primer3's and is not part of the timed arithmetic.  The gate: the same columns through
+    oracle/pf_oracle_pairs.c."""
+    import torch
+    from primerforge_b200.pairs import PairSearch, _columns
+    kw = dict(max_bin=64, min_primer_len=16, min_pcr=120, max_pcr=2400, max_tm_diff=5.0)      # bin/Parameters.py defaults
+    word, k, tm, names, per_genome, _lists = _columns(candidates, first_name)
+    with PairSearch(device=device) as ps:
+        ps.set_candidates(word, k, tm)
+        for g in per_genome:
+            ps.add_genome(*g)
+        ms, parts, wall = [], [], []
+        for i in range(2 + steps):
+            flush.zero_()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            ps.run(**kw)                  # H2D of the columns, every kernel, D2H of the pairs and their per-genome products
+            dt = time.perf_counter() - t0
+            if i >= 2:
+                t = ps.timing()
+                ms.append(t["ms_total"]); parts.append((t["ms_bin"], t["ms_pairs"], t["ms_shared"])); wall.append(dt)
+        res = ps.result()
+        t = ps.timing()
+    S, G = int(word.size), len(per_genome)
+    b, p2, sh = (float(x) for x in np.mean(np.array(parts), axis=0))
+    step_ms = float(np.mean(ms))
+    out = {"what": "pair search (bin/getPrimerPairs.py:505-564) without primer3's heterodimer check",
+           "workload": f"the {S} candidates of the drop-in leg in {G} genomes, maxBinSize 64, product size 120-2400, maxTmDiff 5",
+           "value": S * G / 1e6 / (step_ms / 1e3), "unit": "M candidate placements/s", "ms_per_step": step_ms, "steps": steps,
+           "phases_ms": {"binning": b, "reduce_binpairs_primerpairs": p2, "other_genomes": sh},
+           "e2e": {"ms_per_step": float(np.mean(wall) * 1e3), "h2d_bytes_per_step": int(S * 17 + G * S * 13),
+                   "d2h_bytes_per_step": int(t["n_pairs"] * (24 + 16 * G))},
+           "gpu_launches_per_step": int(t["n_launches"]),
+           "counts": {"n_candidates": S, "n_genomes": G, "n_bins_first_genome": int(t["n_bins"]), "n_pairs": int(t["n_pairs"]),
+                      "n_kept": int(t["n_kept"])}}
+    if with_cpu:
+        from oracle import pf_oracle as po
+        t0 = time.perf_counter()
+        o = po.run_pairs(word, k, tm, per_genome, **kw)
+        dt = time.perf_counter() - t0
+        pr, s = res.pairs, res.shared
+        pairs = np.stack([pr["fwd"], pr["rev"], pr["contig"], pr["fbin"], pr["rbin"], pr["pcr_len"]], axis=1).astype(np.uint32).reshape(-1, 6)
+        shared = np.stack([s["valid"], s["length"], s["fbin"], s["rbin"]], axis=2).astype(np.uint32)
+        ok_p, ok_s = bool(np.array_equal(pairs, o.pairs)), bool(np.array_equal(shared, o.shared))
+        out["cpu_baseline"] = {"value": S * G / 1e6 / dt, "unit": "M candidate placements/s", "cores": 1, "kind": "port",
+                               "sample": f"the same columns, oracle/pf_oracle_pairs.c (C restatement of the reference's list walk, one thread), {dt:.2f} s"}
+        out["parity"] = {"against": "oracle/pf_oracle_pairs.c on the same columns", "ok": ok_p and ok_s, "pairs_in_order": ok_p,
+                         "per_genome_products": ok_s, "n_pairs": int(pairs.shape[0])}
+    return out
+
+
 def parity_vs_oracle(gens, o, cfg, device: int) -> dict:
     """the correctness gate: the CUDA path on the very genomes the CPU sample ran on, compared
     bit for bit with the oracle's result -- the shared k-mers in dict order, flags and picks, Tm, and
@@ -361,6 +415,7 @@ def main():
     ap.add_argument("--no-fasta-leg", action="store_true")
     ap.add_argument("--no-strong-c4", action="store_true", help="skip the strong-scaling block (BASELINE config 4: 200 genomes over the GPUs)")
     ap.add_argument("--no-dropin-leg", action="store_true", help="skip the timing of the drop-in entry point from FASTA files on disk")
+    ap.add_argument("--no-pairs", action="store_true", help="skip the pair-search block (the drop-in leg's candidates through _getPrimerPairs' arithmetic)")
     ap.add_argument("--no-outgroup", action="store_true", help="skip the outgroup-screen block (BASELINE config 3's 10 outgroup genomes)")
     ap.add_argument("--scan-mode", type=int, default=0, help="0 auto, 1 plain L2 probe, 2 shared-memory filter (debug)")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
@@ -728,6 +783,8 @@ def main():
             out = _getAllCandidateKmers(prm, False, thal="off", device=local)
             dt = time.perf_counter() - t0
             n_obj = sum(len(v) for per in out.values() for v in per.values())
+        if not args.no_pairs:
+            line["pairs"] = pairs_block(out, os.path.basename(paths[0]), local, flush, with_cpu=not args.no_cpu_baseline)
         line["e2e_dropin"] = {"value": distinct_bases / 1e6 / dt, "unit": UNIT, "seconds": dt, "primers": int(n_obj),
                               "what": "_getAllCandidateKmers(params, False) from FASTA files on disk to dict[str, dict[str, list[Primer]]] "
                                       "(hairpin / homodimer screening off): the call the reference's main.py:86 makes"}

@@ -108,3 +108,39 @@ def test_config3_outgroup_screen_full_size_equals_oracle():
     assert np.array_equal(res.removed_at, o.removed_at) and 0 < int(res.kept.sum()) < res.kept.size
     p = res.products
     assert np.array_equal(np.stack([p["pair"], p["genome"], p["contig"], p["size"].astype(np.uint32)], axis=1), o.products)
+
+
+def test_pair_search_full_size_equals_oracle():
+    """the candidates of 3 x 5 Mbp (BASELINE config 2's genomes; ~930 000 candidates, ~3.7 M proposed pairs) through the
+    CUDA pair search and through oracle/pf_oracle_pairs.c: bins of every genome, reductions, pairs in order, products"""
+    import tempfile
+    from types import SimpleNamespace
+    from oracle import pf_oracle as po
+    from primerforge_b200 import synth
+    from primerforge_b200.candidates import _getAllCandidateKmers
+    from primerforge_b200.pairs import PairSearch, _columns
+    gens = synth.make_genomes(3, 5_000_000, seed=synth.BASE_SEED + 2)
+    log = SimpleNamespace(rename=lambda *a: None, info=lambda *a: None, debug=lambda *a: None, error=lambda *a: None)
+    with tempfile.TemporaryDirectory() as d:
+        paths = synth.write_fasta(gens, d)
+        prm = SimpleNamespace(ingroupFns=paths, format="fasta", minLen=16, maxLen=20, minGc=40.0, maxGc=60.0, minTm=55.0, maxTm=68.0,
+                              maxRepeatLen=4, tempTolerance=5.0, numThreads=1, p3_mvConc=50.0, p3_dvConc=1.5, p3_dntpConc=0.6,
+                              p3_dnaConc=50.0, p3_tempC=37.0, p3_maxLoop=30, log=log, pickles={1: "s.p", 2: "c.p"},
+                              dumpObj=lambda *a, **k: None, loadObj=lambda *a: None, debug=False)
+        lazy = _getAllCandidateKmers(prm, False, thal="off")
+    word, k, tm, names, per_genome, _ = _columns(lazy, gens[0].name)
+    kw = dict(max_bin=64, min_primer_len=16, min_pcr=120, max_pcr=2400, max_tm_diff=5.0)
+    o = po.run_pairs(word, k, tm, per_genome, **kw)
+    with PairSearch(device=0) as ps:
+        ps.set_candidates(word, k, tm)
+        for g in per_genome:
+            ps.add_genome(*g)
+        ps.run(**kw)
+        res = ps.result()
+        for g in range(3):
+            assert np.array_equal(ps.bins(g), o.bin_of[g])
+        assert np.array_equal(ps.bins(0, with_reduced=True)[1], o.reduced)
+    p, s = res.pairs, res.shared
+    assert p.size > 1_000_000
+    assert np.array_equal(np.stack([p["fwd"], p["rev"], p["contig"], p["fbin"], p["rbin"], p["pcr_len"]], axis=1).astype(np.uint32), o.pairs)
+    assert np.array_equal(np.stack([s["valid"], s["length"], s["fbin"], s["rbin"]], axis=2).astype(np.uint32), o.shared)
