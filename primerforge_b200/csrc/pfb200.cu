@@ -36,6 +36,7 @@
 
 #include "../../include/pfb200.h"
 #include "pfb_fasta.cuh"
+#include "pfb_bulk.cuh"
 
 #include <cuda_runtime.h>
 #include <dlfcn.h>
@@ -951,7 +952,7 @@ __device__ __forceinline__ void scan2_pass(const K &p, int ki, int k, Scan2 &sw,
 
 template <bool FIRST>
 __global__ void __launch_bounds__(1024, 1) k_scan_filtered2(const __grid_constant__ K p, uint32_t w0_, uint32_t w1) {
-    extern __shared__ uint32_t s_filter[];
+    extern __shared__ __align__(128) uint32_t s_filter[];
     Scan2 sw;
     sw.lane = threadIdx.x & 31;
     const uint32_t warp = threadIdx.x >> 5;
@@ -960,17 +961,17 @@ __global__ void __launch_bounds__(1024, 1) k_scan_filtered2(const __grid_constan
     sw.lt_mask = (1u << sw.lane) - 1u;
     const uint32_t stride = gridDim.x * blockDim.x;
     const uint32_t w0 = w0_ + blockIdx.x * blockDim.x;
+    // the filter of a length arrives as ONE bulk copy (cp.async.bulk -> UBLKCP) that completes on an mbarrier: the last 16
+    // bytes of the shared window -- item 95 of the last warp's queue, which no pass ever reaches (at most 31 + 2 * 32 items)
+    const uint32_t bar = f_addr + SCAN2_SMEM - 16u;
+    uint32_t parity = 0;
+    if (threadIdx.x == 0) bulk::mbar_init(bar, 1u);
     for (int ki = 0; ki < p.nk; ki++) {
         const int k = p.kmin + ki;
-        __syncthreads();
-        {   // LDGSTS: every thread has all its 16 B pieces in flight at once, nothing goes through registers
-            const uint8_t *src = (const uint8_t *)(p.filter + (size_t)ki * FILTER_WORDS);
-            for (uint32_t t = threadIdx.x; t < FILTER_WORDS / 4; t += blockDim.x)
-                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(f_addr + t * 16u), "l"(src + (size_t)t * 16u) : "memory");
-            asm volatile("cp.async.commit_group;" ::: "memory");
-            asm volatile("cp.async.wait_group 0;" ::: "memory");
-        }
-        __syncthreads();
+        __syncthreads();                                     // every warp is done with the previous filter (and the barrier exists)
+        if (threadIdx.x == 0) bulk::load(f_addr, p.filter + (size_t)ki * FILTER_WORDS, FILTER_BYTES, bar);
+        bulk::wait(bar, parity);
+        parity ^= 1u;
         sw.qn = 0; sw.pend = false;
         sw.pd.e = make_uint2(0u, 0u); sw.pd.meta = 0; sw.pd.g = 0;
         const bool fastmod = k <= 20 && p.P < (1u << 24);

@@ -20,6 +20,7 @@
 
 #include "../../include/pfb200.h"
 #include "pfb_devscan.cuh"
+#include "pfb_bulk.cuh"
 
 #include <cuda_runtime.h>
 
@@ -246,10 +247,11 @@ __global__ void __launch_bounds__(256) k_og_scan(const __grid_constant__ Args p)
     if (occupied) atomicAdd(&p.cnt[2], occupied);
 }
 
-// the table probe of one queued window: {canonical word lo, hi, end, contig << 8 | k << 2 | (h == canon) << 1 | (r == canon)}
+// the table probe of one queued window: {forward word lo, hi, end, contig << 8 | k << 2}
 __device__ __forceinline__ void probe_item(const Args &p, const uint4 it, uint32_t &occupied) {
-    const uint64_t canon = (uint64_t)it.x | ((uint64_t)it.y << 32);
     const int k = (int)(it.w >> 2) & 63, ki = k - p.kmin;
+    const uint64_t h = (uint64_t)it.x | ((uint64_t)it.y << 32), r = rc64(h) >> (64 - 2 * k);
+    const uint64_t canon = h < r ? h : r;
     const uint32_t size = p.tabSize[ki];
     const uint2 *tab = p.tab + p.tabOff[ki];
     const uint32_t tag = key_tag(canon);
@@ -260,9 +262,10 @@ __device__ __forceinline__ void probe_item(const Args &p, const uint4 it, uint32
         occupied++;
         if (e.x == tag) {
             const uint4 rec = __ldg(&p.recs[e.y]);
-            if (rec.x == it.x && rec.y == it.y) {
-                emit_hit(p, (it.w & 2u) ? rec.z : rec.w, it.w >> 8, it.z - (uint32_t)k + 1u, 0u);   // start = end - len + 1 (:51)
-                emit_hit(p, (it.w & 1u) ? rec.z : rec.w, it.w >> 8, it.z, 1u);                      // len(seq) - start_in_rc - 1 (:54-55)
+            if (rec.x == (uint32_t)canon && rec.y == (uint32_t)(canon >> 32)) {
+                // rec.z: the key whose string is the canonical word, rec.w: the key whose string is its rc
+                emit_hit(p, h == canon ? rec.z : rec.w, it.w >> 8, it.z - (uint32_t)k + 1u, 0u);   // start = end - len + 1 (:51)
+                emit_hit(p, r == canon ? rec.z : rec.w, it.w >> 8, it.z, 1u);                      // len(seq) - start_in_rc - 1 (:54-55)
                 return;
             }
         }
@@ -278,18 +281,21 @@ constexpr uint32_t OGQ_ITEMS = 64;      // per-warp queue of filter-positive win
 // but QUEUED per warp in shared memory; when 32 are waiting the warp probes them together, one per lane.
 template <int KMIN, int NK>
 __global__ void __launch_bounds__(1024, 1) k_og_scan_smem(const __grid_constant__ Args p) {
-    extern __shared__ uint4 og_smem[];
+    extern __shared__ __align__(128) uint4 og_smem[];
+    __shared__ __align__(8) uint64_t og_bar;
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     uint4 *q = og_smem + warp * OGQ_ITEMS;
     const uint32_t *bits = (const uint32_t *)(og_smem + 32u * OGQ_ITEMS);
-    {
-        const uint4 *src = (const uint4 *)p.bits;
-        uint4 *dst = og_smem + 32u * OGQ_ITEMS;
-        const uint32_t n16 = (p.bitWords + 3u) / 4u;
-        for (uint32_t j = threadIdx.x; j < n16; j += 1024) dst[j] = __ldg(&src[j]);
+    {   // the filter arrives as one bulk copy (cp.async.bulk -> UBLKCP) completing on an mbarrier
+        const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&og_bar);
+        if (threadIdx.x == 0) bulk::mbar_init(bar, 1u);
+        __syncthreads();
+        if (threadIdx.x == 0)
+            bulk::load((uint32_t)__cvta_generic_to_shared(og_smem + 32u * OGQ_ITEMS), p.bits, ((p.bitWords + 3u) / 4u) * 16u, bar);
+        bulk::wait(bar, 0u);
     }
-    __syncthreads();
     uint32_t occupied = 0, qn = 0;
+    const uint32_t lt_mask = (1u << lane) - 1u;
     const int kmin = KMIN ? KMIN : p.kmin, kmax = p.kmin + p.nk - 1;
     for (uint32_t wb = blockIdx.x * 1024u + warp * 32u; wb < p.totalWords; wb += gridDim.x * 1024u) {   // warp-uniform
         const uint32_t w = wb + lane;
@@ -311,39 +317,38 @@ __global__ void __launch_bounds__(1024, 1) k_og_scan_smem(const __grid_constant_
             inv = (inv << 1) | ((cinv >> (31 - t)) & 1u);
             const uint32_t end = base0 + t;
             for (int kb = kmin; kb <= kmax; kb += NK) {
-                uint64_t cn[NK];
-                uint32_t fw[NK], fb[NK], ori[NK];
+                uint32_t fw[NK], fb[NK];
 #pragma unroll
                 for (int j = 0; j < NK; j++) {
                     const int k = KMIN ? KMIN + j : min(kb + j, 32), ki = KMIN ? j : min(kb + j, kmax) - p.kmin;
                     const bool live = (KMIN || kb + j <= kmax) && !(inv & (0xFFFFFFFFu >> (32 - k)));
                     const uint64_t h = hf & (~0ull >> (64 - 2 * k));
                     const uint64_t r = rr >> (64 - 2 * k);
-                    cn[j] = h < r ? h : r;
-                    ori[j] = (h <= r ? 2u : 0u) | (r <= h ? 1u : 0u);
-                    fb[j] = __umulhi(key_hash(cn[j]), p.nBits[ki]);
+                    fb[j] = __umulhi(key_hash(h < r ? h : r), p.nBits[ki]);
                     fw[j] = live ? bits[p.bitOff[ki] + (fb[j] >> 5)] : 0u;
                 }
+                // straight-line append: ballot, predicated store, uniform counter; the only branch is the (warp-uniform) drain
 #pragma unroll
                 for (int j = 0; j < NK; j++) {
+                    const int k = KMIN ? KMIN + j : min(kb + j, 32);
                     const bool hit = (fw[j] >> (fb[j] & 31u)) & 1u;
                     const uint32_t m = __ballot_sync(0xFFFFFFFFu, hit);
-                    if (m) {
-                        const int k = KMIN ? KMIN + j : kb + j;
-                        if (hit) q[qn + __popc(m & ((1u << lane) - 1u))] =
-                            make_uint4((uint32_t)cn[j], (uint32_t)(cn[j] >> 32), end, cw | ((uint32_t)k << 2) | ori[j]);
-                        qn += __popc(m);
+                    if (hit) {
+                        const uint64_t h = hf & (~0ull >> (64 - 2 * k));
+                        q[qn + __popc(m & lt_mask)] = make_uint4((uint32_t)h, (uint32_t)(h >> 32), end, cw | ((uint32_t)k << 2));
+                    }
+                    qn += __popc(m);
+                    if (qn >= 32u) {
                         __syncwarp();
-                        if (qn >= 32u) {
-                            qn -= 32u;
-                            probe_item(p, q[qn + lane], occupied);
-                            __syncwarp();
-                        }
+                        qn -= 32u;
+                        probe_item(p, q[qn + lane], occupied);
+                        __syncwarp();
                     }
                 }
             }
         }
     }
+    __syncwarp();
     if (lane < qn) probe_item(p, q[lane], occupied);
     if (occupied) atomicAdd(&p.cnt[2], occupied);
 }
