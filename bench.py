@@ -232,7 +232,10 @@ def pairs_block(candidates, first_name: str, device: int, flush, with_cpu: bool,
             flush.zero_()
             torch.cuda.synchronize()
             t0 = time.perf_counter()
-            ps.run(**kw)                  # H2D of the columns, every kernel, D2H of the pairs and their per-genome products
+            ps.set_candidates(word, k, tm)      # H2D of the columns ...
+            for g in per_genome:
+                ps.add_genome(*g)
+            ps.run(**kw)                  # ... every kernel, D2H of the pairs and their per-genome product sizes
             dt = time.perf_counter() - t0
             if i >= 2:
                 t = ps.timing()
@@ -247,7 +250,7 @@ def pairs_block(candidates, first_name: str, device: int, flush, with_cpu: bool,
            "value": S * G / 1e6 / (step_ms / 1e3), "unit": "M candidate placements/s", "ms_per_step": step_ms, "steps": steps,
            "phases_ms": {"binning": b, "reduce_binpairs_primerpairs": p2, "other_genomes": sh},
            "e2e": {"ms_per_step": float(np.mean(wall) * 1e3), "h2d_bytes_per_step": int(S * 17 + G * S * 13),
-                   "d2h_bytes_per_step": int(t["n_pairs"] * (24 + 16 * G))},
+                   "d2h_bytes_per_step": int(t["n_pairs"] * (25 + 4 * G))},
            "gpu_launches_per_step": int(t["n_launches"]),
            "counts": {"n_candidates": S, "n_genomes": G, "n_bins_first_genome": int(t["n_bins"]), "n_pairs": int(t["n_pairs"]),
                       "n_kept": int(t["n_kept"])}}
@@ -256,9 +259,9 @@ def pairs_block(candidates, first_name: str, device: int, flush, with_cpu: bool,
         t0 = time.perf_counter()
         o = po.run_pairs(word, k, tm, per_genome, **kw)
         dt = time.perf_counter() - t0
-        pr, s = res.pairs, res.shared
+        pr = res.pairs
         pairs = np.stack([pr["fwd"], pr["rev"], pr["contig"], pr["fbin"], pr["rbin"], pr["pcr_len"]], axis=1).astype(np.uint32).reshape(-1, 6)
-        shared = np.stack([s["valid"], s["length"], s["fbin"], s["rbin"]], axis=2).astype(np.uint32)
+        shared = res.shared4()
         ok_p, ok_s = bool(np.array_equal(pairs, o.pairs)), bool(np.array_equal(shared, o.shared))
         out["cpu_baseline"] = {"value": S * G / 1e6 / dt, "unit": "M candidate placements/s", "cores": 1, "kind": "port",
                                "sample": f"the same columns, oracle/pf_oracle_pairs.c (C restatement of the reference's list walk, one thread), {dt:.2f} s"}

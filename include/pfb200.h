@@ -296,10 +296,7 @@ typedef struct pfb_pp_pair {  /* one pair the generator yields (:297-341), in it
     uint32_t fwd, rev;        /* candidate indices: p1 = fwd, p2 = reverse complement of rev (:333) */
     uint32_t contig, fbin, rbin, pcr_len;
 } pfb_pp_pair;
-typedef struct pfb_pp_product {   /* a pair in one genome (:463, :501-502); genome 0 = the first genome */
-    uint32_t valid;           /* 0: no Product in this genome (other contig / other strand / size out of range) */
-    uint32_t length, fbin, rbin;
-} pfb_pp_product;
+#define PFB_PP_VALID 0x80000000u   /* pfb_pp_shared: the pair has a Product in this genome; the low bits are its size */
 typedef struct pfb_pp_timing {
     float    ms_bin, ms_pairs, ms_shared, ms_total;    /* CUDA events: binning of all genomes; reduction + bin pairs + primer pairs; cross-genome look-up */
     uint64_t n_candidates, n_genomes, n_bins, n_pairs, n_kept, n_launches;
@@ -309,13 +306,18 @@ void pfb_pp_destroy(pfb_pp *pp);
 const char *pfb_pp_last_error(const pfb_pp *pp);   /* pp may be NULL: error of the last failed pfb_pp_create */
 int  pfb_pp_set_candidates(pfb_pp *pp, const uint64_t *word, const uint8_t *k, const double *tm, uint64_t n);
 /* one call per genome, the first genome first: n = the number of candidates; per list position the candidate index,
- * the contig number (dense, in dict order: non-decreasing), min(Primer.start, Primer.end) and the strand (0 '+', 1 '-') */
+ * the contig number (dense, in dict order: non-decreasing), min(Primer.start, Primer.end) and the strand (0 '+', 1 '-').
+ * The columns are copied to the device inside the call (pfb_pp_set_candidates likewise). */
 int  pfb_pp_add_genome(pfb_pp *pp, const uint32_t *id, const uint32_t *contig, const uint32_t *left, const uint8_t *strand, uint64_t n);
 int  pfb_pp_clear_genomes(pfb_pp *pp);
 int  pfb_pp_run(pfb_pp *pp, const pfb_pp_params *params);
 int  pfb_pp_counts(pfb_pp *pp, uint64_t *n_pairs, uint64_t *n_kept, uint64_t *n_bins);   /* kept = valid in every genome (:459-462) */
 int  pfb_pp_pairs(pfb_pp *pp, pfb_pp_pair *out, uint64_t cap);
-int  pfb_pp_shared(pfb_pp *pp, pfb_pp_product *out, uint64_t cap);      /* [n_pairs][n_genomes] */
+/* out[pair * n_genomes + genome] (genome 0 = the first genome) = PFB_PP_VALID | product size (:455-463), or 0 when the
+ * pair has no Product there (other contig / other strand / size out of range).  The Product's bin numbers (:501-502) are
+ * pfb_pp_bins(genome)[fwd] and [rev]. */
+int  pfb_pp_shared(pfb_pp *pp, uint32_t *out, uint64_t cap);
+int  pfb_pp_kept(pfb_pp *pp, uint8_t *out, uint64_t cap);           /* [n_pairs] 1 = a Product in every genome (:459-462) */
 /* bin number of every candidate within its contig in one genome; reduced (first genome only, may be NULL): 1 = dropped
  * from its bin by __reduceBinSize */
 int  pfb_pp_bins(pfb_pp *pp, uint32_t genome, uint32_t *bin_of, uint8_t *reduced, uint64_t cap);

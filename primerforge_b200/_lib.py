@@ -39,7 +39,7 @@ EXPORTS = ["pfb_create", "pfb_destroy", "pfb_last_error", "pfb_default_params", 
            "pfb_og_clear_genomes", "pfb_og_set_scan_mode", "pfb_og_run", "pfb_og_compute", "pfb_og_counts", "pfb_og_hits", "pfb_og_products",
            "pfb_og_removed_at", "pfb_og_timings",
            "pfb_pp_create", "pfb_pp_destroy", "pfb_pp_last_error", "pfb_pp_set_candidates", "pfb_pp_add_genome",
-           "pfb_pp_clear_genomes", "pfb_pp_run", "pfb_pp_counts", "pfb_pp_pairs", "pfb_pp_shared", "pfb_pp_bins", "pfb_pp_timings"]
+           "pfb_pp_clear_genomes", "pfb_pp_run", "pfb_pp_counts", "pfb_pp_pairs", "pfb_pp_shared", "pfb_pp_kept", "pfb_pp_bins", "pfb_pp_timings"]
 
 
 class PfbParams(C.Structure):
@@ -85,7 +85,7 @@ class PfbPpTiming(C.Structure):
 
 
 PP_PAIR_DTYPE = np.dtype([("fwd", "<u4"), ("rev", "<u4"), ("contig", "<u4"), ("fbin", "<u4"), ("rbin", "<u4"), ("pcr_len", "<u4")])
-PP_PRODUCT_DTYPE = np.dtype([("valid", "<u4"), ("length", "<u4"), ("fbin", "<u4"), ("rbin", "<u4")])
+PP_VALID = 0x80000000
 OG_HIT_DTYPE = np.dtype([("key", "<u4"), ("genome", "<u4"), ("contig", "<u4"), ("start", "<u4"), ("strand", "<u4")])
 OG_PRODUCT_DTYPE = np.dtype([("pair", "<u4"), ("genome", "<u4"), ("contig", "<u4"), ("size", "<i4")])
 RECORD_DTYPE = np.dtype([("word", "<u8"), ("tm", "<f8"), ("slot", "<u4"), ("gc_count", "<u2"), ("k", "u1"), ("flags", "u1")])
@@ -186,6 +186,7 @@ def load():
     lib.pfb_pp_counts.argtypes = [vp, C.POINTER(u64), C.POINTER(u64), C.POINTER(u64)]
     lib.pfb_pp_pairs.argtypes = [vp, vp, u64]
     lib.pfb_pp_shared.argtypes = [vp, vp, u64]
+    lib.pfb_pp_kept.argtypes = [vp, vp, u64]
     lib.pfb_pp_bins.argtypes = [vp, u32, vp, vp, u64]
     lib.pfb_pp_timings.argtypes = [vp, C.POINTER(PfbPpTiming)]
     for name in EXPORTS:

@@ -55,8 +55,9 @@ struct Args {
     uint32_t *pairCount, *pairOff; // [nb + 1] pairs contributed by every first bin; exclusive scan
     uint4 *pairsA;                 // [nPairs] {fwd id, rev id, contig, pcrLen}
     uint2 *pairsB;                 // [nPairs] {fbin, rbin}
-    uint4 *shared;                 // [nPairs][G] {valid, length, fbin, rbin}
-    uint32_t *cnt;                 // [0] bins of the first genome, [1] pairs, [2] error flags
+    uint32_t *shared;              // [nPairs][G] product length | 1 << 31 when the pair has a Product in that genome
+    uint8_t *kept;                 // [nPairs] 1 = a Product in every genome
+    uint32_t *cnt;                 // [0] bins of the first genome, [1] pairs, [2] error flags, [4] kept pairs
     uint32_t nb, pairCap;
     int32_t maxBin, minPrimerLen, minPcr, maxPcr;
     double maxTmDiff;
@@ -235,15 +236,16 @@ __global__ void __launch_bounds__(128) k_pp_pairs(const __grid_constant__ Args a
     if (!EMIT) a.pairCount[b1] = n;
 }
 
-// __getAllSharedPrimerPairs (:367-464) + __updateBinsForUnprocessedGenomes (:467-502), one thread per (pair, genome)
+// __getAllSharedPrimerPairs (:367-464), one thread per (pair, genome): the product length, or "no Product here".  The bin
+// numbers of :467-502 are binOf[genome][fwd] / binOf[genome][rev]: columns the host already has, not repeated per pair.
+constexpr uint32_t PP_VALID = 0x80000000u;
 __global__ void __launch_bounds__(256) k_pp_shared(const __grid_constant__ Args a, uint32_t nPairs) {
     const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x, g = blockIdx.y;
     if (q >= nPairs) return;
     const uint4 pr = a.pairsA[q];
-    const uint2 pb = a.pairsB[q];
-    uint4 o = make_uint4(0u, 0u, 0u, 0u);
+    uint32_t o = 0u;
     if (g == 0) {
-        o = make_uint4(1u, pr.w, pb.x, pb.y);                                  // out[(p1, p2)][firstName] = product (:398)
+        o = PP_VALID | pr.w;                                                   // out[(p1, p2)][firstName] = product (:398)
     } else {
         const size_t base = (size_t)g * a.S;
         const uint32_t x = pr.x, y = pr.y;
@@ -262,12 +264,28 @@ __global__ void __launch_bounds__(256) k_pp_shared(const __grid_constant__ Args 
                 const int64_t lf = xfwd ? lx : ly, lr = xfwd ? ly : lx;
                 const int kr = xfwd ? ky : kx;
                 const int64_t length = (lr + kr - 1) - lf + 1;                 // :455 (both on (+) after :450-452)
-                if (length >= a.minPcr && length <= a.maxPcr)                  // :456
-                    o = make_uint4(1u, (uint32_t)length, a.binOf[base + x], a.binOf[base + y]);      // :463, :497-502
+                if (length >= a.minPcr && length <= a.maxPcr) o = PP_VALID | (uint32_t)length;      // :456, :463
             }
         }
     }
     a.shared[(size_t)q * a.G + g] = o;
+}
+
+// pairs with a Product in every genome (:459-462)
+__global__ void __launch_bounds__(256) k_pp_kept(const __grid_constant__ Args a, uint32_t nPairs) {
+    const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= nPairs) return;
+    uint32_t all = PP_VALID;
+    for (uint32_t g = 0; g < a.G; g++) all &= a.shared[(size_t)q * a.G + g];
+    a.kept[q] = all ? 1 : 0;
+    const uint32_t m = __ballot_sync(__activemask(), all != 0u);
+    if ((threadIdx.x & 31u) == (uint32_t)(__ffs(__activemask()) - 1)) atomicAdd(&a.cnt[4], (uint32_t)__popc(m));
+}
+
+// reduced[candidate] for the caller: the alive flags are kept by list position
+__global__ void __launch_bounds__(256) k_pp_reduced_by_id(const __grid_constant__ Args a, uint8_t *out) {
+    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p < a.S) out[a.gid[p]] = a.alive[p] ? 0 : 1;
 }
 
 struct Buf {
@@ -279,23 +297,20 @@ struct Buf {
 
 struct pfb_pp {
     int device = 0;
-    cudaStream_t stream = nullptr;
-    cudaEvent_t ev[4] = {};
+    cudaStream_t stream = nullptr, copyStream = nullptr;     // results leave on the second stream while the next kernels run
+    cudaEvent_t ev[4] = {}, evPairs = nullptr;
     std::string err;
     uint64_t S = 0;
-    std::vector<uint64_t> word;
-    std::vector<uint8_t> k;
-    std::vector<double> tm;
-    std::vector<std::vector<uint32_t>> gid, gcontig, gleft;
-    std::vector<std::vector<uint8_t>> gstrand;
+    uint32_t G = 0, capG = 0;
     pp::Args a{};
     pp::Buf dWord, dK, dTm, dGid, dGcontig, dGleft, dGstrand, ctOf, lfOf, binOf, stOf, seen, jump, isStart, binIdx, contigFirst,
-        binPos, alive, binFirst, binLast, pairCount, pairOff, pairsA, pairsB, shared, cnt, tiles;
+        binPos, alive, binFirst, binLast, pairCount, pairOff, pairsA, pairsB, shared, kept, cnt, tiles, scratch;
     bool ran = false;
     uint64_t nPairs = 0, nKept = 0, nBins = 0, nLaunches = 0;
     float msBin = 0, msPairs = 0, msShared = 0, msTotal = 0;
-    std::vector<uint4> pairsAHost, sharedHost;
-    std::vector<uint2> pairsBHost;
+    // results in pinned host memory
+    void *hPairsA = nullptr, *hPairsB = nullptr, *hShared = nullptr, *hKept = nullptr;
+    size_t hCapPairs = 0, hCapShared = 0;
 };
 
 static std::string g_pp_create_err;
@@ -323,31 +338,57 @@ int ensure(pfb_pp *o, Buf &b, size_t bytes) {
     return PFB_OK;
 }
 
+// per-genome device arrays with room for capG genomes (grown by doubling; the genomes already copied are kept)
+int ensure_genomes(pfb_pp *o, uint32_t want) {
+    if (want <= o->capG) return PFB_OK;
+    const uint32_t cap = std::max(want, std::max(4u, 2u * o->capG));
+    const uint64_t S = o->S;
+    Buf *bufs[4] = {&o->dGid, &o->dGcontig, &o->dGleft, &o->dGstrand};
+    const size_t elt[4] = {4, 4, 4, 1};
+    for (int j = 0; j < 4; j++) {
+        Buf nb;
+        int rc = ensure(o, nb, (size_t)cap * S * elt[j] + 16);
+        if (rc != PFB_OK) return rc;
+        if (bufs[j]->p && o->G) PPCK(cudaMemcpy(nb.p, bufs[j]->p, (size_t)o->G * S * elt[j], cudaMemcpyDeviceToDevice));
+        if (bufs[j]->p) PPCK(cudaFree(bufs[j]->p));
+        *bufs[j] = nb;
+    }
+    o->capG = cap;
+    return PFB_OK;
+}
+
+int ensure_pinned(pfb_pp *o, uint64_t nPairs, uint32_t G) {
+    if (nPairs > o->hCapPairs) {
+        if (o->hPairsA) { cudaFreeHost(o->hPairsA); cudaFreeHost(o->hPairsB); cudaFreeHost(o->hKept); }
+        o->hPairsA = o->hPairsB = o->hKept = nullptr; o->hCapPairs = 0;
+        const size_t cap = nPairs + nPairs / 4 + 64;
+        PPCK(cudaHostAlloc(&o->hPairsA, cap * 16, cudaHostAllocDefault));
+        PPCK(cudaHostAlloc(&o->hPairsB, cap * 8, cudaHostAllocDefault));
+        PPCK(cudaHostAlloc(&o->hKept, cap, cudaHostAllocDefault));
+        o->hCapPairs = cap;
+    }
+    if (nPairs * G > o->hCapShared) {
+        if (o->hShared) cudaFreeHost(o->hShared);
+        o->hShared = nullptr; o->hCapShared = 0;
+        const size_t cap = nPairs * G + nPairs * G / 4 + 64;
+        PPCK(cudaHostAlloc(&o->hShared, cap * 4, cudaHostAllocDefault));
+        o->hCapShared = cap;
+    }
+    return PFB_OK;
+}
+
 int run(pfb_pp *o, const pfb_pp_params &prm) {
     const uint64_t S = o->S;
-    const uint32_t G = (uint32_t)o->gid.size();
+    const uint32_t G = o->G;
     Args &a = o->a;
     int rc;
 #define ENS(buf, bytes) if ((rc = ensure(o, o->buf, (bytes))) != PFB_OK) return rc
-    ENS(dWord, S * 8 + 8); ENS(dK, S + 8); ENS(dTm, S * 8 + 8);
-    ENS(dGid, (size_t)G * S * 4 + 4); ENS(dGcontig, (size_t)G * S * 4 + 4); ENS(dGleft, (size_t)G * S * 4 + 4); ENS(dGstrand, (size_t)G * S + 4);
     ENS(ctOf, (size_t)G * S * 4 + 4); ENS(lfOf, (size_t)G * S * 4 + 4); ENS(binOf, (size_t)G * S * 4 + 4); ENS(stOf, (size_t)G * S + 4);
     ENS(seen, (size_t)G * S * 4 + 4); ENS(jump, (size_t)G * S * 4 + 4); ENS(contigFirst, (size_t)G * S * 4 + 4);
     ENS(isStart, (size_t)G * (S + 1) * 4 + 4); ENS(binIdx, (size_t)G * (S + 1) * 4 + 4);
     ENS(binPos, (S + 2) * 4); ENS(alive, S + 4); ENS(binFirst, (S + 2) * 4); ENS(binLast, (S + 2) * 4);
     ENS(pairCount, (S + 2) * 4); ENS(pairOff, (S + 2) * 4); ENS(cnt, 64); ENS(tiles, (devscan::n_tiles((uint32_t)S + 1) + 4) * 4);
 #undef ENS
-    if (S) {
-        PPCK(cudaMemcpyAsync(o->dWord.p, o->word.data(), S * 8, cudaMemcpyHostToDevice, o->stream));
-        PPCK(cudaMemcpyAsync(o->dK.p, o->k.data(), S, cudaMemcpyHostToDevice, o->stream));
-        PPCK(cudaMemcpyAsync(o->dTm.p, o->tm.data(), S * 8, cudaMemcpyHostToDevice, o->stream));
-        for (uint32_t g = 0; g < G; g++) {
-            PPCK(cudaMemcpyAsync((uint32_t *)o->dGid.p + (size_t)g * S, o->gid[g].data(), S * 4, cudaMemcpyHostToDevice, o->stream));
-            PPCK(cudaMemcpyAsync((uint32_t *)o->dGcontig.p + (size_t)g * S, o->gcontig[g].data(), S * 4, cudaMemcpyHostToDevice, o->stream));
-            PPCK(cudaMemcpyAsync((uint32_t *)o->dGleft.p + (size_t)g * S, o->gleft[g].data(), S * 4, cudaMemcpyHostToDevice, o->stream));
-            PPCK(cudaMemcpyAsync((uint8_t *)o->dGstrand.p + (size_t)g * S, o->gstrand[g].data(), S, cudaMemcpyHostToDevice, o->stream));
-        }
-    }
     a.S = (uint32_t)S; a.G = G;
     a.word = (const uint64_t *)o->dWord.p; a.k = (const uint8_t *)o->dK.p; a.tm = (const double *)o->dTm.p;
     a.gid = (const uint32_t *)o->dGid.p; a.gcontig = (const uint32_t *)o->dGcontig.p; a.gleft = (const uint32_t *)o->dGleft.p;
@@ -359,7 +400,6 @@ int run(pfb_pp *o, const pfb_pp_params &prm) {
     a.pairOff = (uint32_t *)o->pairOff.p; a.cnt = (uint32_t *)o->cnt.p;
     a.maxBin = prm.max_bin; a.minPrimerLen = prm.min_primer_len; a.minPcr = prm.min_pcr; a.maxPcr = prm.max_pcr; a.maxTmDiff = prm.max_tm_diff;
     o->nLaunches = 0; o->nPairs = 0; o->nKept = 0; o->nBins = 0;
-    o->pairsAHost.clear(); o->pairsBHost.clear(); o->sharedHost.clear();
     PPCK(cudaEventRecord(o->ev[0], o->stream));
     PPCK(cudaMemsetAsync(o->cnt.p, 0, 64, o->stream));
     if (S == 0 || G == 0) { PPCK(cudaStreamSynchronize(o->stream)); o->ran = true; return PFB_OK; }
@@ -378,8 +418,8 @@ int run(pfb_pp *o, const pfb_pp_params &prm) {
     }
     k_pp_bin_numbers<<<gridSG, 256, 0, o->stream>>>(a);
     o->nLaunches++;
-    uint32_t cnt[4] = {0, 0, 0, 0};
-    PPCK(cudaMemcpyAsync(cnt, o->cnt.p, 16, cudaMemcpyDeviceToHost, o->stream));
+    uint32_t cnt[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    PPCK(cudaMemcpyAsync(cnt, o->cnt.p, 32, cudaMemcpyDeviceToHost, o->stream));
     PPCK(cudaStreamSynchronize(o->stream));
     if (cnt[2] & ERR_DUP) return fail(o, PFB_EINVAL, "every genome must list every candidate exactly once");
     a.nb = cnt[0]; o->nBins = cnt[0];
@@ -389,35 +429,37 @@ int run(pfb_pp *o, const pfb_pp_params &prm) {
     k_pp_pairs<false><<<(a.nb + 127) / 128, 128, 0, o->stream>>>(a);
     devscan::exscan(a.pairCount, a.nb, a.pairOff, (uint32_t *)o->tiles.p, a.cnt + 1, o->stream);
     o->nLaunches += 5;
-    PPCK(cudaMemcpyAsync(cnt, o->cnt.p, 16, cudaMemcpyDeviceToHost, o->stream));
+    PPCK(cudaMemcpyAsync(cnt, o->cnt.p, 32, cudaMemcpyDeviceToHost, o->stream));
     PPCK(cudaStreamSynchronize(o->stream));
     const uint64_t nPairs = cnt[1];
     if ((rc = ensure(o, o->pairsA, nPairs * 16 + 16)) != PFB_OK) return rc;
     if ((rc = ensure(o, o->pairsB, nPairs * 8 + 8)) != PFB_OK) return rc;
-    if ((rc = ensure(o, o->shared, nPairs * G * 16 + 16)) != PFB_OK) return rc;
-    a.pairsA = (uint4 *)o->pairsA.p; a.pairsB = (uint2 *)o->pairsB.p; a.shared = (uint4 *)o->shared.p;
+    if ((rc = ensure(o, o->shared, nPairs * G * 4 + 16)) != PFB_OK) return rc;
+    if ((rc = ensure(o, o->kept, nPairs + 16)) != PFB_OK) return rc;
+    if ((rc = ensure_pinned(o, nPairs, G)) != PFB_OK) return rc;
+    a.pairsA = (uint4 *)o->pairsA.p; a.pairsB = (uint2 *)o->pairsB.p; a.shared = (uint32_t *)o->shared.p; a.kept = (uint8_t *)o->kept.p;
     k_pp_pairs<true><<<(a.nb + 127) / 128, 128, 0, o->stream>>>(a);
     o->nLaunches++;
     PPCK(cudaEventRecord(o->ev[2], o->stream));
     if (nPairs) {
+        PPCK(cudaEventRecord(o->evPairs, o->stream));
+        PPCK(cudaStreamWaitEvent(o->copyStream, o->evPairs, 0));
+        PPCK(cudaMemcpyAsync(o->hPairsA, o->pairsA.p, nPairs * 16, cudaMemcpyDeviceToHost, o->copyStream));     // (beside the look-up below)
+        PPCK(cudaMemcpyAsync(o->hPairsB, o->pairsB.p, nPairs * 8, cudaMemcpyDeviceToHost, o->copyStream));
         k_pp_shared<<<dim3((uint32_t)((nPairs + 255) / 256), G), 256, 0, o->stream>>>(a, (uint32_t)nPairs);
-        o->nLaunches++;
+        k_pp_kept<<<(uint32_t)((nPairs + 255) / 256), 256, 0, o->stream>>>(a, (uint32_t)nPairs);
+        o->nLaunches += 2;
     }
     PPCK(cudaEventRecord(o->ev[3], o->stream));
-    o->pairsAHost.resize(nPairs); o->pairsBHost.resize(nPairs); o->sharedHost.resize(nPairs * G);
     if (nPairs) {
-        PPCK(cudaMemcpyAsync(o->pairsAHost.data(), o->pairsA.p, nPairs * 16, cudaMemcpyDeviceToHost, o->stream));
-        PPCK(cudaMemcpyAsync(o->pairsBHost.data(), o->pairsB.p, nPairs * 8, cudaMemcpyDeviceToHost, o->stream));
-        PPCK(cudaMemcpyAsync(o->sharedHost.data(), o->shared.p, nPairs * G * 16, cudaMemcpyDeviceToHost, o->stream));
+        PPCK(cudaMemcpyAsync(o->hShared, o->shared.p, nPairs * G * 4, cudaMemcpyDeviceToHost, o->stream));
+        PPCK(cudaMemcpyAsync(o->hKept, o->kept.p, nPairs, cudaMemcpyDeviceToHost, o->stream));
     }
+    PPCK(cudaMemcpyAsync(cnt, o->cnt.p, 32, cudaMemcpyDeviceToHost, o->stream));
     PPCK(cudaStreamSynchronize(o->stream));
+    PPCK(cudaStreamSynchronize(o->copyStream));
     PPCK(cudaGetLastError());
-    o->nPairs = nPairs;
-    for (uint64_t q = 0; q < nPairs; q++) {
-        bool all = true;
-        for (uint32_t g = 0; g < G; g++) all &= o->sharedHost[q * G + g].x != 0;
-        o->nKept += all;
-    }
+    o->nPairs = nPairs; o->nKept = cnt[4];
     PPCK(cudaEventElapsedTime(&o->msBin, o->ev[0], o->ev[1]));
     PPCK(cudaEventElapsedTime(&o->msPairs, o->ev[1], o->ev[2]));
     PPCK(cudaEventElapsedTime(&o->msShared, o->ev[2], o->ev[3]));
@@ -438,7 +480,9 @@ int pfb_pp_create(pfb_pp **out, int device) {
     if (device < 0 || device >= n) return pp::fail(nullptr, PFB_EINVAL, "no such device");
     pfb_pp *ctx = new pfb_pp();
     ctx->device = device;
-    if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
+    if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&ctx->copyStream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ctx->evPairs, cudaEventDisableTiming) != cudaSuccess) {
         delete ctx;
         return pp::fail(nullptr, PFB_ECUDA, "cudaSetDevice / cudaStreamCreate failed");
     }
@@ -454,9 +498,12 @@ void pfb_pp_destroy(pfb_pp *o) {
     if (o->stream) cudaStreamSynchronize(o->stream);
     for (pp::Buf *b : {&o->dWord, &o->dK, &o->dTm, &o->dGid, &o->dGcontig, &o->dGleft, &o->dGstrand, &o->ctOf, &o->lfOf, &o->binOf,
                        &o->stOf, &o->seen, &o->jump, &o->isStart, &o->binIdx, &o->contigFirst, &o->binPos, &o->alive, &o->binFirst,
-                       &o->binLast, &o->pairCount, &o->pairOff, &o->pairsA, &o->pairsB, &o->shared, &o->cnt, &o->tiles})
+                       &o->binLast, &o->pairCount, &o->pairOff, &o->pairsA, &o->pairsB, &o->shared, &o->kept, &o->cnt, &o->tiles, &o->scratch})
         if (b->p) cudaFree(b->p);
+    for (void *h : {o->hPairsA, o->hPairsB, o->hShared, o->hKept}) if (h) cudaFreeHost(h);
     for (auto &e : o->ev) if (e) cudaEventDestroy(e);
+    if (o->evPairs) cudaEventDestroy(o->evPairs);
+    if (o->copyStream) cudaStreamDestroy(o->copyStream);
     if (o->stream) cudaStreamDestroy(o->stream);
     delete o;
 }
@@ -469,9 +516,17 @@ int pfb_pp_set_candidates(pfb_pp *o, const uint64_t *word, const uint8_t *k, con
     if (n >= (1ull << 31)) return pp::fail(o, PFB_ETOOLARGE, "too many candidates");
     for (uint64_t i = 0; i < n; i++)
         if (k[i] < 1 || k[i] > 32) return pp::fail(o, PFB_EINVAL, "candidate length must be 1..32");
-    o->S = n;
-    o->word.assign(word, word + n); o->k.assign(k, k + n); o->tm.assign(tm, tm + n);
-    o->gid.clear(); o->gcontig.clear(); o->gleft.clear(); o->gstrand.clear();
+    if (cudaSetDevice(o->device) != cudaSuccess) return pp::fail(o, PFB_ECUDA, "cudaSetDevice failed");
+    int rc;
+    if ((rc = pp::ensure(o, o->dWord, n * 8 + 8)) != PFB_OK || (rc = pp::ensure(o, o->dK, n + 8)) != PFB_OK ||
+        (rc = pp::ensure(o, o->dTm, n * 8 + 8)) != PFB_OK) return rc;
+    if (n) {      // the columns go to the device as they are: the caller's buffers are free again when the call returns
+        PPCK(cudaMemcpy(o->dWord.p, word, n * 8, cudaMemcpyHostToDevice));
+        PPCK(cudaMemcpy(o->dK.p, k, n, cudaMemcpyHostToDevice));
+        PPCK(cudaMemcpy(o->dTm.p, tm, n * 8, cudaMemcpyHostToDevice));
+    }
+    o->S = n; o->G = 0; o->capG = 0;
+    for (pp::Buf *b : {&o->dGid, &o->dGcontig, &o->dGleft, &o->dGstrand}) { if (b->p) cudaFree(b->p); b->p = nullptr; b->cap = 0; }
     o->ran = false;
     return PFB_OK;
 }
@@ -482,18 +537,27 @@ int pfb_pp_add_genome(pfb_pp *o, const uint32_t *id, const uint32_t *contig, con
     if (n && (!id || !contig || !left || !strand)) return pp::fail(o, PFB_EINVAL, "bad genome arguments");
     for (uint64_t p = 1; p < n; p++)
         if (contig[p] < contig[p - 1]) return pp::fail(o, PFB_EINVAL, "contig numbers must follow the order of the lists");
-    if (o->gid.empty())
+    if (o->G == 0)
         for (uint64_t p = 0; p < n; p++)
             if (strand[p]) return pp::fail(o, PFB_EINVAL, "the first genome's candidates are all on (+) (getCandidateKmers.py:58-63)");
-    o->gid.emplace_back(id, id + n); o->gcontig.emplace_back(contig, contig + n); o->gleft.emplace_back(left, left + n);
-    o->gstrand.emplace_back(strand, strand + n);
+    if (cudaSetDevice(o->device) != cudaSuccess) return pp::fail(o, PFB_ECUDA, "cudaSetDevice failed");
+    int rc = pp::ensure_genomes(o, o->G + 1);
+    if (rc != PFB_OK) return rc;
+    const size_t at = (size_t)o->G * n;
+    if (n) {
+        PPCK(cudaMemcpy((uint32_t *)o->dGid.p + at, id, n * 4, cudaMemcpyHostToDevice));
+        PPCK(cudaMemcpy((uint32_t *)o->dGcontig.p + at, contig, n * 4, cudaMemcpyHostToDevice));
+        PPCK(cudaMemcpy((uint32_t *)o->dGleft.p + at, left, n * 4, cudaMemcpyHostToDevice));
+        PPCK(cudaMemcpy((uint8_t *)o->dGstrand.p + at, strand, n, cudaMemcpyHostToDevice));
+    }
+    o->G++;
     o->ran = false;
     return PFB_OK;
 }
 
 int pfb_pp_clear_genomes(pfb_pp *o) {
     if (!o) return PFB_EINVAL;
-    o->gid.clear(); o->gcontig.clear(); o->gleft.clear(); o->gstrand.clear();
+    o->G = 0;
     o->ran = false;
     return PFB_OK;
 }
@@ -518,37 +582,46 @@ int pfb_pp_pairs(pfb_pp *o, pfb_pp_pair *out, uint64_t cap) {
     if (!o || (!out && cap)) return PFB_EINVAL;
     if (!o->ran) return pp::fail(o, PFB_ESTATE, "no run yet");
     if (cap < o->nPairs) return pp::fail(o, PFB_EINVAL, "pair buffer too small");
+    const uint4 *A = (const uint4 *)o->hPairsA;
+    const uint2 *B = (const uint2 *)o->hPairsB;
     for (uint64_t q = 0; q < o->nPairs; q++) {
-        const uint4 a = o->pairsAHost[q];
-        const uint2 b = o->pairsBHost[q];
-        out[q].fwd = a.x; out[q].rev = a.y; out[q].contig = a.z; out[q].fbin = b.x; out[q].rbin = b.y; out[q].pcr_len = a.w;
+        out[q].fwd = A[q].x; out[q].rev = A[q].y; out[q].contig = A[q].z; out[q].fbin = B[q].x; out[q].rbin = B[q].y; out[q].pcr_len = A[q].w;
     }
     return PFB_OK;
 }
 
-int pfb_pp_shared(pfb_pp *o, pfb_pp_product *out, uint64_t cap) {
+int pfb_pp_shared(pfb_pp *o, uint32_t *out, uint64_t cap) {
     if (!o || (!out && cap)) return PFB_EINVAL;
     if (!o->ran) return pp::fail(o, PFB_ESTATE, "no run yet");
-    const uint64_t n = o->sharedHost.size();
-    if (cap < n) return pp::fail(o, PFB_EINVAL, "product buffer too small");
-    static_assert(sizeof(pfb_pp_product) == sizeof(uint4), "pfb_pp_product layout");
-    if (n) memcpy(out, o->sharedHost.data(), n * sizeof(uint4));
+    const uint64_t n = o->nPairs * o->G;
+    if (cap < n) return pp::fail(o, PFB_EINVAL, "buffer too small");
+    if (n) memcpy(out, o->hShared, n * 4);
+    return PFB_OK;
+}
+
+int pfb_pp_kept(pfb_pp *o, uint8_t *out, uint64_t cap) {
+    if (!o || (!out && cap)) return PFB_EINVAL;
+    if (!o->ran) return pp::fail(o, PFB_ESTATE, "no run yet");
+    if (cap < o->nPairs) return pp::fail(o, PFB_EINVAL, "buffer too small");
+    if (o->nPairs) memcpy(out, o->hKept, o->nPairs);
     return PFB_OK;
 }
 
 int pfb_pp_bins(pfb_pp *o, uint32_t genome, uint32_t *bin_of, uint8_t *reduced, uint64_t cap) {
     if (!o || !bin_of) return PFB_EINVAL;
     if (!o->ran) return pp::fail(o, PFB_ESTATE, "no run yet");
-    if (genome >= o->gid.size() || cap < o->S) return pp::fail(o, PFB_EINVAL, "bad genome / buffer too small");
+    if (genome >= o->G || cap < o->S) return pp::fail(o, PFB_EINVAL, "bad genome / buffer too small");
     if (cudaSetDevice(o->device) != cudaSuccess) return pp::fail(o, PFB_ECUDA, "cudaSetDevice failed");
     const uint64_t S = o->S;
     if (!S) return PFB_OK;
     PPCK(cudaMemcpy(bin_of, (uint32_t *)o->binOf.p + (size_t)genome * S, S * 4, cudaMemcpyDeviceToHost));
     if (reduced) {
         if (genome != 0) return pp::fail(o, PFB_EINVAL, "only the first genome's bins are reduced");
-        std::vector<uint8_t> alive(S);
-        PPCK(cudaMemcpy(alive.data(), o->alive.p, S, cudaMemcpyDeviceToHost));
-        for (uint64_t p = 0; p < S; p++) reduced[o->gid[0][p]] = alive[p] ? 0 : 1;
+        int rc = pp::ensure(o, o->scratch, S + 16);
+        if (rc != PFB_OK) return rc;
+        pp::k_pp_reduced_by_id<<<(uint32_t)((S + 255) / 256), 256, 0, o->stream>>>(o->a, (uint8_t *)o->scratch.p);
+        PPCK(cudaStreamSynchronize(o->stream));
+        PPCK(cudaMemcpy(reduced, o->scratch.p, S, cudaMemcpyDeviceToHost));
     }
     return PFB_OK;
 }
@@ -557,7 +630,7 @@ int pfb_pp_timings(pfb_pp *o, pfb_pp_timing *out) {
     if (!o || !out) return PFB_EINVAL;
     memset(out, 0, sizeof(*out));
     out->ms_bin = o->msBin; out->ms_pairs = o->msPairs; out->ms_shared = o->msShared; out->ms_total = o->msTotal;
-    out->n_candidates = o->S; out->n_genomes = o->gid.size(); out->n_bins = o->nBins; out->n_pairs = o->nPairs; out->n_kept = o->nKept;
+    out->n_candidates = o->S; out->n_genomes = o->G; out->n_bins = o->nBins; out->n_pairs = o->nPairs; out->n_kept = o->nKept;
     out->n_launches = o->nLaunches;
     return PFB_OK;
 }

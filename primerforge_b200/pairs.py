@@ -31,13 +31,22 @@ ERR_NO_SHARED_PAIRS = "could not identify primer pairs present in every ingroup 
 @dataclass
 class PairResult:
     pairs: np.ndarray      # PP_PAIR_DTYPE [n]: what the generator of __getCandidatePrimerPairs yields, in its order
-    shared: np.ndarray     # PP_PRODUCT_DTYPE [n, G]
+    valid: np.ndarray      # bool [n, G]: the pair has a Product in that genome (genome 0 = the first genome)
+    length: np.ndarray     # uint32 [n, G]: its size there
+    kept: np.ndarray       # bool [n]: a Product in every genome (getPrimerPairs.py:459-462)
+    bin_of: list           # per genome: uint32 [S] bin number of every candidate within its contig
     timing: dict
 
-    @property
-    def kept(self) -> np.ndarray:
-        """a Product in every genome (getPrimerPairs.py:459-462)"""
-        return self.shared["valid"].all(axis=1) if self.pairs.size else np.zeros(0, dtype=bool)
+    def shared4(self) -> np.ndarray:
+        """[n, G, 4] uint32: valid, length, fbin, rbin -- the layout of oracle/pf_oracle_pairs.c's result"""
+        n, G = self.valid.shape
+        out = np.zeros((n, G, 4), dtype=np.uint32)
+        out[:, :, 0] = self.valid
+        out[:, :, 1] = self.length * self.valid
+        for g in range(G):
+            out[:, g, 2] = self.bin_of[g][self.pairs["fwd"]] * self.valid[:, g]
+            out[:, g, 3] = self.bin_of[g][self.pairs["rev"]] * self.valid[:, g]
+        return out
 
 
 class PairSearch:
@@ -110,16 +119,19 @@ class PairSearch:
         return (b, r) if with_reduced else b
 
     def result(self) -> PairResult:
-        n, kept, nb = C.c_uint64(), C.c_uint64(), C.c_uint64()
-        self._ck(self._lib.pfb_pp_counts(self._h, C.byref(n), C.byref(kept), C.byref(nb)))
+        n, kept_n, nb = C.c_uint64(), C.c_uint64(), C.c_uint64()
+        self._ck(self._lib.pfb_pp_counts(self._h, C.byref(n), C.byref(kept_n), C.byref(nb)))
+        G = self.n_genomes
         pairs = np.empty(n.value, dtype=_lib.PP_PAIR_DTYPE)
-        shared = np.empty((n.value, max(self.n_genomes, 1)), dtype=_lib.PP_PRODUCT_DTYPE)
+        shared = np.zeros((n.value, G), dtype=np.uint32)
+        kept = np.zeros(n.value, dtype=np.uint8)
         self._ck(self._lib.pfb_pp_pairs(self._h, pairs.ctypes.data, pairs.size))
-        if self.n_genomes:
+        if G and n.value:
             self._ck(self._lib.pfb_pp_shared(self._h, shared.ctypes.data, shared.size))
-        else:
-            shared = shared[:, :0]
-        return PairResult(pairs=pairs, shared=shared, timing=self.timing())
+            self._ck(self._lib.pfb_pp_kept(self._h, kept.ctypes.data, kept.size))
+        bins = [self.bins(g) for g in range(G)] if self.n_candidates else [np.zeros(0, np.uint32) for _ in range(G)]
+        return PairResult(pairs=pairs, valid=(shared & np.uint32(_lib.PP_VALID)) != 0, length=shared & np.uint32(0x7FFFFFFF),
+                          kept=kept.astype(bool), bin_of=bins, timing=self.timing())
 
 
 # ------------------------------------------------------------------------------------------------------------------
@@ -237,12 +249,11 @@ def _getPrimerPairs(candidateKmers, params, dimer=None, device: int | None = Non
         per = {}
         for g, name in enumerate(names):
             c_of, l_of, s_of = place[g]
-            sh = res.shared[q, g]
             la, lb, sa, sb = int(l_of[a]), int(l_of[b]), int(s_of[a]), int(s_of[b])
             f_start, f_end = (la, la + ka - 1) if sa == 0 else (la + ka - 1, la)
             r_minus = 1 - sb                                                              # k2.reverseComplement() (:458)
             r_start, r_end = (lb, lb + kb - 1) if r_minus == 0 else (lb + kb - 1, lb)
-            per[name] = Product(contig_names[g][int(c_of[a])], int(sh["length"]), int(sh["fbin"]), int(sh["rbin"]), dimer_tm,
+            per[name] = Product(contig_names[g][int(c_of[a])], int(res.length[q, g]), int(res.bin_of[g][a]), int(res.bin_of[g][b]), dimer_tm,
                                 f_start, f_end, "-" if sa else "+", r_start, r_end, "-" if r_minus else "+")
         out[(fwd, rev)] = per
     if not out:                                                                           # :550-553

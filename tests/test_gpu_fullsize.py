@@ -140,7 +140,7 @@ def test_pair_search_full_size_equals_oracle():
         for g in range(3):
             assert np.array_equal(ps.bins(g), o.bin_of[g])
         assert np.array_equal(ps.bins(0, with_reduced=True)[1], o.reduced)
-    p, s = res.pairs, res.shared
+    p = res.pairs
     assert p.size > 1_000_000
     assert np.array_equal(np.stack([p["fwd"], p["rev"], p["contig"], p["fbin"], p["rbin"], p["pcr_len"]], axis=1).astype(np.uint32), o.pairs)
-    assert np.array_equal(np.stack([s["valid"], s["length"], s["fbin"], s["rbin"]], axis=2).astype(np.uint32), o.shared)
+    assert np.array_equal(res.shared4(), o.shared) and np.array_equal(res.kept, o.kept)

@@ -19,16 +19,15 @@ def _search(word, k, tm, genomes, **kw):
             ps.add_genome(*g)
         ps.run(**kw)
         res = ps.result()
-        bins = [ps.bins(g) for g in range(len(genomes))]
-        reduced = ps.bins(0, with_reduced=True)[1] if genomes else None
+        bins = res.bin_of
+        reduced = ps.bins(0, with_reduced=True)[1] if genomes and len(word) else None
     return res, bins, reduced
 
 
 def _as_arrays(res):
-    p, s = res.pairs, res.shared
+    p = res.pairs
     pairs = np.stack([p["fwd"], p["rev"], p["contig"], p["fbin"], p["rbin"], p["pcr_len"]], axis=1).astype(np.uint32).reshape(-1, 6)
-    shared = np.stack([s["valid"], s["length"], s["fbin"], s["rbin"]], axis=2).astype(np.uint32) if p.size else np.zeros((0, s.shape[1], 4), np.uint32)
-    return pairs, shared
+    return pairs, res.shared4()
 
 
 @pytest.mark.parametrize("name", pp_cases())

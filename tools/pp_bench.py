@@ -28,13 +28,17 @@ with PairSearch(0) as ps:
     for g in per_genome:
         ps.add_genome(*g)
     for _ in range(3):
-        t2 = time.time(); ps.run(**kw); t3 = time.time()
+        t2 = time.time()
+        ps.set_candidates(word, k, tm)
+        for g in per_genome:
+            ps.add_genome(*g)
+        ps.run(**kw); t3 = time.time()
     res = ps.result()
     print({**ps.timing(), "columns_s": t1 - t0, "run_wall_s": t3 - t2, "kept": int(res.kept.sum())})
 if check:
     from oracle import pf_oracle as po
     t4 = time.time(); o = po.run_pairs(word, k, tm, per_genome, **kw); t5 = time.time()
-    p, s = res.pairs, res.shared
+    p = res.pairs
     pairs = np.stack([p["fwd"], p["rev"], p["contig"], p["fbin"], p["rbin"], p["pcr_len"]], axis=1).astype(np.uint32)
-    shared = np.stack([s["valid"], s["length"], s["fbin"], s["rbin"]], axis=2).astype(np.uint32)
+    shared = res.shared4()
     print("oracle s", t5 - t4, "pairs equal", np.array_equal(pairs, o.pairs), "shared equal", np.array_equal(shared, o.shared))
