@@ -144,7 +144,7 @@ struct K {  // kernel arguments (by value, __grid_constant__)
 enum { XP_CANDS = 0, XP_ROWS_A = 1, XP_ROWS_B = 2, XP_ALIVE = 3, XP_PICK = 4, XP_DONE = 5, XP_PHASES = 6 };
 constexpr uint32_t X_FLAGS_BYTES = 4096;       // [XP_PHASES][16] uint32 (+ slack) at the start of an arena
 
-enum { C_NSLOTS = 0, C_NIDS = 1, C_NALIVE = 2, C_NPICK = 3, C_OVF = 4, C_FLAGS = 5, C_MAXCAND = 6 };
+enum { C_NSLOTS = 0, C_NIDS = 1, C_NALIVE = 2, C_NPICK = 3, C_OVF = 4, C_FLAGS = 5, C_MAXCAND = 6, C_TICKET = 7 };
 enum { OVF_SLOTS = 1u, OVF_IDS = 2u, OVF_LISTS = 4u, OVF_CAND = 8u, OVF_PEER_TIMEOUT = 16u };
 
 // SantaLucia (1998) nearest-neighbour table in oligotm's integer units; index = 4*first + second
@@ -1336,14 +1336,6 @@ __global__ void __launch_bounds__(256) k_rows0_unpack(const __grid_constant__ K 
 // flag table (after a system-wide fence; the kernel boundary before it has made the data visible); a consumer
 // waits until every slot of its own table has reached that number, then reads the peers' arenas with loads that
 // bypass L1 (peer memory is cached at its home, not here).  The wait is bounded (~9 s): a rank that never signals ends in an error, not in a hang.
-__global__ void k_xsignal(const __grid_constant__ K p, int phase) {
-    if (threadIdx.x < p.nRanks) {
-        __threadfence_system();
-        volatile uint32_t *f = (volatile uint32_t *)(p.peer[threadIdx.x]) + phase * 16 + p.rank;
-        *f = p.xEpoch;
-    }
-}
-
 // both in one launch (a producer's signal is always followed by its own wait for the others)
 __global__ void k_xsync(const __grid_constant__ K p, int phase) {
     if (threadIdx.x < p.nRanks) {
@@ -1543,24 +1535,49 @@ __global__ void __launch_bounds__(256) k_pick(const __grid_constant__ K p) {
     if (picked) p.pick[id] = 1;
 }
 
-// k_count: shared k-mers and picked ones (the two numbers the host reports; the arrays stay indexed by id)
-__global__ void __launch_bounds__(256) k_count(const __grid_constant__ K p) {
+// the end of a run in ONE launch: (peer mode) pick = MAX over the ranks' arenas; the counts of shared and picked ids; the
+// block that finishes last publishes the counters to host-mapped memory and (peer mode) tells the peers that this rank
+// has read everything it needed from their arenas
+template <bool PEER>
+__global__ void __launch_bounds__(256) k_finish(const __grid_constant__ K p, uint32_t *host_counts) {
+    __shared__ bool last;
     const uint32_t n = min(p.cnt[C_NIDS], p.capIds);
+    const uint32_t n4 = (p.capIds + 3u) / 4u;
     uint32_t a = 0, b = 0;
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) { a += p.alive[i]; b += p.pick[i]; }
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += gridDim.x * blockDim.x) {
+        uint32_t pk;
+        if (PEER) {
+            pk = 0u;
+            for (uint32_t r = 0; r < p.nRanks; r++) pk = __vmaxu4(pk, __ldcg((const uint32_t *)(p.peer[r] + p.xPick) + i));
+            ((uint32_t *)p.pick)[i] = pk;
+        } else {
+            pk = ((const uint32_t *)p.pick)[i];
+        }
+        const uint32_t left = n > 4u * i ? n - 4u * i : 0u;                        // ids of this word below the id count
+        const uint32_t m = (left >= 4u ? 0xFFFFFFFFu : (1u << (8u * left)) - 1u) & 0x01010101u;
+        a += __popc(((const uint32_t *)p.alive)[i] & m);
+        b += __popc(pk & m);
+    }
     for (int o = 16; o; o >>= 1) { a += __shfl_xor_sync(0xFFFFFFFFu, a, o); b += __shfl_xor_sync(0xFFFFFFFFu, b, o); }
     if ((threadIdx.x & 31) == 0) {
         if (a) atomicAdd(&p.cnt[C_NALIVE], a);
         if (b) atomicAdd(&p.cnt[C_NPICK], b);
     }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        last = atomicAdd(&p.cnt[C_TICKET], 1u) == gridDim.x - 1u;
+    }
+    __syncthreads();
+    if (last) {
+        __threadfence();
+        if (threadIdx.x < 8) host_counts[threadIdx.x] = ((volatile uint32_t *)p.cnt)[threadIdx.x];
+        if (PEER && threadIdx.x < p.nRanks) {
+            __threadfence_system();
+            *((volatile uint32_t *)(p.peer[threadIdx.x]) + XP_DONE * 16 + p.rank) = p.xEpoch;
+        }
+    }
 }
-
-// the counters -> host-mapped memory (read by the host after the stream synchronise that ends a run: no
-// device -> host copy that would queue up behind the result copies)
-__global__ void k_publish(const uint32_t *cnt, uint32_t *host_counts) {
-    if (threadIdx.x < 8) host_counts[threadIdx.x] = cnt[threadIdx.x];
-}
-
 __global__ void k_oligo(const __grid_constant__ K p, uint64_t h, int k, double *out) {
     __shared__ uint32_t s_nn[16];
     for (int i = 0; i < 16; i++) s_nn[i] = c_nn[i];
@@ -1714,6 +1731,7 @@ struct pfb_ctx {
         int n_out = 0;
         std::vector<size_t> cuts;               // ends (exclusive) of the batches of genomes 2..G
         bool packed_aside = false;              // ... and whether they are being packed on the side stream
+        bool rows_zeroed = false;               // the rows of genomes 2..G have been zeroed on the side stream (by capacity)
     } run;
 };
 
@@ -2575,6 +2593,10 @@ static int pack_aside(pfb_ctx *ctx) {
     }
     CK(cudaEventRecord(ctx->evSide, ctx->stream));               // (tables uploaded, previous run's readers done)
     CK(cudaStreamWaitEvent(ctx->sideStream, ctx->evSide, 0));
+    // the rows of genomes 2..G are zeroed here as well, beside genome 1's pipeline: by capacity (the id count is not
+    // known yet), but off the path that the scan waits for
+    CK(cudaMemsetAsync(k.rows, 0, (size_t)(nG - 1) * ctx->capIds * 8, ctx->sideStream));
+    R.rows_zeroed = true;
     size_t g = 1;
     for (size_t b = 0; b < R.cuts.size(); b++) {
         const size_t g2 = R.cuts[b];
@@ -2994,9 +3016,11 @@ static int phaseC(pfb_ctx *ctx) {
         ZeroBatch zb;
         if (nG > 1) {
             // the per-genome rows: allocated by capacity, zeroed by need (the count is on the device)
-            const unsigned ry = (unsigned)std::min<size_t>(nG - 1, 65535);
-            k_zero_rows<<<dim3(nblk((ctx->capIds + 1) / 2, 256), ry), 256, 0, st>>>(k.rows, k.capIds, (uint32_t)(nG - 1), k.cnt + C_NIDS, k.capIds);
-            ctx->launches++;
+            if (!R.rows_zeroed) {
+                const unsigned ry = (unsigned)std::min<size_t>(nG - 1, 65535);
+                k_zero_rows<<<dim3(nblk((ctx->capIds + 1) / 2, 256), ry), 256, 0, st>>>(k.rows, k.capIds, (uint32_t)(nG - 1), k.cnt + C_NIDS, k.capIds);
+                ctx->launches++;
+            }
             // the other genomes only meet the keys that survived genome 1: decide again whether their filter
             // stays sparse enough (long genomes lose most keys to collisions inside genome 1).  The decision must
             // not wait for the id count: it is made from the last run's count, or from an estimate
@@ -3088,14 +3112,13 @@ static int phaseE(pfb_ctx *ctx) {
     CK(cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
     int rc;
-    if (ctx->peer_now) {      // pick = MAX over the ranks
+    if (ctx->peer_now) {      // pick = MAX over the ranks, the counts, "done with the peers' arenas": one launch
         x_wait(ctx, XP_PICK);
-        k_bytes_merge<true><<<nblk(ctx->capIds / 4, 256), 256, 0, st>>>(ctx->k, ctx->k.xPick); ctx->launches++;
+        k_finish<true><<<ctx->num_sms * 2, 256, 0, st>>>(ctx->k, ctx->countsDev); ctx->launches++;
         x_done(ctx, XP_PICK);
-        k_xsignal<<<1, 32, 0, st>>>(ctx->k, XP_DONE); ctx->launches++;
+    } else {
+        k_finish<false><<<ctx->num_sms * 2, 256, 0, st>>>(ctx->k, ctx->countsDev); ctx->launches++;
     }
-    k_count<<<ctx->num_sms * 2, 256, 0, st>>>(ctx->k); ctx->launches++;
-    k_publish<<<1, 32, 0, st>>>(ctx->k.cnt, ctx->countsDev); ctx->launches++;
     CK(cudaEventRecord(ctx->ev[6], st));
     if (ctx->stream_out) {
         if ((rc = copy_out(ctx, ctx->hAlive.p, ctx->k.alive, ctx->capIds, "alive")) != PFB_OK) return rc;
