@@ -1417,7 +1417,10 @@ __global__ void __launch_bounds__(256) k_bytes_merge(const __grid_constant__ K p
 // genome 1's coordinates, so the rows stream and -- for genomes that are largely collinear with genome 1 -- so do
 // the read-backs.  The verdict goes to alive[], the place and strand to pos32 (what the output and k_pick read:
 // half the bytes of the rows, which are not touched again).
-constexpr uint32_t ALIVE_GPT = 2;   // genomes per thread: two independent row -> genome-word load chains in flight
+#ifndef PFB_ALIVE_GPT
+#define PFB_ALIVE_GPT 4
+#endif
+constexpr uint32_t ALIVE_GPT = PFB_ALIVE_GPT;   // genomes per thread: independent row -> genome-word load chains in flight
 
 __global__ void __launch_bounds__(256) k_aliveN(const __grid_constant__ K p, uint32_t ga, uint32_t gb) {
     const uint64_t id = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
