@@ -3,18 +3,22 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--config 2] [--impl reference]
 
-A step = one full pass of the stage (2-bit encode, genome-1 sketch, key table, scan of every other
+A step = one full pass of the stage (2-bit encode, genome-1 candidate table, key table, scan of every other
 genome, uniqueness rules, ordered emit, filters, grouping) over one batch of synthetic genomes of
 BASELINE.json's config (default: configs[1] = 10 x 5 Mbp, primer_len 16-20, default GC/Tm).
 
-  value : device-resident ASCII bases -> device-resident records, CUDA events on the library's
+  value : device-resident ASCII bases -> device-resident results, CUDA events on the library's
           stream, L2 flushed between steps, max over ranks.
-  e2e   : the same stage through the C ABI with HOST (pinned) buffers: H2D of the bases, compute,
-          D2H of the records and of the picked candidates' coordinates in every genome.
-  N > 1 : launched by torchrun, one rank per GPU; every rank holds genome 0 (it defines the key
-          table) plus its own shard of the other genomes; the only exchanges are a MIN all-reduce of
-          the per-key alive bytes and a MAX all-reduce of the pick bytes (NCCL).  Weak scaling:
-          1 + 9 genomes per rank, throughput counts DISTINCT ingroup bases.
+  e2e   : the same stage through the C ABI with HOST (pinned) buffers: H2D of the bases, compute, the per-id
+          result columns streaming to pinned host memory while the run goes on.
+  N > 1 : launched by torchrun, one rank per GPU; every rank holds genome 0 (it defines the key table) plus its own
+          shard of the other genomes; genome 0's own pipeline is shared out by position; the exchanges (candidate
+          lists, packed rows, alive and pick bytes) happen inside the library over mapped peer memory or NCCL.
+          Weak scaling: 1 + 9 genomes per rank, throughput counts DISTINCT ingroup bases.  Rank 0 also runs the
+          whole job on ONE GPU outside the timed region and compares (the `parity` block), and the line carries a
+          `strong_c4` block: BASELINE config 4's 200 genomes dealt over the ranks.
+  blocks: `parity` (GPU vs oracle on the cpu_baseline sample), `outgroup` (outgroup screen on config 3's outgroup
+          shape), `pairs` (pair search on the drop-in leg's candidates), `e2e_fasta`, `e2e_dropin`, `cpu_baseline`.
   --impl reference : the CPU restatement of the reference (oracle/pf_oracle.c, OpenMP, all host
           threads) on a bounded sample of the same workload; the reference itself is pure Python +
           khmer/primer3/pyahocorasick which are not installable in this image.
