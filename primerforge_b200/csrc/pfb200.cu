@@ -77,6 +77,7 @@ constexpr int SCAN_TILE = 2048;                 // elements per block of the dev
 
 struct K {  // kernel arguments (by value, __grid_constant__)
     int kmin, kmax, nk;
+    int kiSplit;              // the filtered scan: lengths [0, kiSplit) by k_scan_filtered2, [kiSplit, nk) by k_scan_filtered
     uint32_t P, PW;           // table prime, words per 1-bit bitmap (the 2-bit table has 2 * PW words)
     uint64_t barrett;         // floor(2^64 / P)
     uint32_t fscale;          // floor(FILTER_WORDS * 2^32 / P): bin -> filter word (the bit is bin & 31)
@@ -779,7 +780,7 @@ __global__ void __launch_bounds__(1024, 1) k_scan_filtered(const __grid_constant
     sw.lt_mask = (1u << sw.lane) - 1u;
     const uint32_t stride = gridDim.x * blockDim.x;
     const uint32_t w0 = w0_ + blockIdx.x * blockDim.x;
-    for (int ki = 0; ki < p.nk; ki++) {
+    for (int ki = p.kiSplit; ki < p.nk; ki++) {        // (the lengths before kiSplit belong to k_scan_filtered2)
         const int k = p.kmin + ki;
         __syncthreads();
         {   // LDGSTS: every thread has all its 16 B pieces in flight at once, nothing goes through registers
@@ -966,7 +967,7 @@ __global__ void __launch_bounds__(1024, 1) k_scan_filtered2(const __grid_constan
     const uint32_t bar = f_addr + SCAN2_SMEM - 16u;
     uint32_t parity = 0;
     if (threadIdx.x == 0) bulk::mbar_init(bar, 1u);
-    for (int ki = 0; ki < p.nk; ki++) {
+    for (int ki = 0; ki < p.kiSplit; ki++) {
         const int k = p.kmin + ki;
         __syncthreads();                                     // every warp is done with the previous filter (and the barrier exists)
         if (threadIdx.x == 0) bulk::load(f_addr, p.filter + (size_t)ki * FILTER_WORDS, FILTER_BYTES, bar);
@@ -2882,6 +2883,23 @@ static int x_connect(std::vector<pfb_ctx *> &C, bool &fallback) {
     return PFB_OK;
 }
 
+// the filtered scan of the words [wa, wb): the second formulation for the lengths it was written for (k <= 20 and a table
+// prime below 2^24: the 32-bit modular reduction), the first one for the longer lengths, where it is the faster of the
+// two (config 5, k 12-30: 14.6 ms against 17.7 ms with the second formulation for every length)
+static void launch_filtered_scan(pfb_ctx *ctx, bool first, uint32_t wa, uint32_t wb) {
+    K &k = ctx->k;
+    cudaStream_t st = ctx->stream;
+    int split = 0;
+    if (ctx->scan_kernel != 1 && k.P < (1u << 24)) split = std::max(0, std::min(k.nk, 21 - k.kmin));
+    k.kiSplit = split;
+    if (split > 0) {
+        if (first) k_scan_filtered2<true><<<ctx->num_sms, 1024, SCAN2_SMEM, st>>>(k, wa, wb);
+        else k_scan_filtered2<false><<<ctx->num_sms, 1024, SCAN2_SMEM, st>>>(k, wa, wb);
+        ctx->launches++;
+    }
+    if (split < k.nk) { k_scan_filtered<<<ctx->num_sms, 1024, SCANF_SMEM, st>>>(k, wa, wb); ctx->launches++; }
+}
+
 static int phaseB(pfb_ctx *ctx) {
     CK(cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
@@ -2923,8 +2941,7 @@ static int phaseB(pfb_ctx *ctx) {
             if (ctx->sharded_now && ctx->emulate_ranks <= 1 && r != ctx->rank) continue;
             const uint32_t wa = (uint32_t)((uint64_t)R.W1 * r / nR), wb = (uint32_t)((uint64_t)R.W1 * (r + 1) / nR);
             if (wb > wa) {
-                if (R.use_filter1 && ctx->scan_kernel == 1) k_scan_filtered<<<ctx->num_sms, 1024, SCANF_SMEM, st>>>(k, wa, wb);
-                else if (R.use_filter1) k_scan_filtered2<true><<<ctx->num_sms, 1024, SCAN2_SMEM, st>>>(k, wa, wb);
+                if (R.use_filter1) { launch_filtered_scan(ctx, true, wa, wb); ctx->launches--; }
                 else k_scan_plain<false><<<nblk(wb - wa, 256), 256, 0, st>>>(k, wa, wb);
                 ctx->launches++;
             }
@@ -2950,10 +2967,8 @@ static int scan_batch(pfb_ctx *ctx, size_t ga, size_t gb, bool encode, bool use_
     if (encode && wb > wa) { k_encode<<<nblk(wb - wa, 256), 256, 0, st>>>(k, wa, wb); ctx->launches++; }
     trace_mark(ctx, st, "scan starts: genomes " + std::to_string(ga) + ".." + std::to_string(gb - 1));
     if (wb > wa) {
-        if (use_filter && ctx->scan_kernel == 1) k_scan_filtered<<<ctx->num_sms, 1024, SCANF_SMEM, st>>>(k, wa, wb);
-        else if (use_filter) k_scan_filtered2<false><<<ctx->num_sms, 1024, SCAN2_SMEM, st>>>(k, wa, wb);
-        else k_scan_plain<false><<<nblk(wb - wa, 256), 256, 0, st>>>(k, wa, wb);
-        ctx->launches++;
+        if (use_filter) launch_filtered_scan(ctx, false, wa, wb);
+        else { k_scan_plain<false><<<nblk(wb - wa, 256), 256, 0, st>>>(k, wa, wb); ctx->launches++; }
     }
     if (cb - ca > gb - ga) {   // some genome of the range has more than one contig
         uint64_t nthr = (uint64_t)(cb - ca) * k.nk * 2 * (2 * P.k_max - 1);

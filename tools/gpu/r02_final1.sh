@@ -7,7 +7,7 @@ for c in 3 5; do python bench.py --config $c --steps 20 --warmup 3 --no-cpu-base
 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/r02_final_ref.json 2> gpurun_out/r02_final_ref.err; echo ref rc=$?
 python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-fasta-leg --no-strong-c4 > gpurun_out/r02_final_plain.log 2>&1 && ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r02_final_launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-fasta-leg --no-strong-c4 > gpurun_out/r02_final_ncu_launches.log 2>&1; echo ncu-launches rc=$?
 ncu --set full --clock-control none --import-source on -k regex:'k_cand1|k_scan_filtered|k_scan_plain|k_pick|k_aliveN|k_build_at|k_finish|k_id_records' --launch-skip 8 --launch-count 9 -o gpurun_out/r02_final_prof -f python tools/prof_one.py 2 > gpurun_out/r02_final_ncu_full.log 2>&1; echo ncu-full rc=$?
-ncu --set full --clock-control none --import-source on -k regex:'k_og_' --launch-skip 8 --launch-count 4 -o gpurun_out/r02_final_og_prof -f python tools/og_bench.py 10 5000000 50000 > gpurun_out/r02_final_ncu_og.log 2>&1; echo ncu-og rc=$?
+ncu --set full --clock-control none --import-source on -k regex:'k_og_' --launch-skip 7 --launch-count 5 -o gpurun_out/r02_final_og_prof -f python tools/og_bench.py 10 5000000 50000 > gpurun_out/r02_final_ncu_og.log 2>&1; echo ncu-og rc=$?
 ncu --set full --clock-control none --import-source on -k regex:'k_pp_' --launch-skip 9 --launch-count 9 -o gpurun_out/r02_final_pp_prof -f python tools/pp_bench.py 10 5000000 > gpurun_out/r02_final_ncu_pp.log 2>&1; echo ncu-pp rc=$?
 python - <<PY
 import json

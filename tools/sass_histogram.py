@@ -9,8 +9,9 @@ kern, hist = None, collections.OrderedDict()
 for line in txt.splitlines():
     m = re.search(r"Function : (\S+)", line)
     if m:
-        kern = subprocess.run(["c++filt", m.group(1)], capture_output=True, text=True).stdout.strip().split("(")[0]
-        hist[kern] = collections.Counter()
+        full = subprocess.run(["c++filt", m.group(1)], capture_output=True, text=True).stdout.strip()
+        kern = full.replace("(anonymous namespace)::", "").replace("void ", "").split("(")[0]
+        hist.setdefault(kern, collections.Counter())
         continue
     m = re.match(r"\s+/\*[0-9a-f]{4,}\*/\s+(?:@!?U?P\w+\s+)?([A-Z0-9_]+)", line)
     if m and kern:
