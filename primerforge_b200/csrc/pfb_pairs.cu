@@ -108,25 +108,43 @@ __global__ void __launch_bounds__(256) k_pp_jump(const __grid_constant__ Args a)
     a.jump[o + p] = j;
 }
 
-// the bin starts = the orbit of J from position 0; one CTA per genome, J staged through shared memory in tiles
-constexpr uint32_t ORBIT_TILE = 8192;
+// the bin starts = the orbit of J from position 0; one CTA per genome, J staged through shared memory in tiles.  Per tile
+// all threads build the powers J^2, J^4 .. J^32 (saturating at the tile end), ONE thread walks the tile in steps of J^32
+// (about ten dependent shared-memory loads instead of a few hundred), then all threads fill in the steps between its
+// anchors: for r = 4 .. 0 every marked position marks J^(2^r) of itself.
+constexpr uint32_t ORBIT_TILE = 4096, ORBIT_LEVELS = 6;
+constexpr uint32_t ORBIT_SMEM = ORBIT_LEVELS * ORBIT_TILE * 4u + ORBIT_TILE;
 __global__ void __launch_bounds__(1024) k_pp_orbit(const __grid_constant__ Args a) {
-    __shared__ uint32_t sJ[ORBIT_TILE];
-    __shared__ uint8_t sF[ORBIT_TILE];
+    extern __shared__ __align__(16) uint32_t orbit_smem[];
+    uint32_t *lv = orbit_smem;                                          // [LEVELS][TILE] absolute positions
+    uint8_t *sF = (uint8_t *)(orbit_smem + ORBIT_LEVELS * ORBIT_TILE);  // [TILE] 1 = a bin starts here
     __shared__ uint32_t sCur;
     const uint32_t g = blockIdx.x;
     const size_t o = (size_t)g * a.S, of = (size_t)g * (a.S + 1);
     if (threadIdx.x == 0) sCur = 0;
     for (uint32_t t0 = 0; t0 < a.S; t0 += ORBIT_TILE) {
-        const uint32_t n = min(ORBIT_TILE, a.S - t0);
-        for (uint32_t j = threadIdx.x; j < n; j += 1024) { sJ[j] = a.jump[o + t0 + j]; sF[j] = 0; }
+        const uint32_t n = min(ORBIT_TILE, a.S - t0), end = t0 + n;
+        for (uint32_t j = threadIdx.x; j < n; j += 1024) { lv[j] = a.jump[o + t0 + j]; sF[j] = 0; }
         __syncthreads();
+        for (uint32_t L = 1; L < ORBIT_LEVELS; L++) {
+            const uint32_t *src = lv + (L - 1) * ORBIT_TILE;
+            uint32_t *dst = lv + L * ORBIT_TILE;
+            for (uint32_t j = threadIdx.x; j < n; j += 1024) { const uint32_t x = src[j]; dst[j] = x < end ? src[x - t0] : x; }
+            __syncthreads();
+        }
         if (threadIdx.x == 0) {
+            const uint32_t *top = lv + (ORBIT_LEVELS - 1) * ORBIT_TILE;
             uint32_t cur = sCur;
-            while (cur < t0 + n) { sF[cur - t0] = 1; cur = sJ[cur - t0]; }
-            sCur = cur;
+            while (cur < end) { sF[cur - t0] = 1; cur = top[cur - t0]; }
+            sCur = cur;                                                 // (saturating powers: the exact first orbit position beyond the tile)
         }
         __syncthreads();
+        for (int L = (int)ORBIT_LEVELS - 2; L >= 0; L--) {
+            const uint32_t *src = lv + L * ORBIT_TILE;
+            for (uint32_t j = threadIdx.x; j < n; j += 1024)
+                if (sF[j]) { const uint32_t y = src[j]; if (y < end) sF[y - t0] = 1; }      // (a mark seen early only marks further orbit positions)
+            __syncthreads();
+        }
         for (uint32_t j = threadIdx.x; j < n; j += 1024) a.isStart[of + t0 + j] = sF[j];
         __syncthreads();
     }
@@ -409,7 +427,7 @@ int run(pfb_pp *o, const pfb_pp_params &prm) {
     k_pp_scatter<<<gridSG, 256, 0, o->stream>>>(a);
     k_pp_contig_first<<<gridSG, 256, 0, o->stream>>>(a);
     k_pp_jump<<<gridSG, 256, 0, o->stream>>>(a);
-    k_pp_orbit<<<G, 1024, 0, o->stream>>>(a);
+    k_pp_orbit<<<G, 1024, ORBIT_SMEM, o->stream>>>(a);
     o->nLaunches += 4;
     for (uint32_t g = 0; g < G; g++) {
         devscan::exscan(a.isStart + (size_t)g * (S + 1), (uint32_t)S, a.binIdx + (size_t)g * (S + 1), (uint32_t *)o->tiles.p,
@@ -488,6 +506,10 @@ int pfb_pp_create(pfb_pp **out, int device) {
     }
     for (auto &e : ctx->ev)
         if (cudaEventCreate(&e) != cudaSuccess) { delete ctx; return pp::fail(nullptr, PFB_ECUDA, "cudaEventCreate failed"); }
+    if (cudaFuncSetAttribute(pp::k_pp_orbit, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pp::ORBIT_SMEM) != cudaSuccess) {
+        delete ctx;
+        return pp::fail(nullptr, PFB_ECUDA, "this device cannot give a CTA 100 KB of shared memory");
+    }
     *out = ctx;
     return PFB_OK;
 }
