@@ -6,7 +6,7 @@ from types import SimpleNamespace
 import numpy as np
 import pytest
 
-from tests.util import expected_products, load_pp, pp_cases
+from tests.util import expected_products, load_pp, pp_cases, synthetic_candidates as _synthetic
 
 pytestmark = pytest.mark.gpu
 
@@ -39,65 +39,6 @@ def test_equals_reference(name):
     kept = res.kept
     assert np.array_equal(pairs[kept, 0], f.pair_fwd) and np.array_equal(pairs[kept, 1], f.pair_rev)      # the dict's keys, in order
     assert np.array_equal(expected_products(f, pairs, shared, kept), f.products)                          # every Product field
-
-
-def _synthetic(seed, S, L, G, kmin=16, kmax=20, n_contigs=3, nested=0.3):
-    """S candidates on a random genome of L bases (many nested: same start or same end, other length), placed in G
-    genomes whose blocks are shuffled, flipped and dealt to contigs"""
-    rng = np.random.default_rng(seed)
-    code = rng.integers(0, 4, L).astype(np.uint64)
-    starts, ks = [], []
-    while len(starts) < S:
-        a = int(rng.integers(0, L - kmax)); k = int(rng.integers(kmin, kmax + 1))
-        starts.append(a); ks.append(k)
-        if rng.random() < nested and k < kmax:                       # a longer one that contains it
-            k2 = int(rng.integers(k + 1, kmax + 1))
-            a2 = a if rng.random() < 0.5 else max(0, a + k - k2)
-            starts.append(a2); ks.append(k2)
-    # distinct (start, k) -> distinct strings with overwhelming probability; drop duplicates of the string
-    seen, cand = set(), []
-    for a, k in zip(starts, ks):
-        w = 0
-        for c in code[a:a + k].tolist():
-            w = (w << 2) | c
-        if (w, k) not in seen:
-            seen.add((w, k)); cand.append((a, k, w))
-    cand = cand[:S]
-    S = len(cand)
-    start = np.array([c[0] for c in cand], dtype=np.int64); k = np.array([c[1] for c in cand], dtype=np.uint8)
-    word = np.array([c[2] for c in cand], dtype=np.uint64)
-    tm = np.round(rng.uniform(55.0, 62.0, S), 3)
-    genomes = []
-    for g in range(G):
-        if g == 0:
-            contig = np.minimum(start * n_contigs // L, n_contigs - 1)
-            left, strand = start.copy(), np.zeros(S, dtype=np.uint8)
-            bounds = np.array([c * L // n_contigs for c in range(n_contigs)], dtype=np.int64)
-            left = left - bounds[contig]
-            # a candidate must not straddle a contig boundary: those that would are put at the end of their contig
-        else:
-            nblk = 12
-            cuts = np.sort(rng.choice(np.arange(100, L - 100), nblk - 1, replace=False))
-            edges = np.r_[0, cuts, L]
-            order = rng.permutation(nblk); flip = rng.random(nblk) < 0.4
-            blk = np.searchsorted(edges, start, side="right") - 1
-            # candidates that straddle a block edge keep their block's transform (coordinates may overlap the next block: harmless)
-            new_off = np.zeros(nblk, dtype=np.int64); acc = 0
-            for b in order:
-                new_off[b] = acc; acc += edges[b + 1] - edges[b]
-            rel = start - edges[blk]
-            blen = edges[blk + 1] - edges[blk]
-            left = np.where(flip[blk], new_off[blk] + blen - rel - k, new_off[blk] + rel)
-            left = np.maximum(left, 0)
-            strand = flip[blk].astype(np.uint8)
-            contig = np.minimum(left * n_contigs // L, n_contigs - 1)
-            bounds = np.array([c * L // n_contigs for c in range(n_contigs)], dtype=np.int64)
-            left = np.maximum(left - bounds[contig], 0)
-        # the genome's lists: per contig sorted by leftmost start; ties in a seeded random order (the reference's is arbitrary)
-        tie = rng.permutation(S)
-        order_p = np.lexsort((tie, left, contig))
-        genomes.append((order_p.astype(np.uint32), contig[order_p].astype(np.uint32), left[order_p].astype(np.uint32), strand[order_p]))
-    return word, k, tm, genomes
 
 
 @pytest.mark.parametrize("seed,S,L,G,kw", [
