@@ -150,3 +150,34 @@ def test_outgroup_oracle_equals_the_live_reference(seed, capsys):
     for g, gen in enumerate(outs):
         gone = int(np.count_nonzero(o.removed_at == g)); remaining -= gone
         assert lines[g] == f"removed {gone} pairs after processing {gen.name} ({remaining} pairs remaining)"
+
+
+@pytest.mark.parametrize("seed,table,kw", [
+    (31, 9999991, dict()),
+    (32, 40009, dict(n_contigs=5)),                                   # small sketch: collisions and junction pollution
+    (33, 65521, dict(n_contigs=3, n_frac=0.002)),                      # N bases
+])
+def test_candidate_stage_oracle_equals_the_live_reference(seed, table, kw, tmp_path, monkeypatch):
+    """oracle/pf_oracle.c against bin/getCandidateKmers.py on genomes no fixture holds: the shared k-mer dict (keys, order,
+    coordinates, strands) and the candidate sets"""
+    from oracle.run_reference import run_reference
+    from primerforge_b200 import synth
+    from tests.util import candidate_set_from_arrays
+    gens = synth.make_genomes(3, 9000, seed=seed, snp_rate=0.003, n_inversions=2, **kw)
+    paths = synth.write_fasta(gens, str(tmp_path))
+    if table != 9999991:
+        monkeypatch.setenv("PF_STANDIN_TABLE", str(table))
+    else:
+        monkeypatch.delenv("PF_STANDIN_TABLE", raising=False)
+    shared, cands = run_reference(paths, thal_mode="pass")
+    o = po.run(gens, po.default_params(table_size=table))
+    kmers = o.kmer_strings()
+    assert kmers == list(shared.keys()) and len(kmers) > 100
+    for gi, gen in enumerate(gens):
+        cidx = {c: i for i, c in enumerate(gen.contig_ids)}
+        assert [cidx[shared[s][gen.name][0]] for s in kmers] == o.contig[gi].tolist()
+        assert [shared[s][gen.name][1] for s in kmers] == o.start[gi].tolist()
+        assert [int(shared[s][gen.name][2] == "-") for s in kmers] == o.strand[gi].tolist()
+        mine = candidate_set_from_arrays(kmers, o.k, (o.flags & 8) != 0, o.contig[gi], o.start[gi], o.strand[gi])
+        theirs = {(str(p.seq), cidx[c], p.start, p.end, int(p.strand == "-")) for c, lst in cands[gen.name].items() for p in lst}
+        assert mine == theirs
