@@ -206,52 +206,69 @@ __global__ void __launch_bounds__(128) k_pp_reduce(const __grid_constant__ Args 
     a.binFirst[b] = first; a.binLast[b] = last;
 }
 
-// __getBinPairs (:101-143) + the generator of __getCandidatePrimerPairs (:283-341) for the bins b2 > b1 of one first bin
+// __getBinPairs (:101-143) + the generator of __getCandidatePrimerPairs (:283-341): one WARP per first bin b1, one lane per
+// second bin b2 > b1 (32 at a time).  The reference leaves the inner loop at the first b2 whose smallest possible product
+// is too large (:134; that bound only grows with b2) or at the end of the contig: the lanes from the first such b2 on
+// are dropped.  A ballot of the lanes that found a pair gives every pair its place in the reference's order.
 template <bool EMIT>
-__global__ void __launch_bounds__(128) k_pp_pairs(const __grid_constant__ Args a) {
-    const uint32_t b1 = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b1 >= a.nb) return;
-    const uint32_t c = a.gcontig[a.binPos[b1]];
+__global__ void __launch_bounds__(256) k_pp_pairs(const __grid_constant__ Args a) {
+    const uint32_t b1 = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31u;
+    if (b1 >= a.nb) return;                                                // (warp-uniform)
+    const uint32_t p0 = a.binPos[b1], p1 = a.binPos[b1 + 1];
+    const uint32_t c = a.gcontig[p0];
     const uint32_t f0 = a.binFirst[b1], fl = a.binLast[b1];
     const int64_t b1_first_start = a.gleft[f0];
     const int64_t b1_last_end = (int64_t)a.gleft[fl] + a.k[a.gid[fl]] - 1;
     uint32_t n = 0;
     uint32_t out = EMIT ? a.pairOff[b1] : 0u;
-    for (uint32_t b2 = b1 + 1; b2 < a.nb; b2++) {
-        const uint32_t q0 = a.binPos[b2], q1 = a.binPos[b2 + 1];
-        if (a.gcontig[q0] != c) break;
-        const uint32_t s0 = a.binFirst[b2], sl = a.binLast[b2];
-        const int64_t smallest = ((int64_t)a.gleft[s0] + a.minPrimerLen) - (b1_last_end - a.minPrimerLen);     // :128
-        const int64_t largest = ((int64_t)a.gleft[sl] + a.k[a.gid[sl]] - 1) - b1_first_start;                  // :131
-        if (smallest > a.maxPcr) break;                                                                        // :134
-        if (largest < a.minPcr) continue;                                                                      // :138
-        bool found = false;
-        for (uint32_t p = a.binPos[b1]; p < a.binPos[b1 + 1] && !found; p++) {
-            if (!a.alive[p]) continue;
-            const uint32_t f = a.gid[p];
-            if (!(a.word[f] & 2ull)) continue;                             // fwd.seq[-1] in {G, C} (:271-272)
-            const int64_t fs = a.gleft[p];
-            const double ftm = a.tm[f];
-            for (uint32_t q = q0; q < q1; q++) {
-                if (!a.alive[q]) continue;
-                const uint32_t r = a.gid[q];
-                const int kr = a.k[r];
-                if (!((a.word[r] >> (2 * (kr - 1))) & 2ull)) continue;     // rev.seq[0] in {G, C} (:273-274)
-                const int64_t pcr = ((int64_t)a.gleft[q] + kr - 1) - fs + 1;                                   // :221
-                if (pcr < a.minPcr || pcr > a.maxPcr) continue;                                                // :224
-                if (!(fabs(ftm - a.tm[r]) <= a.maxTmDiff)) continue;                                           // :227
-                if (EMIT) {
-                    a.pairsA[out] = make_uint4(f, r, c, (uint32_t)pcr);
-                    a.pairsB[out] = make_uint2(a.binOf[f], a.binOf[r]);
-                    out++;
+    for (uint32_t base = b1 + 1; base < a.nb; base += 32) {
+        const uint32_t b2 = base + lane;
+        bool stop = b2 >= a.nb, found = false;
+        uint32_t pf = 0, pr = 0, ppcr = 0;
+        if (!stop) {
+            const uint32_t q0 = a.binPos[b2], q1 = a.binPos[b2 + 1];
+            if (a.gcontig[q0] != c) stop = true;
+            else {
+                const uint32_t s0 = a.binFirst[b2], sl = a.binLast[b2];
+                const int64_t smallest = ((int64_t)a.gleft[s0] + a.minPrimerLen) - (b1_last_end - a.minPrimerLen);     // :128
+                const int64_t largest = ((int64_t)a.gleft[sl] + a.k[a.gid[sl]] - 1) - b1_first_start;                  // :131
+                if (smallest > a.maxPcr) stop = true;                                                                  // :134
+                else if (largest >= a.minPcr) {                                                                        // :138
+                    for (uint32_t p = p0; p < p1 && !found; p++) {
+                        if (!a.alive[p]) continue;
+                        const uint32_t f = a.gid[p];
+                        if (!(a.word[f] & 2ull)) continue;                             // fwd.seq[-1] in {G, C} (:271-272)
+                        const int64_t fs = a.gleft[p];
+                        const double ftm = a.tm[f];
+                        for (uint32_t q = q0; q < q1; q++) {
+                            if (!a.alive[q]) continue;
+                            const uint32_t r = a.gid[q];
+                            const int kr = a.k[r];
+                            if (!((a.word[r] >> (2 * (kr - 1))) & 2ull)) continue;     // rev.seq[0] in {G, C} (:273-274)
+                            const int64_t pcr = ((int64_t)a.gleft[q] + kr - 1) - fs + 1;                               // :221
+                            if (pcr < a.minPcr || pcr > a.maxPcr) continue;                                            // :224
+                            if (!(fabs(ftm - a.tm[r]) <= a.maxTmDiff)) continue;                                       // :227
+                            pf = f; pr = r; ppcr = (uint32_t)pcr;
+                            found = true;
+                            break;
+                        }
+                    }
                 }
-                n++;
-                found = true;
-                break;
             }
         }
+        const uint32_t stopMask = __ballot_sync(0xFFFFFFFFu, stop);
+        const uint32_t valid = stopMask ? ((1u << (__ffs(stopMask) - 1)) - 1u) : 0xFFFFFFFFu;     // the lanes before the first stop
+        const uint32_t fmask = __ballot_sync(0xFFFFFFFFu, found) & valid;
+        if (EMIT && ((fmask >> lane) & 1u)) {
+            const uint32_t at = out + __popc(fmask & ((1u << lane) - 1u));
+            a.pairsA[at] = make_uint4(pf, pr, c, ppcr);
+            a.pairsB[at] = make_uint2(a.binOf[pf], a.binOf[pr]);
+        }
+        n += __popc(fmask);
+        out += __popc(fmask);
+        if (stopMask) break;
     }
-    if (!EMIT) a.pairCount[b1] = n;
+    if (!EMIT && lane == 0) a.pairCount[b1] = n;
 }
 
 // __getAllSharedPrimerPairs (:367-464), one thread per (pair, genome): the product length, or "no Product here".  The bin
@@ -444,7 +461,7 @@ int run(pfb_pp *o, const pfb_pp_params &prm) {
     PPCK(cudaEventRecord(o->ev[1], o->stream));
     // first genome: reduction, bin pairs, the first suitable primer pair of each
     k_pp_reduce<<<(a.nb + 127) / 128, 128, 0, o->stream>>>(a);
-    k_pp_pairs<false><<<(a.nb + 127) / 128, 128, 0, o->stream>>>(a);
+    k_pp_pairs<false><<<(a.nb + 7) / 8, 256, 0, o->stream>>>(a);
     devscan::exscan(a.pairCount, a.nb, a.pairOff, (uint32_t *)o->tiles.p, a.cnt + 1, o->stream);
     o->nLaunches += 5;
     PPCK(cudaMemcpyAsync(cnt, o->cnt.p, 32, cudaMemcpyDeviceToHost, o->stream));
@@ -456,7 +473,7 @@ int run(pfb_pp *o, const pfb_pp_params &prm) {
     if ((rc = ensure(o, o->kept, nPairs + 16)) != PFB_OK) return rc;
     if ((rc = ensure_pinned(o, nPairs, G)) != PFB_OK) return rc;
     a.pairsA = (uint4 *)o->pairsA.p; a.pairsB = (uint2 *)o->pairsB.p; a.shared = (uint32_t *)o->shared.p; a.kept = (uint8_t *)o->kept.p;
-    k_pp_pairs<true><<<(a.nb + 127) / 128, 128, 0, o->stream>>>(a);
+    k_pp_pairs<true><<<(a.nb + 7) / 8, 256, 0, o->stream>>>(a);
     o->nLaunches++;
     PPCK(cudaEventRecord(o->ev[2], o->stream));
     if (nPairs) {
