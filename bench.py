@@ -719,10 +719,11 @@ def main():
     achieved = alg_bytes / (ms_scan / 1e3) / 1e9 if ms_scan > 0 else 0.0
     nk = cfg["k_max"] - cfg["k_min"] + 1
     windows = scan_bases * nk
-    traffic, traffic_src = None, None
+    traffic, traffic_src, stored = None, None, {}
     try:
         with open(next(p for p in (os.path.join(ROOT, "profiles", n) for n in ("r02_scan_traffic.json", "r01_scan_traffic.json")) if os.path.exists(p))) as fh:
             tj = json.load(fh)
+        stored = tj
         if args.config == 2 and world == 1 and not args.genomes and not args.length:
             traffic, traffic_src = tj["dram_bytes_total"], tj["source"] + " -- a STORED figure of that capture, not measured in this run"
     except Exception:
@@ -738,7 +739,11 @@ def main():
                 "actual_limiter": {"kind": "instruction issue / INT32 ALU pipe (hash + filter + queue append per window); the kernel's DRAM traffic is "
                                            "~10 % of the modelled bytes, i.e. ~10 % of HBM peak: HBM is not the binding roof",
                                    "windows_per_s_G": windows / (ms_scan / 1e3) / 1e9 if ms_scan > 0 else 0.0,
-                                   "evidence": "profiles/ (ncu summary, SASS opcode histogram, ablations)"}}
+                                   "windows_per_clock_per_sm": windows / (ms_scan / 1e3) / 148 / ((clocks or {}).get("sm_mhz") or 1965.0) / 1e6 if ms_scan > 0 else 0.0,
+                                   "stored_ncu_capture": {"issue_active_pct": stored.get("issue_active_pct"), "alu_pipe_pct": stored.get("alu_pipe_pct"),
+                                                          "thread_instructions_per_window": (stored["warp_instructions"] * 32 / 225e6) if stored.get("warp_instructions") else None,
+                                                          "source": stored.get("source")},
+                                   "evidence": "profiles/README.md (ncu summaries, SASS opcode histogram), profiles/r01_scan_ablation.md"}}
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": step_ms, "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": "u64",
             "data": "synthetic", "config": workload_config(args.config, world, strong) | ({"genomes_per_gpu": per_rank, "genome_bp": cfg["length"]}),
