@@ -313,7 +313,7 @@ int  pfb_pp_clear_genomes(pfb_pp *pp);
 int  pfb_pp_run(pfb_pp *pp, const pfb_pp_params *params);
 int  pfb_pp_counts(pfb_pp *pp, uint64_t *n_pairs, uint64_t *n_kept, uint64_t *n_bins);   /* kept = valid in every genome (:459-462) */
 int  pfb_pp_pairs(pfb_pp *pp, pfb_pp_pair *out, uint64_t cap);
-/* out[pair * n_genomes + genome] (genome 0 = the first genome) = PFB_PP_VALID | product size (:455-463), or 0 when the
+/* out[genome * n_pairs + pair] (genome 0 = the first genome) = PFB_PP_VALID | product size (:455-463), or 0 when the
  * pair has no Product there (other contig / other strand / size out of range).  The Product's bin numbers (:501-502) are
  * pfb_pp_bins(genome)[fwd] and [rev]. */
 int  pfb_pp_shared(pfb_pp *pp, uint32_t *out, uint64_t cap);

@@ -55,7 +55,7 @@ struct Args {
     uint32_t *pairCount, *pairOff; // [nb + 1] pairs contributed by every first bin; exclusive scan
     uint4 *pairsA;                 // [nPairs] {fwd id, rev id, contig, pcrLen}
     uint2 *pairsB;                 // [nPairs] {fbin, rbin}
-    uint32_t *shared;              // [nPairs][G] product length | 1 << 31 when the pair has a Product in that genome
+    uint32_t *shared;              // [G][nPairs] product length | 1 << 31 when the pair has a Product in that genome
     uint8_t *kept;                 // [nPairs] 1 = a Product in every genome
     uint32_t *cnt;                 // [0] bins of the first genome, [1] pairs, [2] error flags, [4] kept pairs
     uint32_t nb, pairCap;
@@ -303,7 +303,7 @@ __global__ void __launch_bounds__(256) k_pp_shared(const __grid_constant__ Args 
             }
         }
     }
-    a.shared[(size_t)q * a.G + g] = o;
+    a.shared[(size_t)g * nPairs + q] = o;             // genome-major: the threads of a warp write neighbouring words
 }
 
 // pairs with a Product in every genome (:459-462)
@@ -311,7 +311,7 @@ __global__ void __launch_bounds__(256) k_pp_kept(const __grid_constant__ Args a,
     const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= nPairs) return;
     uint32_t all = PP_VALID;
-    for (uint32_t g = 0; g < a.G; g++) all &= a.shared[(size_t)q * a.G + g];
+    for (uint32_t g = 0; g < a.G; g++) all &= a.shared[(size_t)g * nPairs + q];
     a.kept[q] = all ? 1 : 0;
     const uint32_t m = __ballot_sync(__activemask(), all != 0u);
     if ((threadIdx.x & 31u) == (uint32_t)(__ffs(__activemask()) - 1)) atomicAdd(&a.cnt[4], (uint32_t)__popc(m));

@@ -123,13 +123,14 @@ class PairSearch:
         self._ck(self._lib.pfb_pp_counts(self._h, C.byref(n), C.byref(kept_n), C.byref(nb)))
         G = self.n_genomes
         pairs = np.empty(n.value, dtype=_lib.PP_PAIR_DTYPE)
-        shared = np.zeros((n.value, G), dtype=np.uint32)
+        shared = np.zeros((G, n.value), dtype=np.uint32)          # genome-major, as the library keeps it
         kept = np.zeros(n.value, dtype=np.uint8)
         self._ck(self._lib.pfb_pp_pairs(self._h, pairs.ctypes.data, pairs.size))
         if G and n.value:
             self._ck(self._lib.pfb_pp_shared(self._h, shared.ctypes.data, shared.size))
             self._ck(self._lib.pfb_pp_kept(self._h, kept.ctypes.data, kept.size))
         bins = [self.bins(g) for g in range(G)] if self.n_candidates else [np.zeros(0, np.uint32) for _ in range(G)]
+        shared = shared.T                                          # views [n, G]
         return PairResult(pairs=pairs, valid=(shared & np.uint32(_lib.PP_VALID)) != 0, length=shared & np.uint32(0x7FFFFFFF),
                           kept=kept.astype(bool), bin_of=bins, timing=self.timing())
 
