@@ -15,20 +15,25 @@
 //     perfect hash of the key set: a bitmap over bins + popcount ranks gives a dense slot id
 //     (k_candbits, k_scan_p*) -- this replaces the string sets and the Aho-Corasick
 //     automaton;
-//   * every genome, the first included, is then ONE pass (k_scan_filtered / k_scan_plain):
+//   * every genome, the first included, is then ONE pass (k_scan_filtered2 / k_scan_filtered / k_scan_plain):
 //     window -> bin -> key-table probe; a window landing in a key's bin adds (1 << 32 | start) to the
 //     (genome, key) row with a fire-and-forget RED; windows touching a '~' junction or a non-ACGT byte
 //     pollute only one strand's table (two flag bits; k_junction).  After the pass "count == 1" is khmer's
 //     get() == 1 and the single occupant is read back and compared with the key (k_alive1 / k_aliveN): a
 //     key is shared iff every genome has exactly one occurrence and a clean bin in the strand table the
 //     reference would have read.  The probe goes through a per-k Bloom-style filter held in shared memory
-//     (192 KB per CTA) so that only ~1 in 5 windows reaches L2;
+//     (179 KB per CTA, bulk-copied per length: pfb_bulk.cuh) so that only ~1 in 5 windows reaches L2;
 //   * genome 1 is scanned first; its survivors get ids in the reference's dict order (genome-1 end
 //     position ascending, longest first) and everything downstream -- rows of the other genomes, verdicts,
 //     records, coordinates -- is indexed by id and streams through memory (k_alive1,
-//     k_build_at, k_aliveN, k_emit_write); filters are evaluated in fp64 with the reference's operation
+//     k_build_at, k_aliveN, k_id_records); filters are evaluated in fp64 with the reference's operation
 //     order, the per-position "first k-mer that passes" pick looks only at the few records that can share
-//     a position (k_positions);
+//     a position (k_pick); the end of a run is one launch (k_finish);
+//   * no step waits for the host: capacities are known to the host, counts stay on the device; results stream to
+//     pinned host memory while the run goes on;
+//   * more than one GPU: genomes are dealt out, genome 1's own pipeline is shared out by position, and what the ranks
+//     exchange (candidate lists, packed rows, alive / pick bytes) is read from the peers' memory over NVLink, or
+//     goes through NCCL;
 //   * FASTA files can be handed over as they are: records and sequence lines are found on the device
 //     (pfb_fasta.cuh).
 //
