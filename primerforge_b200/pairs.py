@@ -191,7 +191,6 @@ def _dimer_provider(params, dimer):
 
 def _getPrimerPairs(candidateKmers, params, dimer=None, device: int | None = None):
     """drop-in for bin/getPrimerPairs.py:505 (same arguments and return value)"""
-    Product = _product_class()
     device = int(os.environ.get("PFB200_DEVICE", "0")) if device is None else device
     first_name = os.path.basename(params.ingroupFns[0])                                   # :523
     word, k, tm, names, per_genome, first_lists = _columns(candidateKmers, first_name)
@@ -202,7 +201,15 @@ def _getPrimerPairs(candidateKmers, params, dimer=None, device: int | None = Non
         ps.run(max_bin=params.maxBinSize, min_primer_len=params.minLen, min_pcr=params.minPcr, max_pcr=params.maxPcr,
                max_tm_diff=params.maxTmDiff)
         res = ps.result()
+    contig_names = [list(candidateKmers[n].keys()) for n in names]
+    return build_pairs_output(res, k, names, per_genome, first_lists, contig_names, params, _dimer_provider(params, dimer))
 
+
+def build_pairs_output(res: PairResult, k, names, per_genome, first_lists, contig_names, params, dimer_fn) -> dict:
+    """the host half of the drop-in: primer3's heterodimer check on the proposed pairs and the reference's return value
+    ``dict[(Primer, Primer)] -> dict[genome] -> Product`` from a PairResult and the candidate columns (no GPU involved: the
+    CPU tests run it on the oracle's result)"""
+    Product = _product_class()
     # the first genome's Primer objects of the proposed pairs (list position -> object)
     ids0 = per_genome[0][0]
     pos_of = np.empty(ids0.size, dtype=np.int64)
@@ -215,7 +222,6 @@ def _getPrimerPairs(candidateKmers, params, dimer=None, device: int | None = Non
         return first_lists[ci][p - int(offs[ci])]
 
     # heterodimer check on the proposed pairs (:146-178, 330-341): each is judged on its own
-    dimer_fn = _dimer_provider(params, dimer)
     accepted = []
     for q in range(res.pairs.size):
         f, r = int(res.pairs["fwd"][q]), int(res.pairs["rev"][q])
@@ -240,7 +246,6 @@ def _getPrimerPairs(candidateKmers, params, dimer=None, device: int | None = Non
         c_of = np.empty(ids.size, dtype=np.int64); l_of = np.empty(ids.size, dtype=np.int64); s_of = np.empty(ids.size, dtype=np.int64)
         c_of[ids] = ct; l_of[ids] = lf; s_of[ids] = st
         place.append((c_of, l_of, s_of))
-    contig_names = [list(candidateKmers[n].keys()) for n in names]
     kk = np.asarray(k, dtype=np.int64)
     for q, fwd, rev, dimer_tm in accepted:
         if not kept[q]:

@@ -77,3 +77,61 @@ def test_reduce_bin_size_skips_the_element_after_a_removed_one():
     assert o.bin_of[0].tolist() == [0, 0, 0, 0]
     # list order of the 16-mers within the bin is [start 0, start 1, start 2] -> the one at start 1 survives
     assert o.reduced.tolist() == [1, 0, 1, 0]
+
+
+class _P:
+    """a stand-in for bin.Primer.Primer with what the pair search reads"""
+    def __init__(self, seq, contig, left, k, minus, tm):
+        self.seq, self.contig, self.strand, self.Tm = seq, contig, "-" if minus else "+", tm
+        self.start, self.end = (left + k - 1, left) if minus else (left, left + k - 1)
+        self.k = k
+
+    def __str__(self):
+        return self.seq
+
+    def reverseComplement(self):
+        rc = self.seq[::-1].translate(str.maketrans("ACGT", "TGCA"))
+        return _P(rc, self.contig, min(self.start, self.end), self.k, self.strand == "+", self.Tm)
+
+
+@pytest.mark.parametrize("name", ["pp_contigs", "pp_widek", "pp_tightbins"])
+def test_host_half_of_the_drop_in_builds_the_reference_products(name):
+    """build_pairs_output on the ORACLE's pair-search result (no GPU): the reference's pairs, in order, with every Product
+    field -- the same check tests/test_gpu_pairs.py makes with the CUDA result"""
+    from types import SimpleNamespace
+    from primerforge_b200 import _lib
+    from primerforge_b200.pairs import ERR_NO_PAIRS, PairResult, build_pairs_output
+    from tests.util import load_pp
+    f = load_pp(name)
+    cands = {}
+    for g, nm in enumerate(f.names):
+        gid, gct, glf, gst = f.genomes[g]
+        per = {}
+        for p in range(gid.size):
+            s = int(gid[p])
+            per.setdefault(f.contig_names[g][int(gct[p])], []).append(_P(f.cand[s], f.contig_names[g][int(gct[p])], int(glf[p]), int(f.k[s]), bool(gst[p]), float(f.tm[s])))
+        cands[nm] = per
+    word, k, tm, names, per_genome, first_lists = _columns(cands, f.names[0])
+    o = po.run_pairs(word, k, tm, per_genome, max_bin=f.max_bin, min_primer_len=f.min_len, min_pcr=f.min_pcr, max_pcr=f.max_pcr,
+                     max_tm_diff=f.max_tm_diff)
+    pairs = np.zeros(o.pairs.shape[0], dtype=_lib.PP_PAIR_DTYPE)
+    for j, nm in enumerate(("fwd", "rev", "contig", "fbin", "rbin", "pcr_len")):
+        pairs[nm] = o.pairs[:, j]
+    res = PairResult(pairs=pairs, valid=o.shared[:, :, 0] != 0, length=o.shared[:, :, 1], kept=o.kept, bin_of=list(o.bin_of), timing={})
+    assert np.array_equal(res.shared4(), o.shared)
+    log = SimpleNamespace(rename=lambda *a: None, info=lambda *a: None, debug=lambda *a: None, error=lambda *a: None)
+    prm = SimpleNamespace(tempTolerance=5.0, log=log)
+    contig_names = [list(cands[n].keys()) for n in names]
+    out = build_pairs_output(res, k, names, per_genome, first_lists, contig_names, prm, None)
+    rc = str.maketrans("ACGT", "TGCA")
+    assert [(str(a), str(b)) for a, b in out] == [(f.cand[int(x)], f.cand[int(y)][::-1].translate(rc)) for x, y in zip(f.pair_fwd, f.pair_rev)]
+    for row, per in enumerate(out.values()):
+        for g, nm in enumerate(f.names):
+            pr = per[nm]
+            got = (f.contig_names[g].index(pr.contig), pr.size, pr.fbin, pr.rbin, pr.fStart, pr.fEnd, int(pr.fStrand == "-"), pr.rStart,
+                   pr.rEnd, int(pr.rStrand == "-"))
+            assert got == tuple(int(x) for x in f.products[row, g]) and pr.dimerTm == 0.0
+    with pytest.raises(RuntimeError, match=ERR_NO_PAIRS):
+        build_pairs_output(res, k, names, per_genome, first_lists, contig_names, prm, lambda a, b: 99.0)
+    some = build_pairs_output(res, k, names, per_genome, first_lists, contig_names, prm, lambda a, b: 99.0 if a[0] == "A" else -10.0)
+    assert 0 < len(some) < len(out) and all(str(a)[0] != "A" for a, _ in some)
