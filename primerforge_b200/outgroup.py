@@ -197,12 +197,9 @@ def _product_class():
 
 def _removeOutgroupPrimers(outgroup, pairs, params, device: int = 0) -> None:
     """drop-in for bin/removeOutgroupPrimers.py:181 (same arguments; ``pairs`` is modified in place)"""
-    Product = _product_class()
     gap = " " * 4
     msg_1 = "removing primer pairs present in the outgroup sequences"
     msg_2 = f"{gap}getting outgroup PCR products"
-    msg_3 = f"{gap}filtering primer pairs"
-    msg_4 = f"{gap}processing outgroup results"
     clock = _Clock()
     log = params.log
     log.rename(_removeOutgroupPrimers.__name__)
@@ -228,6 +225,18 @@ def _removeOutgroupPrimers(outgroup, pairs, params, device: int = 0) -> None:
         res = scr.result(with_hits=False)
     clock.printDone()
     log.info(f"done {clock.getTimeString()}")
+    apply_outgroup_result(res, pairs, pair_list, names, contig_ids, params, clock)
+
+
+def apply_outgroup_result(res: OutgroupResult, pairs, pair_list, names, contig_ids, params, clock=None) -> None:
+    """the host half of the drop-in (no GPU involved: the CPU tests run it on the oracle's result): the deletions of
+    :281-287 with the debug lines of :240-247, 294, the error of :299-303, and __processOutgroupResults (:125-178)"""
+    Product = _product_class()
+    clock = clock or _Clock()
+    log = params.log
+    gap = " " * 4
+    msg_3 = f"{gap}filtering primer pairs"
+    msg_4 = f"{gap}processing outgroup results"
     clock.printStart(msg_3)
     log.info(msg_3)
 
@@ -248,7 +257,7 @@ def _removeOutgroupPrimers(outgroup, pairs, params, device: int = 0) -> None:
     log.info(msg_4)
     clock.printStart(msg_4)
     # __processOutgroupResults (:125-178): one Product per kept pair and outgroup genome
-    ingroup_name = next(n for v in pairs.values() for n in v.keys() if n not in outgroup)
+    ingroup_name = next(n for v in pairs.values() for n in v.keys() if n not in names)
     prod = res.products
     by_pair = {}
     if prod.size:

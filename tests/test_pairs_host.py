@@ -135,3 +135,55 @@ def test_host_half_of_the_drop_in_builds_the_reference_products(name):
         build_pairs_output(res, k, names, per_genome, first_lists, contig_names, prm, lambda a, b: 99.0)
     some = build_pairs_output(res, k, names, per_genome, first_lists, contig_names, prm, lambda a, b: 99.0 if a[0] == "A" else -10.0)
     assert 0 < len(some) < len(out) and all(str(a)[0] != "A" for a, _ in some)
+
+
+@pytest.mark.parametrize("name", ["og_multi", "og_widek", "og_allgone"])
+def test_host_half_of_the_outgroup_drop_in(name, capsys):
+    """apply_outgroup_result on the ORACLE's result (no GPU): the reference's deletions, debug lines, error and Products"""
+    from types import SimpleNamespace
+    from primerforge_b200 import _lib
+    from primerforge_b200.outgroup import ERR_ALL_IN_OUTGROUP, OutgroupResult, apply_outgroup_result
+    from tests.util import load_og
+    g = load_og(name)
+    o = po.run_outgroup(g.keys, g.pair_fwd, g.pair_rev, g.bad_lo, g.bad_hi, g.genomes)
+    prod = np.zeros(o.products.shape[0], dtype=_lib.OG_PRODUCT_DTYPE)
+    for j, nm in enumerate(("pair", "genome", "contig", "size")):
+        prod[nm] = o.products[:, j]
+    res = OutgroupResult(removed_at=o.removed_at, products=prod, hits=np.zeros(0, dtype=_lib.OG_HIT_DTYPE), timing={})
+
+    class P:
+        def __init__(self, s):
+            self.s = s
+
+        def __str__(self):
+            return self.s
+    pair_keys = [(P(f), P(r)) for f, r in zip(g.fwd, g.rev)]
+    pairs = {pk: {"ingroup_000.fasta": SimpleNamespace(dimerTm=7.25)} for pk in pair_keys}
+    lines = []
+    log = SimpleNamespace(rename=lambda *a: None, info=lambda *a: None, error=lambda *a: None, debug=lines.append)
+    params = SimpleNamespace(log=log)
+    contig_ids = [gen.contig_ids for gen in g.genomes]
+    if g.error:
+        with pytest.raises(RuntimeError, match=ERR_ALL_IN_OUTGROUP):
+            apply_outgroup_result(res, pairs, pair_keys, g.names, contig_ids, params)
+        assert not pairs
+        return
+    apply_outgroup_result(res, pairs, pair_keys, g.names, contig_ids, params)
+    assert "filtering primer pairs" in capsys.readouterr().out
+    assert list(pairs.keys()) == [pk for pk, keep in zip(pair_keys, g.kept) if keep] and lines == g.debug
+    want = {}
+    for pi, gi, c, size in g.products.tolist():
+        want.setdefault((pi, gi), []).append((g.genomes[gi].contig_ids[c], size))
+    for pi, pk in enumerate(pair_keys):
+        if not g.kept[pi]:
+            continue
+        for gi, gen in enumerate(g.genomes):
+            pr = pairs[pk][gen.name]
+            assert pr.dimerTm == 7.25 and pr.fbin == -1 and pr.rStrand == ""
+            exp = want.get((pi, gi))
+            if exp is None:
+                assert (pr.contig, pr.size) == ("NA", 0)
+            elif len(exp) == 1:
+                assert (pr.contig, pr.size) == exp[0]
+            else:
+                assert sorted(zip(pr.contig.split(","), map(int, pr.size.split(",")))) == sorted(exp)
